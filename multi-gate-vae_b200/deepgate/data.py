@@ -1,0 +1,85 @@
+"""Batch container for circuits: the data boundary of ``Model.forward(G)``.
+
+Mirrors what the reference gets from PyG's ``Batch`` of ``OrderedData``
+(parser_func_others.py:10-40): a batch is the disjoint union of circuits; keys
+whose name contains ``index`` are shifted by the running node count,
+``edge_index`` / ``tt_pair_index`` concatenate along dim 1, everything else
+along dim 0 un-shifted (so ``forward_level`` is shared across circuits).
+PyTorch-Geometric is not a dependency of this package.
+"""
+import torch
+
+_CAT_LAST = ("edge_index", "tt_pair_index", "rc_pair_index")
+
+
+class OrderedData(object):
+    """Attribute bag with the reference's batching rules (parser_func_others.py:28-40)."""
+
+    def __init__(self, **fields):
+        for k, v in fields.items():
+            setattr(self, k, v)
+
+    # mapping-style access, as PyG's Data offers (trainer.py:155-162 uses batch['prob'])
+    def __getitem__(self, key):
+        return getattr(self, key)
+
+    def __setitem__(self, key, value):
+        setattr(self, key, value)
+
+    def __contains__(self, key):
+        return getattr(self, key, None) is not None
+
+    def keys(self):
+        return [k for k, v in vars(self).items() if v is not None and not k.startswith("_")]
+
+    @property
+    def num_nodes(self):
+        return int(self.x.size(0))
+
+    def __inc__(self, key, value=None):
+        return self.num_nodes if ("index" in key or "face" in key) else 0
+
+    def __cat_dim__(self, key, value=None):
+        return 1 if key in _CAT_LAST else 0
+
+    def to(self, device, non_blocking=False):
+        for k, v in list(vars(self).items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device, non_blocking=non_blocking))
+        return self
+
+    def pin_memory(self):
+        for k, v in list(vars(self).items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.pin_memory())
+        return self
+
+
+def collate(circuits):
+    """Disjoint union of ``OrderedData`` circuits (adds ``batch`` and ``ptr``)."""
+    first = circuits[0]
+    out = OrderedData()
+    counts = [c.num_nodes for c in circuits]
+    starts = [0]
+    for n in counts:
+        starts.append(starts[-1] + n)
+    for key in first.keys():
+        vals = [c[key] for c in circuits]
+        if not torch.is_tensor(vals[0]):
+            out[key] = vals[0]
+            continue
+        if first.__inc__(key):
+            vals = [v + s for v, s in zip(vals, starts)]
+        out[key] = torch.cat(vals, dim=first.__cat_dim__(key))
+    out.batch = torch.repeat_interleave(torch.arange(len(circuits)), torch.tensor(counts))
+    out.ptr = torch.tensor(starts, dtype=torch.long)
+    out.num_graphs = len(circuits)
+    return out
+
+
+class DataLoader(torch.utils.data.DataLoader):
+    """``torch_geometric.loader.DataLoader`` stand-in used by ``Trainer`` (trainer.py:189-195)."""
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, **kw):
+        kw.pop("collate_fn", None)
+        super().__init__(dataset, batch_size, shuffle, collate_fn=collate, **kw)
