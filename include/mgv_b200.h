@@ -1,0 +1,191 @@
+/*
+ * mgv_b200 -- C ABI of the B200 (sm_100a) level-synchronous DAG message-passing library.
+ *
+ * This is the drop-in boundary for the hot path of 959AI994/Multi-Gate-VAE
+ * (DG_VAE/deepgate).  The reference has no native code; each entry point below
+ * replaces the Python/PyG code cited next to it (paths relative to
+ * /root/reference/DG_VAE/deepgate).  The host-side mirror of the reference's
+ * Python API (multi-gate-vae_b200/deepgate) binds these with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the caller (PyTorch) owns every buffer; the library allocates nothing
+ *    persistent and frees nothing; workspaces are caller-provided and sized by
+ *    the *_workspace_bytes() helpers;
+ *  - every call takes the CUDA stream explicitly and is asynchronous on it,
+ *    except where "synchronises" is stated;
+ *  - return value: 0 = ok, negative = error; mgv_last_error_string() gives the
+ *    message (thread-local).  No CPU fallback exists anywhere in the library.
+ *  - re-entrant, no global mutable state, no cudaSetDevice: the current device
+ *    of the calling thread must be the one that owns the pointers.
+ *
+ * Vocabulary: node = gate or primary input; level = ASAP topological level
+ * (top_sort); code = gate code 0..5 {INPUT, MAJ, NOT, AND, OR, XOR} (AIG: AND=1,
+ * NOT=2); D = dim_hidden = 64 (compile-time constant of the kernels).
+ */
+#ifndef MGV_B200_H
+#define MGV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGV_D 64                 /* dim_hidden the kernels are specialised for (config.py:13)   */
+#define MGV_NCODE 8              /* code buckets per level: 0..5 real codes, 6 = other, 7 unused */
+#define MGV_CODE_SHIFT 28        /* out_pack = dst | (code(dst) << 28)                          */
+#define MGV_MAX_FEAT 8           /* struct encoder: dim_feature <= 8 (config.py:14 default 6)   */
+
+/* Floats per gate-code weight block of the level sweep (see mgv_sweep_pack layout below). */
+#define MGV_SWEEP_PACK_FLOATS 66112
+/* Floats per gate-code gradient block returned by the backward sweep. */
+#define MGV_SWEEP_GRAD_FLOATS 33344
+/* Floats per (encoder, direction) weight block of the struct encoder. */
+#define MGV_STRUCT_PACK_FLOATS 61824
+#define MGV_STRUCT_GRAD_FLOATS 30912
+
+typedef void* mgv_stream_t;      /* cudaStream_t */
+
+const char* mgv_last_error_string(void);
+int mgv_version(void);
+/* Number of SMs of the current device (grid sizing for the persistent kernels). */
+int mgv_sm_count(void);
+
+/* ------------------------------------------------------------------ schedule (integer work)
+ * In/out-edge CSR by node id, ascending ORIGINAL EDGE ID inside a node -- the order in which
+ * utils/dag_utils.py:91-105 `subgraph` concatenates a node's incoming edges.
+ *   edge_index  int64 [2,E] row-major (row 0 = src/"parent", row 1 = dst/"child")
+ *   code        int32 [N] or NULL (then out_pack carries no code bits)
+ *   in_ptr[N+1], in_src[E]                      : predecessors of node v = in_src[in_ptr[v] .. in_ptr[v+1])
+ *   out_ptr[N+1], out_pack[E], out_slot[E]      : successors; out_slot = position of that edge in in_src
+ */
+size_t mgv_csr_workspace_bytes(int64_t N, int64_t E);
+int mgv_build_csr(const int64_t* edge_index, int64_t E, int32_t N, const int32_t* code,
+                  int32_t* in_ptr, int32_t* in_src, int32_t* out_ptr, int32_t* out_pack, int32_t* out_slot,
+                  void* ws, size_t ws_bytes, mgv_stream_t stream);
+
+/* ASAP level of every node == utils/dag_utils.py:10-37 top_sort(edge_index, N) (level 0 = no
+ * predecessor, else 1 + max over predecessors).  reverse != 0 levelises the reversed graph
+ * (return_order_info's backward_level, dag_utils.py:83-84): pass the out-CSR as the in-CSR and
+ * vice versa.  info[0] = number of levels, info[1] = number of nodes levelised (< N means the
+ * graph has a cycle; the reference would loop forever, this returns MGV_ERR_CYCLE after the
+ * synchronising read-back).  SYNCHRONISES the stream (the caller needs the level count).
+ */
+size_t mgv_levelize_workspace_bytes(int64_t N);
+int mgv_levelize(const int32_t* in_ptr, const int32_t* out_ptr, const int32_t* out_pack, int32_t N,
+                 int32_t* level, int32_t* info_host, void* ws, size_t ws_bytes, mgv_stream_t stream);
+
+/* Node lists per (level, code): order[N] = node ids stably sorted by (level, code) -- ascending
+ * id inside a segment, i.e. G.forward_index[layer_mask & type_mask] (dg_ae_model_mig.py:89);
+ * seg_ptr[L*MGV_NCODE + 1]; code_count_host[MGV_NCODE] = nodes of each code with level >= 1.
+ * SYNCHRONISES (returns the per-code counts used to size the persistent grids).
+ */
+size_t mgv_level_lists_workspace_bytes(int64_t N, int32_t L);
+int mgv_build_level_lists(const int32_t* level, const int32_t* code, int32_t N, int32_t L,
+                          int32_t* order, int32_t* seg_ptr, int64_t* code_count_host,
+                          void* ws, size_t ws_bytes, mgv_stream_t stream);
+
+/* ------------------------------------------------------------------ level sweep (fp32)
+ * Replaces the level loop of Model.forward (dg_ae_model_mig.py:84-129 and the aig/xmg/xag
+ * twins): per round, per level >= 1, per handled code: TFMlpAggr (arch/tfmlp.py:31-46) over the
+ * predecessors' [hs || hf] rows, then the code's nn.GRU cell with h = hf[node], hf[node] <- h'.
+ *
+ * weights: float [MGV_NCODE][MGV_SWEEP_PACK_FLOATS]; handled_mask bit c set = code c has an
+ * aggregator/GRU pair.  Block layout (floats), D = 64:
+ *      0  u[128]          = msg_k.weight^T attn_lin.weight[0,64:128]   (query part cancels in the softmax)
+ *    128  WvT[128][64]    = msg_v.weight^T          8320 bv[64]
+ *   8384  WihT[64][192]   = weight_ih_l0^T         20672 WhhT[64][192] = weight_hh_l0^T
+ *  32960  bih[192]        33152 bhh[192]
+ *  33344  Wv[64][128]     41536 Wih[192][64]       53824 Whh[192][64]          (natural copies, backward)
+ * hf_all: float [R][N][64], zero-initialised by the caller; slot r = hf after round r.
+ * sync: int32 [64] zero-initialised (grid barrier state).
+ */
+typedef struct mgv_schedule {
+    int32_t N, L;
+    int64_t E;
+    const int32_t* order;      /* [N]   */
+    const int32_t* seg_ptr;    /* [L*MGV_NCODE+1] */
+    const int32_t* in_ptr;     /* [N+1] */
+    const int32_t* in_src;     /* [E]   */
+    const int32_t* out_ptr;    /* [N+1] */
+    const int32_t* out_pack;   /* [E]   */
+    const int32_t* out_slot;   /* [E]   */
+    int64_t code_count[MGV_NCODE];   /* host values: nodes per code at level >= 1 */
+} mgv_schedule;
+
+int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,
+                        const float* weights, const float* hs, float* hf_all,
+                        int32_t* sync, mgv_stream_t stream);
+
+/* Backward of the sweep.  ghs [N][64] in/out: += d loss / d hs through every gather of every
+ * round.  ghf [N][64] in/out: in = d loss / d hf (final round); clobbered.  grads: float
+ * [MGV_NCODE][MGV_SWEEP_GRAD_FLOATS] out, natural layouts:
+ *      0 du[128]   128 dWv[64][128]   8320 dbv[64]   8384 dWih[192][64]   20672 dWhh[192][64]
+ *  32960 dbih[192]   33152 dbhh[192]
+ * Workspace: mgv_sweep_bwd_workspace_bytes(N, E, grid) with grid = mgv_sweep_bwd_grid().
+ */
+int mgv_sweep_bwd_grid(void);
+size_t mgv_sweep_bwd_workspace_bytes(int64_t N, int64_t E);
+int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,
+                        const float* weights, const float* hs, const float* hf_all,
+                        float* ghs, float* ghf, float* grads,
+                        void* ws, size_t ws_bytes, int32_t* sync, mgv_stream_t stream);
+
+/* ------------------------------------------------------------------ struct encoder (fp32)
+ * Replaces MultiGCNEncoder.forward (digae_layer.py:257-277) with AggConv (arch/gcn_conv.py:30-42):
+ * state_0 = 1; per round: state <- LN(GRU([W sum_{in-nbrs} state + deg b || x], state)), then the
+ * same over out-neighbours with aggr_r/update_r and the SAME LayerNorm.  num_enc encoders (source_conv,
+ * target_conv of DirectMultiGCNEncoder, digae_layer.py:294-297) run batched over the same graph.
+ *
+ * weights: float [num_enc][2 dirs][MGV_STRUCT_PACK_FLOATS]; block layout:
+ *      0 WT[64][64] (msg.weight^T)   4096 b[64]   4160 WihT[72][192] (weight_ih_l0^T, rows 70,71 zero)
+ *  17984 WhhT[64][192]   30272 bih[192]   30464 bhh[192]   30656 ln_w[64]   30720 ln_b[64]  (ln only in dir 0 block
+ *  but duplicated in both)   30784 pad[128]
+ *  30912 W[64][64]   35008 Wih[192][72]   48832 Whh[192][64]  (natural copies, backward) -> 61120, pad to 61824
+ * x: float [N][feat] (feat <= MGV_MAX_FEAT).  states: float [num_enc][2*rounds+1][N][64] out
+ * (slot 0 = ones, written by the call; slot 2*rounds = encoder output).
+ */
+int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
+                           int32_t feat, const float* x, const float* weights, float* states,
+                           mgv_stream_t stream);
+/* gout: float [num_enc][N][64] = d loss / d (encoder output).  grads: float
+ * [num_enc][2][MGV_STRUCT_GRAD_FLOATS] out: 0 dW[64][64]  4096 db[64]  4160 dWih[192][72]  17984 dWhh[192][64]
+ * 30272 dbih[192]  30464 dbhh[192]  30656 dln_w[64]  30720 dln_b[64]. */
+int mgv_struct_bwd_grid(void);
+size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc);
+int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
+                           int32_t feat, const float* x, const float* weights, const float* states,
+                           const float* gout, float* grads, void* ws, size_t ws_bytes, mgv_stream_t stream);
+
+/* ------------------------------------------------------------------ fused reparam + KL + func loss
+ * Replaces DirectedGVAE.sample's elementwise part (digvae_model.py:138-141), the KL of
+ * trainer.py:145-148 and the truth-table-similarity loss of trainer.py:157-163 with
+ * zero_normalization (utils/utils.py:32-36) in ONE launch.
+ *   mu/logstd/eps: float [2][N][64] (s then t); z out [2][N][64]          (N may be 0: VAE part skipped)
+ *   hf float [Nf][64]; pair int64 [2][P]; tt_sim float [P]                 (P may be 0: func part skipped)
+ *   out float [8]: 0 kl, 1 func_loss, 2 mean(dis), 3 std(dis), 4 mean(tt), 5 std(tt), 6 sum g*zd, 7 mean g
+ *   ws: float/double scratch, mgv_vae_func_workspace_bytes(P), zero-initialised by the caller.
+ */
+size_t mgv_vae_func_workspace_bytes(int64_t P);
+int mgv_vae_func_loss_fwd(const float* mu, const float* logstd, const float* eps, float* z, int64_t N,
+                          const float* hf, const int64_t* pair, const float* tt_sim, int64_t P,
+                          float* out, void* ws, size_t ws_bytes, mgv_stream_t stream);
+/* g_out float [2] on device: d L / d kl, d L / d func_loss; gz float [2][N][64] = d L / d z.
+ * gmu, glogstd out [2][N][64]; ghf [Nf][64] in/out: func-loss gradient is atomically ADDED. */
+int mgv_vae_func_loss_bwd(const float* g_out, const float* gz, const float* mu, const float* logstd,
+                          const float* eps, float* gmu, float* glogstd, int64_t N,
+                          const float* hf, const int64_t* pair, const float* tt_sim, int64_t P,
+                          const float* out, const void* ws, float* ghf, mgv_stream_t stream);
+
+#define MGV_OK 0
+#define MGV_ERR_ARG (-1)
+#define MGV_ERR_CUDA (-2)
+#define MGV_ERR_WORKSPACE (-3)
+#define MGV_ERR_CYCLE (-4)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGV_B200_H */

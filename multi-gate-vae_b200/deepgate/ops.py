@@ -1,0 +1,262 @@
+"""Autograd bindings of the CUDA kernels (libmgv_b200.so) for the hot path.
+
+  level_sweep(...)        dg_ae_model_*.py level loop  (TFMlpAggr + GRU per level / gate code)
+  struct_encoder(...)     MultiGCNEncoder x {source, target}  (digae_layer.py:257-297)
+  vae_func_loss(...)      reparam + KL + func loss  (digvae_model.py:134-142, trainer.py:145-163)
+
+Every function fails loudly when its inputs are not on a CUDA device or the library is
+missing; nothing here falls back to PyTorch ops for the arithmetic.
+"""
+import torch
+
+from . import _native as nat
+
+_AGGR_KEYS = ("attn_lin.weight", "attn_lin.bias", "msg_q.weight", "msg_q.bias", "msg_k.weight", "msg_k.bias",
+              "msg_v.weight", "msg_v.bias")
+_GRU_KEYS = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")
+PARAMS_PER_CODE = len(_AGGR_KEYS) + len(_GRU_KEYS)      # 12
+
+
+def _f32(t, name):
+    return nat.require_cuda(t.detach().contiguous(), name, torch.float32)
+
+
+# =========================================================================== level sweep
+def _sweep_pack(params, codes, device):
+    """[8][66112] weight blocks in the kernel layout (include/mgv_b200.h)."""
+    D = nat.D
+    pack = torch.zeros(nat.NCODE, nat.SWEEP_PACK_FLOATS, dtype=torch.float32, device=device)
+    for i, c in enumerate(codes):
+        aw, ab, qw, qb, kw, kb, vw, vb, wih, whh, bih, bhh = [p.detach() for p in
+                                                              params[i * PARAMS_PER_CODE:(i + 1) * PARAMS_PER_CODE]]
+        if tuple(vw.shape) != (D, 2 * D) or tuple(wih.shape) != (3 * D, D):
+            raise RuntimeError("mgv_b200: level sweep kernels are built for dim_hidden=%d" % D)
+        u = aw[0, D:] @ kw                                   # [128] = W_k^T w_a[64:]
+        pack[c] = torch.cat([u, vw.t().reshape(-1), vb, wih.t().reshape(-1), whh.t().reshape(-1), bih, bhh,
+                             vw.reshape(-1), wih.reshape(-1), whh.reshape(-1)])
+    return pack
+
+
+class LevelSweepFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hs, sched, rounds, codes, *params):
+        lib = nat.lib()
+        dev = hs.device
+        hs_c = _f32(hs, "hs")
+        N = sched.N
+        if hs_c.shape != (N, nat.D):
+            raise RuntimeError("mgv_b200: hs must be [N, %d]" % nat.D)
+        mask = 0
+        for c in codes:
+            mask |= 1 << c
+        pack = _sweep_pack(params, codes, dev)
+        hf_all = torch.zeros(rounds, max(N, 1), nat.D, dtype=torch.float32, device=dev)
+        sync = torch.zeros(64, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            nat.check(lib.mgv_level_sweep_fwd(sched.c_struct(), rounds, mask, nat.ptr(pack), nat.ptr(hs_c),
+                                              nat.ptr(hf_all), nat.ptr(sync), nat.stream_of(dev)),
+                      "mgv_level_sweep_fwd")
+        ctx.sched, ctx.rounds, ctx.codes, ctx.mask = sched, rounds, tuple(codes), mask
+        ctx.save_for_backward(hs_c, hf_all, pack, *params)
+        ctx.launches = 1
+        return hf_all[rounds - 1][:N]
+
+    @staticmethod
+    def backward(ctx, g_hf):
+        lib = nat.lib()
+        hs_c, hf_all, pack = ctx.saved_tensors[:3]
+        params = ctx.saved_tensors[3:]
+        sched, rounds, codes = ctx.sched, ctx.rounds, ctx.codes
+        dev = hs_c.device
+        N, D = sched.N, nat.D
+        ghs = torch.zeros(max(N, 1), D, dtype=torch.float32, device=dev)
+        ghf = torch.zeros(max(N, 1), D, dtype=torch.float32, device=dev)
+        ghf[:N] = g_hf
+        grads = torch.empty(nat.NCODE, nat.SWEEP_GRAD_FLOATS, dtype=torch.float32, device=dev)
+        sync = torch.zeros(64, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            nb = lib.mgv_sweep_bwd_workspace_bytes(N, sched.E)
+            ws = nat.workspace(nb, dev)
+            nat.check(lib.mgv_level_sweep_bwd(sched.c_struct(), rounds, ctx.mask, nat.ptr(pack), nat.ptr(hs_c),
+                                              nat.ptr(hf_all), nat.ptr(ghs), nat.ptr(ghf), nat.ptr(grads),
+                                              nat.ptr(ws), nb, nat.ptr(sync), nat.stream_of(dev)),
+                      "mgv_level_sweep_bwd")
+        out = []
+        for i, c in enumerate(codes):
+            aw, ab, qw, qb, kw, kb, vw, vb, wih, whh, bih, bhh = params[i * PARAMS_PER_CODE:(i + 1) * PARAMS_PER_CODE]
+            g = grads[c]
+            du = g[0:128]
+            d_aw = torch.zeros_like(aw)
+            d_aw[0, D:] = kw.detach() @ du                    # u = W_k^T w_a[64:]
+            d_kw = torch.outer(aw.detach()[0, D:], du)
+            out += [d_aw, torch.zeros_like(ab), torch.zeros_like(qw), torch.zeros_like(qb), d_kw,
+                    torch.zeros_like(kb),                     # query / key-bias / attn-bias cancel in the softmax
+                    g[128:8320].view(D, 2 * D), g[8320:8384],
+                    g[8384:20672].view(3 * D, D), g[20672:32960].view(3 * D, D), g[32960:33152], g[33152:33344]]
+        return (ghs[:N], None, None, None) + tuple(out)
+
+
+def level_sweep(hs, sched, rounds, codes, modules):
+    """hf [N, 64] after ``rounds`` sweeps.  ``modules`` = [(TFMlpAggr, nn.GRU)] aligned with ``codes``."""
+    params = []
+    for aggr, gru in modules:
+        sd = dict(aggr.named_parameters())
+        params += [sd[k] for k in _AGGR_KEYS]
+        gd = dict(gru.named_parameters())
+        params += [gd[k] for k in _GRU_KEYS]
+    return LevelSweepFunction.apply(hs, sched, int(rounds), tuple(int(c) for c in codes), *params)
+
+
+# =========================================================================== struct encoder
+def _struct_pack(enc_params, layernorm, device):
+    """[num_enc][2][61824] weight blocks.  enc_params[e] = (aggr.w, aggr.b, upd.wih, upd.whh, upd.bih, upd.bhh,
+    aggr_r.w, aggr_r.b, upd_r.wih, upd_r.whh, upd_r.bih, upd_r.bhh[, ln.w, ln.b])."""
+    D, KX = nat.D, nat.D + nat.MAX_FEAT
+    pack = torch.zeros(len(enc_params), 2, nat.STRUCT_PACK_FLOATS, dtype=torch.float32, device=device)
+    for e, ps in enumerate(enc_params):
+        ps = [p.detach() for p in ps]
+        lnw = ps[12] if layernorm else torch.ones(D, device=device)
+        lnb = ps[13] if layernorm else torch.zeros(D, device=device)
+        for d in range(2):
+            w, b, wih, whh, bih, bhh = ps[6 * d:6 * d + 6]
+            feat = wih.shape[1] - D
+            if tuple(w.shape) != (D, D) or feat < 0 or feat > nat.MAX_FEAT:
+                raise RuntimeError("mgv_b200: struct encoder kernels need dim_hidden=%d, dim_feature<=%d"
+                                   % (D, nat.MAX_FEAT))
+            wih_p = torch.zeros(3 * D, KX, dtype=torch.float32, device=device)
+            wih_p[:, :D + feat] = wih
+            pack[e, d, :61120] = torch.cat([
+                w.t().reshape(-1), b, wih_p.t().reshape(-1), whh.t().reshape(-1), bih, bhh, lnw, lnb,
+                torch.zeros(128, device=device), w.reshape(-1), wih_p.reshape(-1), whh.reshape(-1)])
+    return pack
+
+
+class StructEncoderFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, csr, rounds, layernorm, num_enc, *params):
+        lib = nat.lib()
+        dev = x.device
+        x_c = _f32(x.to(torch.float32), "x")
+        N = csr.N
+        feat = int(x_c.shape[1])
+        per = len(params) // num_enc
+        enc_params = [params[e * per:(e + 1) * per] for e in range(num_enc)]
+        pack = _struct_pack(enc_params, layernorm, dev)
+        states = torch.empty(num_enc, 2 * rounds + 1, max(N, 1), nat.D, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nat.check(lib.mgv_struct_encoder_fwd(csr.c_struct(), num_enc, rounds, int(layernorm), feat,
+                                                 nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.stream_of(dev)),
+                      "mgv_struct_encoder_fwd")
+        ctx.csr, ctx.rounds, ctx.layernorm, ctx.num_enc, ctx.feat, ctx.per = csr, rounds, layernorm, num_enc, feat, per
+        ctx.save_for_backward(x_c, pack, states)
+        ctx.param_shapes = [tuple(p.shape) for p in params]
+        return states[:, 2 * rounds, :N]
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = nat.lib()
+        x_c, pack, states = ctx.saved_tensors
+        csr, rounds, num_enc, feat, per = ctx.csr, ctx.rounds, ctx.num_enc, ctx.feat, ctx.per
+        dev = x_c.device
+        N, D, KX = csr.N, nat.D, nat.D + nat.MAX_FEAT
+        g = torch.zeros(num_enc, max(N, 1), D, dtype=torch.float32, device=dev)
+        g[:, :N] = gout
+        grads = torch.empty(num_enc, 2, nat.STRUCT_GRAD_FLOATS, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nb = lib.mgv_struct_bwd_workspace_bytes(N, num_enc)
+            ws = nat.workspace(nb, dev)
+            nat.check(lib.mgv_struct_encoder_bwd(csr.c_struct(), num_enc, rounds, int(ctx.layernorm), feat,
+                                                 nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(g),
+                                                 nat.ptr(grads), nat.ptr(ws), nb, nat.stream_of(dev)),
+                      "mgv_struct_encoder_bwd")
+        out = []
+        for e in range(num_enc):
+            for d in range(2):
+                gd = grads[e, d]
+                out += [gd[0:4096].view(D, D), gd[4096:4160],
+                        gd[4160:17984].view(3 * D, KX)[:, :D + feat], gd[17984:30272].view(3 * D, D),
+                        gd[30272:30464], gd[30464:30656]]
+            if ctx.layernorm:
+                out += [grads[e, 0, 30656:30720] + grads[e, 1, 30656:30720],
+                        grads[e, 0, 30720:30784] + grads[e, 1, 30720:30784]]
+        return (None, None, None, None, None) + tuple(out)
+
+
+def struct_encoder(x, csr, rounds, layernorm, encoders):
+    """Final node states [num_enc, N, 64] of ``encoders`` (MultiGCNEncoder modules, same rounds)."""
+    params = []
+    for enc in encoders:
+        params += [enc.aggr.msg.weight, enc.aggr.msg.bias, enc.update.weight_ih_l0, enc.update.weight_hh_l0,
+                   enc.update.bias_ih_l0, enc.update.bias_hh_l0,
+                   enc.aggr_r.msg.weight, enc.aggr_r.msg.bias, enc.update_r.weight_ih_l0, enc.update_r.weight_hh_l0,
+                   enc.update_r.bias_ih_l0, enc.update_r.bias_hh_l0]
+        if layernorm:
+            params += [enc.ln.weight, enc.ln.bias]
+    return StructEncoderFunction.apply(x, csr, int(rounds), bool(layernorm), len(encoders), *params)
+
+
+# =========================================================================== reparam + KL + func loss
+class VaeFuncLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logstd, eps, hf, pair, tt_sim):
+        """mu/logstd/eps [2,N,64] or None; hf [Nf,64], pair [2,P] int64, tt_sim [P] or None.
+        Returns (z [2,N,64], kl, func_loss)."""
+        lib = nat.lib()
+        has_vae, has_func = mu is not None, pair is not None
+        dev = mu.device if has_vae else hf.device
+        N = int(mu.shape[1]) if has_vae else 0
+        P = int(pair.shape[1]) if has_func else 0
+        mu_c = _f32(mu, "mu") if has_vae else None
+        ls_c = _f32(logstd, "logstd") if has_vae else None
+        eps_c = _f32(eps, "eps") if has_vae else None
+        hf_c = _f32(hf, "hf") if has_func else None
+        pair_c = nat.require_cuda(pair.contiguous(), "tt_pair_index", torch.int64) if has_func else None
+        tt_c = _f32(tt_sim.to(torch.float32), "tt_sim") if has_func else None
+        z = torch.empty(2, N, nat.D, dtype=torch.float32, device=dev)
+        out = torch.zeros(8, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nb = lib.mgv_vae_func_workspace_bytes(P)
+            ws = nat.workspace(nb, dev, zero=True)
+            nat.check(lib.mgv_vae_func_loss_fwd(nat.ptr(mu_c), nat.ptr(ls_c), nat.ptr(eps_c), nat.ptr(z), N,
+                                                nat.ptr(hf_c), nat.ptr(pair_c), nat.ptr(tt_c), P, nat.ptr(out),
+                                                nat.ptr(ws), nb, nat.stream_of(dev)), "mgv_vae_func_loss_fwd")
+        ctx.N, ctx.P, ctx.has_vae, ctx.has_func = N, P, has_vae, has_func
+        ctx.hf_shape = tuple(hf.shape) if has_func else None
+        ctx.save_for_backward(mu_c, ls_c, eps_c, hf_c, pair_c, tt_c, out, ws)
+        return z, out[0].clone(), out[1].clone()
+
+    @staticmethod
+    def backward(ctx, gz, gkl, gfunc):
+        lib = nat.lib()
+        mu_c, ls_c, eps_c, hf_c, pair_c, tt_c, out, ws = ctx.saved_tensors
+        dev = out.device
+        N, P = ctx.N, ctx.P
+        g2 = torch.zeros(2, dtype=torch.float32, device=dev)
+        if gkl is not None:
+            g2[0] = gkl
+        if gfunc is not None:
+            g2[1] = gfunc
+        gmu = gls = ghf = None
+        gz_c = None
+        if ctx.has_vae:
+            gz_c = _f32(gz, "gz") if gz is not None else torch.zeros(2, N, nat.D, dtype=torch.float32, device=dev)
+            gmu, gls = torch.empty_like(mu_c), torch.empty_like(mu_c)
+        if ctx.has_func:
+            ghf = torch.zeros(ctx.hf_shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nat.check(lib.mgv_vae_func_loss_bwd(nat.ptr(g2), nat.ptr(gz_c), nat.ptr(mu_c), nat.ptr(ls_c),
+                                                nat.ptr(eps_c), nat.ptr(gmu), nat.ptr(gls), N, nat.ptr(hf_c),
+                                                nat.ptr(pair_c), nat.ptr(tt_c), P, nat.ptr(out), nat.ptr(ws),
+                                                nat.ptr(ghf), nat.stream_of(dev)), "mgv_vae_func_loss_bwd")
+        return gmu, gls, None, ghf, None, None
+
+
+def vae_func_loss(mu=None, logstd=None, eps=None, hf=None, tt_pair_index=None, tt_sim=None):
+    """Fused reparameterisation + KL + truth-table-similarity loss (one launch).  Either half may be
+    omitted.  Returns (z_s, z_t, kl, func_loss); absent halves come back as None."""
+    if mu is None and tt_pair_index is None:
+        raise RuntimeError("mgv_b200: vae_func_loss needs the VAE inputs, the func-loss inputs, or both")
+    z, kl, func = VaeFuncLossFunction.apply(mu, logstd, eps, hf, tt_pair_index, tt_sim)
+    if mu is None:
+        return None, None, None, func
+    return z[0], z[1], kl, (func if tt_pair_index is not None else None)

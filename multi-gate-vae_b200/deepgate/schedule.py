@@ -1,0 +1,158 @@
+"""Device-built level schedule of a circuit batch.
+
+Replaces, on the GPU and once per batch, what the reference recomputes on the host for
+every level, gate type and node: ``layer_mask & type_mask`` node selection
+(dg_ae_model_mig.py:86-89) and ``subgraph`` (utils/dag_utils.py:91-105), plus ``top_sort``
+(utils/dag_utils.py:10-37) when a batch carries no ``forward_level``.
+
+Holds int32 device arrays:
+  in_ptr/in_src      predecessors by node id, ascending original edge id
+  out_ptr/out_pack/out_slot  successors (out_pack = dst | code(dst) << 28)
+  level              ASAP level per node
+  order/seg_ptr      node ids sorted by (level, code), segment boundaries [L*8+1]
+"""
+import ctypes
+
+import torch
+
+from . import _native as nat
+
+
+class GraphCSR(object):
+    """In/out-edge CSR of ``edge_index`` ([2, E] int64, row 0 = source)."""
+
+    def __init__(self, edge_index, num_nodes, code=None):
+        nat.require_cuda(edge_index, "edge_index", torch.int64)
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise RuntimeError("mgv_b200: edge_index must be [2, E]")
+        dev = edge_index.device
+        self.device = dev
+        self.N = int(num_nodes)
+        self.E = int(edge_index.size(1))
+        self.edge_index = edge_index
+        self.code = None
+        if code is not None:
+            self.code = nat.require_cuda(code.to(torch.int32).contiguous(), "code", torch.int32)
+            if self.code.numel() != self.N:
+                raise RuntimeError("mgv_b200: code must have one entry per node")
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.in_ptr = torch.empty(self.N + 1, **i32)
+        self.in_src = torch.empty(max(self.E, 1), **i32)
+        self.out_ptr = torch.empty(self.N + 1, **i32)
+        self.out_pack = torch.empty(max(self.E, 1), **i32)
+        self.out_slot = torch.empty(max(self.E, 1), **i32)
+        lib = nat.lib()
+        with torch.cuda.device(dev):
+            nb = lib.mgv_csr_workspace_bytes(self.N, self.E)
+            ws = nat.workspace(nb, dev)
+            nat.check(lib.mgv_build_csr(nat.ptr(edge_index), self.E, self.N, nat.ptr(self.code),
+                                        nat.ptr(self.in_ptr), nat.ptr(self.in_src), nat.ptr(self.out_ptr),
+                                        nat.ptr(self.out_pack), nat.ptr(self.out_slot), nat.ptr(ws), nb,
+                                        nat.stream_of(dev)), "mgv_build_csr")
+        self.level = None
+        self.L = 1
+        self.order = None
+        self.seg_ptr = None
+        self.code_count = [0] * nat.NCODE
+        self._struct = None
+
+    # ------------------------------------------------------------------ levels
+    def levelize(self, reverse=False):
+        """ASAP levels (== top_sort).  Returns (int32 level tensor, number of levels)."""
+        lib = nat.lib()
+        level = torch.empty(max(self.N, 1), dtype=torch.int32, device=self.device)
+        info = (ctypes.c_int32 * 2)()
+        a_ptr, b_ptr, b_idx = ((self.in_ptr, self.out_ptr, self.out_pack) if not reverse
+                               else (self.out_ptr, self.in_ptr, self.in_src))
+        with torch.cuda.device(self.device):
+            nb = lib.mgv_levelize_workspace_bytes(self.N)
+            ws = nat.workspace(nb, self.device)
+            nat.check(lib.mgv_levelize(nat.ptr(a_ptr), nat.ptr(b_ptr), nat.ptr(b_idx), self.N, nat.ptr(level),
+                                       info, nat.ptr(ws), nb, nat.stream_of(self.device)), "mgv_levelize")
+        return level[:self.N], max(int(info[0]), 1)
+
+    def set_levels(self, level=None):
+        """Attach levels (given, e.g. ``G.forward_level``, or computed) and build the
+        (level, code)-segmented node lists."""
+        if self.code is None:
+            raise RuntimeError("mgv_b200: a level schedule needs gate codes")
+        if level is None:
+            lvl, L = self.levelize()
+        else:
+            lvl = nat.require_cuda(level.reshape(-1).to(torch.int32).contiguous(), "forward_level", torch.int32)
+            if lvl.numel() != self.N:
+                raise RuntimeError("mgv_b200: forward_level must have one entry per node")
+            # one device->host sync, as the reference's max(G.forward_level).item() (dg_ae_model_mig.py:67)
+            L = int(lvl.max().item()) + 1 if self.N > 0 else 1
+        self.level, self.L = lvl, L
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.order = torch.empty(max(self.N, 1), **i32)
+        self.seg_ptr = torch.empty(L * nat.NCODE + 1, **i32)
+        counts = (ctypes.c_int64 * nat.NCODE)()
+        lib = nat.lib()
+        with torch.cuda.device(self.device):
+            nb = lib.mgv_level_lists_workspace_bytes(self.N, L)
+            ws = nat.workspace(nb, self.device)
+            nat.check(lib.mgv_build_level_lists(nat.ptr(lvl), nat.ptr(self.code), self.N, L, nat.ptr(self.order),
+                                                nat.ptr(self.seg_ptr), counts, nat.ptr(ws), nb,
+                                                nat.stream_of(self.device)), "mgv_build_level_lists")
+        self.code_count = [int(c) for c in counts]
+        self._struct = None
+        return self
+
+    # ------------------------------------------------------------------ C view
+    def c_struct(self):
+        if self._struct is None:
+            s = nat.mgv_schedule()
+            s.N, s.L, s.E = self.N, self.L, self.E
+            s.order, s.seg_ptr = nat.ptr(self.order), nat.ptr(self.seg_ptr)
+            s.in_ptr, s.in_src = nat.ptr(self.in_ptr), nat.ptr(self.in_src)
+            s.out_ptr, s.out_pack, s.out_slot = nat.ptr(self.out_ptr), nat.ptr(self.out_pack), nat.ptr(self.out_slot)
+            for c in range(nat.NCODE):
+                s.code_count[c] = self.code_count[c]
+            self._struct = s
+        return ctypes.byref(self._struct)
+
+    def num_propagated(self, handled_codes):
+        """Nodes the sweep updates per round: level >= 1 and a handled gate code."""
+        return sum(self.code_count[c] for c in handled_codes)
+
+
+_last = {"key": None, "csr": None}
+
+
+def _key(edge_index, num_nodes):
+    return (edge_index.data_ptr(), tuple(edge_index.shape), int(num_nodes), edge_index._version, str(edge_index.device))
+
+
+def csr_for(edge_index, num_nodes):
+    """CSR of ``edge_index`` with a one-entry cache, so the struct encoder called through its
+    public ``forward(s, t, edge_index)`` reuses the CSR the model just built for the batch."""
+    k = _key(edge_index, num_nodes)
+    if _last["key"] == k:
+        return _last["csr"]
+    csr = GraphCSR(edge_index.contiguous(), num_nodes)
+    _last["key"], _last["csr"] = k, csr
+    return csr
+
+
+def schedule_for_batch(G):
+    """Level schedule of a batch ``G`` (cached on the object).  Uses ``G.forward_level`` when the
+    batch carries it (the reference computes it at dataset build, parser_func_others.py:63)."""
+    sch = getattr(G, "_mgv_schedule", None)
+    ei = G.edge_index
+    n = int(G.gate.shape[0])
+    if sch is not None and sch.N == n and sch.edge_index.data_ptr() == ei.data_ptr() and sch.E == ei.size(1):
+        return sch
+    if not ei.is_cuda:
+        raise RuntimeError("mgv_b200: the batch must be on a CUDA device (no CPU path); call batch.to('cuda')")
+    code = G.gate.reshape(-1)
+    sch = GraphCSR(ei.contiguous(), n, code=code)
+    level = getattr(G, "forward_level", None)
+    sch.set_levels(level if (level is not None and level.numel() == n) else None)
+    try:
+        G._mgv_schedule = sch
+    except Exception:
+        pass
+    _last["key"], _last["csr"] = _key(ei, n), sch
+    return sch

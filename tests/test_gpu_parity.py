@@ -1,0 +1,234 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors produced by the
+unmodified reference and against the CPU oracle on fresh seeded inputs.
+
+Tolerances (north_star): level schedule / CSR bit-exact; embeddings, losses and gradients within
+1e-4 relative (max-norm per tensor) in fp32; scale-relative for the mathematically-zero gradients."""
+import pytest
+import torch
+
+from oracle import dg_oracle as O
+from util import (batch_from_arrays, build_model, check_grads, load_golden, oracle_inputs, oracle_train_grads, rel)
+
+pytestmark = pytest.mark.gpu
+CASES = ["mig_b4_r1", "aig_b4_r1", "xmg_b3_r2", "xag_b3_r1"]
+TOL = 1e-4
+
+
+def golden_batch(g):
+    return batch_from_arrays(g["code"], g["edge_index"], g["forward_level"], g["prob"], g["tt_pair_index"], g["tt_sim"])
+
+
+# --------------------------------------------------------------------------- schedule (bit-exact)
+def test_kats_on_device():
+    from deepgate.utils import dag_utils
+    k = load_golden("kats")
+    ei = k["edge_index"].cuda()
+    assert dag_utils.top_sort(ei, 9).cpu().tolist() == [0, 0, 0, 1, 2, 3, 4, 4, 0]
+    sub, _ = dag_utils.subgraph(torch.tensor([5, 3]), ei, dim=1)
+    assert sub.cpu().tolist() == [[4, 1, 0, 1, 2], [5, 5, 3, 3, 3]]
+    fl, fi, bl, bi = dag_utils.return_order_info(ei, 9)
+    assert torch.equal(bl.cpu(), O.top_sort(k["edge_index"].flip(0), 9)) and torch.equal(fi.cpu(), torch.arange(9))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_level_csr_bit_exact(name):
+    from deepgate.schedule import GraphCSR
+    g = load_golden(name)
+    n = g["code"].numel()
+    csr = GraphCSR(g["edge_index"].cuda(), n, code=g["code"].cuda())
+    level, L = csr.levelize()
+    assert torch.equal(level.cpu().long(), g["forward_level"]) and L == int(g["forward_level"].max()) + 1
+    rlevel, _ = csr.levelize(reverse=True)
+    assert torch.equal(rlevel.cpu().long(), g["backward_level"])
+    csr.set_levels(g["forward_level"].cuda())
+    order, seg = csr.order.cpu().long(), csr.seg_ptr.cpu().long()
+    in_ptr, in_src = csr.in_ptr.cpu().long(), csr.in_src.cpu().long()
+    # node order == stable sort by (level, code); segments == G.forward_index[layer_mask & type_mask]
+    key = g["forward_level"] * 8 + g["code"].long()
+    assert torch.equal(order[:n], torch.sort(key, stable=True).indices)
+    nodes, ptr = g["kat_nodes"].long(), g["kat_ptr"].tolist()
+    keys = nodes[0] * 8 + nodes[1]
+    for si, kk in enumerate(torch.unique_consecutive(keys).tolist()):
+        sel = nodes[2][keys == kk]
+        assert torch.equal(order[seg[kk]:seg[kk + 1]], sel)
+        want = g["kat_edges"][:, ptr[si]:ptr[si + 1]]              # reference subgraph(l_node, edge_index, dim=1)
+        got_src = torch.cat([in_src[in_ptr[v]:in_ptr[v + 1]] for v in sel.tolist()])
+        got_dst = torch.cat([torch.full((int(in_ptr[v + 1] - in_ptr[v]),), v) for v in sel.tolist()])
+        assert torch.equal(torch.stack([got_src, got_dst]), want)
+    # out-CSR: ascending edge id per source, slots point back into the in-CSR
+    ei = g["edge_index"]
+    out_ptr, out_pack, out_slot = csr.out_ptr.cpu().long(), csr.out_pack.cpu().long(), csr.out_slot.cpu().long()
+    stable = torch.sort(ei[0], stable=True).indices
+    assert torch.equal(out_pack[:ei.size(1)] & ((1 << 28) - 1), ei[1][stable])
+    assert torch.equal(out_pack[:ei.size(1)] >> 28, g["code"].long()[ei[1][stable]])
+    assert torch.equal(in_src[out_slot[:ei.size(1)]], ei[0][stable])
+    assert torch.equal(out_ptr, torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(torch.bincount(ei[0], minlength=n), 0)]))
+
+
+def test_levelize_large_and_cycle():
+    from deepgate import synth
+    from deepgate.schedule import GraphCSR
+    c = synth.make_circuit("mig", 16, 30000, seed=4242, window=300)
+    ei = torch.as_tensor(c["edge_index"]).t().contiguous()
+    n = c["x"].shape[0]
+    csr = GraphCSR(ei.cuda(), n, code=torch.as_tensor(c["x"][:, 1]).cuda())
+    level, L = csr.levelize()
+    ref = O.top_sort(ei, n)
+    assert torch.equal(level.cpu().long(), ref) and L == int(ref.max()) + 1 and L > 150
+    csr.set_levels()
+    key = ref * 8 + torch.as_tensor(c["x"][:, 1])
+    assert torch.equal(csr.order.cpu().long(), torch.sort(key, stable=True).indices)
+    stable = torch.sort(ei[1], stable=True).indices                 # in-CSR == stable sort by destination
+    assert torch.equal(csr.in_src.cpu().long(), ei[0][stable])
+    cyc = torch.tensor([[0, 1, 2, 3], [1, 2, 0, 0]]).cuda()
+    with pytest.raises(RuntimeError, match="cycle"):
+        GraphCSR(cyc, 4).levelize()
+    with pytest.raises(RuntimeError, match="outside"):
+        GraphCSR(torch.tensor([[0, 9], [1, 2]]).cuda(), 4)
+    empty = GraphCSR(torch.zeros(2, 0, dtype=torch.long).cuda(), 5, code=torch.zeros(5, dtype=torch.int32).cuda())
+    lv, L0 = empty.levelize()
+    assert lv.cpu().tolist() == [0] * 5 and L0 == 1
+
+
+# --------------------------------------------------------------------------- forward / losses / grads vs golden
+@pytest.mark.parametrize("name", CASES)
+def test_forward_losses_grads_match_reference_golden(name):
+    import deepgate
+    g = load_golden(name)
+    sd = O.synth_state_dict(g["kind"], g["weight_seed"])
+    model = build_model(g["kind"], sd, g["num_rounds"])
+    batch = golden_batch(g)
+    hs, hf = model(batch)
+    assert rel(hs, g["hs"]) < TOL and rel(hf, g["hf"]) < TOL
+    assert float(hf[g["forward_level"].cuda() == 0].abs().max()) == 0.0        # PI rows exactly zero
+    rec, pred_bin, _ = model.recon_loss(hs, g["train_pos_edge_index"].cuda(), g["neg_edge_index"].cuda())
+    prob_loss = torch.nn.L1Loss()(model.pred_prob(hf), batch.prob)
+    _, _, _, func = deepgate.ops.vae_func_loss(hf=hf, tt_pair_index=batch.tt_pair_index, tt_sim=batch.tt_sim)
+    for got, key in ((rec, "recon_loss"), (prob_loss, "prob_loss"), (func, "func_loss")):
+        assert abs(float(got) - float(g[key])) < TOL * max(1.0, abs(float(g[key]))), key
+    assert float((pred_bin.cpu() != g["pred_bin"].int()).float().mean()) < 0.01
+    if "grads" in g:
+        w = g["loss_weights"]
+        (w[0] * rec + w[1] * prob_loss + w[2] * func).backward()
+        named = {k: p.grad for k, p in model.named_parameters()}
+        assert all(v is not None for v in named.values()), "every parameter must receive a gradient"
+        check_grads(named, g["grads"], TOL, name)
+
+
+# --------------------------------------------------------------------------- fresh inputs vs the oracle
+@pytest.mark.parametrize("kind,mix,batch,n_pi,n_gates,window,rounds", [
+    ("mig", "mig4", 6, 16, 400, None, 1),
+    ("xmg", "xmg", 4, 12, 300, 40, 3),
+    ("aig", "aig", 5, (8, 24), (100, 500), None, 2),
+    ("xag", "xag", 2, 8, 900, 6, 1),          # deep: > 150 levels
+])
+def test_train_step_matches_oracle(kind, mix, batch, n_pi, n_gates, window, rounds):
+    import deepgate
+    from deepgate import synth
+    circuits = synth.make_circuits(mix, batch, n_pi, n_gates, cfg=21 + rounds, window=window, n_pairs=40)
+    G = deepgate.circuits_to_batch(circuits, "cuda")
+    sd = O.synth_state_dict(kind, 5 + rounds)
+    model = build_model(kind, sd, rounds)
+    gen = torch.Generator().manual_seed(3)
+    E, n = G.edge_index.size(1), G.x.size(0)
+    pos = G.edge_index.cpu()[:, torch.randperm(E, generator=gen)]
+    neg = torch.randint(0, n, (2, E), generator=gen)
+    weights = (1.0, 4.0, 4.0)
+    hs, hf = model(G)
+    rec, _, _ = model.recon_loss(hs, pos.cuda(), neg.cuda())
+    prb = torch.nn.L1Loss()(model.pred_prob(hf), G.prob)
+    _, _, _, fnc = deepgate.ops.vae_func_loss(hf=hf, tt_pair_index=G.tt_pair_index, tt_sim=G.tt_sim)
+    (weights[0] * rec + weights[1] * prb + weights[2] * fnc).backward()
+    total, parts, grads = oracle_train_grads(kind, sd, oracle_inputs(G, pos, neg), weights, rounds)
+    assert rel(hs, parts["hs"]) < TOL and rel(hf, parts["hf"]) < TOL
+    for got, key in ((rec, "recon"), (prb, "prob"), (fnc, "func")):
+        assert abs(float(got) - float(parts[key])) < TOL * max(1.0, abs(float(parts[key]))), key
+    check_grads({k: p.grad for k, p in model.named_parameters()}, grads, TOL, kind)
+
+
+def test_struct_encoder_standalone_and_no_layernorm():
+    import deepgate
+    from deepgate import synth
+    c = synth.make_circuits("mig", 2, 8, 120, cfg=31)
+    G = deepgate.circuits_to_batch(c, "cuda")
+    for layernorm, rounds in ((False, 1), (True, 2)):
+        sd = O.synth_state_dict("mig", 40, layernorm=layernorm)
+        enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, s_rounds=rounds,
+                                                         t_rounds=rounds + 1, layernorm=layernorm).cuda()
+        enc.load_state_dict({k[len("mig_struct_encoder."):]: v for k, v in sd.items() if k.startswith("mig_struct_encoder.")})
+        code = G.gate.reshape(-1).long()
+        feat = torch.nn.functional.one_hot((code == 1).long(), 6).float()
+        s, t = enc(feat, feat, G.edge_index)                       # different round counts -> two separate launches
+        (s.sin().sum() + (t * t).sum()).backward()
+        P = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("mig_struct_encoder.")}
+        so = O.multi_gcn_encoder(P, "mig_struct_encoder.source_conv", feat.cpu(), G.edge_index.cpu(), rounds, layernorm)
+        to = O.multi_gcn_encoder(P, "mig_struct_encoder.target_conv", feat.cpu(), G.edge_index.cpu(), rounds + 1, layernorm)
+        (so.sin().sum() + (to * to).sum()).backward()
+        assert rel(s, so) < TOL and rel(t, to) < TOL
+        for k, p in enc.named_parameters():
+            assert rel(p.grad, P["mig_struct_encoder." + k].grad) < TOL, k
+
+
+def test_vae_kernel_matches_reference_golden():
+    import deepgate
+    v = load_golden("vae")
+    vae = deepgate.digvae_model.DirectedGVAE(torch.nn.Identity(), 64).cuda()
+    vae.load_state_dict(v["params"])
+    s, t = v["s"].cuda().requires_grad_(True), v["t"].cuda().requires_grad_(True)
+    zs, zt = vae.sample(s, t, v["eps_s"].cuda(), v["eps_t"].cuda())
+    kl = vae.kl_loss()
+    assert rel(zs, v["z_s"]) < 1e-5 and rel(zt, v["z_t"]) < 1e-5
+    assert abs(float(kl) - float(v["kl"])) < 1e-5 * abs(float(v["kl"]))
+    (kl * 1000.0 + (zs * zs).mean() + zt.sin().mean()).backward()
+    assert rel(s.grad, v["grad_s"]) < TOL and rel(t.grad, v["grad_t"]) < TOL
+    for k, p in vae.named_parameters():
+        assert rel(p.grad, v["grads"][k]) < TOL, k
+
+
+def test_func_loss_edge_cases():
+    import deepgate
+    torch.manual_seed(0)
+    hf = torch.randn(50, 64)
+    hf[:5] = 0.0                                                   # zero rows (PIs): cos = 0, eps-clamped
+    pair = torch.randint(0, 50, (2, 300))
+    pair[:, :10] = torch.tensor([[0, 1, 2, 3, 4, 0, 7, 8, 9, 9], [9, 8, 7, 3, 11, 0, 7, 1, 2, 9]])
+    tt = torch.rand(300)
+    hf_o = hf.clone().requires_grad_(True)
+    lo = O.func_loss(hf_o, pair, tt)
+    lo.backward()
+    hf_g = hf.cuda().requires_grad_(True)
+    _, _, _, lg = deepgate.ops.vae_func_loss(hf=hf_g, tt_pair_index=pair.cuda(), tt_sim=tt.cuda())
+    lg.backward()
+    assert abs(float(lg) - float(lo)) < 1e-5
+    nz = hf.abs().sum(1) > 0                                       # gradient into zero rows is 1e8-scaled junk the
+    assert rel(hf_g.grad[nz.cuda()], hf_o.grad[nz]) < TOL          # sweep drops; compare the live rows
+
+
+# --------------------------------------------------------------------------- size-independent properties at bench size
+def test_properties_at_cfg2_size():
+    import deepgate
+    from deepgate import synth
+    circuits = synth.make_circuits("aig", 64, (16, 64), (500, 1500), cfg=2)
+    G = deepgate.circuits_to_batch(circuits, "cuda")
+    model = build_model("aig", O.synth_state_dict("aig", 2), 1)
+    hs1, hf1 = model(G)
+    hs2, hf2 = model(G)
+    assert torch.equal(hs1, hs2) and torch.equal(hf1, hf2)                     # deterministic, run to run
+    assert torch.isfinite(hf1).all() and torch.isfinite(hs1).all()
+    code = G.gate.reshape(-1)
+    untouched = (G.forward_level == 0) | ~((code == 1) | (code == 2))
+    assert float(hf1[untouched].abs().max()) == 0.0
+    assert float(hf1[~untouched].abs().min(dim=1).values.max()) > 0.0
+    # circuits are independent: a circuit's rows do not change when it is evaluated alone
+    sub = deepgate.circuits_to_batch(circuits[:1], "cuda")
+    hs_s, hf_s = model(sub)
+    n0 = sub.x.size(0)
+    assert rel(hf_s, hf1[:n0]) < 1e-5 and rel(hs_s, hs1[:n0]) < 1e-5
+    # backward determinism of the pull-style sweep
+    def grads():
+        model.zero_grad()
+        hs, hf = model(G)
+        (hf.square().mean() + hs.mean()).backward()
+        return torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    g1, g2 = grads(), grads()
+    assert torch.isfinite(g1).all() and rel(g1, g2) < 1e-6
