@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the level-synchronous DAG message-passing path (BASELINE.json metric:
+gates/s propagated fwd+bwd, all rounds, and train-step ms).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+
+A "step" is one training step of the reference's loop on one synthetic batch: Model.forward(G)
+(level schedule + struct encoder + level sweep), recon / prob / func losses, backward, gradient
+all-reduce (N > 1) and Adam.  ``value`` = gates propagated per second over all ranks with the
+batches resident in HBM; ``e2e`` = the same through Trainer.train_step with the batch in pinned
+HOST memory (H2D copy and loss read-back inside the timed region).  ``--impl reference`` times the
+reference algorithm's CPU restatement (oracle/dg_oracle.py, per-node ``subgraph`` loop included)
+on the host cores -- the one other place this file executes oracle/.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "multi-gate-vae_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: kind, gate mix, circuits per GPU, n_pi, n_gates, window, sweep rounds   
+    "cfg1": dict(kind="mig", mix="mig4", batch=4, n_pi=16, n_gates=200, window=None, rounds=1, cfg=1),
+    "cfg2": dict(kind="aig", mix="aig", batch=64, n_pi=(16, 64), n_gates=(500, 1500), window=None, rounds=1, cfg=2),
+    "cfg3-xmg": dict(kind="xmg", mix="xmg", batch=64, n_pi=(16, 64), n_gates=(500, 1500), window=None, rounds=2, cfg=3),
+    "cfg3-xag": dict(kind="xag", mix="xag", batch=64, n_pi=(16, 64), n_gates=(500, 1500), window=None, rounds=2, cfg=3),
+    "cfg5-k1": dict(kind="mig", mix="mig", batch=1, n_pi=16, n_gates=100000, window=880, rounds=1, cfg=5),
+    "cfg5-k8": dict(kind="mig", mix="mig", batch=8, n_pi=16, n_gates=100000, window=880, rounds=1, cfg=5),
+    "cfg5-k64": dict(kind="mig", mix="mig", batch=64, n_pi=16, n_gates=100000, window=880, rounds=1, cfg=5),
+}
+HANDLED = {"aig": (1, 2), "mig": (1, 2, 3, 4), "xmg": (1, 2, 3, 4, 5), "xag": (2, 3, 5)}
+LOSS_W = (1.0, 4.0, 4.0)      # stage-3 weights of the reference schedule (train.py:91)
+
+
+def make_host_batch(w, rank, idx):
+    import deepgate
+    from deepgate import synth
+    circuits = synth.make_circuits(w["mix"], w["batch"], w["n_pi"], w["n_gates"],
+                                   cfg=w["cfg"] + 100 * rank + 10 * idx, window=w["window"])
+    return deepgate.circuits_to_batch(circuits)
+
+
+def batch_stats(b, kind):
+    code = b.gate.reshape(-1).long()
+    lvl = b.forward_level.long()
+    indeg = torch.bincount(b.edge_index[1], minlength=code.numel())
+    handled = torch.zeros_like(code, dtype=torch.bool)
+    for c in HANDLED[kind]:
+        handled |= code == c
+    live = handled & (lvl >= 1)
+    d = indeg[live].double()
+    n, e = code.numel(), b.edge_index.size(1)
+    return {
+        "N": n, "E": e, "L": int(lvl.max()) + 1, "gates": int(live.sum()),
+        # algorithmic bytes, SURVEY.md section 8d (fp32): fwd 516 d + 520, bwd 1540 d + 776 per gate
+        "sweep_fwd_bytes": float((516 * d + 520).sum()), "sweep_bwd_bytes": float((1540 * d + 776).sum()),
+        # struct encoder per half-step launch, both encoders: fwd 256 (deg + 2), bwd 256 (3 deg + 3) per node
+        "struct_fwd_bytes": 2.0 * 256 * (e + 2 * n), "struct_bwd_bytes": 2.0 * 256 * (3 * e + 3 * n),
+    }
+
+
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.path)
+        top = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_step(kind, P, host_batch, rounds, n_sample):
+    """One train step of the reference algorithm (oracle port) on the first ``n_sample`` circuits."""
+    from oracle import dg_oracle as O
+    ptr = host_batch.ptr.tolist()
+    n = ptr[n_sample]
+    emask = host_batch.edge_index[1] < n
+    ei = host_batch.edge_index[:, emask]
+    pmask = (host_batch.tt_pair_index[0] < n) & (host_batch.tt_pair_index[1] < n)
+    g = torch.Generator().manual_seed(0)
+    G = {"code": host_batch.gate.reshape(-1).long()[:n], "edge_index": ei, "forward_level": host_batch.forward_level[:n],
+         "prob": host_batch.prob[:n], "tt_pair_index": host_batch.tt_pair_index[:, pmask], "tt_sim": host_batch.tt_sim[pmask],
+         "train_pos_edge_index": ei[:, torch.randperm(ei.size(1), generator=g)],
+         "neg_edge_index": torch.randint(0, n, (2, ei.size(1)), generator=g)}
+    for p in P.values():
+        if p.requires_grad:
+            p.grad = None
+    t0 = time.perf_counter()
+    total, _ = O.train_step_losses(P, kind, G, LOSS_W, rounds, literal_subgraph=True)
+    total.backward()
+    dt = time.perf_counter() - t0
+    code, lvl = G["code"], G["forward_level"]
+    handled = torch.zeros_like(code, dtype=torch.bool)
+    for c in HANDLED[kind]:
+        handled |= code == c
+    return dt, int((handled & (lvl >= 1)).sum()) * rounds
+
+
+def cpu_params(kind):
+    from oracle import dg_oracle as O
+    P = O.synth_state_dict(kind, 2)
+    for k, p in P.items():
+        p.requires_grad_("running" not in k)
+    return P
+
+
+def pick_sample(w, budget_s=20.0):
+    """Circuits in the CPU sample.  The reference's per-node subgraph loop costs ~ nodes * edges compares;
+    calibrated on 8 Xeon cores: 64 x ~1000-gate circuits -> 17.5 s per train step (c = 4.3e-9 s / node^2)."""
+    per = (w["n_gates"] if isinstance(w["n_gates"], int) else sum(w["n_gates"]) / 2)
+    if per >= 50000:
+        return 1
+    return max(1, min(w["batch"], int((budget_s / 4.3e-9) ** 0.5 / per)))
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hb = make_host_batch(w, 0, 0)
+    P = cpu_params(w["kind"])
+    ns = pick_sample(w, min(8.0, 120.0 / max(args.steps, 1)))
+    for _ in range(args.warmup):
+        cpu_step(w["kind"], P, hb, w["rounds"], max(1, ns // 4))
+    tot_t, tot_g = 0.0, 0
+    for _ in range(args.steps):
+        dt, gates = cpu_step(w["kind"], P, hb, w["rounds"], ns)
+        tot_t += dt
+        tot_g += gates
+    val = tot_g / tot_t
+    sample = "%d of %d circuits per step (%d gates), oracle port, per-node subgraph loop as in the reference" % (
+        ns, w["batch"], tot_g // max(args.steps, 1))
+    print(json.dumps({
+        "impl": "reference", "metric": "gates_per_s_fwd_bwd", "value": val, "unit": "gates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": "DG_AE-" + w["kind"], "circuits_per_gpu": w["batch"],
+                   "note": "CPU host cores; step = bounded sample of the workload"},
+        "cpu_baseline": {"value": val, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------- our arm (B200)
+def run_ours(args, w):
+    import deepgate
+    from deepgate import _native, ops
+    from oracle import dg_oracle as O   # only for cpu_baseline (rank 0, N == 1) and the seeded weights helper
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, enable_reverse=True, s_rounds=4,
+                                                     t_rounds=4, layernorm=True)
+    mod = getattr(deepgate, "dg_ae_model_" + w["kind"])
+    model = mod.Model(struct_encoder=enc, num_rounds=w["rounds"], dim_hidden=64)
+    model.load_state_dict(O.synth_state_dict(w["kind"], 2), strict=False)      # same random-init weights on every rank
+    tmp = tempfile.mkdtemp(prefix="mgv_bench_")
+    trainer = deepgate.Trainer(None, model, training_id="bench", save_dir=tmp, lr=1e-4,
+                               rc_prob_func_weight=list(LOSS_W), device=str(dev), batch_size=w["batch"],
+                               distributed=False)
+    model.train()
+    nb = args.batches
+    host = [make_host_batch(w, rank, i).pin_memory() for i in range(nb)]
+    stats = [batch_stats(b, w["kind"]) for b in host]
+    resident = [b.copy_to(dev, non_blocking=False) for b in host]
+    gates_per_step = [s["gates"] * w["rounds"] for s in stats]
+
+    def fresh(b):
+        b._mgv_schedule = None            # a new batch every step: the level-CSR is rebuilt inside the step
+        b.train_pos_edge_index = None
+        return b
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize(dev)
+
+    def step_resident(i):
+        st = trainer.train_step(fresh(resident[i % nb]))
+        return st["loss"]
+
+    def step_e2e(i):
+        st = trainer.train_step(host[i % nb].copy_to(dev, non_blocking=True))
+        return float(st["loss"].item())          # device -> host read of the step's result
+
+    def timed(fn, k):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(k):
+            fn(i)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(args.warmup):
+        step_resident(i)
+        step_e2e(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _native.lib().mgv_kernel_launches()
+    ops.PROFILE = {}
+    ms = timed(step_resident, args.steps)
+    torch.cuda.synchronize(dev)
+    prof = ops.profile_summary()
+    ops.PROFILE = None
+    launches = _native.lib().mgv_kernel_launches() - launches0
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+
+    g_local = sum(gates_per_step[i % nb] for i in range(args.steps))
+    g_all = torch.tensor([float(g_local)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(g_all)
+    value = float(g_all.item()) / (ms * 1e-3)
+    e2e = float(g_all.item()) / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (largest share of the timed region), algorithmic bytes per launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    per_launch = {
+        "level_sweep_fwd": ("sweep_fwd_kernel", 1, "sweep_fwd_bytes"),
+        "level_sweep_bwd": ("sweep_bwd_kernel", 1, "sweep_bwd_bytes"),
+        "struct_encoder_fwd": ("struct_fwd_kernel", 8, "struct_fwd_bytes"),      # 2 * s_rounds step launches per call
+        "struct_encoder_bwd": ("struct_bwd_kernel", 8, "struct_bwd_bytes"),
+    }
+    mean_stats = {k: sum(s[k] for s in stats) / len(stats) for k in stats[0]}
+    kernels = {}
+    for name, (kern, nl, key) in per_launch.items():
+        if name in prof and prof[name][0] > 0:
+            calls, tot = prof[name]
+            avg_launch_ms = tot / calls / nl
+            ach = mean_stats[key] * (w["rounds"] if "sweep" in name else 1) / (avg_launch_ms * 1e-3) / 1e9
+            kernels[kern] = {"ms_per_step": tot / args.steps, "avg_launch_ms": avg_launch_ms, "launches_per_step": nl,
+                             "achieved_gbs": ach, "frac": ach / peak}
+    top = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    roofline = None
+    if top:
+        roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                    "share_of_step": kernels[top]["ms_per_step"] / (ms / args.steps)}
+    sweep_ms = sum(kernels[k]["ms_per_step"] for k in ("sweep_fwd_kernel", "sweep_bwd_kernel") if k in kernels)
+    sweep = None
+    if sweep_ms > 0:
+        sweep_bytes = (mean_stats["sweep_fwd_bytes"] + mean_stats["sweep_bwd_bytes"]) * w["rounds"]
+        sweep = {"gates_per_s": mean_stats["gates"] * w["rounds"] / (sweep_ms * 1e-3), "ms_fwd_bwd": sweep_ms,
+                 "achieved_gbs": sweep_bytes / (sweep_ms * 1e-3) / 1e9, "frac": sweep_bytes / (sweep_ms * 1e-3) / 1e9 / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        P = cpu_params(w["kind"])
+        ns = pick_sample(w)
+        cpu_step(w["kind"], P, host[0], w["rounds"], max(1, ns // 4))        # warm-up
+        dt, gates = cpu_step(w["kind"], P, host[0], w["rounds"], ns)
+        cpu = {"value": gates / dt, "unit": "gates/s", "cores": cores, "kind": "port",
+               "sample": "1 train step on %d of %d circuits (%d gates, %.1f s), oracle port with the reference's "
+                         "per-node subgraph loop" % (ns, w["batch"], gates, dt)}
+    if rank == 0:
+        h2d = sum(b.nbytes() for b in host) / len(host)
+        print(json.dumps({
+            "metric": "gates_per_s_fwd_bwd", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "model": "DG_AE-" + w["kind"], "circuits_per_gpu": w["batch"],
+                       "nodes_per_gpu": mean_stats["N"], "edges_per_gpu": mean_stats["E"], "levels": mean_stats["L"],
+                       "gates_per_step_per_gpu": mean_stats["gates"] * w["rounds"], "sweep_rounds": w["rounds"],
+                       "s_rounds": 4, "t_rounds": 4, "layernorm": True, "dim_hidden": 64, "parallelism": "dp%d" % world,
+                       "step": "schedule build + forward + recon/prob/func losses + backward + allreduce + Adam",
+                       "l2": "%d distinct batches rotated; per-batch working set (struct states %d MB) exceeds the 126 MB L2"
+                             % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},
+            "e2e": {"value": e2e, "unit": "gates/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "level_sweep": sweep, "cpu_baseline": cpu}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches rotated through the steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,8 @@ const char* mgv_last_error_string(void);
 int mgv_version(void);
 /* Number of SMs of the current device (grid sizing for the persistent kernels). */
 int mgv_sm_count(void);
+/* Kernels launched by this library in this process so far (statistics only). */
+long long mgv_kernel_launches(void);
 
 /* ------------------------------------------------------------------ schedule (integer work)
  * In/out-edge CSR by node id, ascending ORIGINAL EDGE ID inside a node -- the order in which

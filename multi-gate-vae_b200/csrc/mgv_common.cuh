@@ -9,6 +9,7 @@
 
 void mgv_set_error(const char* fmt, ...);
 int mgv_check_cuda(cudaError_t e, const char* what);
+void mgv_count_launches(int n);
 
 #define MGV_CUDA(call)                                            \
     do {                                                          \

@@ -1,6 +1,7 @@
 // Error reporting + tiny device queries for the mgv_b200 C ABI.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "mgv_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -26,3 +27,8 @@ extern "C" int mgv_sm_count(void) {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     return n;
 }
+
+// Process-wide statistics counter: kernels launched by this library (bench.py reports it).
+static std::atomic<long long> g_launches{0};
+void mgv_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long mgv_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -81,9 +81,12 @@ int exclusive_scan(const uint32_t* in, uint32_t* out, int n, uint32_t* tmp, cuda
     if (n <= 0) return MGV_OK;
     const int nt = (n + SCAN_TILE - 1) / SCAN_TILE;
     scan_tiles_kernel<<<nt, SCAN_THREADS, 0, st>>>(in, out, n, tmp);
+    mgv_count_launches(1);
     if (nt > 1) {
         scan_sums_kernel<<<1, 1024, 0, st>>>(tmp, nt);
+        mgv_count_launches(1);
         scan_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, n, tmp);
+        mgv_count_launches(1);
     }
     return mgv_check_cuda(cudaGetLastError(), "exclusive_scan");
 }
@@ -169,9 +172,11 @@ int radix_sort_pairs(SortBufs b, int m, int bits, uint32_t** kres, uint32_t** vr
         const int nblk = (m + RS_TILE - 1) / RS_TILE;
         for (int shift = 0; shift < bits; shift += 8) {
             radix_hist_kernel<<<nblk, RS_THREADS, 0, st>>>(ki, m, shift, b.hist, nblk);
+            mgv_count_launches(1);
             int rc = exclusive_scan(b.hist, b.hist, RS_BINS * nblk, b.tmp, st);
             if (rc != MGV_OK) return rc;
             radix_scatter_kernel<<<nblk, RS_THREADS, 0, st>>>(ki, vi, ko, vo, m, shift, b.hist, nblk);
+            mgv_count_launches(1);
             uint32_t* t;
             t = ki; ki = ko; ko = t;
             t = vi; vi = vo; vo = t;
@@ -364,15 +369,24 @@ extern "C" int mgv_build_csr(const int64_t* edge_index, int64_t E, int32_t N, co
         // dir 0: bucket by dst (row 1) -> in-CSR;  dir 1: bucket by src (row 0) -> out-CSR
         int32_t* ptr = dir == 0 ? in_ptr : out_ptr;
         MGV_CUDA(cudaMemsetAsync(deg, 0, (size_t)(N + 1) * 4, st));
-        if (E > 0) edge_keys_kernel<<<eb, 256, 0, st>>>(edge_index, E, dir == 0 ? 1 : 0, sb.k0, sb.v0, deg, N, bad);
+        if (E > 0) {
+            edge_keys_kernel<<<eb, 256, 0, st>>>(edge_index, E, dir == 0 ? 1 : 0, sb.k0, sb.v0, deg, N, bad);
+            mgv_count_launches(1);
+        }
         int rc = exclusive_scan(deg, (uint32_t*)ptr, N + 1, sb.tmp, st);
         if (rc != MGV_OK) return rc;
         uint32_t *ks, *vs;
         rc = radix_sort_pairs(sb, (int)E, bits, &ks, &vs, st);
         if (rc != MGV_OK) return rc;
         if (E > 0) {
-            if (dir == 0) fill_in_kernel<<<eb, 256, 0, st>>>(vs, edge_index, E, in_src, slot_of_eid);
-            else fill_out_kernel<<<eb, 256, 0, st>>>(vs, edge_index, E, slot_of_eid, code, out_pack, out_slot);
+            if (dir == 0) {
+                fill_in_kernel<<<eb, 256, 0, st>>>(vs, edge_index, E, in_src, slot_of_eid);
+                mgv_count_launches(1);
+            }
+            else {
+                fill_out_kernel<<<eb, 256, 0, st>>>(vs, edge_index, E, slot_of_eid, code, out_pack, out_slot);
+                mgv_count_launches(1);
+            }
         }
     }
     MGV_CUDA(cudaGetLastError());
@@ -418,6 +432,7 @@ extern "C" int mgv_levelize(const int32_t* in_ptr, const int32_t* out_ptr, const
     if (grid > need) grid = need > 0 ? need : 1;
     void* args[] = {&p};
     MGV_CUDA(cudaLaunchCooperativeKernel((void*)levelize_kernel, dim3(grid), dim3(256), args, 0, st));
+    mgv_count_launches(1);
     unsigned res[2] = {0, 0};
     MGV_CUDA(cudaMemcpyAsync(res, p.counters + 4, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     MGV_CUDA(cudaStreamSynchronize(st));
@@ -465,14 +480,21 @@ extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, 
     int* bad = a.take<int>(1);
     MGV_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
     MGV_CUDA(cudaMemsetAsync(khist, 0, (size_t)(nkeys + 1) * 4, st));
-    if (N > 0) node_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(level, code, N, L, sb.k0, sb.v0, khist, bad);
+    if (N > 0) {
+        node_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(level, code, N, L, sb.k0, sb.v0, khist, bad);
+        mgv_count_launches(1);
+    }
     int rc = exclusive_scan(khist, (uint32_t*)seg_ptr, nkeys + 1, sb.tmp, st);
     if (rc != MGV_OK) return rc;
     uint32_t *ks, *vs;
     rc = radix_sort_pairs(sb, N, bits_for((uint64_t)(nkeys > 0 ? nkeys - 1 : 0)), &ks, &vs, st);
     if (rc != MGV_OK) return rc;
-    if (N > 0) copy_u32_to_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(vs, order, N);
+    if (N > 0) {
+        copy_u32_to_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(vs, order, N);
+        mgv_count_launches(1);
+    }
     code_count_kernel<<<1, 32, 0, st>>>(seg_ptr, L, counts);
+    mgv_count_launches(1);
     MGV_CUDA(cudaGetLastError());
     unsigned long long ch[MGV_NCODE];
     int bad_h = 0;

@@ -444,6 +444,7 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
     MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int e = 0; e < num_enc; ++e)
         fill_ones_kernel<<<(unsigned)((slot + 255) / 256), 256, 0, st>>>(states + e * enc_stride, slot);
+        mgv_count_launches(1);
     for (int k = 1; k <= steps; ++k) {
         StepDev p{};
         const int dir = (k & 1) ? 0 : 1;
@@ -457,6 +458,7 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         p.enc_stride = enc_stride;
         dim3 grid((N + FTM - 1) / FTM, num_enc);
         struct_fwd_kernel<<<grid, THREADS, smem, st>>>(p);
+        mgv_count_launches(1);
     }
     return mgv_check_cuda(cudaGetLastError(), "mgv_struct_encoder_fwd");
 }
@@ -525,8 +527,10 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
         p.partial = partial;
         dim3 grid(gx, num_enc);
         struct_bwd_kernel<<<grid, THREADS, smem, st>>>(p);
+        mgv_count_launches(1);
     }
     const size_t total = (size_t)num_enc * 2 * SGRAD;
     struct_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, gx, grads, num_enc);
+    mgv_count_launches(1);
     return mgv_check_cuda(cudaGetLastError(), "mgv_struct_encoder_bwd");
 }

@@ -581,6 +581,7 @@ extern "C" int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint
     MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
     void* args[] = {&d};
     MGV_CUDA(cudaLaunchCooperativeKernel((void*)sweep_fwd_kernel, dim3(grid), dim3(THREADS), args, smem, st));
+    mgv_count_launches(1);
     return MGV_OK;
 }
 
@@ -631,5 +632,6 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
     void* args[] = {&d};
     MGV_CUDA(cudaLaunchCooperativeKernel((void*)sweep_bwd_kernel, dim3(grid), dim3(THREADS), args, smem, st));
+    mgv_count_launches(1);
     return MGV_OK;
 }

@@ -208,6 +208,7 @@ extern "C" int mgv_vae_func_loss_fwd(const float* mu, const float* logstd, const
     vae_func_fwd_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(mu, logstd, eps, z, (long long)N, hf,
                                                                    (const long long*)pair, tt_sim, (long long)P, out,
                                                                    (VfWs*)ws, nb_vae);
+    mgv_count_launches(1);
     return mgv_check_cuda(cudaGetLastError(), "mgv_vae_func_loss_fwd");
 }
 
@@ -221,5 +222,6 @@ extern "C" int mgv_vae_func_loss_bwd(const float* g_out, const float* gz, const 
     vae_func_bwd_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(g_out, gz, mu, logstd, eps, gmu, glogstd,
                                                                    (long long)N, hf, (const long long*)pair, tt_sim,
                                                                    (long long)P, out, (const VfWs*)ws, ghf, nb_vae);
+    mgv_count_launches(1);
     return mgv_check_cuda(cudaGetLastError(), "mgv_vae_func_loss_bwd");
 }

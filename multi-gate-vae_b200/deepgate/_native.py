@@ -40,6 +40,7 @@ _PROTOTYPES = {
     "mgv_last_error_string": (ctypes.c_char_p, []),
     "mgv_version": (ctypes.c_int, []),
     "mgv_sm_count": (ctypes.c_int, []),
+    "mgv_kernel_launches": (ctypes.c_longlong, []),
     "mgv_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "mgv_build_csr": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgv_levelize_workspace_bytes": (_sz, [_i64]),

@@ -48,6 +48,18 @@ class OrderedData(object):
                 setattr(self, k, v.to(device, non_blocking=non_blocking))
         return self
 
+    def copy_to(self, device, non_blocking=True):
+        """A new batch object on ``device`` (the source, e.g. pinned host memory, is left untouched)."""
+        out = OrderedData()
+        for k, v in vars(self).items():
+            if k.startswith("_"):
+                continue
+            setattr(out, k, v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
+        return out
+
+    def nbytes(self):
+        return sum(v.numel() * v.element_size() for v in vars(self).values() if torch.is_tensor(v))
+
     def pin_memory(self):
         for k, v in list(vars(self).items()):
             if torch.is_tensor(v):

@@ -17,6 +17,33 @@ _GRU_KEYS = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")
 PARAMS_PER_CODE = len(_AGGR_KEYS) + len(_GRU_KEYS)      # 12
 
 
+# Optional per-kernel timing (bench.py): PROFILE = {} enables CUDA-event brackets around each
+# library call on the launching stream; entries are name -> [(start_event, end_event), ...].
+PROFILE = None
+
+
+class _timed(object):
+    def __init__(self, name, device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.ev[1].record(torch.cuda.current_stream(self.device))
+            PROFILE.setdefault(self.name, []).append(self.ev)
+        return False
+
+
+def profile_summary():
+    """name -> (calls, total ms); call after torch.cuda.synchronize()."""
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (PROFILE or {}).items()}
+
+
 def _f32(t, name):
     return nat.require_cuda(t.detach().contiguous(), name, torch.float32)
 
@@ -53,7 +80,8 @@ class LevelSweepFunction(torch.autograd.Function):
         hf_all = torch.zeros(rounds, max(N, 1), nat.D, dtype=torch.float32, device=dev)
         sync = torch.zeros(64, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            nat.check(lib.mgv_level_sweep_fwd(sched.c_struct(), rounds, mask, nat.ptr(pack), nat.ptr(hs_c),
+            with _timed("level_sweep_fwd", dev):
+              nat.check(lib.mgv_level_sweep_fwd(sched.c_struct(), rounds, mask, nat.ptr(pack), nat.ptr(hs_c),
                                               nat.ptr(hf_all), nat.ptr(sync), nat.stream_of(dev)),
                       "mgv_level_sweep_fwd")
         ctx.sched, ctx.rounds, ctx.codes, ctx.mask = sched, rounds, tuple(codes), mask
@@ -77,7 +105,8 @@ class LevelSweepFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             nb = lib.mgv_sweep_bwd_workspace_bytes(N, sched.E)
             ws = nat.workspace(nb, dev)
-            nat.check(lib.mgv_level_sweep_bwd(sched.c_struct(), rounds, ctx.mask, nat.ptr(pack), nat.ptr(hs_c),
+            with _timed("level_sweep_bwd", dev):
+              nat.check(lib.mgv_level_sweep_bwd(sched.c_struct(), rounds, ctx.mask, nat.ptr(pack), nat.ptr(hs_c),
                                               nat.ptr(hf_all), nat.ptr(ghs), nat.ptr(ghf), nat.ptr(grads),
                                               nat.ptr(ws), nb, nat.ptr(sync), nat.stream_of(dev)),
                       "mgv_level_sweep_bwd")
@@ -144,7 +173,8 @@ class StructEncoderFunction(torch.autograd.Function):
         pack = _struct_pack(enc_params, layernorm, dev)
         states = torch.empty(num_enc, 2 * rounds + 1, max(N, 1), nat.D, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            nat.check(lib.mgv_struct_encoder_fwd(csr.c_struct(), num_enc, rounds, int(layernorm), feat,
+            with _timed("struct_encoder_fwd", dev):
+              nat.check(lib.mgv_struct_encoder_fwd(csr.c_struct(), num_enc, rounds, int(layernorm), feat,
                                                  nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.stream_of(dev)),
                       "mgv_struct_encoder_fwd")
         ctx.csr, ctx.rounds, ctx.layernorm, ctx.num_enc, ctx.feat, ctx.per = csr, rounds, layernorm, num_enc, feat, per
@@ -165,7 +195,8 @@ class StructEncoderFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             nb = lib.mgv_struct_bwd_workspace_bytes(N, num_enc)
             ws = nat.workspace(nb, dev)
-            nat.check(lib.mgv_struct_encoder_bwd(csr.c_struct(), num_enc, rounds, int(ctx.layernorm), feat,
+            with _timed("struct_encoder_bwd", dev):
+              nat.check(lib.mgv_struct_encoder_bwd(csr.c_struct(), num_enc, rounds, int(ctx.layernorm), feat,
                                                  nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(g),
                                                  nat.ptr(grads), nat.ptr(ws), nb, nat.stream_of(dev)),
                       "mgv_struct_encoder_bwd")
@@ -217,7 +248,8 @@ class VaeFuncLossFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             nb = lib.mgv_vae_func_workspace_bytes(P)
             ws = nat.workspace(nb, dev, zero=True)
-            nat.check(lib.mgv_vae_func_loss_fwd(nat.ptr(mu_c), nat.ptr(ls_c), nat.ptr(eps_c), nat.ptr(z), N,
+            with _timed("vae_func_loss_fwd", dev):
+              nat.check(lib.mgv_vae_func_loss_fwd(nat.ptr(mu_c), nat.ptr(ls_c), nat.ptr(eps_c), nat.ptr(z), N,
                                                 nat.ptr(hf_c), nat.ptr(pair_c), nat.ptr(tt_c), P, nat.ptr(out),
                                                 nat.ptr(ws), nb, nat.stream_of(dev)), "mgv_vae_func_loss_fwd")
         ctx.N, ctx.P, ctx.has_vae, ctx.has_func = N, P, has_vae, has_func
@@ -244,7 +276,8 @@ class VaeFuncLossFunction(torch.autograd.Function):
         if ctx.has_func:
             ghf = torch.zeros(ctx.hf_shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            nat.check(lib.mgv_vae_func_loss_bwd(nat.ptr(g2), nat.ptr(gz_c), nat.ptr(mu_c), nat.ptr(ls_c),
+            with _timed("vae_func_loss_bwd", dev):
+              nat.check(lib.mgv_vae_func_loss_bwd(nat.ptr(g2), nat.ptr(gz_c), nat.ptr(mu_c), nat.ptr(ls_c),
                                                 nat.ptr(eps_c), nat.ptr(gmu), nat.ptr(gls), N, nat.ptr(hf_c),
                                                 nat.ptr(pair_c), nat.ptr(tt_c), P, nat.ptr(out), nat.ptr(ws),
                                                 nat.ptr(ghf), nat.stream_of(dev)), "mgv_vae_func_loss_bwd")

@@ -100,7 +100,7 @@ def test_forward_losses_grads_match_reference_golden(name):
     batch = golden_batch(g)
     hs, hf = model(batch)
     assert rel(hs, g["hs"]) < TOL and rel(hf, g["hf"]) < TOL
-    assert float(hf[g["forward_level"].cuda() == 0].abs().max()) == 0.0        # PI rows exactly zero
+    assert float(hf.detach()[g["forward_level"].cuda() == 0].abs().max()) == 0.0        # PI rows exactly zero
     rec, pred_bin, _ = model.recon_loss(hs, g["train_pos_edge_index"].cuda(), g["neg_edge_index"].cuda())
     prob_loss = torch.nn.L1Loss()(model.pred_prob(hf), batch.prob)
     _, _, _, func = deepgate.ops.vae_func_loss(hf=hf, tt_pair_index=batch.tt_pair_index, tt_sim=batch.tt_sim)
@@ -229,6 +229,6 @@ def test_properties_at_cfg2_size():
         model.zero_grad()
         hs, hf = model(G)
         (hf.square().mean() + hs.mean()).backward()
-        return torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        return torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
     g1, g2 = grads(), grads()
     assert torch.isfinite(g1).all() and rel(g1, g2) < 1e-6
