@@ -43,8 +43,8 @@ extern "C" {
 /* Floats per gate-code gradient block returned by the backward sweep. */
 #define MGV_SWEEP_GRAD_FLOATS 33344
 /* Floats per (encoder, direction) weight block of the struct encoder. */
-#define MGV_STRUCT_PACK_FLOATS 61824
-#define MGV_STRUCT_GRAD_FLOATS 30912
+#define MGV_STRUCT_PACK_FLOATS 28416
+#define MGV_STRUCT_GRAD_FLOATS 28416
 
 typedef void* mgv_stream_t;      /* cudaStream_t */
 
@@ -141,11 +141,11 @@ int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint32_t handle
  * same over out-neighbours with aggr_r/update_r and the SAME LayerNorm.  num_enc encoders (source_conv,
  * target_conv of DirectMultiGCNEncoder, digae_layer.py:294-297) run batched over the same graph.
  *
- * weights: float [num_enc][2 dirs][MGV_STRUCT_PACK_FLOATS]; block layout:
- *      0 WT[64][64] (msg.weight^T)   4096 b[64]   4160 WihT[72][192] (weight_ih_l0^T, rows 70,71 zero)
- *  17984 WhhT[64][192]   30272 bih[192]   30464 bhh[192]   30656 ln_w[64]   30720 ln_b[64]  (ln only in dir 0 block
- *  but duplicated in both)   30784 pad[128]
- *  30912 W[64][64]   35008 Wih[192][72]   48832 Whh[192][64]  (natural copies, backward) -> 61120, pad to 61824
+ * weights: float [num_enc][2 dirs][MGV_STRUCT_PACK_FLOATS], host-prepared natural layouts with the AggConv
+ * linear pre-composed into the GRU input weights (Wc = weight_ih_l0[:, :64] msg.weight, bc = weight_ih_l0[:, :64] msg.bias):
+ *      0 Wcx[192][76]  cols 0..63 = Wc, cols 64..64+feat-1 = weight_ih_l0[:, 64:], rest 0
+ *  14592 Whh[192][68]  weight_hh_l0, cols 64..67 = 0
+ *  27648 bc[192]   27840 bih[192]   28032 bhh[192]   28224 ln_w[64]   28288 ln_b[64]   (pad to 28416)
  * x: float [N][feat] (feat <= MGV_MAX_FEAT).  states: float [num_enc][2*rounds+1][N][64] out
  * (slot 0 = ones, written by the call; slot 2*rounds = encoder output).
  */
@@ -153,8 +153,8 @@ int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, int32_t rou
                            int32_t feat, const float* x, const float* weights, float* states,
                            mgv_stream_t stream);
 /* gout: float [num_enc][N][64] = d loss / d (encoder output).  grads: float
- * [num_enc][2][MGV_STRUCT_GRAD_FLOATS] out: 0 dW[64][64]  4096 db[64]  4160 dWih[192][72]  17984 dWhh[192][64]
- * 30272 dbih[192]  30464 dbhh[192]  30656 dln_w[64]  30720 dln_b[64]. */
+ * [num_enc][2][MGV_STRUCT_GRAD_FLOATS] out, SAME layout as the weight block (d Wcx, d Whh, d bc, d bih, d bhh,
+ * d ln_w, d ln_b; padding columns are zero).  The host maps d Wc / d bc back to msg.* and weight_ih_l0. */
 int mgv_struct_bwd_grid(void);
 size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc);
 int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,

@@ -1,34 +1,43 @@
 // Struct encoder: MultiGCNEncoder.forward (digae_layer.py:257-277) with AggConv
 // (arch/gcn_conv.py:30-42), one fused kernel per half-round step:
-//   gather-sum of neighbour states -> msg = W agg + deg b -> GRU_{70->64}([msg || x], state) -> LayerNorm
+//   gather-sum of neighbour states -> GRU_{70->64}([W agg + deg b || x], state) -> LayerNorm
 // Step k = 1..2R uses in-neighbours when k is odd (aggr/update) and out-neighbours when k is
 // even (aggr_r/update_r); LayerNorm parameters are shared by both directions (digae_layer.py:270,275).
 // source_conv and target_conv (digae_layer.py:294-297) run batched: blockIdx.y = encoder.
-// Backward recomputes each step from the saved post-LN states and keeps the weight-gradient
-// accumulators of a CTA in shared memory for the whole launch.
-#include "mgv_common.cuh"
+//
+// The AggConv linear is pre-composed into the GRU input weights on the host:
+//   W_ih[:, :64] (W agg + deg b) = Wc agg + deg bc,   Wc = W_ih[:, :64] W,  bc = W_ih[:, :64] b
+// so a step is ONE tile GEMM  [agg || x || h] (32 x 136)  x  [Wc | W_ih_x | W_hh]^T  on the tensor
+// cores (3xTF32, fp32 accuracy), with one copy of the weights resident in shared memory for the
+// whole launch (persistent CTAs loop over 32-node tiles).
+// Backward recomputes the step from the saved post-LN states, runs LN/GRU backward in registers,
+// the two data-gradient GEMMs from the same weight copy, and keeps the weight-gradient
+// accumulators as persistent MMA fragments in registers (flushed once per launch).
+#include "mgv_mma.cuh"
 
 namespace {
 
 constexpr int D = MGV_D;              // 64
 constexpr int G3 = 3 * D;             // 192
-constexpr int KX = D + MGV_MAX_FEAT;  // 72: [msg || x || pad]
+constexpr int KX = D + MGV_MAX_FEAT;  // 72: [agg || x]
 constexpr int SPACK = MGV_STRUCT_PACK_FLOATS;
 constexpr int SGRAD = MGV_STRUCT_GRAD_FLOATS;
-constexpr int O_WT = 0, O_B = 4096, O_WIHT = 4160, O_WHHT = 17984, O_BIH = 30272, O_BHH = 30464, O_LNW = 30656, O_LNB = 30720;
-constexpr int O_W = 30912, O_WIH = 35008, O_WHH = 48832;
-constexpr int G_W = 0, G_B = 4096, G_WIH = 4160, G_WHH = 17984, G_BIH = 30272, G_BHH = 30464, G_LNW = 30656, G_LNB = 30720;
+constexpr int LDC = KX + 4;           // 76: row stride of Wcx and of the [agg || x] tile
+constexpr int LDM = D + 4;            // 68
+constexpr int LDG = G3 + 8;           // 200: d gi / d gh tiles (also read transposed)
+// weight / gradient block offsets (floats) -- see include/mgv_b200.h
+constexpr int O_WCX = 0, O_WHH = 14592, O_BC = 27648, O_BIH = 27840, O_BHH = 28032, O_LNW = 28224, O_LNB = 28288;
 constexpr int NODE_MASK = (1 << MGV_CODE_SHIFT) - 1;
 
-constexpr int THREADS = 256;
-constexpr int WARPS = THREADS / 32;
-constexpr int LDM = D + 4;            // 68
-constexpr int LDK = KX + 4;           // 76
-constexpr int LDG = G3 + 4;           // 196
+constexpr int THREADS = 512;
+constexpr int WARPS = THREADS / 32;   // 16
+constexpr int TM = 32;                // nodes per tile
 constexpr float LN_EPS = 1e-5f;
 
+static_assert(O_LNB + D <= SPACK && SPACK % 4 == 0, "struct pack layout");
+
 struct StepDev {
-    int N, feat, layernorm, first, last;
+    int N, feat, layernorm, first, last, dir;
     const int* ptr;            // neighbour CSR of this step's direction
     const int* idx;
     const float* x;            // [N][feat]
@@ -41,124 +50,136 @@ struct StepDev {
     const float* in_part; const float* in_agg;
     float* out_part; float* out_agg;     // [enc][N][64]
     float* partial;            // [enc][gx][2][SGRAD]
-    int dir;
 };
 
-// Sum of neighbour rows (and optionally of a second array over the same neighbours); the two
-// half-warps take alternate neighbours, 16 lanes x float4 cover a 64-wide row.
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// One half-warp per node: sum of the neighbours' rows of `a` (and of `b` over the same neighbours).
 template <bool TWO>
-__device__ __forceinline__ void gather_sum(const StepDev& p, const float* a, const float* b, int node, int lane,
+__device__ __forceinline__ void gather_sum(const StepDev& p, const float* a, const float* b, int node, int l16,
                                            float4& sa, float4& sb, int& deg) {
     const int beg = p.ptr[node], end = p.ptr[node + 1];
     deg = end - beg;
-    const int half = lane >> 4, l16 = lane & 15;
     sa = make_float4(0.f, 0.f, 0.f, 0.f);
     sb = sa;
     for (int q0 = beg; q0 < end; q0 += 4) {
-        float4 va[2], vb[2];
+        float4 va[4], vb[4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int q = q0 + 2 * i + half;
+        for (int i = 0; i < 4; ++i) {
             va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             vb[i] = va[i];
-            if (q < end) {
-                const int j = p.idx[q] & NODE_MASK;
+            if (q0 + i < end) {
+                const int j = p.idx[q0 + i] & NODE_MASK;
                 va[i] = mgv_ld4(a + (size_t)j * D + 4 * l16);
                 if (TWO) vb[i] = mgv_ld4(b + (size_t)j * D + 4 * l16);
             }
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            sa.x += va[i].x; sa.y += va[i].y; sa.z += va[i].z; sa.w += va[i].w;
-            if (TWO) { sb.x += vb[i].x; sb.y += vb[i].y; sb.z += vb[i].z; sb.w += vb[i].w; }
+        for (int i = 0; i < 4; ++i) {
+            add4(sa, va[i]);
+            if (TWO) add4(sb, vb[i]);
         }
     }
-    sa.x += __shfl_xor_sync(0xffffffffu, sa.x, 16); sa.y += __shfl_xor_sync(0xffffffffu, sa.y, 16);
-    sa.z += __shfl_xor_sync(0xffffffffu, sa.z, 16); sa.w += __shfl_xor_sync(0xffffffffu, sa.w, 16);
-    if (TWO) {
-        sb.x += __shfl_xor_sync(0xffffffffu, sb.x, 16); sb.y += __shfl_xor_sync(0xffffffffu, sb.y, 16);
-        sb.z += __shfl_xor_sync(0xffffffffu, sb.z, 16); sb.w += __shfl_xor_sync(0xffffffffu, sb.w, 16);
+}
+
+__device__ __forceinline__ void load_weights(float* Ws, const float* Wg, int tid) {
+    for (int i = tid * 4; i < SPACK; i += THREADS * 4) mgv_st4(Ws + i, mgv_ldg4(Wg + i));
+}
+
+// GRU pre-activations of the 4 fragment elements a thread owns (rows g / g+8, units u0+2t / +1).
+struct Gates { float r[4], z[4], n[4], hnb[4]; };
+
+__device__ __forceinline__ void step_gemm(const float* Ws, const float* As, const float* Hs, const float* Dg,
+                                          int mt, int u0, int lane, Gates& o) {
+    const int n0[3] = {u0, D + u0, 2 * D + u0};
+    float ci[1][3][4], ch[1][3][4];
+    mgv_zero_frag(ci);
+    mgv_zero_frag(ch);
+    mgv_warp_gemm<1, 3, KX / 8, false, true>(ci, As, LDC, mt * 16, Ws + O_WCX, LDC, n0, lane);
+    mgv_warp_gemm<1, 3, D / 8, false, true>(ch, Hs, LDM, mt * 16, Ws + O_WHH, LDM, n0, lane);
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
+        const int u = u0 + 2 * t + (e & 1);
+        const float dg = Dg[row];
+        const float gir = ci[0][0][e] + dg * Ws[O_BC + u] + Ws[O_BIH + u];
+        const float giz = ci[0][1][e] + dg * Ws[O_BC + D + u] + Ws[O_BIH + D + u];
+        const float gin = ci[0][2][e] + dg * Ws[O_BC + 2 * D + u] + Ws[O_BIH + 2 * D + u];
+        o.r[e] = mgv_sigmoid(gir + ch[0][0][e] + Ws[O_BHH + u]);
+        o.z[e] = mgv_sigmoid(giz + ch[0][1][e] + Ws[O_BHH + D + u]);
+        o.hnb[e] = ch[0][2][e] + Ws[O_BHH + 2 * D + u];
+        o.n[e] = tanhf(gin + o.r[e] * o.hnb[e]);
     }
 }
 
 // ======================================================================================= forward step
-constexpr int FTM = 32;
-constexpr int F_SMEM_FLOATS = 3 * FTM * LDM + FTM * LDK + FTM;
+constexpr int F_SMEM_FLOATS = SPACK + TM * LDC + 2 * TM * LDM + TM;
 
-__global__ void __launch_bounds__(THREADS, 2) struct_fwd_kernel(const StepDev p) {
+__global__ void __launch_bounds__(THREADS, 1) struct_fwd_kernel(const StepDev p) {
     extern __shared__ __align__(16) float smem[];
-    float* As = smem;                    // [32][68] neighbour sum
-    float* Hs = As + FTM * LDM;          // [32][68] own state
-    float* Os = Hs + FTM * LDM;          // [32][68] GRU output (pre-LN)
-    float* Ms = Os + FTM * LDM;          // [32][76] [msg || x || 0]
-    float* Dg = Ms + FTM * LDK;          // [32] degree
+    float* Ws = smem;                    // weight block
+    float* As = Ws + SPACK;              // [32][76] [neighbour sum || x]
+    float* Hs = As + TM * LDC;           // [32][68] own state
+    float* Os = Hs + TM * LDM;           // [32][68] GRU output (pre-LN)
+    float* Dg = Os + TM * LDM;           // [32] degree
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int enc = blockIdx.y;
-    const float* W = p.weights + (size_t)enc * 2 * SPACK;
     const float* prev = p.prev + (size_t)enc * p.enc_stride;
     float* next = p.next + (size_t)enc * p.enc_stride;
-    const int t0 = blockIdx.x * FTM;
-    const int col = tid & 63, rg = tid >> 6;
+    load_weights(Ws, p.weights + (size_t)enc * 2 * SPACK, tid);
+    const int ntiles = (p.N + TM - 1) / TM;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int mt = warp & 1, u0 = (warp >> 1) * 8;
+    const int g = lane >> 2, t = lane & 3;
 
-    for (int row = warp; row < FTM; row += WARPS) {
-        const int node = t0 + row;
-        float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, h4 = sa;
-        int deg = 0;
-        float xf = 0.f;
-        if (node < p.N) {
-            gather_sum<false>(p, prev, nullptr, node, lane, sa, sb, deg);
-            if (lane >= 16) h4 = mgv_ld4(prev + (size_t)node * D + 4 * (lane - 16));
-            if (lane < p.feat) xf = p.x[(size_t)node * p.feat + lane];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t0 = tile * TM;
+        {   // ---- gather: one half-warp per node
+            const int row = warp * 2 + half, node = t0 + row;
+            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, h4 = sa;
+            int deg = 0;
+            float xf = 0.f;
+            if (node < p.N) {
+                gather_sum<false>(p, prev, nullptr, node, l16, sa, sb, deg);
+                h4 = mgv_ld4(prev + (size_t)node * D + 4 * l16);
+                if (l16 < p.feat) xf = p.x[(size_t)node * p.feat + l16];
+            }
+            mgv_st4(As + row * LDC + 4 * l16, sa);
+            mgv_st4(Hs + row * LDM + 4 * l16, h4);
+            if (l16 < MGV_MAX_FEAT) As[row * LDC + D + l16] = xf;
+            if (l16 == 0) Dg[row] = (float)deg;
         }
-        if (lane < 16) mgv_st4(As + row * LDM + 4 * lane, sa);
-        else mgv_st4(Hs + row * LDM + 4 * (lane - 16), h4);
-        if (lane < MGV_MAX_FEAT) Ms[row * LDK + D + lane] = xf;
-        if (lane == 0) Dg[row] = (float)deg;
-    }
-    __syncthreads();
-    {
-        float acc[8];
+        __syncthreads();
+        {   // ---- tile GEMM + GRU
+            Gates G;
+            step_gemm(Ws, As, Hs, Dg, mt, u0, lane, G);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        mgv_gemm_col<8, D>(As + rg * 8 * LDM, LDM, W + O_WT, D, col, acc);
-        const float b = __ldg(W + O_B + col);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) Ms[(rg * 8 + i) * LDK + col] = fmaf(b, Dg[rg * 8 + i], acc[i]);
-    }
-    __syncthreads();
-    {
-        float ar[8], az[8], an[8], hr[8], hz[8], hn[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ar[i] = az[i] = an[i] = 0.f; hr[i] = hz[i] = hn[i] = 0.f; }
-        mgv_gemm_col3<8, KX>(Ms + rg * 8 * LDK, LDK, W + O_WIHT, col, ar, az, an);
-        mgv_gemm_col3<8, D>(Hs + rg * 8 * LDM, LDM, W + O_WHHT, col, hr, hz, hn);
-        const float bir = __ldg(W + O_BIH + col), biz = __ldg(W + O_BIH + D + col), bin = __ldg(W + O_BIH + 2 * D + col);
-        const float bhr = __ldg(W + O_BHH + col), bhz = __ldg(W + O_BHH + D + col), bhn = __ldg(W + O_BHH + 2 * D + col);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = rg * 8 + i;
-            const float rr = mgv_sigmoid(ar[i] + bir + hr[i] + bhr);
-            const float zz = mgv_sigmoid(az[i] + biz + hz[i] + bhz);
-            const float nn = tanhf(an[i] + bin + rr * (hn[i] + bhn));
-            const float o = (1.0f - zz) * nn + zz * Hs[row * LDM + col];
-            if (p.layernorm) Os[row * LDM + col] = o;
-            else if (t0 + row < p.N) next[(size_t)(t0 + row) * D + col] = o;
+            for (int e = 0; e < 4; ++e) {
+                const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
+                const int u = u0 + 2 * t + (e & 1);
+                Os[row * LDM + u] = (1.0f - G.z[e]) * G.n[e] + G.z[e] * Hs[row * LDM + u];
+            }
         }
-    }
-    if (!p.layernorm) return;
-    __syncthreads();
-    const float g0 = __ldg(W + O_LNW + lane), g1 = __ldg(W + O_LNW + 32 + lane);
-    const float b0 = __ldg(W + O_LNB + lane), b1 = __ldg(W + O_LNB + 32 + lane);
-    for (int row = warp; row < FTM; row += WARPS) {
-        const int node = t0 + row;
-        if (node >= p.N) continue;
-        const float v0 = Os[row * LDM + lane], v1 = Os[row * LDM + 32 + lane];
-        const float mean = mgv_warp_sum(v0 + v1) * (1.0f / D);
-        const float d0 = v0 - mean, d1 = v1 - mean;
-        const float var = mgv_warp_sum(d0 * d0 + d1 * d1) * (1.0f / D);
-        const float rstd = 1.0f / sqrtf(var + LN_EPS);
-        next[(size_t)node * D + lane] = d0 * rstd * g0 + b0;
-        next[(size_t)node * D + 32 + lane] = d1 * rstd * g1 + b1;
+        __syncthreads();
+        // ---- LayerNorm + store: two rows per warp, lane owns columns lane and lane + 32
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int row = warp * 2 + rr, node = t0 + row;
+            if (node >= p.N) continue;
+            float v0 = Os[row * LDM + lane], v1 = Os[row * LDM + 32 + lane];
+            if (p.layernorm) {
+                const float mean = mgv_warp_sum(v0 + v1) * (1.0f / D);
+                const float d0 = v0 - mean, d1 = v1 - mean;
+                const float var = mgv_warp_sum(d0 * d0 + d1 * d1) * (1.0f / D);
+                const float rstd = 1.0f / sqrtf(var + LN_EPS);
+                v0 = d0 * rstd * Ws[O_LNW + lane] + Ws[O_LNB + lane];
+                v1 = d1 * rstd * Ws[O_LNW + 32 + lane] + Ws[O_LNB + 32 + lane];
+            }
+            next[(size_t)node * D + lane] = v0;
+            next[(size_t)node * D + 32 + lane] = v1;
+        }
+        __syncthreads();
     }
 }
 
@@ -168,93 +189,82 @@ __global__ void fill_ones_kernel(float* p, size_t n) {
 }
 
 // ======================================================================================= backward step
-constexpr int BTM = 16;
-constexpr int B_SMEM_FLOATS = SGRAD + 5 * BTM * LDM + BTM * LDK + 2 * BTM * LDG + 2 * BTM;
+constexpr int B_SMEM_FLOATS = SPACK + TM * LDC + 3 * TM * LDM + 2 * TM * LDG + TM + 2 * D;
 
 __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p) {
     extern __shared__ __align__(16) float smem[];
-    float* ACC = smem;                   // [SGRAD]
-    float* As = ACC + SGRAD;             // [16][68] neighbour sum of state_{k-1}
-    float* Hs = As + BTM * LDM;          // [16][68] state_{k-1} of the node
-    float* Gs = Hs + BTM * LDM;          // [16][68] d state_k, then d (pre-LN GRU output)
-    float* Xh = Gs + BTM * LDM;          // [16][68] pre-LN output, then xhat
-    float* DMs = Xh + BTM * LDM;         // [16][68] d msg
-    float* Ms = DMs + BTM * LDM;         // [16][76] [msg || x || 0]
-    float* DGI = Ms + BTM * LDK;         // [16][196]
-    float* DGH = DGI + BTM * LDG;        // [16][196]
-    float* Dg = DGH + BTM * LDG;         // [16]
+    float* Ws = smem;
+    float* As = Ws + SPACK;              // [32][76] [neighbour sum of state_{k-1} || x]
+    float* Hs = As + TM * LDC;           // [32][68] state_{k-1} of the node
+    float* Gs = Hs + TM * LDM;           // [32][68] d state_k, then d (pre-LN GRU output)
+    float* Xh = Gs + TM * LDM;           // [32][68] pre-LN GRU output
+    float* DGI = Xh + TM * LDM;          // [32][200] d gi (r, z, n)
+    float* DGH = DGI + TM * LDG;         // [32][200] d gh
+    float* Dg = DGH + TM * LDG;          // [32]
+    float* LNA = Dg + TM;                // [128] d ln_w, d ln_b accumulators
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int enc = blockIdx.y;
-    const float* W = p.weights + (size_t)enc * 2 * SPACK;
     const float* prev = p.prev + (size_t)enc * p.enc_stride;
     const size_t eoff = (size_t)enc * p.N * D;
-    const int col = tid & 63, rg = tid >> 6;
-    const int ntiles = (p.N + BTM - 1) / BTM;
+    load_weights(Ws, p.weights + (size_t)enc * 2 * SPACK, tid);
+    if (tid < 2 * D) LNA[tid] = 0.f;
+    const int ntiles = (p.N + TM - 1) / TM;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int mt = warp & 1, u0 = (warp >> 1) * 8;
+    const int g = lane >> 2, t = lane & 3;
 
-    for (int i = tid; i < SGRAD; i += THREADS) ACC[i] = 0.f;
-    __syncthreads();
+    // persistent weight-gradient fragments: d Wcx[:, 0:64] and d Whh as 6 m-tiles x 1 n-tile per warp,
+    // the feature columns of d Wcx as one fragment on warps 0..11
+    const int wn0[1] = {8 * (warp & 7)};
+    const int wm0 = (warp >> 3) * 96;
+    const int fn0[1] = {D};
+    float acc_cx[6][1][4], acc_hh[6][1][4], acc_f[1][1][4];
+    mgv_zero_frag(acc_cx);
+    mgv_zero_frag(acc_hh);
+    mgv_zero_frag(acc_f);
+    float s_bc = 0.f, s_bih = 0.f, s_bhh = 0.f;      // column sums owned by threads 0..191
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int t0 = tile * BTM;
-        // ---- phase A: gathers
-        for (int row = warp; row < BTM; row += WARPS) {
-            const int node = t0 + row;
+        const int t0 = tile * TM;
+        {   // ---- gathers: neighbour sum of state_{k-1}; d state_k = part + sum of neighbours' d agg_{k+1}
+            const int row = warp * 2 + half, node = t0 + row;
             float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, h4 = sa, g4 = sa;
             int deg = 0;
             float xf = 0.f;
             if (node < p.N) {
                 if (p.last) {
-                    gather_sum<false>(p, prev, nullptr, node, lane, sa, sb, deg);
-                    if (lane < 16) g4 = mgv_ld4(p.gout + eoff + (size_t)node * D + 4 * lane);
+                    gather_sum<false>(p, prev, nullptr, node, l16, sa, sb, deg);
+                    g4 = mgv_ld4(p.gout + eoff + (size_t)node * D + 4 * l16);
                 } else {
-                    gather_sum<true>(p, prev, p.in_agg + eoff, node, lane, sa, sb, deg);
-                    if (lane < 16) {
-                        const float4 pt = mgv_ld4(p.in_part + eoff + (size_t)node * D + 4 * lane);
-                        g4 = make_float4(pt.x + sb.x, pt.y + sb.y, pt.z + sb.z, pt.w + sb.w);
-                    }
+                    gather_sum<true>(p, prev, p.in_agg + eoff, node, l16, sa, sb, deg);
+                    g4 = mgv_ld4(p.in_part + eoff + (size_t)node * D + 4 * l16);
+                    add4(g4, sb);
                 }
-                if (lane >= 16) h4 = mgv_ld4(prev + (size_t)node * D + 4 * (lane - 16));
-                if (lane < p.feat) xf = p.x[(size_t)node * p.feat + lane];
+                h4 = mgv_ld4(prev + (size_t)node * D + 4 * l16);
+                if (l16 < p.feat) xf = p.x[(size_t)node * p.feat + l16];
             }
-            if (lane < 16) { mgv_st4(As + row * LDM + 4 * lane, sa); mgv_st4(Gs + row * LDM + 4 * lane, g4); }
-            else mgv_st4(Hs + row * LDM + 4 * (lane - 16), h4);
-            if (lane < MGV_MAX_FEAT) Ms[row * LDK + D + lane] = xf;
-            if (lane == 0) Dg[row] = (float)deg;
+            mgv_st4(As + row * LDC + 4 * l16, sa);
+            mgv_st4(Hs + row * LDM + 4 * l16, h4);
+            mgv_st4(Gs + row * LDM + 4 * l16, g4);
+            if (l16 < MGV_MAX_FEAT) As[row * LDC + D + l16] = xf;
+            if (l16 == 0) Dg[row] = (float)deg;
         }
         __syncthreads();
-        // ---- phase B: msg
-        {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            mgv_gemm_col<4, D>(As + rg * 4 * LDM, LDM, W + O_WT, D, col, acc);
-            const float b = __ldg(W + O_B + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) Ms[(rg * 4 + i) * LDK + col] = fmaf(b, Dg[rg * 4 + i], acc[i]);
-        }
-        __syncthreads();
-        // ---- phase C: GRU recompute (registers), LayerNorm backward, GRU backward
-        float rr[4], zz[4], nn[4], hnb[4];
-        {
-            float ar[4], az[4], an[4], hr[4], hz[4], hn[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { ar[i] = az[i] = an[i] = 0.f; hr[i] = hz[i] = hn[i] = 0.f; }
-            mgv_gemm_col3<4, KX>(Ms + rg * 4 * LDK, LDK, W + O_WIHT, col, ar, az, an);
-            mgv_gemm_col3<4, D>(Hs + rg * 4 * LDM, LDM, W + O_WHHT, col, hr, hz, hn);
-            const float bir = __ldg(W + O_BIH + col), biz = __ldg(W + O_BIH + D + col), bin = __ldg(W + O_BIH + 2 * D + col);
-            const float bhr = __ldg(W + O_BHH + col), bhz = __ldg(W + O_BHH + D + col), bhn = __ldg(W + O_BHH + 2 * D + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = rg * 4 + i;
-                rr[i] = mgv_sigmoid(ar[i] + bir + hr[i] + bhr);
-                zz[i] = mgv_sigmoid(az[i] + biz + hz[i] + bhz);
-                hnb[i] = hn[i] + bhn;
-                nn[i] = tanhf(an[i] + bin + rr[i] * hnb[i]);
-                if (p.layernorm) Xh[row * LDM + col] = (1.0f - zz[i]) * nn[i] + zz[i] * Hs[row * LDM + col];
-            }
-        }
+        // ---- recompute the step (gates stay in registers)
+        Gates G;
+        step_gemm(Ws, As, Hs, Dg, mt, u0, lane, G);
         if (p.layernorm) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
+                const int u = u0 + 2 * t + (e & 1);
+                Xh[row * LDM + u] = (1.0f - G.z[e]) * G.n[e] + G.z[e] * Hs[row * LDM + u];
+            }
             __syncthreads();
-            const float g0 = __ldg(W + O_LNW + lane), g1 = __ldg(W + O_LNW + 32 + lane);
-            for (int row = warp; row < BTM; row += WARPS) {
+            // LayerNorm backward, two rows per warp; d ln_w / d ln_b accumulate in shared memory
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int row = warp * 2 + rr;
                 const float v0 = Xh[row * LDM + lane], v1 = Xh[row * LDM + 32 + lane];
                 const float mean = mgv_warp_sum(v0 + v1) * (1.0f / D);
                 const float d0 = v0 - mean, d1 = v1 - mean;
@@ -262,11 +272,11 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
                 const float rstd = 1.0f / sqrtf(var + LN_EPS);
                 const float x0 = d0 * rstd, x1 = d1 * rstd;
                 const float gy0 = Gs[row * LDM + lane], gy1 = Gs[row * LDM + 32 + lane];
-                atomicAdd(ACC + G_LNW + lane, gy0 * x0);
-                atomicAdd(ACC + G_LNW + 32 + lane, gy1 * x1);
-                atomicAdd(ACC + G_LNB + lane, gy0);
-                atomicAdd(ACC + G_LNB + 32 + lane, gy1);
-                const float dx0 = gy0 * g0, dx1 = gy1 * g1;
+                atomicAdd(LNA + lane, gy0 * x0);
+                atomicAdd(LNA + 32 + lane, gy1 * x1);
+                atomicAdd(LNA + D + lane, gy0);
+                atomicAdd(LNA + D + 32 + lane, gy1);
+                const float dx0 = gy0 * Ws[O_LNW + lane], dx1 = gy1 * Ws[O_LNW + 32 + lane];
                 const float c1 = mgv_warp_sum(dx0 + dx1) * (1.0f / D);
                 const float c2 = mgv_warp_sum(dx0 * x0 + dx1 * x1) * (1.0f / D);
                 Gs[row * LDM + lane] = rstd * (dx0 - c1 - x0 * c2);
@@ -274,128 +284,87 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             }
             __syncthreads();
         }
+        // ---- GRU backward on the owned elements
         float dh_direct[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = rg * 4 + i;
-            const float g = Gs[row * LDM + col];
-            const float hp = Hs[row * LDM + col];
-            const float dn = g * (1.0f - zz[i]);
-            const float dz = g * (hp - nn[i]);
-            const float dnpre = dn * (1.0f - nn[i] * nn[i]);
-            const float drpre = dnpre * hnb[i] * rr[i] * (1.0f - rr[i]);
-            const float dzpre = dz * zz[i] * (1.0f - zz[i]);
-            dh_direct[i] = g * zz[i];
-            DGI[row * LDG + col] = drpre;
-            DGI[row * LDG + D + col] = dzpre;
-            DGI[row * LDG + 2 * D + col] = dnpre;
-            DGH[row * LDG + col] = drpre;
-            DGH[row * LDG + D + col] = dzpre;
-            DGH[row * LDG + 2 * D + col] = dnpre * rr[i];
+        for (int e = 0; e < 4; ++e) {
+            const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
+            const int u = u0 + 2 * t + (e & 1);
+            const float gg = Gs[row * LDM + u];
+            const float hp = Hs[row * LDM + u];
+            const float dn = gg * (1.0f - G.z[e]);
+            const float dz = gg * (hp - G.n[e]);
+            const float dnpre = dn * (1.0f - G.n[e] * G.n[e]);
+            const float drpre = dnpre * G.hnb[e] * G.r[e] * (1.0f - G.r[e]);
+            const float dzpre = dz * G.z[e] * (1.0f - G.z[e]);
+            dh_direct[e] = gg * G.z[e];
+            DGI[row * LDG + u] = drpre;
+            DGI[row * LDG + D + u] = dzpre;
+            DGI[row * LDG + 2 * D + u] = dnpre;
+            DGH[row * LDG + u] = drpre;
+            DGH[row * LDG + D + u] = dzpre;
+            DGH[row * LDG + 2 * D + u] = dnpre * G.r[e];
         }
         __syncthreads();
-        // ---- phase D: d msg = d gi . Wih[:, :64] ; d part = g z + d gh . Whh
-        {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            mgv_gemm_col<4, G3>(DGI + rg * 4 * LDG, LDG, W + O_WIH, KX, col, acc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) DMs[(rg * 4 + i) * LDM + col] = acc[i];
-            if (!p.first) {
-                float acch[4] = {0.f, 0.f, 0.f, 0.f};
-                mgv_gemm_col<4, G3>(DGH + rg * 4 * LDG, LDG, W + O_WHH, D, col, acch);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int node = t0 + rg * 4 + i;
-                    if (node < p.N) p.out_part[eoff + (size_t)node * D + col] = dh_direct[i] + acch[i];
-                }
-            }
-        }
-        __syncthreads();
-        // ---- phase E: d agg = d msg . W
+        // ---- data gradients: d agg = d gi . Wc ;  d part = g z + d gh . Whh   (both 32 x 64, K = 192)
         if (!p.first) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            mgv_gemm_col<4, D>(DMs + rg * 4 * LDM, LDM, W + O_W, D, col, acc);
+            const int n0[1] = {u0};
+            float ca[1][1][4], cp[1][1][4];
+            mgv_zero_frag(ca);
+            mgv_zero_frag(cp);
+            mgv_warp_gemm<1, 1, G3 / 8, false, false>(ca, DGI, LDG, mt * 16, Ws + O_WCX, LDC, n0, lane);
+            mgv_warp_gemm<1, 1, G3 / 8, false, false>(cp, DGH, LDG, mt * 16, Ws + O_WHH, LDM, n0, lane);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int node = t0 + rg * 4 + i;
-                if (node < p.N) p.out_agg[eoff + (size_t)node * D + col] = acc[i];
-            }
-        }
-        // ---- phase G: weight gradients (tile buffers are read-only here)
-        {
-            const int og = rg * 48;
-            float acc[48];
-#pragma unroll
-            for (int i = 0; i < 48; ++i) acc[i] = 0.f;
-            for (int row = 0; row < BTM; ++row) {
-                const float mv = Ms[row * LDK + col];
-#pragma unroll
-                for (int i = 0; i < 48; i += 4) {
-                    const float4 d4 = mgv_ld4(DGI + row * LDG + og + i);
-                    acc[i] = fmaf(d4.x, mv, acc[i]); acc[i + 1] = fmaf(d4.y, mv, acc[i + 1]);
-                    acc[i + 2] = fmaf(d4.z, mv, acc[i + 2]); acc[i + 3] = fmaf(d4.w, mv, acc[i + 3]);
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int node = t0 + mt * 16 + g + 8 * hrow;
+                if (node < p.N) {
+                    const size_t o = eoff + (size_t)node * D + u0 + 2 * t;
+                    *reinterpret_cast<float2*>(p.out_agg + o) = make_float2(ca[0][0][2 * hrow], ca[0][0][2 * hrow + 1]);
+                    *reinterpret_cast<float2*>(p.out_part + o) =
+                        make_float2(cp[0][0][2 * hrow] + dh_direct[2 * hrow], cp[0][0][2 * hrow + 1] + dh_direct[2 * hrow + 1]);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 48; ++i) ACC[G_WIH + (og + i) * KX + col] += acc[i];
-#pragma unroll
-            for (int i = 0; i < 48; ++i) acc[i] = 0.f;
-            for (int row = 0; row < BTM; ++row) {
-                const float hv = Hs[row * LDM + col];
-#pragma unroll
-                for (int i = 0; i < 48; i += 4) {
-                    const float4 d4 = mgv_ld4(DGH + row * LDG + og + i);
-                    acc[i] = fmaf(d4.x, hv, acc[i]); acc[i + 1] = fmaf(d4.y, hv, acc[i + 1]);
-                    acc[i + 2] = fmaf(d4.z, hv, acc[i + 2]); acc[i + 3] = fmaf(d4.w, hv, acc[i + 3]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 48; ++i) ACC[G_WHH + (og + i) * D + col] += acc[i];
         }
-        {
-            // dW[c][j] += sum_row dmsg[row][c] agg[row][j]   (c in [16 rg, 16 rg + 16), j = col)
-            const int cg = rg * 16;
-            float acc[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-            for (int row = 0; row < BTM; ++row) {
-                const float av = As[row * LDM + col];
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 d4 = mgv_ld4(DMs + row * LDM + cg + i);
-                    acc[i] = fmaf(d4.x, av, acc[i]); acc[i + 1] = fmaf(d4.y, av, acc[i + 1]);
-                    acc[i + 2] = fmaf(d4.z, av, acc[i + 2]); acc[i + 3] = fmaf(d4.w, av, acc[i + 3]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ACC[G_W + (cg + i) * D + col] += acc[i];
-        }
+        // ---- weight gradients (tile buffers are read-only here): d Wcx += d gi^T [agg || x], d Whh += d gh^T h
+        mgv_warp_gemm<6, 1, TM / 8, true, false>(acc_cx, DGI, LDG, wm0, As, LDC, wn0, lane);
+        mgv_warp_gemm<6, 1, TM / 8, true, false>(acc_hh, DGH, LDG, wm0, Hs, LDM, wn0, lane);
+        if (warp < 12) mgv_warp_gemm<1, 1, TM / 8, true, false>(acc_f, DGI, LDG, warp * 16, As, LDC, fn0, lane);
         if (tid < G3) {
-            float sgi = 0.f, sgh = 0.f;
-            float fx[MGV_MAX_FEAT];
-#pragma unroll
-            for (int f = 0; f < MGV_MAX_FEAT; ++f) fx[f] = 0.f;
-            for (int row = 0; row < BTM; ++row) {
+            for (int row = 0; row < TM; ++row) {
                 const float dgi = DGI[row * LDG + tid];
-                sgi += dgi;
-                sgh += DGH[row * LDG + tid];
-#pragma unroll
-                for (int f = 0; f < MGV_MAX_FEAT; ++f) fx[f] = fmaf(dgi, Ms[row * LDK + D + f], fx[f]);
+                s_bih += dgi;
+                s_bc = fmaf(dgi, Dg[row], s_bc);
+                s_bhh += DGH[row * LDG + tid];
             }
-            ACC[G_BIH + tid] += sgi;
-            ACC[G_BHH + tid] += sgh;
-#pragma unroll
-            for (int f = 0; f < MGV_MAX_FEAT; ++f) ACC[G_WIH + tid * KX + D + f] += fx[f];
-        } else {
-            const int c = tid - G3;
-            float s = 0.f;
-            for (int row = 0; row < BTM; ++row) s = fmaf(DMs[row * LDM + c], Dg[row], s);
-            ACC[G_B + c] += s;
         }
         __syncthreads();
     }
+    // ---- flush this CTA's accumulators into its private partial block (summed over the 8 launches)
     float* part = p.partial + (((size_t)enc * gridDim.x + blockIdx.x) * 2 + p.dir) * SGRAD;
-    for (int i = tid; i < SGRAD; i += THREADS) part[i] += ACC[i];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int o = wm0 + 16 * m + g + ((e & 2) ? 8 : 0);
+            const int c = wn0[0] + 2 * t + (e & 1);
+            part[O_WCX + o * LDC + c] += acc_cx[m][0][e];
+            part[O_WHH + o * LDM + c] += acc_hh[m][0][e];
+        }
+    }
+    if (warp < 12) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int o = warp * 16 + g + ((e & 2) ? 8 : 0);
+            part[O_WCX + o * LDC + D + 2 * t + (e & 1)] += acc_f[0][0][e];
+        }
+    }
+    if (tid < G3) {
+        part[O_BC + tid] += s_bc;
+        part[O_BIH + tid] += s_bih;
+        part[O_BHH + tid] += s_bhh;
+    }
+    __syncthreads();
+    if (tid < 2 * D) part[O_LNW + tid] += LNA[tid];
 }
 
 __global__ void struct_reduce_kernel(const float* __restrict__ partial, int gx, float* __restrict__ grads, int num_enc) {
@@ -409,11 +378,13 @@ __global__ void struct_reduce_kernel(const float* __restrict__ partial, int gx, 
     grads[idx] = s;
 }
 
-int struct_bwd_gx(int num_enc, int* gx_out) {
+int persistent_gx(int num_enc, int N, int* gx_out) {
     int dev = 0, sms = 0;
     MGV_CUDA(cudaGetDevice(&dev));
     MGV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int gx = sms / (num_enc > 0 ? num_enc : 1);
+    const int ntiles = (N + TM - 1) / TM;
+    if (gx > ntiles) gx = ntiles;
     if (gx < 1) gx = 1;
     *gx_out = gx;
     return MGV_OK;
@@ -425,6 +396,19 @@ int check_args(const mgv_schedule* sch, int num_enc, int rounds, int feat) {
     MGV_REQUIRE(rounds >= 1, "struct encoder: rounds must be >= 1");
     MGV_REQUIRE(feat >= 0 && feat <= MGV_MAX_FEAT, "struct encoder: dim_feature %d > %d", feat, MGV_MAX_FEAT);
     return MGV_OK;
+}
+
+void fill_step(StepDev& p, const mgv_schedule* sch, int k, int steps, int layernorm, int feat, const float* x,
+               const float* weights, const float* states, size_t slot, size_t enc_stride) {
+    const int dir = (k & 1) ? 0 : 1;
+    p.N = sch->N; p.feat = feat; p.layernorm = layernorm; p.first = (k == 1); p.last = (k == steps); p.dir = dir;
+    p.ptr = dir == 0 ? sch->in_ptr : sch->out_ptr;
+    p.idx = dir == 0 ? sch->in_src : sch->out_pack;
+    p.x = x;
+    p.weights = weights + (size_t)dir * SPACK;
+    p.prev = states + (size_t)(k - 1) * slot;
+    p.next = nullptr;
+    p.enc_stride = enc_stride;
 }
 
 }  // namespace
@@ -442,22 +426,18 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
     const size_t enc_stride = (size_t)(steps + 1) * slot;
     const size_t smem = (size_t)F_SMEM_FLOATS * sizeof(float);
     MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (int e = 0; e < num_enc; ++e)
+    int gx = 0;
+    rc = persistent_gx(num_enc, N, &gx);
+    if (rc != MGV_OK) return rc;
+    for (int e = 0; e < num_enc; ++e) {
         fill_ones_kernel<<<(unsigned)((slot + 255) / 256), 256, 0, st>>>(states + e * enc_stride, slot);
         mgv_count_launches(1);
+    }
     for (int k = 1; k <= steps; ++k) {
         StepDev p{};
-        const int dir = (k & 1) ? 0 : 1;
-        p.N = N; p.feat = feat; p.layernorm = layernorm; p.first = (k == 1); p.last = (k == steps); p.dir = dir;
-        p.ptr = dir == 0 ? sch->in_ptr : sch->out_ptr;
-        p.idx = dir == 0 ? sch->in_src : sch->out_pack;
-        p.x = x;
-        p.weights = weights + (size_t)dir * SPACK;
-        p.prev = states + (size_t)(k - 1) * slot;
+        fill_step(p, sch, k, steps, layernorm, feat, x, weights, states, slot, enc_stride);
         p.next = states + (size_t)k * slot;
-        p.enc_stride = enc_stride;
-        dim3 grid((N + FTM - 1) / FTM, num_enc);
-        struct_fwd_kernel<<<grid, THREADS, smem, st>>>(p);
+        struct_fwd_kernel<<<dim3(gx, num_enc), THREADS, smem, st>>>(p);
         mgv_count_launches(1);
     }
     return mgv_check_cuda(cudaGetLastError(), "mgv_struct_encoder_fwd");
@@ -465,13 +445,13 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
 
 extern "C" int mgv_struct_bwd_grid(void) {
     int gx = 0;
-    if (struct_bwd_gx(1, &gx) != MGV_OK) return -1;
+    if (persistent_gx(1, 1 << 30, &gx) != MGV_OK) return -1;
     return gx;
 }
 
 extern "C" size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc) {
-    int gx = 0;
-    if (struct_bwd_gx(1, &gx) != MGV_OK) gx = 256;
+    int gx = mgv_struct_bwd_grid();
+    if (gx < 1) gx = 256;
     size_t b = 0;
     b += 4 * mgv_align_up((size_t)num_enc * N * D * 4 + 256, 256);              // part/agg ping-pong
     b += mgv_align_up((size_t)gx * 2 * SGRAD * 4 + 256, 256);                    // partial: num_enc * (sms / num_enc) <= sms CTAs
@@ -494,10 +474,8 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
         return MGV_ERR_WORKSPACE;
     }
     int gx = 0;
-    rc = struct_bwd_gx(num_enc, &gx);
+    rc = persistent_gx(num_enc, N, &gx);
     if (rc != MGV_OK) return rc;
-    const int ntiles = (N + BTM - 1) / BTM;
-    if (gx > ntiles) gx = ntiles;
     const int steps = 2 * rounds;
     const size_t slot = (size_t)N * D;
     const size_t enc_stride = (size_t)(steps + 1) * slot;
@@ -512,21 +490,12 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int k = steps; k >= 1; --k) {
         StepDev p{};
-        const int dir = (k & 1) ? 0 : 1;
-        p.N = N; p.feat = feat; p.layernorm = layernorm; p.first = (k == 1); p.last = (k == steps); p.dir = dir;
-        p.ptr = dir == 0 ? sch->in_ptr : sch->out_ptr;
-        p.idx = dir == 0 ? sch->in_src : sch->out_pack;
-        p.x = x;
-        p.weights = weights + (size_t)dir * SPACK;
-        p.prev = states + (size_t)(k - 1) * slot;
-        p.next = nullptr;
-        p.enc_stride = enc_stride;
+        fill_step(p, sch, k, steps, layernorm, feat, x, weights, states, slot, enc_stride);
         p.gout = gout;
         p.in_part = part[k & 1]; p.in_agg = agg[k & 1];
         p.out_part = part[(k - 1) & 1]; p.out_agg = agg[(k - 1) & 1];
         p.partial = partial;
-        dim3 grid(gx, num_enc);
-        struct_bwd_kernel<<<grid, THREADS, smem, st>>>(p);
+        struct_bwd_kernel<<<dim3(gx, num_enc), THREADS, smem, st>>>(p);
         mgv_count_launches(1);
     }
     const size_t total = (size_t)num_enc * 2 * SGRAD;

@@ -18,8 +18,8 @@ CODE_SHIFT = 28
 MAX_FEAT = 8
 SWEEP_PACK_FLOATS = 66112
 SWEEP_GRAD_FLOATS = 33344
-STRUCT_PACK_FLOATS = 61824
-STRUCT_GRAD_FLOATS = 30912
+STRUCT_PACK_FLOATS = 28416
+STRUCT_GRAD_FLOATS = 28416
 
 _vp = ctypes.c_void_p
 _i32 = ctypes.c_int32

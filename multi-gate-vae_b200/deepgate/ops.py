@@ -137,26 +137,37 @@ def level_sweep(hs, sched, rounds, codes, modules):
 
 
 # =========================================================================== struct encoder
+_S_WCX, _S_WHH, _S_BC, _S_BIH, _S_BHH, _S_LNW, _S_LNB = 0, 14592, 27648, 27840, 28032, 28224, 28288
+_LDC, _LDM = 76, 68
+
+
 def _struct_pack(enc_params, layernorm, device):
-    """[num_enc][2][61824] weight blocks.  enc_params[e] = (aggr.w, aggr.b, upd.wih, upd.whh, upd.bih, upd.bhh,
-    aggr_r.w, aggr_r.b, upd_r.wih, upd_r.whh, upd_r.bih, upd_r.bhh[, ln.w, ln.b])."""
-    D, KX = nat.D, nat.D + nat.MAX_FEAT
+    """[num_enc][2][28416] weight blocks (include/mgv_b200.h).  enc_params[e] = (aggr.w, aggr.b, upd.wih, upd.whh,
+    upd.bih, upd.bhh, aggr_r.w, aggr_r.b, upd_r.wih, upd_r.whh, upd_r.bih, upd_r.bhh[, ln.w, ln.b]).
+    The AggConv linear is pre-composed into the GRU input weights: Wc = wih[:, :64] @ w, bc = wih[:, :64] @ b."""
+    D = nat.D
     pack = torch.zeros(len(enc_params), 2, nat.STRUCT_PACK_FLOATS, dtype=torch.float32, device=device)
     for e, ps in enumerate(enc_params):
         ps = [p.detach() for p in ps]
-        lnw = ps[12] if layernorm else torch.ones(D, device=device)
-        lnb = ps[13] if layernorm else torch.zeros(D, device=device)
         for d in range(2):
             w, b, wih, whh, bih, bhh = ps[6 * d:6 * d + 6]
             feat = wih.shape[1] - D
             if tuple(w.shape) != (D, D) or feat < 0 or feat > nat.MAX_FEAT:
                 raise RuntimeError("mgv_b200: struct encoder kernels need dim_hidden=%d, dim_feature<=%d"
                                    % (D, nat.MAX_FEAT))
-            wih_p = torch.zeros(3 * D, KX, dtype=torch.float32, device=device)
-            wih_p[:, :D + feat] = wih
-            pack[e, d, :61120] = torch.cat([
-                w.t().reshape(-1), b, wih_p.t().reshape(-1), whh.t().reshape(-1), bih, bhh, lnw, lnb,
-                torch.zeros(128, device=device), w.reshape(-1), wih_p.reshape(-1), whh.reshape(-1)])
+            blk = pack[e, d]
+            wcx = blk[_S_WCX:_S_WHH].view(3 * D, _LDC)
+            wcx[:, :D] = wih[:, :D] @ w
+            wcx[:, D:D + feat] = wih[:, D:]
+            blk[_S_WHH:_S_BC].view(3 * D, _LDM)[:, :D] = whh
+            blk[_S_BC:_S_BIH] = wih[:, :D] @ b
+            blk[_S_BIH:_S_BHH] = bih
+            blk[_S_BHH:_S_LNW] = bhh
+            if layernorm:
+                blk[_S_LNW:_S_LNB] = ps[12]
+                blk[_S_LNB:_S_LNB + D] = ps[13]
+            else:
+                blk[_S_LNW:_S_LNB] = 1.0
     return pack
 
 
@@ -179,7 +190,7 @@ class StructEncoderFunction(torch.autograd.Function):
                       "mgv_struct_encoder_fwd")
         ctx.csr, ctx.rounds, ctx.layernorm, ctx.num_enc, ctx.feat, ctx.per = csr, rounds, layernorm, num_enc, feat, per
         ctx.save_for_backward(x_c, pack, states)
-        ctx.param_shapes = [tuple(p.shape) for p in params]
+        ctx.saved_params = params
         return states[:, 2 * rounds, :N]
 
     @staticmethod
@@ -188,7 +199,7 @@ class StructEncoderFunction(torch.autograd.Function):
         x_c, pack, states = ctx.saved_tensors
         csr, rounds, num_enc, feat, per = ctx.csr, ctx.rounds, ctx.num_enc, ctx.feat, ctx.per
         dev = x_c.device
-        N, D, KX = csr.N, nat.D, nat.D + nat.MAX_FEAT
+        N, D = csr.N, nat.D
         g = torch.zeros(num_enc, max(N, 1), D, dtype=torch.float32, device=dev)
         g[:, :N] = gout
         grads = torch.empty(num_enc, 2, nat.STRUCT_GRAD_FLOATS, dtype=torch.float32, device=dev)
@@ -201,15 +212,22 @@ class StructEncoderFunction(torch.autograd.Function):
                                                  nat.ptr(grads), nat.ptr(ws), nb, nat.stream_of(dev)),
                       "mgv_struct_encoder_bwd")
         out = []
+        params = ctx.saved_params
         for e in range(num_enc):
+            ps = params[e * per:(e + 1) * per]
             for d in range(2):
+                w, b, wih = ps[6 * d].detach(), ps[6 * d + 1].detach(), ps[6 * d + 2].detach()
                 gd = grads[e, d]
-                out += [gd[0:4096].view(D, D), gd[4096:4160],
-                        gd[4160:17984].view(3 * D, KX)[:, :D + feat], gd[17984:30272].view(3 * D, D),
-                        gd[30272:30464], gd[30464:30656]]
+                g_wcx = gd[_S_WCX:_S_WHH].view(3 * D, _LDC)
+                g_wc, g_bc = g_wcx[:, :D], gd[_S_BC:_S_BIH]
+                wih_m = wih[:, :D]
+                # Wc = wih_m @ w, bc = wih_m @ b  ->  chain rule back to the reference's parameters
+                g_wih = torch.cat([g_wc @ w.t() + torch.outer(g_bc, b), g_wcx[:, D:D + feat]], dim=1)
+                out += [wih_m.t() @ g_wc, wih_m.t() @ g_bc, g_wih,
+                        gd[_S_WHH:_S_BC].view(3 * D, _LDM)[:, :D], gd[_S_BIH:_S_BHH], gd[_S_BHH:_S_LNW]]
             if ctx.layernorm:
-                out += [grads[e, 0, 30656:30720] + grads[e, 1, 30656:30720],
-                        grads[e, 0, 30720:30784] + grads[e, 1, 30720:30784]]
+                out += [grads[e, 0, _S_LNW:_S_LNB] + grads[e, 1, _S_LNW:_S_LNB],
+                        grads[e, 0, _S_LNB:_S_LNB + D] + grads[e, 1, _S_LNB:_S_LNB + D]]
         return (None, None, None, None, None) + tuple(out)
 
 
