@@ -1,6 +1,6 @@
 // Warp-level tensor-core tiles with fp32 accuracy: mma.sync m16n8k8 TF32 with the 3xTF32 split done
 // in registers (a = a_hi + a_lo, b = b_hi + b_lo; d += a_lo b_hi + a_hi b_lo + a_hi b_hi).
-// Operands are ordinary fp32 tiles in shared memory (or global memory for B), read straight into
+// Operands are ordinary fp32 tiles in SHARED memory (ldmatrix for the row-major cases), read straight into
 // MMA fragments -- either orientation of a matrix can be consumed from ONE copy, which is what lets
 // a gate code's / encoder's weights stay resident in shared memory once (fp32, 108-138 KB) next to
 // the activation tiles.  (A tcgen05 path would need hi and lo copies of every weight matrix in the
@@ -19,9 +19,20 @@ __device__ __forceinline__ uint32_t mgv_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// hi = x with the 13 low mantissa bits cleared (exactly what the tensor core reads from a 32-bit
+// operand), lo = x - hi (exact in fp32; the hardware truncates it to tf32 again: residual 2^-21).
 __device__ __forceinline__ void mgv_split(float x, uint32_t& hi, uint32_t& lo) {
-    hi = mgv_tf32(x);
-    lo = mgv_tf32(x - __uint_as_float(hi));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mgv_ldmatrix_x4(const float* p, uint32_t (&r)[4]) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mgv_ldmatrix_x2(const float* p, uint32_t (&r)[2]) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
 }
 __device__ __forceinline__ void mgv_mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile(
@@ -36,8 +47,12 @@ __device__ __forceinline__ void mgv_load_a(const float* A, int lda, int m0, int 
                                            uint32_t (&hi)[4], uint32_t (&lo)[4]) {
     float v0, v1, v2, v3;
     if (!TRANS) {
-        const float* p = A + (m0 + g) * lda + k0 + t;
-        v0 = p[0]; v1 = p[8 * lda]; v2 = p[4]; v3 = p[8 * lda + 4];
+        // one ldmatrix: an 8x8 b16 matrix row is 16 bytes = 4 tf32; lanes 8i..8i+7 address matrix i
+        // (0: rows 0-7 / k 0-3, 1: rows 8-15 / k 0-3, 2: rows 0-7 / k 4-7, 3: rows 8-15 / k 4-7)
+        const int lane = g * 4 + t, mi = lane >> 3, r = lane & 7;
+        uint32_t v[4];
+        mgv_ldmatrix_x4(A + (m0 + (mi & 1) * 8 + r) * lda + k0 + (mi >> 1) * 4, v);
+        v0 = __uint_as_float(v[0]); v1 = __uint_as_float(v[1]); v2 = __uint_as_float(v[2]); v3 = __uint_as_float(v[3]);
     } else {
         const float* p = A + (k0 + t) * lda + m0 + g;
         v0 = p[0]; v1 = p[8]; v2 = p[4 * lda]; v3 = p[4 * lda + 8];
@@ -52,8 +67,10 @@ __device__ __forceinline__ void mgv_load_b(const float* B, int ldb, int k0, int 
                                            uint32_t (&hi)[2], uint32_t (&lo)[2]) {
     float v0, v1;
     if (NK) {
-        const float* p = B + (n0 + g) * ldb + k0 + t;
-        v0 = p[0]; v1 = p[4];
+        const int lane = g * 4 + t, mi = (lane >> 3) & 1, r = lane & 7;   // lanes 16..31 repeat valid addresses
+        uint32_t v[2];
+        mgv_ldmatrix_x2(B + (n0 + r) * ldb + k0 + mi * 4, v);
+        v0 = __uint_as_float(v[0]); v1 = __uint_as_float(v[1]);
     } else {
         const float* p = B + (k0 + t) * ldb + n0 + g;
         v0 = p[0]; v1 = p[4 * ldb];
