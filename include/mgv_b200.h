@@ -37,6 +37,8 @@ extern "C" {
 #define MGV_NCODE 8              /* code buckets per level: 0..5 real codes, 6 = other, 7 unused */
 #define MGV_CODE_SHIFT 28        /* out_pack = dst | (code(dst) << 28)                          */
 #define MGV_MAX_FEAT 8           /* struct encoder: dim_feature <= 8 (config.py:14 default 6)   */
+#define MGV_TILE_ROWS 128        /* nodes per tensor-core tile (UMMA M)                          */
+#define MGV_TILE_FIXED_COST 512  /* per-tile fixed cost, in node-row reads, of the tile cost model */
 
 /* Floats per gate-code weight block of the level sweep (see mgv_sweep_pack layout below). */
 #define MGV_SWEEP_PACK_FLOATS 66112
@@ -89,6 +91,16 @@ int mgv_build_level_lists(const int32_t* level, const int32_t* code, int32_t N, 
                           int32_t* order, int32_t* seg_ptr, int64_t* code_count_host,
                           void* ws, size_t ws_bytes, mgv_stream_t stream);
 
+/* Degree order of one CSR direction, for the tensor-core tiles of the struct encoder: order[N] = node ids sorted
+ * by DESCENDING degree (degrees >= 255 tie), ascending id inside a degree, so the 128 rows of a tile have
+ * near-equal fan-in/out and the gather lanes of a warp run the same trip count.  tile_cost[ntiles + 1], ntiles =
+ * ceil(N / MGV_TILE_ROWS): exclusive prefix of (MGV_TILE_FIXED_COST + rows + neighbours) per tile; persistent CTAs
+ * take contiguous tile ranges of equal cost.
+ */
+size_t mgv_degree_order_workspace_bytes(int64_t N);
+int mgv_build_degree_order(const int32_t* ptr, int32_t N, int32_t* order, uint32_t* tile_cost,
+                           void* ws, size_t ws_bytes, mgv_stream_t stream);
+
 /* ------------------------------------------------------------------ level sweep (fp32)
  * Replaces the level loop of Model.forward (dg_ae_model_mig.py:84-129 and the aig/xmg/xag
  * twins): per round, per level >= 1, per handled code: TFMlpAggr (arch/tfmlp.py:31-46) over the
@@ -115,6 +127,10 @@ typedef struct mgv_schedule {
     const int32_t* out_pack;   /* [E]   */
     const int32_t* out_slot;   /* [E]   */
     int64_t code_count[MGV_NCODE];   /* host values: nodes per code at level >= 1 */
+    const int32_t* deg_order_in;     /* [N] mgv_build_degree_order(in_ptr)   */
+    const int32_t* deg_order_out;    /* [N] mgv_build_degree_order(out_ptr)  */
+    const uint32_t* tile_cost_in;    /* [ceil(N/128)+1] */
+    const uint32_t* tile_cost_out;
 } mgv_schedule;
 
 int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,
@@ -149,9 +165,10 @@ int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint32_t handle
  * x: float [N][feat] (feat <= MGV_MAX_FEAT).  states: float [num_enc][2*rounds+1][N][64] out
  * (slot 0 = ones, written by the call; slot 2*rounds = encoder output).
  */
+size_t mgv_struct_fwd_workspace_bytes(int64_t N, int32_t num_enc);
 int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
                            int32_t feat, const float* x, const float* weights, float* states,
-                           mgv_stream_t stream);
+                           void* ws, size_t ws_bytes, mgv_stream_t stream);
 /* gout: float [num_enc][N][64] = d loss / d (encoder output).  grads: float
  * [num_enc][2][MGV_STRUCT_GRAD_FLOATS] out, SAME layout as the weight block (d Wcx, d Whh, d bc, d bih, d bhh,
  * d ln_w, d ln_b; padding columns are zero).  The host maps d Wc / d bc back to msg.* and weight_ih_l0. */
@@ -180,6 +197,17 @@ int mgv_vae_func_loss_bwd(const float* g_out, const float* gz, const float* mu, 
                           const float* eps, float* gmu, float* glogstd, int64_t N,
                           const float* hf, const int64_t* pair, const float* tt_sim, int64_t P,
                           const float* out, const void* ws, float* ghf, mgv_stream_t stream);
+
+/* ------------------------------------------------------------------ tensor-core self test (diagnostic)
+ * One 128-row tcgen05 tile product through the operand layouts / descriptors / fp16 hi-lo split the kernels
+ * use (csrc/mgv_tc.cuh).  D is fp32 row-major.
+ *   mode 0: D[128][N]  = A[128][K] . B[N][K]^T                K in {64,128}     (K-major SW128 operands)
+ *   mode 1: D[128][N]  = A[128 rows][128]^T . B[128 rows][N]  N % 64 == 0       (both read MN-major: weight-gradient form)
+ *   mode 2: D[128][N]  = A[128][16] . B[N][16]^T                                (plain 16-column tiles)
+ *   mode 3: D[128][16] = A[128 rows][128]^T . B[128 rows][16]                   (MN-major SW128 x MN-major plain)
+ *   mode 4: D[128][64] = A[128][192] . B[192][64]                               (K-major x MN-major: data-gradient form)
+ */
+int mgv_tc_selftest(int32_t mode, const float* A, const float* B, float* D, int32_t K, int32_t N, mgv_stream_t stream);
 
 #define MGV_OK 0
 #define MGV_ERR_ARG (-1)

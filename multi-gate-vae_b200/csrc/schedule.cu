@@ -326,9 +326,81 @@ __global__ void code_count_kernel(const int32_t* __restrict__ seg_ptr, int L, un
     out[c] = s;
 }
 
+// ------------------------------------------------------------------------------------ degree order
+// key = 255 - min(degree, 255): one stable 8-bit radix pass sorts nodes by DESCENDING degree, ascending id inside
+// a degree (so the large equal-degree runs keep their memory locality).
+__global__ void degree_keys_kernel(const int32_t* __restrict__ ptr, int n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int d = ptr[v + 1] - ptr[v];
+    keys[v] = 255u - (uint32_t)(d < 255 ? d : 255);
+    vals[v] = (uint32_t)v;
+}
+// cost[t] = MGV_TILE_FIXED_COST + rows + neighbours of the 128-row tile t of the degree order (one warp per tile)
+__global__ void tile_cost_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ order, int n, int ntiles,
+                                 uint32_t* __restrict__ cost) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (t > ntiles) return;
+    uint32_t c = 0;
+    if (t < ntiles) {
+        for (int r = t * MGV_TILE_ROWS + lane; r < n && r < (t + 1) * MGV_TILE_ROWS; r += 32) {
+            const int v = order[r];
+            c += 1u + (uint32_t)(ptr[v + 1] - ptr[v]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        c += MGV_TILE_FIXED_COST;
+    }
+    if (lane == 0) cost[t] = c;                      // cost[ntiles] = 0: the scan turns it into the total
+}
+
 }  // namespace
 
 // ======================================================================================= C ABI
+extern "C" size_t mgv_degree_order_workspace_bytes(int64_t N) {
+    size_t b = 4 * mgv_align_up((size_t)N * 4 + 256, 256);
+    b += mgv_align_up(sort_hist_count(N) * 4 + 256, 256);
+    const size_t nt = (size_t)(N / MGV_TILE_ROWS) + 2;
+    const size_t scan_n = sort_hist_count(N) > nt ? sort_hist_count(N) : nt;
+    b += mgv_align_up(scan_tmp_count(scan_n) * 4 + 256, 256);
+    return b + 1024;
+}
+
+extern "C" int mgv_build_degree_order(const int32_t* ptr, int32_t N, int32_t* order, uint32_t* tile_cost,
+                                      void* ws, size_t ws_bytes, mgv_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MGV_REQUIRE(N >= 0 && ptr && order && tile_cost, "mgv_build_degree_order: bad argument");
+    if (ws_bytes < mgv_degree_order_workspace_bytes(N)) {
+        mgv_set_error("mgv_build_degree_order: workspace too small");
+        return MGV_ERR_WORKSPACE;
+    }
+    const int ntiles = (N + MGV_TILE_ROWS - 1) / MGV_TILE_ROWS;
+    MgvArena a(ws, ws_bytes);
+    SortBufs sb;
+    sb.k0 = a.take<uint32_t>(N + 1); sb.v0 = a.take<uint32_t>(N + 1);
+    sb.k1 = a.take<uint32_t>(N + 1); sb.v1 = a.take<uint32_t>(N + 1);
+    sb.hist = a.take<uint32_t>(sort_hist_count(N));
+    const size_t nt = (size_t)ntiles + 2;
+    const size_t scan_n = sort_hist_count(N) > nt ? sort_hist_count(N) : nt;
+    sb.tmp = a.take<uint32_t>(scan_tmp_count(scan_n));
+    if (N > 0) {
+        degree_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(ptr, N, sb.k0, sb.v0);
+        mgv_count_launches(1);
+    }
+    uint32_t *ks, *vs;
+    int rc = radix_sort_pairs(sb, N, 8, &ks, &vs, st);
+    if (rc != MGV_OK) return rc;
+    if (N > 0) {
+        copy_u32_to_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(vs, order, N);
+        mgv_count_launches(1);
+    }
+    tile_cost_kernel<<<(ntiles + 1 + 7) / 8, 256, 0, st>>>(ptr, order, N, ntiles, tile_cost);
+    mgv_count_launches(1);
+    rc = exclusive_scan(tile_cost, tile_cost, ntiles + 1, sb.tmp, st);
+    if (rc != MGV_OK) return rc;
+    return mgv_check_cuda(cudaGetLastError(), "mgv_build_degree_order");
+}
+
 extern "C" size_t mgv_csr_workspace_bytes(int64_t N, int64_t E) {
     size_t b = 0;
     b += 4 * mgv_align_up((size_t)E * 4 + 256, 256);                 // k0 v0 k1 v1

@@ -1,4 +1,5 @@
-// Struct encoder: MultiGCNEncoder.forward (digae_layer.py:257-277) with AggConv
+// Struct encoder BACKWARD (mma.sync 3xTF32 generation; the forward lives in struct_tc.cu on tcgen05).
+// MultiGCNEncoder.forward (digae_layer.py:257-277) with AggConv
 // (arch/gcn_conv.py:30-42), one fused kernel per half-round step:
 //   gather-sum of neighbour states -> GRU_{70->64}([W agg + deg b || x], state) -> LayerNorm
 // Step k = 1..2R uses in-neighbours when k is odd (aggr/update) and out-neighbours when k is
@@ -111,81 +112,6 @@ __device__ __forceinline__ void step_gemm(const float* Ws, const float* As, cons
         o.hnb[e] = ch[0][2][e] + Ws[O_BHH + 2 * D + u];
         o.n[e] = tanhf(gin + o.r[e] * o.hnb[e]);
     }
-}
-
-// ======================================================================================= forward step
-constexpr int F_SMEM_FLOATS = SPACK + TM * LDC + 2 * TM * LDM + TM;
-
-__global__ void __launch_bounds__(THREADS, 1) struct_fwd_kernel(const StepDev p) {
-    extern __shared__ __align__(16) float smem[];
-    float* Ws = smem;                    // weight block
-    float* As = Ws + SPACK;              // [32][76] [neighbour sum || x]
-    float* Hs = As + TM * LDC;           // [32][68] own state
-    float* Os = Hs + TM * LDM;           // [32][68] GRU output (pre-LN)
-    float* Dg = Os + TM * LDM;           // [32] degree
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int enc = blockIdx.y;
-    const float* prev = p.prev + (size_t)enc * p.enc_stride;
-    float* next = p.next + (size_t)enc * p.enc_stride;
-    load_weights(Ws, p.weights + (size_t)enc * 2 * SPACK, tid);
-    const int ntiles = (p.N + TM - 1) / TM;
-    const int half = lane >> 4, l16 = lane & 15;
-    const int mt = warp & 1, u0 = (warp >> 1) * 8;
-    const int g = lane >> 2, t = lane & 3;
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int t0 = tile * TM;
-        {   // ---- gather: one half-warp per node
-            const int row = warp * 2 + half, node = t0 + row;
-            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, h4 = sa;
-            int deg = 0;
-            float xf = 0.f;
-            if (node < p.N) {
-                gather_sum<false>(p, prev, nullptr, node, l16, sa, sb, deg);
-                h4 = mgv_ld4(prev + (size_t)node * D + 4 * l16);
-                if (l16 < p.feat) xf = p.x[(size_t)node * p.feat + l16];
-            }
-            mgv_st4(As + row * LDC + 4 * l16, sa);
-            mgv_st4(Hs + row * LDM + 4 * l16, h4);
-            if (l16 < MGV_MAX_FEAT) As[row * LDC + D + l16] = xf;
-            if (l16 == 0) Dg[row] = (float)deg;
-        }
-        __syncthreads();
-        {   // ---- tile GEMM + GRU
-            Gates G;
-            step_gemm(Ws, As, Hs, Dg, mt, u0, lane, G);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
-                const int u = u0 + 2 * t + (e & 1);
-                Os[row * LDM + u] = (1.0f - G.z[e]) * G.n[e] + G.z[e] * Hs[row * LDM + u];
-            }
-        }
-        __syncthreads();
-        // ---- LayerNorm + store: two rows per warp, lane owns columns lane and lane + 32
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int row = warp * 2 + rr, node = t0 + row;
-            if (node >= p.N) continue;
-            float v0 = Os[row * LDM + lane], v1 = Os[row * LDM + 32 + lane];
-            if (p.layernorm) {
-                const float mean = mgv_warp_sum(v0 + v1) * (1.0f / D);
-                const float d0 = v0 - mean, d1 = v1 - mean;
-                const float var = mgv_warp_sum(d0 * d0 + d1 * d1) * (1.0f / D);
-                const float rstd = 1.0f / sqrtf(var + LN_EPS);
-                v0 = d0 * rstd * Ws[O_LNW + lane] + Ws[O_LNB + lane];
-                v1 = d1 * rstd * Ws[O_LNW + 32 + lane] + Ws[O_LNB + 32 + lane];
-            }
-            next[(size_t)node * D + lane] = v0;
-            next[(size_t)node * D + 32 + lane] = v1;
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void fill_ones_kernel(float* p, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 1.0f;
 }
 
 // ======================================================================================= backward step
@@ -412,36 +338,6 @@ void fill_step(StepDev& p, const mgv_schedule* sch, int k, int steps, int layern
 }
 
 }  // namespace
-
-extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
-                                      int32_t feat, const float* x, const float* weights, float* states,
-                                      mgv_stream_t stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc = check_args(sch, num_enc, rounds, feat);
-    if (rc != MGV_OK) return rc;
-    const int N = sch->N;
-    if (N == 0) return MGV_OK;
-    const int steps = 2 * rounds;
-    const size_t slot = (size_t)N * D;
-    const size_t enc_stride = (size_t)(steps + 1) * slot;
-    const size_t smem = (size_t)F_SMEM_FLOATS * sizeof(float);
-    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int gx = 0;
-    rc = persistent_gx(num_enc, N, &gx);
-    if (rc != MGV_OK) return rc;
-    for (int e = 0; e < num_enc; ++e) {
-        fill_ones_kernel<<<(unsigned)((slot + 255) / 256), 256, 0, st>>>(states + e * enc_stride, slot);
-        mgv_count_launches(1);
-    }
-    for (int k = 1; k <= steps; ++k) {
-        StepDev p{};
-        fill_step(p, sch, k, steps, layernorm, feat, x, weights, states, slot, enc_stride);
-        p.next = states + (size_t)k * slot;
-        struct_fwd_kernel<<<dim3(gx, num_enc), THREADS, smem, st>>>(p);
-        mgv_count_launches(1);
-    }
-    return mgv_check_cuda(cudaGetLastError(), "mgv_struct_encoder_fwd");
-}
 
 extern "C" int mgv_struct_bwd_grid(void) {
     int gx = 0;

@@ -16,6 +16,7 @@ D = 64
 NCODE = 8
 CODE_SHIFT = 28
 MAX_FEAT = 8
+TILE_ROWS = 128
 SWEEP_PACK_FLOATS = 66112
 SWEEP_GRAD_FLOATS = 33344
 STRUCT_PACK_FLOATS = 28416
@@ -32,7 +33,8 @@ class mgv_schedule(ctypes.Structure):
     _fields_ = [("N", _i32), ("L", _i32), ("E", _i64),
                 ("order", _vp), ("seg_ptr", _vp), ("in_ptr", _vp), ("in_src", _vp),
                 ("out_ptr", _vp), ("out_pack", _vp), ("out_slot", _vp),
-                ("code_count", _i64 * NCODE)]
+                ("code_count", _i64 * NCODE),
+                ("deg_order_in", _vp), ("deg_order_out", _vp), ("tile_cost_in", _vp), ("tile_cost_out", _vp)]
 
 
 _SP = ctypes.POINTER(mgv_schedule)
@@ -47,11 +49,14 @@ _PROTOTYPES = {
     "mgv_levelize": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, ctypes.POINTER(_i32), _vp, _sz, _vp]),
     "mgv_level_lists_workspace_bytes": (_sz, [_i64, _i32]),
     "mgv_build_level_lists": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _vp]),
+    "mgv_degree_order_workspace_bytes": (_sz, [_i64]),
+    "mgv_build_degree_order": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mgv_level_sweep_fwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "mgv_sweep_bwd_grid": (ctypes.c_int, []),
     "mgv_sweep_bwd_workspace_bytes": (_sz, [_i64, _i64]),
     "mgv_level_sweep_bwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
-    "mgv_struct_encoder_fwd": (ctypes.c_int, [_SP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "mgv_struct_fwd_workspace_bytes": (_sz, [_i64, _i32]),
+    "mgv_struct_encoder_fwd": (ctypes.c_int, [_SP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgv_struct_bwd_grid": (ctypes.c_int, []),
     "mgv_struct_bwd_workspace_bytes": (_sz, [_i64, _i32]),
     "mgv_struct_encoder_bwd": (ctypes.c_int, [_SP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -59,6 +64,7 @@ _PROTOTYPES = {
     "mgv_vae_func_loss_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "mgv_vae_func_loss_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64,
                                              _vp, _vp, _vp, _vp]),
+    "mgv_tc_selftest": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _i32, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

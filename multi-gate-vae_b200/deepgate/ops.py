@@ -184,9 +184,12 @@ class StructEncoderFunction(torch.autograd.Function):
         pack = _struct_pack(enc_params, layernorm, dev)
         states = torch.empty(num_enc, 2 * rounds + 1, max(N, 1), nat.D, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            nb = lib.mgv_struct_fwd_workspace_bytes(N, num_enc)
+            ws = nat.workspace(nb, dev)
             with _timed("struct_encoder_fwd", dev):
               nat.check(lib.mgv_struct_encoder_fwd(csr.c_struct(), num_enc, rounds, int(layernorm), feat,
-                                                 nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.stream_of(dev)),
+                                                 nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(ws), nb,
+                                                 nat.stream_of(dev)),
                       "mgv_struct_encoder_fwd")
         ctx.csr, ctx.rounds, ctx.layernorm, ctx.num_enc, ctx.feat, ctx.per = csr, rounds, layernorm, num_enc, feat, per
         ctx.save_for_backward(x_c, pack, states)

@@ -49,6 +49,18 @@ class GraphCSR(object):
                                         nat.ptr(self.in_ptr), nat.ptr(self.in_src), nat.ptr(self.out_ptr),
                                         nat.ptr(self.out_pack), nat.ptr(self.out_slot), nat.ptr(ws), nb,
                                         nat.stream_of(dev)), "mgv_build_csr")
+            # degree orders + tile cost prefixes for the tensor-core tiles of the struct encoder
+            ntiles = (self.N + nat.TILE_ROWS - 1) // nat.TILE_ROWS
+            self.deg_order_in = torch.empty(max(self.N, 1), **i32)
+            self.deg_order_out = torch.empty(max(self.N, 1), **i32)
+            self.tile_cost_in = torch.empty(ntiles + 1, **i32)
+            self.tile_cost_out = torch.empty(ntiles + 1, **i32)
+            nb = lib.mgv_degree_order_workspace_bytes(self.N)
+            ws = nat.workspace(nb, dev)
+            for p_, o_, c_ in ((self.in_ptr, self.deg_order_in, self.tile_cost_in),
+                               (self.out_ptr, self.deg_order_out, self.tile_cost_out)):
+                nat.check(lib.mgv_build_degree_order(nat.ptr(p_), self.N, nat.ptr(o_), nat.ptr(c_), nat.ptr(ws), nb,
+                                                     nat.stream_of(dev)), "mgv_build_degree_order")
         self.level = None
         self.L = 1
         self.order = None
@@ -110,6 +122,8 @@ class GraphCSR(object):
             s.out_ptr, s.out_pack, s.out_slot = nat.ptr(self.out_ptr), nat.ptr(self.out_pack), nat.ptr(self.out_slot)
             for c in range(nat.NCODE):
                 s.code_count[c] = self.code_count[c]
+            s.deg_order_in, s.deg_order_out = nat.ptr(self.deg_order_in), nat.ptr(self.deg_order_out)
+            s.tile_cost_in, s.tile_cost_out = nat.ptr(self.tile_cost_in), nat.ptr(self.tile_cost_out)
             self._struct = s
         return ctypes.byref(self._struct)
 
