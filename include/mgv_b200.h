@@ -96,10 +96,11 @@ int mgv_build_level_lists(const int32_t* level, const int32_t* code, int32_t N, 
  * near-equal fan-in/out and the gather lanes of a warp run the same trip count.  tile_cost[ntiles + 1], ntiles =
  * ceil(N / MGV_TILE_ROWS): exclusive prefix of (MGV_TILE_FIXED_COST + rows + neighbours) per tile; persistent CTAs
  * take contiguous tile ranges of equal cost.
+ * gdesc[N][4] (16-byte aligned): {node, first CSR slot, degree, first neighbour id} per row of the order.
  */
 size_t mgv_degree_order_workspace_bytes(int64_t N);
-int mgv_build_degree_order(const int32_t* ptr, int32_t N, int32_t* order, uint32_t* tile_cost,
-                           void* ws, size_t ws_bytes, mgv_stream_t stream);
+int mgv_build_degree_order(const int32_t* ptr, const int32_t* idx, int32_t N, int32_t* order, int32_t* gdesc,
+                           uint32_t* tile_cost, void* ws, size_t ws_bytes, mgv_stream_t stream);
 
 /* ------------------------------------------------------------------ level sweep (fp32)
  * Replaces the level loop of Model.forward (dg_ae_model_mig.py:84-129 and the aig/xmg/xag
@@ -131,6 +132,8 @@ typedef struct mgv_schedule {
     const int32_t* deg_order_out;    /* [N] mgv_build_degree_order(out_ptr)  */
     const uint32_t* tile_cost_in;    /* [ceil(N/128)+1] */
     const uint32_t* tile_cost_out;
+    const int32_t* gdesc_in;         /* [N][4] */
+    const int32_t* gdesc_out;
 } mgv_schedule;
 
 int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,

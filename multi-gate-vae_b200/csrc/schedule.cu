@@ -336,6 +336,16 @@ __global__ void degree_keys_kernel(const int32_t* __restrict__ ptr, int n, uint3
     keys[v] = 255u - (uint32_t)(d < 255 ? d : 255);
     vals[v] = (uint32_t)v;
 }
+// gdesc[r] = {node, first CSR slot, degree, first neighbour id} of row r of the degree order: the gather warps
+// of the tile kernels start their row loads after ONE dependent load instead of order -> ptr -> idx.
+__global__ void gather_desc_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const int32_t* __restrict__ order,
+                                   int n, int4* __restrict__ gdesc) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int v = order[r];
+    const int b = ptr[v], c = ptr[v + 1] - b;
+    gdesc[r] = make_int4(v, b, c, c > 0 ? (idx[b] & ((1 << MGV_CODE_SHIFT) - 1)) : 0);
+}
 // cost[t] = MGV_TILE_FIXED_COST + rows + neighbours of the 128-row tile t of the degree order (one warp per tile)
 __global__ void tile_cost_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ order, int n, int ntiles,
                                  uint32_t* __restrict__ cost) {
@@ -366,10 +376,10 @@ extern "C" size_t mgv_degree_order_workspace_bytes(int64_t N) {
     return b + 1024;
 }
 
-extern "C" int mgv_build_degree_order(const int32_t* ptr, int32_t N, int32_t* order, uint32_t* tile_cost,
-                                      void* ws, size_t ws_bytes, mgv_stream_t stream) {
+extern "C" int mgv_build_degree_order(const int32_t* ptr, const int32_t* idx, int32_t N, int32_t* order, int32_t* gdesc,
+                                      uint32_t* tile_cost, void* ws, size_t ws_bytes, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    MGV_REQUIRE(N >= 0 && ptr && order && tile_cost, "mgv_build_degree_order: bad argument");
+    MGV_REQUIRE(N >= 0 && ptr && idx && order && gdesc && tile_cost, "mgv_build_degree_order: bad argument");
     if (ws_bytes < mgv_degree_order_workspace_bytes(N)) {
         mgv_set_error("mgv_build_degree_order: workspace too small");
         return MGV_ERR_WORKSPACE;
@@ -392,7 +402,8 @@ extern "C" int mgv_build_degree_order(const int32_t* ptr, int32_t N, int32_t* or
     if (rc != MGV_OK) return rc;
     if (N > 0) {
         copy_u32_to_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(vs, order, N);
-        mgv_count_launches(1);
+        gather_desc_kernel<<<(N + 255) / 256, 256, 0, st>>>(ptr, idx, order, N, reinterpret_cast<int4*>(gdesc));
+        mgv_count_launches(2);
     }
     tile_cost_kernel<<<(ntiles + 1 + 7) / 8, 256, 0, st>>>(ptr, order, N, ntiles, tile_cost);
     mgv_count_launches(1);

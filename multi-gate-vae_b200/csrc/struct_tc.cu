@@ -12,10 +12,11 @@
 // memory; biases and the degree term ride along as two extra K columns, so the epilogue is gates + LayerNorm.
 //
 // Persistent CTAs (one per SM, weights resident in shared memory for the whole launch), warp-specialised:
-//   warps 8-15  gather: neighbour sums, own state and [x deg 1] -> fp16 hi/lo -> operand tile (UMMA layout)
-//   warp  8/l0  issues the MMAs of a tile once the tile is full; completion frees the tile (tcgen05.commit)
-//   warps 0-7   epilogue: tensor memory -> GRU gates -> LayerNorm -> state_k   (two accumulator buffers, so the
-//               epilogue of tile t overlaps the gather and MMAs of tile t+1)
+//   warps 4-11  gather: neighbour sums, own state and [x deg 1] -> fp16 hi/lo -> operand tile (UMMA layout);
+//               rows come in descending-degree order (mgv_build_degree_order) so a warp's lanes run equal trip counts
+//   warp  12    one thread issues the MMAs of a tile once the tile is full; completion frees the tile (tcgen05.commit)
+//   warps 0-3   epilogue, thread = node = TMEM lane: tensor memory -> GRU gates -> LayerNorm -> state_k
+//               (two accumulator buffers: the epilogue of tile t overlaps the gather and MMAs of tile t+1)
 #include "mgv_tc.cuh"
 
 namespace {
@@ -43,24 +44,25 @@ constexpr uint32_t S_BAR = S_EX + 2048;             // 7 mbarriers
 constexpr uint32_t S_TMEM = S_BAR + 64;
 constexpr uint32_t F_SMEM = S_TMEM + 64 + 1024;     // + alignment slack
 
-constexpr int THREADS = 512;
-constexpr int EPI_WARPS = 8, GATHER_WARPS = 8;
+constexpr int EPI_WARPS = 4, GATHER_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + GATHER_WARPS + 1) * 32;   // + the MMA warp  (13 warps: register pools are per 4 warps -> 128 regs/thread)
 
 struct StepTC {
     int N, feat, layernorm;
     const int* ptr;            // neighbour CSR of this step's direction
     const int* idx;
     const int* order;          // degree order of this direction (tile row -> node id)
+    const int* gdesc;          // [N][4] row descriptors of the degree order
     const unsigned* tile_cost; // [ntiles + 1] exclusive prefix of the tile cost model
     const float* x;            // [N][feat]
     const uint8_t* image;      // weight image of (enc 0, this dir); encoder stride 2 * IMG_BYTES
     const float* prev;         // state_{k-1}, enc 0
     float* next;               // state_k, enc 0
     size_t enc_stride;         // floats between encoders in the states buffer
+    long long* trace;          // optional [CTA][16 tiles][16] clock64 samples (dev tool), may be null
 };
+#define TRACE(slot) do { if (p.trace && it < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + it) * 16 + (slot)] = clock64(); } while (0)
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 __device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -75,6 +77,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr) : "memory");
+}
+// r, z, gi_n, gh_n of 4 consecutive units: columns c, 64 + c, 128 + c, 192 + c (4 each) of the accumulator
+__device__ __forceinline__ void tmem_ld4x4(uint32_t taddr, float (&v)[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[4 * k]), "=r"(r[4 * k + 1]), "=r"(r[4 * k + 2]), "=r"(r[4 * k + 3]) : "r"(taddr + 64u * k) : "memory");
 }
 __device__ __forceinline__ void split_store_sw128(uint32_t hi_base, uint32_t lo_base, int row, int c, const float (&v)[8]) {
     uint4 hi, lo;
@@ -135,6 +145,19 @@ __global__ void struct_image_kernel(const float* __restrict__ pack, uint8_t* __r
 }
 
 // ======================================================================================= forward step
+// GRU gates with 5 MUFU ops per unit (3 ex2 + 2 rcp): r and z share one reciprocal.  Pre-activations are
+// clamped to +-28 / +-14 (sigmoid / tanh saturate to 1 - 1e-12 there) so the shared product cannot overflow.
+__device__ __forceinline__ void gru_gates(float gr, float gz, float gi, float gh, float& r, float& z, float& n, float& hnb) {
+    const float a = __expf(-fminf(fmaxf(gr, -28.f), 28.f));
+    const float b = __expf(-fminf(fmaxf(gz, -28.f), 28.f));
+    const float inv = __fdividef(1.0f, (1.0f + a) * (1.0f + b));
+    r = (1.0f + b) * inv;
+    z = (1.0f + a) * inv;
+    hnb = gh;
+    const float y = fminf(fmaxf(fmaf(r, gh, gi), -14.f), 14.f);
+    n = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y));
+}
+
 __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -147,12 +170,11 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
 
     const uint32_t bar_a_full = sbase + S_BAR, bar_a_empty = bar_a_full + 8;
     const uint32_t bar_acc_full = bar_a_full + 16, bar_acc_empty = bar_a_full + 32;      // [2] each
+    const uint32_t bar_w = bar_a_full + 48;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + S_TMEM);
     float* s_ln = reinterpret_cast<float*>(sgen + S_LN);
-    float* s_ex = reinterpret_cast<float*>(sgen + S_EX);
 
     // ---- one-time setup: barriers, weights -> shared memory (bulk async copy, overlaps the first gather), tensor memory
-    const uint32_t bar_w = bar_a_full + 48;
     if (tid == 0) {
         tc::mbar_init(bar_a_full, GATHER_WARPS * 32);
         tc::mbar_init(bar_a_empty, 1);
@@ -182,58 +204,52 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= EPI_WARPS) {
-        // ===================================================================== gather (+ MMA issue)
+    if (warp >= EPI_WARPS && warp < EPI_WARPS + GATHER_WARPS) {
+        // ===================================================================== gather
+        // lane = (row group rg, 16-byte chunk c): 8 lanes cover one 256-byte state row; a lane owns 4 rows of the tile.
         const int gw = warp - EPI_WARPS, rg = lane >> 3, c = lane & 7;
+        const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
+        int4 dn[4];                                   // row descriptors of the NEXT tile, loaded one tile ahead
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            const int r = tile_beg * TM + gw * 16 + ps * 4 + rg;
+            dn[ps] = (tile_beg < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
+        }
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
-            const int t0 = tile * TM;
-            // ---- prologue in registers (overlaps the previous tile's MMAs): node ids, CSR ranges, first neighbour,
-            //      then the own-state rows, the lane's feature element and the first neighbour rows
+            if (warp == EPI_WARPS && lane == 0) TRACE(0);
+            // ---- loads into registers (overlap the previous tile's MMAs): own-state rows, the lane's feature element,
+            //      first neighbour rows, second neighbour ids, next tile's descriptors
             int node[4], beg[4], cnt[4], jn[4];
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int r = t0 + gw * 16 + ps * 4 + rg;
-                node[ps] = r < p.N ? p.order[r] : -1;
-            }
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                beg[ps] = 0; cnt[ps] = 0;
-                if (node[ps] >= 0) { beg[ps] = p.ptr[node[ps]]; cnt[ps] = p.ptr[node[ps] + 1] - beg[ps]; }
-            }
+            for (int ps = 0; ps < 4; ++ps) { node[ps] = dn[ps].x; beg[ps] = dn[ps].y; cnt[ps] = dn[ps].z; jn[ps] = dn[ps].w; }
+            float4 ha[4], hb[4], va[4], vb[4];
+            float xe[4];
             int maxc = 0;
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
-                jn[ps] = cnt[ps] > 0 ? (p.idx[beg[ps]] & NODE_MASK) : 0;
-                maxc = max(maxc, cnt[ps]);
-            }
-            float4 ha[4], hb[4], va[4], vb[4];
-            float xe[4];
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                ha[ps] = make_float4(0.f, 0.f, 0.f, 0.f); hb[ps] = ha[ps];
+                ha[ps] = make_float4(0.f, 0.f, 0.f, 0.f); hb[ps] = ha[ps]; va[ps] = ha[ps]; vb[ps] = ha[ps];
                 xe[ps] = 0.f;
+                maxc = max(maxc, cnt[ps]);
                 if (node[ps] >= 0) {
                     ha[ps] = mgv_ld4(prev + (size_t)node[ps] * D + c * 8);
                     hb[ps] = mgv_ld4(prev + (size_t)node[ps] * D + c * 8 + 4);
                     if (c < p.feat) xe[ps] = p.x[(size_t)node[ps] * p.feat + c];
                 }
-            }
-            int j[4];
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                j[ps] = jn[ps];
-                if (1 < cnt[ps]) jn[ps] = p.idx[beg[ps] + 1] & NODE_MASK;
-            }
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                va[ps] = make_float4(0.f, 0.f, 0.f, 0.f); vb[ps] = va[ps];
-                if (0 < cnt[ps]) {
-                    va[ps] = mgv_ld4(prev + (size_t)j[ps] * D + c * 8);
-                    vb[ps] = mgv_ld4(prev + (size_t)j[ps] * D + c * 8 + 4);
+                if (cnt[ps] > 0) {
+                    va[ps] = mgv_ld4(prev + (size_t)jn[ps] * D + c * 8);
+                    vb[ps] = mgv_ld4(prev + (size_t)jn[ps] * D + c * 8 + 4);
                 }
+                if (cnt[ps] > 1) jn[ps] = p.idx[beg[ps] + 1] & NODE_MASK;
             }
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const int r = (tile + 1) * TM + gw * 16 + ps * 4 + rg;
+                dn[ps] = (tile + 1 < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
+            }
+            if (warp == EPI_WARPS && lane == 0) TRACE(1);
             tc::mbar_wait(bar_a_empty, (uint32_t)((it & 1) ^ 1));            // previous tile's MMAs have read the stage
+            if (warp == EPI_WARPS && lane == 0) TRACE(2);
             // ---- own state rows and the [x deg 1] block
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
@@ -256,6 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                     tc::st_shared_v4(sbase + A_X_LO + off, lo);
                 }
             }
+            if (warp == EPI_WARPS && lane == 0) TRACE(3);
             // ---- neighbour sums: one neighbour of each of the lane's 4 rows per trip (8 x 16-byte loads in flight),
             //      next trip's neighbour ids prefetched
             float acc[4][8];
@@ -265,6 +282,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                 acc[ps][4] = vb[ps].x; acc[ps][5] = vb[ps].y; acc[ps][6] = vb[ps].z; acc[ps][7] = vb[ps].w;
             }
             for (int sl = 1; sl < maxc; ++sl) {
+                int j[4];
 #pragma unroll
                 for (int ps = 0; ps < 4; ++ps) {
                     j[ps] = jn[ps];
@@ -287,23 +305,26 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps)
                 split_store_sw128(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps]);
+            if (warp == EPI_WARPS && lane == 0) TRACE(4);
             tc::fence_async_smem();
             tc::mbar_arrive(bar_a_full);
-            if (warp == EPI_WARPS && lane == 0) {
+        }
+    } else if (warp == EPI_WARPS + GATHER_WARPS) {
+        // ===================================================================== MMA issue (one thread)
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
                 const int b = it & 1;
                 if (it == 0) tc::mbar_wait(bar_w, 0u);                              // weight image has landed
-                tc::mbar_wait(bar_a_full, (uint32_t)(it & 1));
+                TRACE(5);
                 tc::mbar_wait(bar_acc_empty + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this buffer
+                tc::mbar_wait(bar_a_full, (uint32_t)(it & 1));
                 tc::fence_after_sync();
+                TRACE(6);
                 const uint32_t d = tmem + (uint32_t)b * 256u;
                 // [x deg 1] block first: initialises all 256 columns (biases, degree term, feature term)
                 tc::mma3(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
                          tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false), 0u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)      // agg . Wc^T -> r, z, gi_n
-                    tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
-                             tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
-                             tc::make_idesc(128, 192, false, false), 1u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)      // h . Whh[r, z]^T -> r, z
                     tc::mma3(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
@@ -314,68 +335,88 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                     tc::mma3(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
                              tc::desc_k_sw128(sbase + WHH_HI + 16384 + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 16384 + 32 * j),
                              tc::make_idesc(128, 64, false, false), 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)      // agg . Wc^T -> r, z, gi_n
+                    tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
+                             tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
+                             tc::make_idesc(128, 192, false, false), 1u);
                 tc::mma_commit(bar_a_empty);
                 tc::mma_commit(bar_acc_full + 8 * b);
+                TRACE(7);
             }
-            __syncwarp();
         }
-    } else {
-        // ===================================================================== epilogue
-        const int q = warp & 3, half = warp >> 2;
-        const int row = q * 32 + lane, ubase = half * 32;
+    } else if (warp < EPI_WARPS) {
+        // ===================================================================== epilogue: thread = tile row = TMEM lane
+        // Gates are read 4 units at a time (r, z, gi_n, gh_n -> 16 registers) with the next chunk's tensor-memory loads
+        // in flight while the current chunk is computed.
+        const int row = warp * 32 + lane;
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
             const int b = it & 1;
             const bool valid = tile * TM + row < p.N;
             const int node = valid ? p.order[tile * TM + row] : 0;
-            float h[32];
+            float h[D];
             if (valid) {
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) ldg8(prev + (size_t)node * D + ubase + 8 * ch, *reinterpret_cast<float(*)[8]>(&h[8 * ch]));
+                for (int ch = 0; ch < 8; ++ch) ldg8(prev + (size_t)node * D + 8 * ch, *reinterpret_cast<float(*)[8]>(&h[8 * ch]));
             } else {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) h[e] = 0.f;
+                for (int e = 0; e < D; ++e) h[e] = 0.f;
             }
+            if (tid == 0) TRACE(8);
             tc::mbar_wait(bar_acc_full + 8 * b, (uint32_t)((it >> 1) & 1));
             tc::fence_after_sync();
-            const uint32_t ta = tmem + (uint32_t)b * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)ubase;
+            if (tid == 0) TRACE(9);
+            const uint32_t ta = tmem + (uint32_t)b * 256u + ((uint32_t)(warp * 32) << 16);
+            float g0[16], g1[16];
+            tmem_ld4x4(ta, g0);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                float gr[8], gz[8], gi[8], gh[8];
-                tmem_ld8(ta + 8 * ch, gr);
-                tmem_ld8(ta + 64 + 8 * ch, gz);
-                tmem_ld8(ta + 128 + 8 * ch, gi);
-                tmem_ld8(ta + 192 + 8 * ch, gh);
+            for (int ch = 0; ch < 16; ch += 2) {
                 tc::tmem_ld_wait();
+                tmem_ld4x4(ta + 4 * (ch + 1), g1);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float r = fast_sigmoid(gr[e]), z = fast_sigmoid(gz[e]);
-                    const float n = fast_tanh(fmaf(r, gh[e], gi[e]));
-                    h[8 * ch + e] = fmaf(z, h[8 * ch + e] - n, n);          // (1 - z) n + z h
+                for (int e = 0; e < 4; ++e) {
+                    float r, z, n, hnb;
+                    gru_gates(g0[e], g0[4 + e], g0[8 + e], g0[12 + e], r, z, n, hnb);
+                    h[4 * ch + e] = fmaf(z, h[4 * ch + e] - n, n);          // (1 - z) n + z h
+                }
+                tc::tmem_ld_wait();
+                if (ch + 2 < 16) tmem_ld4x4(ta + 4 * (ch + 2), g0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float r, z, n, hnb;
+                    gru_gates(g1[e], g1[4 + e], g1[8 + e], g1[12 + e], r, z, n, hnb);
+                    h[4 * (ch + 1) + e] = fmaf(z, h[4 * (ch + 1) + e] - n, n);
                 }
             }
             tc::fence_before_sync();
             tc::mbar_arrive(bar_acc_empty + 8 * b);
+            if (tid == 0) TRACE(10);
             if (p.layernorm) {
-                float s = 0.f;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) s += h[e];
-                s_ex[row * 2 + half] = s;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float mean = (s_ex[row * 2] + s_ex[row * 2 + 1]) * (1.0f / D);
-                float v = 0.f;
+                for (int e = 0; e < D; e += 4) { s0 += h[e]; s1 += h[e + 1]; s2 += h[e + 2]; s3 += h[e + 3]; }
+                const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / D);
+                s0 = s1 = s2 = s3 = 0.f;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) { h[e] -= mean; v = fmaf(h[e], h[e], v); }
-                s_ex[256 + row * 2 + half] = v;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float rstd = rsqrtf((s_ex[256 + row * 2] + s_ex[256 + row * 2 + 1]) * (1.0f / D) + LN_EPS);
+                for (int e = 0; e < D; e += 4) {
+                    h[e] -= mean; h[e + 1] -= mean; h[e + 2] -= mean; h[e + 3] -= mean;
+                    s0 = fmaf(h[e], h[e], s0); s1 = fmaf(h[e + 1], h[e + 1], s1);
+                    s2 = fmaf(h[e + 2], h[e + 2], s2); s3 = fmaf(h[e + 3], h[e + 3], s3);
+                }
+                const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / D) + LN_EPS);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) h[e] = fmaf(h[e] * rstd, s_ln[ubase + e], s_ln[D + ubase + e]);
+                for (int e = 0; e < D; e += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(s_ln + e), b4 = *reinterpret_cast<const float4*>(s_ln + D + e);
+                    h[e] = fmaf(h[e] * rstd, w4.x, b4.x); h[e + 1] = fmaf(h[e + 1] * rstd, w4.y, b4.y);
+                    h[e + 2] = fmaf(h[e + 2] * rstd, w4.z, b4.z); h[e + 3] = fmaf(h[e + 3] * rstd, w4.w, b4.w);
+                }
             }
             if (valid) {
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) stg8(next + (size_t)node * D + ubase + 8 * ch, *reinterpret_cast<float(*)[8]>(&h[8 * ch]));
+                for (int ch = 0; ch < 8; ++ch) stg8(next + (size_t)node * D + 8 * ch, *reinterpret_cast<float(*)[8]>(&h[8 * ch]));
             }
+            if (tid == 0) TRACE(11);
         }
     }
     tc::fence_before_sync();
@@ -389,6 +430,9 @@ __global__ void fill_ones_kernel(float* p, size_t n) {
 }
 
 }  // namespace
+
+static long long* g_trace = nullptr;
+extern "C" void mgv_debug_set_trace(void* p) { g_trace = (long long*)p; }
 
 size_t mgv_struct_image_bytes(int num_enc) { return mgv_align_up((size_t)num_enc * 2 * IMG_BYTES, 256); }
 
@@ -414,7 +458,7 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
     MGV_REQUIRE(feat >= 0 && feat <= MGV_MAX_FEAT, "struct encoder: dim_feature %d > %d", feat, MGV_MAX_FEAT);
     const int N = sch->N;
     if (N == 0) return MGV_OK;
-    MGV_REQUIRE(sch->deg_order_in && sch->deg_order_out && sch->tile_cost_in && sch->tile_cost_out,
+    MGV_REQUIRE(sch->deg_order_in && sch->deg_order_out && sch->tile_cost_in && sch->tile_cost_out && sch->gdesc_in && sch->gdesc_out,
                 "struct encoder: the schedule carries no degree order (mgv_build_degree_order)");
     if (ws_bytes < mgv_struct_fwd_workspace_bytes(N, num_enc)) {
         mgv_set_error("mgv_struct_encoder_fwd: workspace %zu < %zu bytes", ws_bytes, mgv_struct_fwd_workspace_bytes(N, num_enc));
@@ -446,12 +490,14 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         p.ptr = dir == 0 ? sch->in_ptr : sch->out_ptr;
         p.idx = dir == 0 ? sch->in_src : sch->out_pack;
         p.order = dir == 0 ? sch->deg_order_in : sch->deg_order_out;
+        p.gdesc = dir == 0 ? sch->gdesc_in : sch->gdesc_out;
         p.tile_cost = dir == 0 ? sch->tile_cost_in : sch->tile_cost_out;
         p.x = x;
         p.image = image + (size_t)dir * IMG_BYTES;
         p.prev = states + (size_t)(k - 1) * slot;
         p.next = states + (size_t)k * slot;
         p.enc_stride = enc_stride;
+        p.trace = (k == steps) ? g_trace : nullptr;
         struct_fwd_tc_kernel<<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
         mgv_count_launches(1);
     }

@@ -34,7 +34,8 @@ class mgv_schedule(ctypes.Structure):
                 ("order", _vp), ("seg_ptr", _vp), ("in_ptr", _vp), ("in_src", _vp),
                 ("out_ptr", _vp), ("out_pack", _vp), ("out_slot", _vp),
                 ("code_count", _i64 * NCODE),
-                ("deg_order_in", _vp), ("deg_order_out", _vp), ("tile_cost_in", _vp), ("tile_cost_out", _vp)]
+                ("deg_order_in", _vp), ("deg_order_out", _vp), ("tile_cost_in", _vp), ("tile_cost_out", _vp),
+                ("gdesc_in", _vp), ("gdesc_out", _vp)]
 
 
 _SP = ctypes.POINTER(mgv_schedule)
@@ -50,7 +51,7 @@ _PROTOTYPES = {
     "mgv_level_lists_workspace_bytes": (_sz, [_i64, _i32]),
     "mgv_build_level_lists": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _vp]),
     "mgv_degree_order_workspace_bytes": (_sz, [_i64]),
-    "mgv_build_degree_order": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "mgv_build_degree_order": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgv_level_sweep_fwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "mgv_sweep_bwd_grid": (ctypes.c_int, []),
     "mgv_sweep_bwd_workspace_bytes": (_sz, [_i64, _i64]),

@@ -55,12 +55,14 @@ class GraphCSR(object):
             self.deg_order_out = torch.empty(max(self.N, 1), **i32)
             self.tile_cost_in = torch.empty(ntiles + 1, **i32)
             self.tile_cost_out = torch.empty(ntiles + 1, **i32)
+            self.gdesc_in = torch.empty(max(self.N, 1), 4, **i32)
+            self.gdesc_out = torch.empty(max(self.N, 1), 4, **i32)
             nb = lib.mgv_degree_order_workspace_bytes(self.N)
             ws = nat.workspace(nb, dev)
-            for p_, o_, c_ in ((self.in_ptr, self.deg_order_in, self.tile_cost_in),
-                               (self.out_ptr, self.deg_order_out, self.tile_cost_out)):
-                nat.check(lib.mgv_build_degree_order(nat.ptr(p_), self.N, nat.ptr(o_), nat.ptr(c_), nat.ptr(ws), nb,
-                                                     nat.stream_of(dev)), "mgv_build_degree_order")
+            for p_, i_, o_, g_, c_ in ((self.in_ptr, self.in_src, self.deg_order_in, self.gdesc_in, self.tile_cost_in),
+                                       (self.out_ptr, self.out_pack, self.deg_order_out, self.gdesc_out, self.tile_cost_out)):
+                nat.check(lib.mgv_build_degree_order(nat.ptr(p_), nat.ptr(i_), self.N, nat.ptr(o_), nat.ptr(g_), nat.ptr(c_),
+                                                     nat.ptr(ws), nb, nat.stream_of(dev)), "mgv_build_degree_order")
         self.level = None
         self.L = 1
         self.order = None
@@ -124,6 +126,7 @@ class GraphCSR(object):
                 s.code_count[c] = self.code_count[c]
             s.deg_order_in, s.deg_order_out = nat.ptr(self.deg_order_in), nat.ptr(self.deg_order_out)
             s.tile_cost_in, s.tile_cost_out = nat.ptr(self.tile_cost_in), nat.ptr(self.tile_cost_out)
+            s.gdesc_in, s.gdesc_out = nat.ptr(self.gdesc_in), nat.ptr(self.gdesc_out)
             self._struct = s
         return ctypes.byref(self._struct)
 
