@@ -1,52 +1,52 @@
-// Struct encoder BACKWARD (mma.sync 3xTF32 generation; the forward lives in struct_tc.cu on tcgen05).
-// MultiGCNEncoder.forward (digae_layer.py:257-277) with AggConv
-// (arch/gcn_conv.py:30-42), one fused kernel per half-round step:
-//   gather-sum of neighbour states -> GRU_{70->64}([W agg + deg b || x], state) -> LayerNorm
-// Step k = 1..2R uses in-neighbours when k is odd (aggr/update) and out-neighbours when k is
-// even (aggr_r/update_r); LayerNorm parameters are shared by both directions (digae_layer.py:270,275).
-// source_conv and target_conv (digae_layer.py:294-297) run batched: blockIdx.y = encoder.
-//
-// The AggConv linear is pre-composed into the GRU input weights on the host:
-//   W_ih[:, :64] (W agg + deg b) = Wc agg + deg bc,   Wc = W_ih[:, :64] W,  bc = W_ih[:, :64] b
-// so a step is ONE tile GEMM  [agg || x || h] (32 x 136)  x  [Wc | W_ih_x | W_hh]^T  on the tensor
-// cores (3xTF32, fp32 accuracy), with one copy of the weights resident in shared memory for the
-// whole launch (persistent CTAs loop over 32-node tiles).
-// Backward recomputes the step from the saved post-LN states, runs LN/GRU backward in registers,
-// the two data-gradient GEMMs from the same weight copy, and keeps the weight-gradient
-// accumulators as persistent MMA fragments in registers (flushed once per launch).
-#include "mgv_mma.cuh"
+// Struct encoder BACKWARD (the forward lives in struct_tc.cu on tcgen05): MultiGCNEncoder.forward
+// (digae_layer.py:257-277) with AggConv (arch/gcn_conv.py:30-42) differentiated step by step in reverse.
+// One fused kernel per half-round step k = 2R .. 1 (blockIdx.y = encoder):
+//   gather   neighbour sum of state_{k-1} (recompute) and of the neighbours' d agg_{k+1} (+ d part) = d state_k
+//   GEMM     recompute the GRU pre-activations  [agg | x | deg 1] Wcx^T,  h Whh^T
+//   pointwise LayerNorm backward, GRU backward -> d gi / d gh  (scaled per tile by a power of two into fp16 range)
+//   GEMM     d agg = d gi Wc,  d part = g z + d gh Whh         (consumed by step k-1)
+//   GEMM     d Wcx += d gi^T [agg | x | deg 1],  d Whh += d gh^T h   (persistent register fragments, flushed once)
+// All products are mma.sync m16n8k16 on fp16 hi/lo planes (mgv_mma16.cuh): tiles and weights are split once when
+// written to shared memory; biases ride along as the "1" column of the [agg | x | deg 1] tile, so d bc / d b_ih /
+// d b_hh fall out of the weight-gradient product.
+#include "mgv_mma16.cuh"
 
 namespace {
 
 constexpr int D = MGV_D;              // 64
 constexpr int G3 = 3 * D;             // 192
-constexpr int KX = D + MGV_MAX_FEAT;  // 72: [agg || x]
 constexpr int SPACK = MGV_STRUCT_PACK_FLOATS;
 constexpr int SGRAD = MGV_STRUCT_GRAD_FLOATS;
-constexpr int LDC = KX + 4;           // 76: row stride of Wcx and of the [agg || x] tile
-constexpr int LDM = D + 4;            // 68
-constexpr int LDG = G3 + 8;           // 200: d gi / d gh tiles (also read transposed)
-// weight / gradient block offsets (floats) -- see include/mgv_b200.h
+// natural fp32 weight / gradient block (include/mgv_b200.h)
 constexpr int O_WCX = 0, O_WHH = 14592, O_BC = 27648, O_BIH = 27840, O_BHH = 28032, O_LNW = 28224, O_LNB = 28288;
+constexpr int NLDC = 76, NLDM = 68;
 constexpr int NODE_MASK = (1 << MGV_CODE_SHIFT) - 1;
+constexpr float LN_EPS = 1e-5f;
 
 constexpr int THREADS = 512;
 constexpr int WARPS = THREADS / 32;   // 16
 constexpr int TM = 32;                // nodes per tile
-constexpr float LN_EPS = 1e-5f;
-
-static_assert(O_LNB + D <= SPACK && SPACK % 4 == 0, "struct pack layout");
+constexpr int KX = 80;                // [agg 64 | x 8 | deg | 1 | 0 x 6]
+constexpr int LDC = 88, LDW = 72, LDG = 264, LDF = 68;   // row strides: halves (planes) / floats (LDF)
+// shared memory (bytes)
+constexpr uint32_t WCX_HI = 0, WCX_LO = WCX_HI + G3 * LDC * 2, WHH_HI = WCX_LO + G3 * LDC * 2, WHH_LO = WHH_HI + G3 * LDW * 2;
+constexpr uint32_t S_BHH = WHH_LO + G3 * LDW * 2, S_LN = S_BHH + G3 * 4;
+constexpr uint32_t AS_HI = S_LN + 2 * D * 4, AS_LO = AS_HI + TM * LDC * 2, HS_HI = AS_LO + TM * LDC * 2, HS_LO = HS_HI + TM * LDW * 2;
+constexpr uint32_t S_H32 = HS_LO + TM * LDW * 2, S_GS = S_H32 + TM * LDF * 4, S_XH = S_GS + TM * LDF * 4;
+constexpr uint32_t DG_HI = S_XH + TM * LDF * 4, DG_LO = DG_HI + TM * LDG * 2;
+constexpr uint32_t S_LNA = DG_LO + TM * LDG * 2, S_MAX = S_LNA + 2 * D * 4;
+constexpr uint32_t B_SMEM = S_MAX + 16;
+static_assert(WCX_LO % 16 == 0 && WHH_HI % 16 == 0 && AS_HI % 16 == 0 && HS_HI % 16 == 0 && DG_HI % 16 == 0 && DG_LO % 16 == 0, "plane alignment");
+static_assert(B_SMEM <= 227 * 1024, "struct backward: shared memory");
 
 struct StepDev {
     int N, feat, layernorm, first, last, dir;
     const int* ptr;            // neighbour CSR of this step's direction
     const int* idx;
     const float* x;            // [N][feat]
-    const float* weights;      // block of (enc 0, this dir); encoder stride 2*SPACK
+    const float* weights;      // natural block of (enc 0, this dir); encoder stride 2*SPACK
     const float* prev;         // state_{k-1}, enc 0
-    float* next;               // state_k, enc 0 (forward only)
     size_t enc_stride;         // floats between encoders in the states buffer
-    // backward
     const float* gout;         // [enc][N][64]
     const float* in_part; const float* in_agg;
     float* out_part; float* out_agg;     // [enc][N][64]
@@ -83,211 +83,279 @@ __device__ __forceinline__ void gather_sum(const StepDev& p, const float* a, con
     }
 }
 
-__device__ __forceinline__ void load_weights(float* Ws, const float* Wg, int tid) {
-    for (int i = tid * 4; i < SPACK; i += THREADS * 4) mgv_st4(Ws + i, mgv_ldg4(Wg + i));
+// GRU gates with 5 MUFU ops per unit (same formulation as the forward kernel, struct_tc.cu).
+__device__ __forceinline__ void gru_gates(float gr, float gz, float gi, float gh, float& r, float& z, float& n) {
+    const float a = __expf(-fminf(fmaxf(gr, -28.f), 28.f));
+    const float b = __expf(-fminf(fmaxf(gz, -28.f), 28.f));
+    const float inv = __fdividef(1.0f, (1.0f + a) * (1.0f + b));
+    r = (1.0f + b) * inv;
+    z = (1.0f + a) * inv;
+    const float y = fminf(fmaxf(fmaf(r, gh, gi), -14.f), 14.f);
+    n = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y));
 }
 
-// GRU pre-activations of the 4 fragment elements a thread owns (rows g / g+8, units u0+2t / +1).
-struct Gates { float r[4], z[4], n[4], hnb[4]; };
-
-__device__ __forceinline__ void step_gemm(const float* Ws, const float* As, const float* Hs, const float* Dg,
-                                          int mt, int u0, int lane, Gates& o) {
-    const int n0[3] = {u0, D + u0, 2 * D + u0};
-    float ci[1][3][4], ch[1][3][4];
-    mgv_zero_frag(ci);
-    mgv_zero_frag(ch);
-    mgv_warp_gemm<1, 3, KX / 8, false, true>(ci, As, LDC, mt * 16, Ws + O_WCX, LDC, n0, lane);
-    mgv_warp_gemm<1, 3, D / 8, false, true>(ch, Hs, LDM, mt * 16, Ws + O_WHH, LDM, n0, lane);
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
-        const int u = u0 + 2 * t + (e & 1);
-        const float dg = Dg[row];
-        const float gir = ci[0][0][e] + dg * Ws[O_BC + u] + Ws[O_BIH + u];
-        const float giz = ci[0][1][e] + dg * Ws[O_BC + D + u] + Ws[O_BIH + D + u];
-        const float gin = ci[0][2][e] + dg * Ws[O_BC + 2 * D + u] + Ws[O_BIH + 2 * D + u];
-        o.r[e] = mgv_sigmoid(gir + ch[0][0][e] + Ws[O_BHH + u]);
-        o.z[e] = mgv_sigmoid(giz + ch[0][1][e] + Ws[O_BHH + D + u]);
-        o.hnb[e] = ch[0][2][e] + Ws[O_BHH + 2 * D + u];
-        o.n[e] = tanhf(gin + o.r[e] * o.hnb[e]);
-    }
+__device__ __forceinline__ void st_plane4(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t half_off, float a, float b, float c, float d) {
+    uint2 hi, lo;
+    m16::split2(a, b, hi.x, lo.x);
+    m16::split2(c, d, hi.y, lo.y);
+    *reinterpret_cast<uint2*>(hi_plane + half_off * 2) = hi;
+    *reinterpret_cast<uint2*>(lo_plane + half_off * 2) = lo;
 }
 
 // ======================================================================================= backward step
-constexpr int B_SMEM_FLOATS = SPACK + TM * LDC + 3 * TM * LDM + 2 * TM * LDG + TM + 2 * D;
-
 __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p) {
-    extern __shared__ __align__(16) float smem[];
-    float* Ws = smem;
-    float* As = Ws + SPACK;              // [32][76] [neighbour sum of state_{k-1} || x]
-    float* Hs = As + TM * LDC;           // [32][68] state_{k-1} of the node
-    float* Gs = Hs + TM * LDM;           // [32][68] d state_k, then d (pre-LN GRU output)
-    float* Xh = Gs + TM * LDM;           // [32][68] pre-LN GRU output
-    float* DGI = Xh + TM * LDM;          // [32][200] d gi (r, z, n)
-    float* DGH = DGI + TM * LDG;         // [32][200] d gh
-    float* Dg = DGH + TM * LDG;          // [32]
-    float* LNA = Dg + TM;                // [128] d ln_w, d ln_b accumulators
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sb = m16::smem_u32(smem);
+    float* Bhh = reinterpret_cast<float*>(smem + S_BHH);
+    float* Ln = reinterpret_cast<float*>(smem + S_LN);
+    float* H32 = reinterpret_cast<float*>(smem + S_H32);
+    float* Gs = reinterpret_cast<float*>(smem + S_GS);          // d state_k, then d (pre-LN GRU output)
+    float* Xh = reinterpret_cast<float*>(smem + S_XH);          // pre-LN GRU output
+    float* LNA = reinterpret_cast<float*>(smem + S_LNA);        // d ln_w, d ln_b accumulators
+    unsigned* smax = reinterpret_cast<unsigned*>(smem + S_MAX);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int enc = blockIdx.y;
     const float* prev = p.prev + (size_t)enc * p.enc_stride;
     const size_t eoff = (size_t)enc * p.N * D;
-    load_weights(Ws, p.weights + (size_t)enc * 2 * SPACK, tid);
-    if (tid < 2 * D) LNA[tid] = 0.f;
+    const float* W = p.weights + (size_t)enc * 2 * SPACK;
+
+    // ---- weights -> fp16 hi/lo planes (split once per launch)
+    for (int i = tid; i < G3 * 10; i += THREADS) {
+        const int o = i / 10, c = i % 10;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (c < 9) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(W + O_WCX + o * NLDC + c * 8 + e);       // c == 8: feature columns 64..71
+        } else {
+            v[0] = __ldg(W + O_BC + o);
+            v[1] = __ldg(W + O_BIH + o);
+        }
+        const uint32_t off = (uint32_t)(o * LDC + c * 8);
+        st_plane4(smem + WCX_HI, smem + WCX_LO, off, v[0], v[1], v[2], v[3]);
+        st_plane4(smem + WCX_HI, smem + WCX_LO, off + 4, v[4], v[5], v[6], v[7]);
+    }
+    for (int i = tid; i < G3 * 8; i += THREADS) {
+        const int o = i >> 3, c = i & 7;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(W + O_WHH + o * NLDM + c * 8 + e);
+        const uint32_t off = (uint32_t)(o * LDW + c * 8);
+        st_plane4(smem + WHH_HI, smem + WHH_LO, off, v[0], v[1], v[2], v[3]);
+        st_plane4(smem + WHH_HI, smem + WHH_LO, off + 4, v[4], v[5], v[6], v[7]);
+    }
+    if (tid < G3) Bhh[tid] = __ldg(W + O_BHH + tid);
+    if (tid < 2 * D) { Ln[tid] = __ldg(W + O_LNW + tid); LNA[tid] = 0.f; }
+    if (tid < 2) smax[tid] = 0u;
     const int ntiles = (p.N + TM - 1) / TM;
     const int half = lane >> 4, l16 = lane & 15;
     const int mt = warp & 1, u0 = (warp >> 1) * 8;
     const int g = lane >> 2, t = lane & 3;
 
-    // persistent weight-gradient fragments: d Wcx[:, 0:64] and d Whh as 6 m-tiles x 1 n-tile per warp,
-    // the feature columns of d Wcx as one fragment on warps 0..11
+    // persistent weight-gradient fragments (scaled by acc_scale):
+    //   d Wcx[:, 0:64] : 6 m-tiles (96 gate rows per warp half) x 8 feature columns per warp
+    //   d Whh          : 2 + 4 m-tiles (gate rows -> d gh columns: r, z contiguous, n at column 192)
+    //   feature / bias : gate-gradient columns 16 warp .. +15  x  tile columns 64..71 (x) and 72..79 (deg, 1)
+    const int wh = warp >> 3;
     const int wn0[1] = {8 * (warp & 7)};
-    const int wm0 = (warp >> 3) * 96;
-    const int fn0[1] = {D};
-    float acc_cx[6][1][4], acc_hh[6][1][4], acc_f[1][1][4];
-    mgv_zero_frag(acc_cx);
-    mgv_zero_frag(acc_hh);
-    mgv_zero_frag(acc_f);
-    float s_bc = 0.f, s_bih = 0.f, s_bhh = 0.f;      // column sums owned by threads 0..191
+    const int fn0[2] = {D, D + 8};
+    float acc_cx[6][1][4], acc_ha[2][1][4], acc_hb[4][1][4], acc_fb[1][2][4];
+    m16::zero_frag(acc_cx);
+    m16::zero_frag(acc_ha);
+    m16::zero_frag(acc_hb);
+    m16::zero_frag(acc_fb);
+    float acc_scale = 1.0f;
+    __syncthreads();
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int t0 = tile * TM;
         {   // ---- gathers: neighbour sum of state_{k-1}; d state_k = part + sum of neighbours' d agg_{k+1}
             const int row = warp * 2 + half, node = t0 + row;
-            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa, h4 = sa, g4 = sa;
+            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sbv = sa, h4 = sa, g4 = sa, x4 = sa;
             int deg = 0;
-            float xf = 0.f;
             if (node < p.N) {
                 if (p.last) {
-                    gather_sum<false>(p, prev, nullptr, node, l16, sa, sb, deg);
+                    gather_sum<false>(p, prev, nullptr, node, l16, sa, sbv, deg);
                     g4 = mgv_ld4(p.gout + eoff + (size_t)node * D + 4 * l16);
                 } else {
-                    gather_sum<true>(p, prev, p.in_agg + eoff, node, l16, sa, sb, deg);
+                    gather_sum<true>(p, prev, p.in_agg + eoff, node, l16, sa, sbv, deg);
                     g4 = mgv_ld4(p.in_part + eoff + (size_t)node * D + 4 * l16);
-                    add4(g4, sb);
+                    add4(g4, sbv);
                 }
                 h4 = mgv_ld4(prev + (size_t)node * D + 4 * l16);
-                if (l16 < p.feat) xf = p.x[(size_t)node * p.feat + l16];
+                if (l16 < 2) {
+                    float xv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) xv[e] = (4 * l16 + e < p.feat) ? p.x[(size_t)node * p.feat + 4 * l16 + e] : 0.f;
+                    x4 = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                } else if (l16 == 2) {
+                    x4 = make_float4((float)deg, 1.0f, 0.f, 0.f);
+                }
             }
-            mgv_st4(As + row * LDC + 4 * l16, sa);
-            mgv_st4(Hs + row * LDM + 4 * l16, h4);
-            mgv_st4(Gs + row * LDM + 4 * l16, g4);
-            if (l16 < MGV_MAX_FEAT) As[row * LDC + D + l16] = xf;
-            if (l16 == 0) Dg[row] = (float)deg;
+            st_plane4(smem + AS_HI, smem + AS_LO, (uint32_t)(row * LDC + 4 * l16), sa.x, sa.y, sa.z, sa.w);
+            if (l16 < 4) st_plane4(smem + AS_HI, smem + AS_LO, (uint32_t)(row * LDC + D + 4 * l16), x4.x, x4.y, x4.z, x4.w);
+            st_plane4(smem + HS_HI, smem + HS_LO, (uint32_t)(row * LDW + 4 * l16), h4.x, h4.y, h4.z, h4.w);
+            mgv_st4(H32 + row * LDF + 4 * l16, h4);
+            mgv_st4(Gs + row * LDF + 4 * l16, g4);
         }
         __syncthreads();
         // ---- recompute the step (gates stay in registers)
-        Gates G;
-        step_gemm(Ws, As, Hs, Dg, mt, u0, lane, G);
+        float gr[4], gz[4], gn[4], hnb[4];
+        {
+            const int n0[3] = {u0, D + u0, 2 * D + u0};
+            float ci[1][3][4], ch[1][3][4];
+            m16::zero_frag(ci);
+            m16::zero_frag(ch);
+            m16::warp_gemm<1, 3, KX / 16, false, false>(ci, sb + AS_HI, sb + AS_LO, LDC, mt * 16, 0, sb + WCX_HI, sb + WCX_LO, LDC, n0, 0, lane);
+            m16::warp_gemm<1, 3, D / 16, false, false>(ch, sb + HS_HI, sb + HS_LO, LDW, mt * 16, 0, sb + WHH_HI, sb + WHH_LO, LDW, n0, 0, lane);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int u = u0 + 2 * t + (e & 1);
+                hnb[e] = ch[0][2][e] + Bhh[2 * D + u];
+                gru_gates(ci[0][0][e] + ch[0][0][e] + Bhh[u], ci[0][1][e] + ch[0][1][e] + Bhh[D + u], ci[0][2][e], hnb[e],
+                          gr[e], gz[e], gn[e]);
+            }
+        }
         if (p.layernorm) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
                 const int u = u0 + 2 * t + (e & 1);
-                Xh[row * LDM + u] = (1.0f - G.z[e]) * G.n[e] + G.z[e] * Hs[row * LDM + u];
+                Xh[row * LDF + u] = (1.0f - gz[e]) * gn[e] + gz[e] * H32[row * LDF + u];
             }
             __syncthreads();
             // LayerNorm backward, two rows per warp; d ln_w / d ln_b accumulate in shared memory
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const int row = warp * 2 + rr;
-                const float v0 = Xh[row * LDM + lane], v1 = Xh[row * LDM + 32 + lane];
+                const float v0 = Xh[row * LDF + lane], v1 = Xh[row * LDF + 32 + lane];
                 const float mean = mgv_warp_sum(v0 + v1) * (1.0f / D);
                 const float d0 = v0 - mean, d1 = v1 - mean;
                 const float var = mgv_warp_sum(d0 * d0 + d1 * d1) * (1.0f / D);
-                const float rstd = 1.0f / sqrtf(var + LN_EPS);
+                const float rstd = rsqrtf(var + LN_EPS);
                 const float x0 = d0 * rstd, x1 = d1 * rstd;
-                const float gy0 = Gs[row * LDM + lane], gy1 = Gs[row * LDM + 32 + lane];
+                const float gy0 = Gs[row * LDF + lane], gy1 = Gs[row * LDF + 32 + lane];
                 atomicAdd(LNA + lane, gy0 * x0);
                 atomicAdd(LNA + 32 + lane, gy1 * x1);
                 atomicAdd(LNA + D + lane, gy0);
                 atomicAdd(LNA + D + 32 + lane, gy1);
-                const float dx0 = gy0 * Ws[O_LNW + lane], dx1 = gy1 * Ws[O_LNW + 32 + lane];
+                const float dx0 = gy0 * Ln[lane], dx1 = gy1 * Ln[32 + lane];
                 const float c1 = mgv_warp_sum(dx0 + dx1) * (1.0f / D);
                 const float c2 = mgv_warp_sum(dx0 * x0 + dx1 * x1) * (1.0f / D);
-                Gs[row * LDM + lane] = rstd * (dx0 - c1 - x0 * c2);
-                Gs[row * LDM + 32 + lane] = rstd * (dx1 - c1 - x1 * c2);
+                Gs[row * LDF + lane] = rstd * (dx0 - c1 - x0 * c2);
+                Gs[row * LDF + 32 + lane] = rstd * (dx1 - c1 - x1 * c2);
             }
             __syncthreads();
         }
-        // ---- GRU backward on the owned elements
-        float dh_direct[4];
+        // ---- GRU backward on the owned elements; tile-wide power-of-two scale for the fp16 planes
+        float dr[4], dz[4], dni[4], dnh[4], dh_direct[4];
+        {
+            float amax = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
-            const int u = u0 + 2 * t + (e & 1);
-            const float gg = Gs[row * LDM + u];
-            const float hp = Hs[row * LDM + u];
-            const float dn = gg * (1.0f - G.z[e]);
-            const float dz = gg * (hp - G.n[e]);
-            const float dnpre = dn * (1.0f - G.n[e] * G.n[e]);
-            const float drpre = dnpre * G.hnb[e] * G.r[e] * (1.0f - G.r[e]);
-            const float dzpre = dz * G.z[e] * (1.0f - G.z[e]);
-            dh_direct[e] = gg * G.z[e];
-            DGI[row * LDG + u] = drpre;
-            DGI[row * LDG + D + u] = dzpre;
-            DGI[row * LDG + 2 * D + u] = dnpre;
-            DGH[row * LDG + u] = drpre;
-            DGH[row * LDG + D + u] = dzpre;
-            DGH[row * LDG + 2 * D + u] = dnpre * G.r[e];
+            for (int e = 0; e < 4; ++e) {
+                const int row = mt * 16 + g + ((e & 2) ? 8 : 0);
+                const int u = u0 + 2 * t + (e & 1);
+                const float gg = Gs[row * LDF + u];
+                const float hp = H32[row * LDF + u];
+                const float dn = gg * (1.0f - gz[e]);
+                const float dzz = gg * (hp - gn[e]);
+                dni[e] = dn * (1.0f - gn[e] * gn[e]);
+                dr[e] = dni[e] * hnb[e] * gr[e] * (1.0f - gr[e]);
+                dz[e] = dzz * gz[e] * (1.0f - gz[e]);
+                dnh[e] = dni[e] * gr[e];
+                dh_direct[e] = gg * gz[e];
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dr[e]), fabsf(dz[e])), fabsf(dni[e])));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            if (lane == 0) atomicMax(smax + (it & 1), __float_as_uint(amax));
+            if (tid == 0) smax[(it + 1) & 1] = 0u;
+        }
+        __syncthreads();
+        const float scale = m16::pow2_scale(__uint_as_float(smax[it & 1]));
+        const float inv_scale = 1.0f / scale;
+        {
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int row = mt * 16 + g + 8 * hrow, e0 = 2 * hrow;
+                const uint32_t off = (uint32_t)(row * LDG + u0 + 2 * t) * 2;
+                uint32_t hi, lo;
+                m16::split2(dr[e0] * scale, dr[e0 + 1] * scale, hi, lo);
+                *reinterpret_cast<uint32_t*>(smem + DG_HI + off) = hi; *reinterpret_cast<uint32_t*>(smem + DG_LO + off) = lo;
+                m16::split2(dz[e0] * scale, dz[e0 + 1] * scale, hi, lo);
+                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 2 * D) = hi; *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 2 * D) = lo;
+                m16::split2(dni[e0] * scale, dni[e0 + 1] * scale, hi, lo);
+                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 4 * D) = hi; *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 4 * D) = lo;
+                m16::split2(dnh[e0] * scale, dnh[e0 + 1] * scale, hi, lo);
+                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 6 * D) = hi; *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 6 * D) = lo;
+            }
         }
         __syncthreads();
         // ---- data gradients: d agg = d gi . Wc ;  d part = g z + d gh . Whh   (both 32 x 64, K = 192)
         if (!p.first) {
             const int n0[1] = {u0};
             float ca[1][1][4], cp[1][1][4];
-            mgv_zero_frag(ca);
-            mgv_zero_frag(cp);
-            mgv_warp_gemm<1, 1, G3 / 8, false, false>(ca, DGI, LDG, mt * 16, Ws + O_WCX, LDC, n0, lane);
-            mgv_warp_gemm<1, 1, G3 / 8, false, false>(cp, DGH, LDG, mt * 16, Ws + O_WHH, LDM, n0, lane);
+            m16::zero_frag(ca);
+            m16::zero_frag(cp);
+            m16::warp_gemm<1, 1, G3 / 16, false, true>(ca, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 0, sb + WCX_HI, sb + WCX_LO, LDC, n0, 0, lane);
+            m16::warp_gemm<1, 1, 2 * D / 16, false, true>(cp, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 0, sb + WHH_HI, sb + WHH_LO, LDW, n0, 0, lane);
+            m16::warp_gemm<1, 1, D / 16, false, true>(cp, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 3 * D, sb + WHH_HI, sb + WHH_LO, LDW, n0, 2 * D, lane);
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
                 const int node = t0 + mt * 16 + g + 8 * hrow;
                 if (node < p.N) {
                     const size_t o = eoff + (size_t)node * D + u0 + 2 * t;
-                    *reinterpret_cast<float2*>(p.out_agg + o) = make_float2(ca[0][0][2 * hrow], ca[0][0][2 * hrow + 1]);
+                    *reinterpret_cast<float2*>(p.out_agg + o) = make_float2(ca[0][0][2 * hrow] * inv_scale, ca[0][0][2 * hrow + 1] * inv_scale);
                     *reinterpret_cast<float2*>(p.out_part + o) =
-                        make_float2(cp[0][0][2 * hrow] + dh_direct[2 * hrow], cp[0][0][2 * hrow + 1] + dh_direct[2 * hrow + 1]);
+                        make_float2(fmaf(cp[0][0][2 * hrow], inv_scale, dh_direct[2 * hrow]),
+                                    fmaf(cp[0][0][2 * hrow + 1], inv_scale, dh_direct[2 * hrow + 1]));
                 }
             }
         }
-        // ---- weight gradients (tile buffers are read-only here): d Wcx += d gi^T [agg || x], d Whh += d gh^T h
-        mgv_warp_gemm<6, 1, TM / 8, true, false>(acc_cx, DGI, LDG, wm0, As, LDC, wn0, lane);
-        mgv_warp_gemm<6, 1, TM / 8, true, false>(acc_hh, DGH, LDG, wm0, Hs, LDM, wn0, lane);
-        if (warp < 12) mgv_warp_gemm<1, 1, TM / 8, true, false>(acc_f, DGI, LDG, warp * 16, As, LDC, fn0, lane);
-        if (tid < G3) {
-            for (int row = 0; row < TM; ++row) {
-                const float dgi = DGI[row * LDG + tid];
-                s_bih += dgi;
-                s_bc = fmaf(dgi, Dg[row], s_bc);
-                s_bhh += DGH[row * LDG + tid];
-            }
+        // ---- weight gradients (tile buffers are read-only here)
+        if (scale != acc_scale) {
+            const float f = scale / acc_scale;
+            m16::scale_frag(acc_cx, f);
+            m16::scale_frag(acc_ha, f);
+            m16::scale_frag(acc_hb, f);
+            m16::scale_frag(acc_fb, f);
+            acc_scale = scale;
         }
+        m16::warp_gemm<6, 1, TM / 16, true, true>(acc_cx, sb + DG_HI, sb + DG_LO, LDG, wh * 96, 0, sb + AS_HI, sb + AS_LO, LDC, wn0, 0, lane);
+        m16::warp_gemm<2, 1, TM / 16, true, true>(acc_ha, sb + DG_HI, sb + DG_LO, LDG, wh * 96, 0, sb + HS_HI, sb + HS_LO, LDW, wn0, 0, lane);
+        m16::warp_gemm<4, 1, TM / 16, true, true>(acc_hb, sb + DG_HI, sb + DG_LO, LDG, wh ? 3 * D : 32, 0, sb + HS_HI, sb + HS_LO, LDW, wn0, 0, lane);
+        m16::warp_gemm<1, 2, TM / 16, true, true>(acc_fb, sb + DG_HI, sb + DG_LO, LDG, 16 * warp, 0, sb + AS_HI, sb + AS_LO, LDC, fn0, 0, lane);
         __syncthreads();
     }
-    // ---- flush this CTA's accumulators into its private partial block (summed over the 8 launches)
+    // ---- flush this CTA's accumulators into its private partial block (summed over the launches of a call)
     float* part = p.partial + (((size_t)enc * gridDim.x + blockIdx.x) * 2 + p.dir) * SGRAD;
+    const float un = 1.0f / acc_scale;
 #pragma unroll
     for (int m = 0; m < 6; ++m) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int o = wm0 + 16 * m + g + ((e & 2) ? 8 : 0);
-            const int c = wn0[0] + 2 * t + (e & 1);
-            part[O_WCX + o * LDC + c] += acc_cx[m][0][e];
-            part[O_WHH + o * LDM + c] += acc_hh[m][0][e];
+            const int r8 = g + ((e & 2) ? 8 : 0), c = wn0[0] + 2 * t + (e & 1);
+            part[O_WCX + (wh * 96 + 16 * m + r8) * NLDC + c] += acc_cx[m][0][e] * un;
+            const int oh = wh * 96 + 16 * m + r8;                              // Whh gate row of fragment m
+            part[O_WHH + oh * NLDM + c] += (m < 2 ? acc_ha[m][0][e] : acc_hb[m - 2][0][e]) * un;
         }
     }
-    if (warp < 12) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int o = warp * 16 + g + ((e & 2) ? 8 : 0);
-            part[O_WCX + o * LDC + D + 2 * t + (e & 1)] += acc_f[0][0][e];
+    for (int e = 0; e < 4; ++e) {
+        const int oc = 16 * warp + g + ((e & 2) ? 8 : 0);                      // d gate column 0..255
+        const int c = 2 * t + (e & 1);
+        if (oc < G3) {
+            part[O_WCX + oc * NLDC + D + c] += acc_fb[0][0][e] * un;           // feature columns
+            if (c == 0) part[O_BC + oc] += acc_fb[0][1][e] * un;
+            if (c == 1) {
+                part[O_BIH + oc] += acc_fb[0][1][e] * un;
+                if (oc < 2 * D) part[O_BHH + oc] += acc_fb[0][1][e] * un;      // r, z: d b_hh = d b_ih
+            }
+        } else if (c == 1) {
+            part[O_BHH + oc - D] += acc_fb[0][1][e] * un;                      // n: sum of d gh_n
         }
-    }
-    if (tid < G3) {
-        part[O_BC + tid] += s_bc;
-        part[O_BIH + tid] += s_bih;
-        part[O_BHH + tid] += s_bhh;
     }
     __syncthreads();
     if (tid < 2 * D) part[O_LNW + tid] += LNA[tid];
@@ -333,7 +401,6 @@ void fill_step(StepDev& p, const mgv_schedule* sch, int k, int steps, int layern
     p.x = x;
     p.weights = weights + (size_t)dir * SPACK;
     p.prev = states + (size_t)(k - 1) * slot;
-    p.next = nullptr;
     p.enc_stride = enc_stride;
 }
 
@@ -382,7 +449,7 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     agg[0] = a.take<float>((size_t)num_enc * slot); agg[1] = a.take<float>((size_t)num_enc * slot);
     float* partial = a.take<float>((size_t)num_enc * gx * 2 * SGRAD);
     MGV_CUDA(cudaMemsetAsync(partial, 0, (size_t)num_enc * gx * 2 * SGRAD * sizeof(float), st));
-    const size_t smem = (size_t)B_SMEM_FLOATS * sizeof(float);
+    const size_t smem = (size_t)B_SMEM;
     MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int k = steps; k >= 1; --k) {
         StepDev p{};
