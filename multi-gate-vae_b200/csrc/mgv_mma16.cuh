@@ -69,17 +69,20 @@ __device__ __forceinline__ uint32_t a_lane_off(int ld, int m0, int k0, int lane)
 }
 //   B, NK: storage S[n][k] (k contiguous; an nn.Linear weight used as y = x W^T)    B(k, n) = S[n0 + n][k0 + k]
 //   B, KN: storage S[k][n] (n contiguous)                                            B(k, n) = S[k0 + k][n0 + n]
+// One ldmatrix.x4 fetches the B fragments of TWO consecutive k-steps (k0 .. k0+31) of one 8-column tile.
 template <bool KN>
 __device__ __forceinline__ uint32_t b_lane_off(int ld, int k0, int n0, int lane) {
-    const int i = (lane >> 3) & 1, r = lane & 7;
+    const int i = lane >> 3, r = lane & 7;
     return KN ? (uint32_t)(((k0 + i * 8 + r) * ld + n0) * 2) : (uint32_t)(((n0 + r) * ld + k0 + i * 8) * 2);
 }
 
 // c[mt][nt] += A[16 mt .., 16 KSTEPS) * B[.., n0[nt] ..)  for one warp; planes given as shared-memory byte addresses.
 // A rows (or storage columns when A_TRANS) start at am0 + 16 mt; its K range starts at ak0; B's K range at bk0.
+// The three products go to separate accumulator chains when MT * NT is small (more independent MMAs in flight).
 template <int MT, int NT, int KSTEPS, bool A_TRANS, bool B_KN>
 __device__ __forceinline__ void warp_gemm(float (&c)[MT][NT][4], uint32_t a_hi, uint32_t a_lo, int lda, int am0, int ak0,
                                           uint32_t b_hi, uint32_t b_lo, int ldb, const int (&n0)[NT], int bk0, int lane) {
+    constexpr bool SPLIT = (MT * NT <= 2);
     uint32_t aoff[MT], boff[NT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) aoff[mt] = a_lane_off<A_TRANS>(lda, am0 + 16 * mt, ak0, lane);
@@ -87,26 +90,66 @@ __device__ __forceinline__ void warp_gemm(float (&c)[MT][NT][4], uint32_t a_hi, 
     for (int nt = 0; nt < NT; ++nt) boff[nt] = b_lane_off<B_KN>(ldb, bk0, n0[nt], lane);
     const uint32_t astep = A_TRANS ? (uint32_t)(16 * lda * 2) : 32u;
     const uint32_t bstep = B_KN ? (uint32_t)(16 * ldb * 2) : 32u;
-#pragma unroll 2
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-        uint32_t ahi[MT][4], alo[MT][4];
+    float c1[SPLIT ? MT : 1][SPLIT ? NT : 1][4], c2[SPLIT ? MT : 1][SPLIT ? NT : 1][4];
+    if (SPLIT) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            if (A_TRANS) { ldsm_x4_t(a_hi + aoff[mt] + ks * astep, ahi[mt]); ldsm_x4_t(a_lo + aoff[mt] + ks * astep, alo[mt]); }
-            else { ldsm_x4(a_hi + aoff[mt] + ks * astep, ahi[mt]); ldsm_x4(a_lo + aoff[mt] + ks * astep, alo[mt]); }
-        }
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { c1[i][j][e] = 0.f; c2[i][j][e] = 0.f; }
+    }
+#pragma unroll
+    for (int kp = 0; kp < (KSTEPS + 1) / 2; ++kp) {
+        uint32_t bhi[NT][4], blo[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-            uint32_t bhi[2], blo[2];
-            if (B_KN) { ldsm_x2_t(b_hi + boff[nt] + ks * bstep, bhi); ldsm_x2_t(b_lo + boff[nt] + ks * bstep, blo); }
-            else { ldsm_x2(b_hi + boff[nt] + ks * bstep, bhi); ldsm_x2(b_lo + boff[nt] + ks * bstep, blo); }
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                mma(c[mt][nt], alo[mt], bhi);
-                mma(c[mt][nt], ahi[mt], blo);
-                mma(c[mt][nt], ahi[mt], bhi);
+            if (2 * kp + 1 < KSTEPS) {
+                if (B_KN) { ldsm_x4_t(b_hi + boff[nt] + 2 * kp * bstep, bhi[nt]); ldsm_x4_t(b_lo + boff[nt] + 2 * kp * bstep, blo[nt]); }
+                else { ldsm_x4(b_hi + boff[nt] + 2 * kp * bstep, bhi[nt]); ldsm_x4(b_lo + boff[nt] + 2 * kp * bstep, blo[nt]); }
+            } else {                                   // odd tail: one k-step (lanes 16..31 re-address rows of the first half)
+                uint32_t t2[2];
+                const uint32_t o = boff[nt] - (B_KN ? (uint32_t)(((lane >> 4) * 16) * ldb * 2) : (uint32_t)((lane >> 4) * 32));
+                if (B_KN) { ldsm_x2_t(b_hi + o + 2 * kp * bstep, t2); bhi[nt][0] = t2[0]; bhi[nt][1] = t2[1]; ldsm_x2_t(b_lo + o + 2 * kp * bstep, t2); blo[nt][0] = t2[0]; blo[nt][1] = t2[1]; }
+                else { ldsm_x2(b_hi + o + 2 * kp * bstep, t2); bhi[nt][0] = t2[0]; bhi[nt][1] = t2[1]; ldsm_x2(b_lo + o + 2 * kp * bstep, t2); blo[nt][0] = t2[0]; blo[nt][1] = t2[1]; }
+                bhi[nt][2] = bhi[nt][3] = blo[nt][2] = blo[nt][3] = 0u;
             }
         }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const int ks = 2 * kp + kk;
+            if (ks < KSTEPS) {
+                uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    if (A_TRANS) { ldsm_x4_t(a_hi + aoff[mt] + ks * astep, ahi[mt]); ldsm_x4_t(a_lo + aoff[mt] + ks * astep, alo[mt]); }
+                    else { ldsm_x4(a_hi + aoff[mt] + ks * astep, ahi[mt]); ldsm_x4(a_lo + aoff[mt] + ks * astep, alo[mt]); }
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const uint32_t bh[2] = {bhi[nt][2 * kk], bhi[nt][2 * kk + 1]}, bl[2] = {blo[nt][2 * kk], blo[nt][2 * kk + 1]};
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (SPLIT) {
+                            mma(c1[mt][nt], alo[mt], bh);
+                            mma(c2[mt][nt], ahi[mt], bl);
+                        } else {
+                            mma(c[mt][nt], alo[mt], bh);
+                            mma(c[mt][nt], ahi[mt], bl);
+                        }
+                        mma(c[mt][nt], ahi[mt], bh);
+                    }
+                }
+            }
+        }
+    }
+    if (SPLIT) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c[i][j][e] += c1[i][j][e] + c2[i][j][e];
     }
 }
 
@@ -133,6 +176,14 @@ __device__ __forceinline__ float pow2_scale(float amax) {
     int k = 8 - e;
     k = k < -100 ? -100 : (k > 100 ? 100 : k);
     return __uint_as_float((uint32_t)(k + 127) << 23);
+}
+
+// Keep the running scale while amax * cur stays inside [2^2, 2^13] (fp16 tops out at 2^16): rescaling the
+// persistent weight-gradient fragments is then rare.
+__device__ __forceinline__ float pow2_scale_keep(float amax, float cur) {
+    const float v = amax * cur;
+    if (v >= 4.0f && v <= 8192.0f) return cur;
+    return (amax > 0.f) ? pow2_scale(amax) : cur;
 }
 
 }  // namespace m16

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             if (tid == 0) smax[(it + 1) & 1] = 0u;
         }
         __syncthreads();
-        const float scale = m16::pow2_scale(__uint_as_float(smax[it & 1]));
+        const float scale = m16::pow2_scale_keep(__uint_as_float(smax[it & 1]), acc_scale);
         const float inv_scale = 1.0f / scale;
         {
 #pragma unroll
