@@ -263,6 +263,8 @@ def run_ours(args, w):
     launches = _native.lib().mgv_kernel_launches() - launches0
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop()
+    from deepgate.schedule import check_deferred_errors
+    check_deferred_errors()                   # asynchronous input validation of every schedule built above
 
     g_local = sum(gates_per_step[i % nb] for i in range(args.steps))
     g_all = torch.tensor([float(g_local)], device=dev, dtype=torch.float64)

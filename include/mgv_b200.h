@@ -64,11 +64,15 @@ long long mgv_kernel_launches(void);
  *   code        int32 [N] or NULL (then out_pack carries no code bits)
  *   in_ptr[N+1], in_src[E]                      : predecessors of node v = in_src[in_ptr[v] .. in_ptr[v+1])
  *   out_ptr[N+1], out_pack[E], out_slot[E]      : successors; out_slot = position of that edge in in_src
+ *   err_flag    int32 device word or NULL.  NULL: the call validates node ids and SYNCHRONISES (error on a bad id).
+ *               Non-NULL: asynchronous; bit 0 is OR-ed in on a node id outside [0, N) (bit 1: level outside [0, L),
+ *               mgv_build_level_lists) and the caller checks the word whenever it next synchronises.  Kernels stay
+ *               memory-safe on bad input either way.
  */
 size_t mgv_csr_workspace_bytes(int64_t N, int64_t E);
 int mgv_build_csr(const int64_t* edge_index, int64_t E, int32_t N, const int32_t* code,
                   int32_t* in_ptr, int32_t* in_src, int32_t* out_ptr, int32_t* out_pack, int32_t* out_slot,
-                  void* ws, size_t ws_bytes, mgv_stream_t stream);
+                  void* ws, size_t ws_bytes, int32_t* err_flag, mgv_stream_t stream);
 
 /* ASAP level of every node == utils/dag_utils.py:10-37 top_sort(edge_index, N) (level 0 = no
  * predecessor, else 1 + max over predecessors).  reverse != 0 levelises the reversed graph
@@ -84,12 +88,14 @@ int mgv_levelize(const int32_t* in_ptr, const int32_t* out_ptr, const int32_t* o
 /* Node lists per (level, code): order[N] = node ids stably sorted by (level, code) -- ascending
  * id inside a segment, i.e. G.forward_index[layer_mask & type_mask] (dg_ae_model_mig.py:89);
  * seg_ptr[L*MGV_NCODE + 1]; code_count_host[MGV_NCODE] = nodes of each code with level >= 1.
- * SYNCHRONISES (returns the per-code counts used to size the persistent grids).
+ * SYNCHRONISES (returns the per-code counts used to size the persistent grids) -- unless code_count_host is NULL
+ * and err_flag is given: then the caller supplies the counts itself (e.g. computed at collate time on the host,
+ * where the reference computes forward_level, parser_func_others.py:63) and nothing synchronises.
  */
 size_t mgv_level_lists_workspace_bytes(int64_t N, int32_t L);
 int mgv_build_level_lists(const int32_t* level, const int32_t* code, int32_t N, int32_t L,
                           int32_t* order, int32_t* seg_ptr, int64_t* code_count_host,
-                          void* ws, size_t ws_bytes, mgv_stream_t stream);
+                          void* ws, size_t ws_bytes, int32_t* err_flag, mgv_stream_t stream);
 
 /* Degree order of one CSR direction, for the tensor-core tiles of the struct encoder: order[N] = node ids sorted
  * by DESCENDING degree (degrees >= 255 tie), ascending id inside a degree, so the 128 rows of a tile have
@@ -200,6 +206,24 @@ int mgv_vae_func_loss_bwd(const float* g_out, const float* gz, const float* mu, 
                           const float* eps, float* gmu, float* glogstd, int64_t N,
                           const float* hf, const int64_t* pair, const float* tt_sim, int64_t P,
                           const float* out, const void* ws, float* ghf, mgv_stream_t stream);
+
+/* ------------------------------------------------------------------ reconstruction loss + negative sampler
+ * Replaces Model.recon_loss (dg_ae_model_mig.py:169-191) around the directed inner-product decoder
+ * (digae_layer.py:26-33): st = hs_decompose(hs) = [s | t] float [N][128]; value(u -> v) = sigmoid(s_u . t_v);
+ *   out float [3]: loss = -mean_pos log(value + 1e-15) - mean_neg log(1 - value + 1e-15), its pos part, its neg part
+ *   sig float [Ep + En], pred int32 [Ep + En] (value > 0.5), positives first  (pred_bin of the reference)
+ *   pos int64 [2][Ep], neg int64 [2][En]; ws >= 16 bytes; err_flag: bit 2 OR-ed in on an edge end outside [0, N).
+ * mgv_negative_sample stands in for torch_geometric.utils.negative_sampling (dg_ae_model_mig.py:177-180): `count`
+ * ordered pairs (u, v), u != v, not an edge u -> v of the out-CSR, drawn by rejection from a counter-based hash of `seed`.
+ */
+int mgv_negative_sample(const int32_t* out_ptr, const int32_t* out_pack, int32_t N, int64_t count, uint64_t seed,
+                        int64_t* neg, mgv_stream_t stream);
+int mgv_recon_loss_fwd(const float* st, int32_t N, const int64_t* pos, int64_t Ep, const int64_t* neg, int64_t En,
+                       float* out, float* sig, int32_t* pred, void* ws, size_t ws_bytes, int32_t* err_flag,
+                       mgv_stream_t stream);
+/* g_loss: device float = d L / d loss; gst float [N][128] zero-initialised by the caller, gradients are atomically added. */
+int mgv_recon_loss_bwd(const float* st, int32_t N, const int64_t* pos, int64_t Ep, const int64_t* neg, int64_t En,
+                       const float* sig, const float* g_loss, float* gst, mgv_stream_t stream);
 
 /* ------------------------------------------------------------------ tensor-core self test (diagnostic)
  * One 128-row tcgen05 tile product through the operand layouts / descriptors / fp16 hi-lo split the kernels

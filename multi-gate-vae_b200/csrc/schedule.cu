@@ -200,7 +200,7 @@ __global__ void edge_keys_kernel(const int64_t* __restrict__ ei, int64_t E, int 
     if (e >= E) return;
     const int64_t v = ei[(int64_t)row * E + e];
     if (v < 0 || v >= n) {
-        atomicExch(bad, 1);
+        atomicOr(bad, 1);
         keys[e] = 0; vals[e] = (uint32_t)e;
         return;
     }
@@ -302,7 +302,7 @@ __global__ void node_keys_kernel(const int32_t* __restrict__ level, const int32_
     if (v >= n) return;
     int lv = level[v];
     if (lv < 0 || lv >= L) {
-        atomicExch(bad, 1);
+        atomicOr(bad, 2);
         lv = 0;
     }
     int c = code[v];
@@ -425,7 +425,7 @@ extern "C" size_t mgv_csr_workspace_bytes(int64_t N, int64_t E) {
 
 extern "C" int mgv_build_csr(const int64_t* edge_index, int64_t E, int32_t N, const int32_t* code,
                              int32_t* in_ptr, int32_t* in_src, int32_t* out_ptr, int32_t* out_pack,
-                             int32_t* out_slot, void* ws, size_t ws_bytes, mgv_stream_t stream) {
+                             int32_t* out_slot, void* ws, size_t ws_bytes, int32_t* err_flag, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MGV_REQUIRE(N >= 0 && E >= 0, "mgv_build_csr: negative size");
     MGV_REQUIRE((int64_t)N < (1ll << MGV_CODE_SHIFT), "mgv_build_csr: N=%d exceeds 2^28 nodes", N);
@@ -444,8 +444,8 @@ extern "C" int mgv_build_csr(const int64_t* edge_index, int64_t E, int32_t N, co
     sb.tmp = a.take<uint32_t>(scan_tmp_count(scan_n));
     uint32_t* slot_of_eid = a.take<uint32_t>(E + 1);
     uint32_t* deg = a.take<uint32_t>(N + 1);
-    int* bad = a.take<int>(1);
-    MGV_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    int* bad = err_flag ? err_flag : a.take<int>(1);
+    if (!err_flag) MGV_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
     const int bits = bits_for(N > 0 ? (uint64_t)(N - 1) : 0);
     const int eb = (int)((E + 255) / 256);
     for (int dir = 0; dir < 2; ++dir) {
@@ -473,6 +473,7 @@ extern "C" int mgv_build_csr(const int64_t* edge_index, int64_t E, int32_t N, co
         }
     }
     MGV_CUDA(cudaGetLastError());
+    if (err_flag) return MGV_OK;                 // deferred validation: the caller reads *err_flag later (no sync here)
     int bad_h = 0;
     MGV_CUDA(cudaMemcpyAsync(&bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     MGV_CUDA(cudaStreamSynchronize(st));
@@ -541,10 +542,10 @@ extern "C" size_t mgv_level_lists_workspace_bytes(int64_t N, int32_t L) {
 
 extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, int32_t N, int32_t L,
                                      int32_t* order, int32_t* seg_ptr, int64_t* code_count_host,
-                                     void* ws, size_t ws_bytes, mgv_stream_t stream) {
+                                     void* ws, size_t ws_bytes, int32_t* err_flag, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    MGV_REQUIRE(N >= 0 && L >= 1 && level && code && order && seg_ptr && code_count_host,
-                "mgv_build_level_lists: bad argument");
+    MGV_REQUIRE(N >= 0 && L >= 1 && level && code && order && seg_ptr, "mgv_build_level_lists: bad argument");
+    MGV_REQUIRE(code_count_host || err_flag, "mgv_build_level_lists: the asynchronous form (no code_count_host) needs err_flag");
     MGV_REQUIRE((int64_t)L * MGV_NCODE < (1ll << 31), "mgv_build_level_lists: too many levels");
     if (ws_bytes < mgv_level_lists_workspace_bytes(N, L)) {
         mgv_set_error("mgv_build_level_lists: workspace too small");
@@ -560,8 +561,8 @@ extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, 
     sb.tmp = a.take<uint32_t>(scan_tmp_count(scan_n));
     uint32_t* khist = a.take<uint32_t>(nkeys + 1);
     unsigned long long* counts = a.take<unsigned long long>(MGV_NCODE);
-    int* bad = a.take<int>(1);
-    MGV_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    int* bad = err_flag ? err_flag : a.take<int>(1);
+    if (!err_flag) MGV_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
     MGV_CUDA(cudaMemsetAsync(khist, 0, (size_t)(nkeys + 1) * 4, st));
     if (N > 0) {
         node_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(level, code, N, L, sb.k0, sb.v0, khist, bad);
@@ -576,6 +577,7 @@ extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, 
         copy_u32_to_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(vs, order, N);
         mgv_count_launches(1);
     }
+    if (!code_count_host) return mgv_check_cuda(cudaGetLastError(), "mgv_build_level_lists");   // asynchronous form
     code_count_kernel<<<1, 32, 0, st>>>(seg_ptr, L, counts);
     mgv_count_launches(1);
     MGV_CUDA(cudaGetLastError());
@@ -584,7 +586,7 @@ extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, 
     MGV_CUDA(cudaMemcpyAsync(ch, counts, sizeof(ch), cudaMemcpyDeviceToHost, st));
     MGV_CUDA(cudaMemcpyAsync(&bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     MGV_CUDA(cudaStreamSynchronize(st));
-    MGV_REQUIRE(bad_h == 0, "mgv_build_level_lists: level outside [0, %d)", L);
+    MGV_REQUIRE(err_flag || bad_h == 0, "mgv_build_level_lists: level outside [0, %d)", L);
     for (int c = 0; c < MGV_NCODE; ++c) code_count_host[c] = (int64_t)ch[c];
     return MGV_OK;
 }

@@ -86,7 +86,25 @@ def collate(circuits):
     out.batch = torch.repeat_interleave(torch.arange(len(circuits)), torch.tensor(counts))
     out.ptr = torch.tensor(starts, dtype=torch.long)
     out.num_graphs = len(circuits)
+    attach_schedule_meta(out)
     return out
+
+
+def attach_schedule_meta(batch):
+    """Host-side schedule metadata, computed where the reference computes ``forward_level`` (at data-preparation
+    time, parser_func_others.py:63): the number of levels and the nodes per gate code at level >= 1.  With these two
+    plain-Python attributes on the batch, ``Model.forward`` builds its device schedule without a host sync (the
+    reference syncs ~2N + 5L times per forward)."""
+    lvl = getattr(batch, "forward_level", None)
+    gate = getattr(batch, "gate", None)
+    if lvl is None or gate is None or lvl.is_cuda or lvl.numel() == 0 or lvl.numel() != gate.shape[0]:
+        return batch
+    lvl = lvl.reshape(-1).to(torch.int64)
+    code = gate.reshape(-1).to(torch.int64).clamp(0, 6)
+    code = torch.where((gate.reshape(-1) < 0) | (gate.reshape(-1) > 6), torch.full_like(code, 6), code)
+    batch.num_levels = int(lvl.max()) + 1
+    batch.level_code_count = torch.bincount(code[lvl >= 1], minlength=8)[:8].tolist()
+    return batch
 
 
 class DataLoader(torch.utils.data.DataLoader):

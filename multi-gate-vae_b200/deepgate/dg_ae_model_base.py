@@ -21,24 +21,6 @@ EPS = 1e-15
 MAX_LOGSTD = 10
 
 
-def negative_sampling(pos_edge_index, num_nodes, num_neg_samples=None):
-    """Random node pairs that are not in ``pos_edge_index`` (same count by default); stands in for
-    torch_geometric.utils.negative_sampling at the reference's call site (dg_ae_model_mig.py:180)."""
-    n = int(num_nodes)
-    k = pos_edge_index.size(1) if num_neg_samples is None else int(num_neg_samples)
-    dev = pos_edge_index.device
-    taken = pos_edge_index[0] * n + pos_edge_index[1]
-    out = torch.empty(0, dtype=torch.long, device=dev)
-    for _ in range(8):
-        cand = torch.randint(0, n * n, (int(1.2 * (k - out.numel())) + 16,), device=dev)
-        cand = cand[~torch.isin(cand, taken)]
-        out = torch.unique(torch.cat([out, cand]))
-        if out.numel() >= k:
-            break
-    out = out[torch.randperm(out.numel(), device=dev)[:k]]
-    return torch.stack([out // n, out % n], dim=0)
-
-
 class LevelModel(nn.Module):
     """Recurrent GNN over circuit levels with structural (hs) and functional (hf) states."""
 
@@ -83,19 +65,20 @@ class LevelModel(nn.Module):
         return torch.clamp(self.readout_prob(hf), min=0.0, max=1.0)
 
     def recon_loss(self, hs, pos_edge_index, neg_edge_index=None):
-        s, t = self.hs_decompose(hs).chunk(2, dim=-1)
-        pos_pred = self.decoder(s, t, pos_edge_index, sigmoid=True)
-        pos_loss = -torch.log(pos_pred + EPS).mean()
+        """dg_ae_model_mig.py:169-191.  The decoder + BCE terms run in one fused kernel (ops.recon_loss); missing
+        negatives are drawn on the device (no self loops, no existing edges) without a host sync."""
+        st = self.hs_decompose(hs)
         if neg_edge_index is None:
-            n = s.size(0)
-            keep = pos_edge_index[0] != pos_edge_index[1]
-            loops = torch.arange(n, device=hs.device).unsqueeze(0).repeat(2, 1)
-            neg_edge_index = negative_sampling(torch.cat([pos_edge_index[:, keep], loops], dim=1), n)
-        neg_pred = self.decoder(s, t, neg_edge_index, sigmoid=True)
-        neg_loss = -torch.log(1 - neg_pred + EPS).mean()
-        pred_bin = torch.cat([pos_pred > 0.5, neg_pred > 0.5], dim=0).int()
-        gt_bin = torch.cat([torch.ones_like(pos_pred), torch.zeros_like(neg_pred)], dim=0).int()
-        return pos_loss + neg_loss, pred_bin, gt_bin
+            from . import schedule
+            csr = schedule._last["csr"]
+            if csr is None or csr.N != st.size(0) or csr.E != pos_edge_index.size(1) or csr.device != st.device:
+                csr = schedule.csr_for(pos_edge_index, st.size(0))
+            neg_edge_index = ops.negative_sample(csr, pos_edge_index.size(1))
+        loss, pred_bin = ops.recon_loss(st, pos_edge_index, neg_edge_index)
+        ep, en = pos_edge_index.size(1), neg_edge_index.size(1)
+        gt_bin = torch.cat([torch.ones(ep, dtype=torch.int32, device=hs.device),
+                            torch.zeros(en, dtype=torch.int32, device=hs.device)])
+        return loss, pred_bin, gt_bin
 
     # ------------------------------------------------------------------ checkpoints
     def load(self, model_path):

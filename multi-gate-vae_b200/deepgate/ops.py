@@ -247,6 +247,73 @@ def struct_encoder(x, csr, rounds, layernorm, encoders):
     return StructEncoderFunction.apply(x, csr, int(rounds), bool(layernorm), len(encoders), *params)
 
 
+# =========================================================================== reconstruction loss + negative sampler
+_NEG_COUNTER = [0]
+
+
+def negative_sample(csr, count):
+    """``count`` random ordered node pairs that are neither self loops nor edges of ``csr`` (device kernel, no host
+    sync) -- the role of torch_geometric.utils.negative_sampling at dg_ae_model_mig.py:177-180.  Seeded from
+    torch's global seed and a call counter."""
+    lib = nat.lib()
+    dev = csr.device
+    if csr.N < 2:
+        raise RuntimeError("mgv_b200: negative sampling needs at least 2 nodes")
+    neg = torch.empty(2, int(count), dtype=torch.int64, device=dev)
+    _NEG_COUNTER[0] += 1
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _NEG_COUNTER[0]) & 0xFFFFFFFFFFFFFFFF
+    with torch.cuda.device(dev):
+        nat.check(lib.mgv_negative_sample(nat.ptr(csr.out_ptr), nat.ptr(csr.out_pack), csr.N, int(count), seed,
+                                          nat.ptr(neg), nat.stream_of(dev)), "mgv_negative_sample")
+    return neg
+
+
+class ReconLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, st, pos, neg):
+        lib = nat.lib()
+        dev = st.device
+        st_c = _f32(st, "st")
+        N = int(st_c.shape[0])
+        if st_c.dim() != 2 or st_c.shape[1] != 2 * nat.D:
+            raise RuntimeError("mgv_b200: recon loss expects hs_decompose(hs) of shape [N, %d]" % (2 * nat.D))
+        pos_c = nat.require_cuda(pos.contiguous(), "pos_edge_index", torch.int64)
+        neg_c = nat.require_cuda(neg.contiguous(), "neg_edge_index", torch.int64)
+        Ep, En = int(pos_c.shape[1]), int(neg_c.shape[1])
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        sig = torch.empty(max(Ep + En, 1), dtype=torch.float32, device=dev)
+        pred = torch.empty(max(Ep + En, 1), dtype=torch.int32, device=dev)
+        ws = nat.workspace(16, dev)
+        from .schedule import error_word
+        with torch.cuda.device(dev):
+            with _timed("recon_loss_fwd", dev):
+              nat.check(lib.mgv_recon_loss_fwd(nat.ptr(st_c), N, nat.ptr(pos_c), Ep, nat.ptr(neg_c), En, nat.ptr(out),
+                                             nat.ptr(sig), nat.ptr(pred), nat.ptr(ws), 16, nat.ptr(error_word(dev)),
+                                             nat.stream_of(dev)), "mgv_recon_loss_fwd")
+        ctx.save_for_backward(st_c, pos_c, neg_c, sig)
+        ctx.mark_non_differentiable(pred)
+        return out[0], pred[:Ep + En]
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_pred):
+        lib = nat.lib()
+        st_c, pos_c, neg_c, sig = ctx.saved_tensors
+        dev = st_c.device
+        gst = torch.zeros_like(st_c)
+        gl = g_loss.detach().to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(dev):
+            with _timed("recon_loss_bwd", dev):
+              nat.check(lib.mgv_recon_loss_bwd(nat.ptr(st_c), int(st_c.shape[0]), nat.ptr(pos_c), int(pos_c.shape[1]),
+                                             nat.ptr(neg_c), int(neg_c.shape[1]), nat.ptr(sig), nat.ptr(gl), nat.ptr(gst),
+                                             nat.stream_of(dev)), "mgv_recon_loss_bwd")
+        return gst, None, None
+
+
+def recon_loss(st, pos_edge_index, neg_edge_index):
+    """(loss, pred_bin int32 [Ep + En]) of the directed inner-product decoder over ``st = [s | t]``."""
+    return ReconLossFunction.apply(st, pos_edge_index, neg_edge_index)
+
+
 # =========================================================================== reparam + KL + func loss
 class VaeFuncLossFunction(torch.autograd.Function):
     @staticmethod

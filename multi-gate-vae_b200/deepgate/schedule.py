@@ -18,10 +18,33 @@ import torch
 from . import _native as nat
 
 
-class GraphCSR(object):
-    """In/out-edge CSR of ``edge_index`` ([2, E] int64, row 0 = source)."""
+_ERR = {}          # device -> int32 word: deferred validation flags of the asynchronous schedule builds
 
-    def __init__(self, edge_index, num_nodes, code=None):
+
+def error_word(device):
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _ERR:
+        _ERR[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return _ERR[key]
+
+
+def check_deferred_errors():
+    """Synchronise and raise if an asynchronous schedule build / fused loss saw invalid input since the last check
+    (bit 0: node id outside [0, N); bit 1: level outside [0, L); bit 2: loss edge end outside [0, N))."""
+    for key, word in _ERR.items():
+        v = int(word.item())
+        if v:
+            word.zero_()
+            raise RuntimeError("mgv_b200: invalid graph input on %s:%s (flags 0x%x: 1 = node id out of range, "
+                               "2 = level out of range, 4 = loss edge out of range)" % (key[0], key[1], v))
+
+
+class GraphCSR(object):
+    """In/out-edge CSR of ``edge_index`` ([2, E] int64, row 0 = source).  ``validate=True`` checks node ids
+    synchronously; ``False`` defers the check to ``check_deferred_errors()`` and never syncs."""
+
+    def __init__(self, edge_index, num_nodes, code=None, validate=True):
         nat.require_cuda(edge_index, "edge_index", torch.int64)
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise RuntimeError("mgv_b200: edge_index must be [2, E]")
@@ -48,6 +71,7 @@ class GraphCSR(object):
             nat.check(lib.mgv_build_csr(nat.ptr(edge_index), self.E, self.N, nat.ptr(self.code),
                                         nat.ptr(self.in_ptr), nat.ptr(self.in_src), nat.ptr(self.out_ptr),
                                         nat.ptr(self.out_pack), nat.ptr(self.out_slot), nat.ptr(ws), nb,
+                                        None if validate else nat.ptr(error_word(dev)),
                                         nat.stream_of(dev)), "mgv_build_csr")
             # degree orders + tile cost prefixes for the tensor-core tiles of the struct encoder
             ntiles = (self.N + nat.TILE_ROWS - 1) // nat.TILE_ROWS
@@ -85,9 +109,10 @@ class GraphCSR(object):
                                        info, nat.ptr(ws), nb, nat.stream_of(self.device)), "mgv_levelize")
         return level[:self.N], max(int(info[0]), 1)
 
-    def set_levels(self, level=None):
+    def set_levels(self, level=None, num_levels=None, code_count=None):
         """Attach levels (given, e.g. ``G.forward_level``, or computed) and build the
-        (level, code)-segmented node lists."""
+        (level, code)-segmented node lists.  With ``num_levels`` and ``code_count`` supplied (host metadata of the
+        batch, data.attach_schedule_meta) nothing here synchronises with the device."""
         if self.code is None:
             raise RuntimeError("mgv_b200: a level schedule needs gate codes")
         if level is None:
@@ -96,21 +121,26 @@ class GraphCSR(object):
             lvl = nat.require_cuda(level.reshape(-1).to(torch.int32).contiguous(), "forward_level", torch.int32)
             if lvl.numel() != self.N:
                 raise RuntimeError("mgv_b200: forward_level must have one entry per node")
-            # one device->host sync, as the reference's max(G.forward_level).item() (dg_ae_model_mig.py:67)
-            L = int(lvl.max().item()) + 1 if self.N > 0 else 1
+            if num_levels is not None:
+                L = max(int(num_levels), 1)
+            else:
+                # one device->host sync, as the reference's max(G.forward_level).item() (dg_ae_model_mig.py:67)
+                L = int(lvl.max().item()) + 1 if self.N > 0 else 1
         self.level, self.L = lvl, L
         i32 = dict(dtype=torch.int32, device=self.device)
         self.order = torch.empty(max(self.N, 1), **i32)
         self.seg_ptr = torch.empty(L * nat.NCODE + 1, **i32)
+        use_async = code_count is not None and level is not None and num_levels is not None
         counts = (ctypes.c_int64 * nat.NCODE)()
         lib = nat.lib()
         with torch.cuda.device(self.device):
             nb = lib.mgv_level_lists_workspace_bytes(self.N, L)
             ws = nat.workspace(nb, self.device)
             nat.check(lib.mgv_build_level_lists(nat.ptr(lvl), nat.ptr(self.code), self.N, L, nat.ptr(self.order),
-                                                nat.ptr(self.seg_ptr), counts, nat.ptr(ws), nb,
+                                                nat.ptr(self.seg_ptr), None if use_async else counts, nat.ptr(ws), nb,
+                                                nat.ptr(error_word(self.device)) if use_async else None,
                                                 nat.stream_of(self.device)), "mgv_build_level_lists")
-        self.code_count = [int(c) for c in counts]
+        self.code_count = [int(c) for c in (code_count if use_async else counts)]
         self._struct = None
         return self
 
@@ -164,9 +194,12 @@ def schedule_for_batch(G):
     if not ei.is_cuda:
         raise RuntimeError("mgv_b200: the batch must be on a CUDA device (no CPU path); call batch.to('cuda')")
     code = G.gate.reshape(-1)
-    sch = GraphCSR(ei.contiguous(), n, code=code)
     level = getattr(G, "forward_level", None)
-    sch.set_levels(level if (level is not None and level.numel() == n) else None)
+    level = level if (level is not None and level.numel() == n) else None
+    L, counts = getattr(G, "num_levels", None), getattr(G, "level_code_count", None)
+    has_meta = level is not None and L is not None and counts is not None and len(counts) == nat.NCODE
+    sch = GraphCSR(ei.contiguous(), n, code=code, validate=not has_meta)
+    sch.set_levels(level, L if has_meta else None, counts if has_meta else None)
     try:
         G._mgv_schedule = sch
     except Exception:

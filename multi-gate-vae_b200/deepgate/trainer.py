@@ -107,6 +107,10 @@ class Trainer(object):
         # the optimizer is created before .to(device), like the reference (trainer.py:73-76)
         self.optimizer = torch.optim.Adam(model.parameters(), lr=self.lr)
         self.model = model.to(self.device)
+        if str(self.device).startswith("cuda"):
+            for group in self.optimizer.param_groups:        # one multi-tensor kernel per step instead of ~100 small ones
+                group["fused"] = True
+                group["foreach"] = False
         self.model_epoch = 0
         self.grad_sync = FlatGradAllReduce(self.model.parameters())
         if self.local_rank == 0:
@@ -217,6 +221,8 @@ class Trainer(object):
                     self.logger.write("{}| Epoch: {:}/{:} |Recon: {:.4f} |ACC: {:.2f} |Prob: {:.4f} |Func: {:.4f}|Net: {:.2f}s\n".format(
                         phase, epoch, num_epoch, meters["recon"].avg, meters["acc"].avg * 100, meters["prob"].avg,
                         meters["func"].avg, meters["time"].avg))
+            from .schedule import check_deferred_errors
+            check_deferred_errors()
             self.model_epoch += 1
             if self.lr_step > 0 and self.model_epoch % self.lr_step == 0:
                 self.lr *= 0.1

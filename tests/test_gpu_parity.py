@@ -232,3 +232,59 @@ def test_properties_at_cfg2_size():
         return torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
     g1, g2 = grads(), grads()
     assert torch.isfinite(g1).all() and rel(g1, g2) < 1e-6
+
+
+def test_recon_loss_kernel_and_negative_sampler():
+    """Fused decoder + BCE (dg_ae_model_mig.py:169-191) against plain torch; sampler: no self loops, no edges."""
+    import deepgate
+    from deepgate import ops, synth
+    from deepgate.schedule import schedule_for_batch, check_deferred_errors
+    G = deepgate.circuits_to_batch(synth.make_circuits("xmg", 3, 16, 300, cfg=31), "cuda")
+    n, E = G.x.size(0), G.edge_index.size(1)
+    g = torch.Generator().manual_seed(3)
+    st = torch.randn(n, 128, generator=g).cuda().requires_grad_(True)
+    pos = G.edge_index[:, torch.randperm(E, generator=g).cuda()]
+    neg = torch.randint(0, n, (2, E + 17), generator=g).cuda()
+    loss, pred = ops.recon_loss(st, pos, neg)
+    (3.0 * loss).backward()
+    st2 = st.detach().clone().requires_grad_(True)
+    s, t = st2.chunk(2, dim=-1)
+    pp = torch.sigmoid((s[pos[0]] * t[pos[1]]).sum(1))
+    pn = torch.sigmoid((s[neg[0]] * t[neg[1]]).sum(1))
+    ref = -torch.log(pp + 1e-15).mean() - torch.log(1 - pn + 1e-15).mean()
+    (3.0 * ref).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel(st.grad, st2.grad) < 1e-5
+    assert torch.equal(pred, torch.cat([pp > 0.5, pn > 0.5]).int())
+    sch = schedule_for_batch(G)
+    smp = ops.negative_sample(sch, 4 * E)
+    assert smp.shape == (2, 4 * E) and int(smp.min()) >= 0 and int(smp.max()) < n
+    assert not bool((smp[0] == smp[1]).any())
+    key = G.edge_index[0] * n + G.edge_index[1]
+    assert not bool(torch.isin(smp[0] * n + smp[1], key).any())
+    assert len(torch.unique(smp[0] * n + smp[1])) > 3 * E          # not degenerate
+    check_deferred_errors()
+
+
+def test_async_schedule_equals_sync_schedule_and_flags_bad_input():
+    """Host metadata attached at collate (data.attach_schedule_meta) removes every sync; results are identical."""
+    import deepgate
+    from deepgate import synth
+    from deepgate.schedule import GraphCSR, schedule_for_batch, check_deferred_errors
+    host = deepgate.circuits_to_batch(synth.make_circuits("mig4", 5, 16, 400, cfg=32, window=30))
+    assert host.num_levels == int(host.forward_level.max()) + 1
+    G = host.copy_to("cuda", non_blocking=False)
+    a = schedule_for_batch(G)                                       # asynchronous form (metadata present)
+    b = GraphCSR(G.edge_index.contiguous(), G.x.size(0), code=G.gate.reshape(-1)).set_levels(G.forward_level)
+    assert a.L == b.L and a.code_count == b.code_count
+    for k in ("in_ptr", "in_src", "out_ptr", "out_pack", "out_slot", "order", "seg_ptr", "deg_order_in", "deg_order_out"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    check_deferred_errors()
+    bad = G.edge_index.clone()
+    bad[0, 0] = G.x.size(0) + 5
+    GraphCSR(bad, G.x.size(0), code=G.gate.reshape(-1), validate=False)
+    with pytest.raises(RuntimeError):
+        check_deferred_errors()
+    check_deferred_errors()                                         # flag was cleared
+    with pytest.raises(RuntimeError):
+        GraphCSR(bad, G.x.size(0), code=G.gate.reshape(-1), validate=True)
