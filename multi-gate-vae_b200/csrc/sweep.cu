@@ -13,7 +13,7 @@
 // CTAs are statically specialised per gate code (proportional to the code's node count) so a
 // CTA streams one code's weights (L1/L2 resident) and, in backward, keeps that code's
 // weight-gradient accumulators in shared memory for the whole sweep.
-#include "mgv_common.cuh"
+#include "mgv_mma16.cuh"
 
 namespace {
 
@@ -115,77 +115,221 @@ __device__ __forceinline__ void find_role(const SweepDev& p, int& code, int& ran
 }
 
 // ======================================================================================= forward
-constexpr int FTM = 32;                                        // nodes per tile
-constexpr int F_SMEM_FLOATS = FTM * LDX + 2 * FTM * LDM + 2 * FTM;
+// Tensor-core tiles (mma.sync m16n8k16 on fp16 hi/lo planes, mgv_mma16.cuh).  A CTA keeps ITS gate code's weights as
+// planes in shared memory for the whole sweep; a tile is 32 nodes of one (level, code) segment:
+//   gather (half-warp per node: [hs || hf] rows of the predecessors, online softmax, xbar)  ->  m = xbar Wv^T + bv S
+//   ->  gi = m Wih^T, gh = h Whh^T  ->  GRU gates  ->  hf[node]
+constexpr int FTM = 32;
+constexpr int FTHREADS = 512;
+constexpr int LDXH = 136, LDMH = 72, LDF32 = 68;                // plane row strides (halves) / fp32 tile stride
+constexpr uint32_t FW_WV_HI = 0, FW_WV_LO = FW_WV_HI + D * LDXH * 2, FW_WIH_HI = FW_WV_LO + D * LDXH * 2,
+                   FW_WIH_LO = FW_WIH_HI + G3 * LDMH * 2, FW_WHH_HI = FW_WIH_LO + G3 * LDMH * 2, FW_WHH_LO = FW_WHH_HI + G3 * LDMH * 2;
+constexpr uint32_t FW_BIAS = FW_WHH_LO + G3 * LDMH * 2;        // u[128] bv[64] bih[192] bhh[192] fp32
+constexpr uint32_t FW_XS_HI = FW_BIAS + 576 * 4, FW_XS_LO = FW_XS_HI + FTM * LDXH * 2;
+constexpr uint32_t FW_MS_HI = FW_XS_LO + FTM * LDXH * 2, FW_MS_LO = FW_MS_HI + FTM * LDMH * 2;
+constexpr uint32_t FW_HS_HI = FW_MS_LO + FTM * LDMH * 2, FW_HS_LO = FW_HS_HI + FTM * LDMH * 2;
+constexpr uint32_t FW_H32 = FW_HS_LO + FTM * LDMH * 2, FW_SS = FW_H32 + FTM * LDF32 * 4, FW_IDS = FW_SS + FTM * 4;
+constexpr uint32_t F_SMEM_BYTES = FW_IDS + FTM * 4;
+static_assert(F_SMEM_BYTES <= 227 * 1024 && FW_XS_HI % 16 == 0 && FW_MS_HI % 16 == 0 && FW_HS_HI % 16 == 0, "sweep forward smem");
 
-__global__ void __launch_bounds__(THREADS, 2) sweep_fwd_kernel(const SweepDev p) {
-    extern __shared__ __align__(16) float smem[];
-    float* Xs = smem;                       // [32][132] xbar
-    float* Ms = Xs + FTM * LDX;             // [32][68]  m
-    float* Hs = Ms + FTM * LDM;             // [32][68]  h (previous round)
-    float* Ss = Hs + FTM * LDM;             // [32]
-    int* Ids = reinterpret_cast<int*>(Ss + FTM);
+__device__ __forceinline__ void st_plane8(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t half_off, const float (&v)[8]) {
+    uint4 hi, lo;
+    m16::split2(v[0], v[1], hi.x, lo.x);
+    m16::split2(v[2], v[3], hi.y, lo.y);
+    m16::split2(v[4], v[5], hi.z, lo.z);
+    m16::split2(v[6], v[7], hi.w, lo.w);
+    *reinterpret_cast<uint4*>(hi_plane + half_off * 2) = hi;
+    *reinterpret_cast<uint4*>(lo_plane + half_off * 2) = lo;
+}
+// [rows][cols] fp32 row-major (global) -> hi/lo planes with row stride ld (halves)
+__device__ __forceinline__ void load_planes(uint8_t* hi_plane, uint8_t* lo_plane, const float* __restrict__ W, int rows, int cols, int ld,
+                                            int tid, int nthr) {
+    const int chunks = cols / 8;
+    for (int i = tid; i < rows * chunks; i += nthr) {
+        const int r = i / chunks, c = i % chunks;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(W + (size_t)r * cols + c * 8 + e);
+        st_plane8(hi_plane, lo_plane, (uint32_t)(r * ld + c * 8), v);
+    }
+}
+__device__ __forceinline__ void gru_gates(float gr, float gz, float gi, float gh, float& r, float& z, float& n) {
+    const float a = __expf(-fminf(fmaxf(gr, -28.f), 28.f));
+    const float b = __expf(-fminf(fmaxf(gz, -28.f), 28.f));
+    const float inv = __fdividef(1.0f, (1.0f + a) * (1.0f + b));
+    r = (1.0f + b) * inv;
+    z = (1.0f + a) * inv;
+    const float y = fminf(fmaxf(fmaf(r, gh, gi), -14.f), 14.f);
+    n = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y));
+}
+
+// Gather + additive attention of one node by one HALF-warp: lane l16 owns columns 8 l16 .. 8 l16 + 7 of the 128-wide
+// row [hs || hf].  Returns the xbar chunk and S; optionally stores raw scores, then alphas.
+template <bool STORE_ALPHA>
+__device__ __forceinline__ void gather_attend16(const SweepDev& p, const float* hf_cur, const float* u8, int node, int l16,
+                                                unsigned hmask, float (&xbar)[8], float& S) {
+    const int beg = p.in_ptr[node], end = p.in_ptr[node + 1];
+    float mx = -INFINITY, sum = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int q0 = beg; q0 < end; q0 += 4) {
+        float x[4][8], sc[4];
+        const int cnt = min(4, end - q0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < cnt) {
+                const int j = p.in_src[q0 + i];
+                const float* row = (l16 < 8) ? (p.hs + (size_t)j * D + 8 * l16) : (hf_cur + (size_t)j * D + 8 * (l16 - 8));
+                const float4 a = mgv_ld4(row), b = mgv_ld4(row + 4);
+                x[i][0] = a.x; x[i][1] = a.y; x[i][2] = a.z; x[i][3] = a.w; x[i][4] = b.x; x[i][5] = b.y; x[i][6] = b.z; x[i][7] = b.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[i][e] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float d = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d = fmaf(x[i][e], u8[e], d);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(hmask, d, o);
+            sc[i] = d;
+        }
+        float nmx = mx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < cnt) nmx = fmaxf(nmx, sc[i]);
+        const float scale = (mx == -INFINITY) ? 0.f : expf(mx - nmx);
+        sum *= scale;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] *= scale;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < cnt) {
+                const float ex = expf(sc[i] - nmx);
+                sum += ex;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(ex, x[i][e], acc[e]);
+                if (STORE_ALPHA && l16 == 0) p.alpha[q0 + i] = sc[i];     // raw score for now
+            }
+        }
+        mx = nmx;
+    }
+    const float inv = 1.0f / (sum + 1e-16f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xbar[e] = acc[e] * inv;
+    S = sum * inv;
+    if (STORE_ALPHA) {
+        __syncwarp(hmask);
+        for (int q = beg + l16; q < end; q += 16) p.alpha[q] = expf(p.alpha[q] - mx) * inv;
+        __syncwarp(hmask);
+    }
+}
+
+__global__ void __launch_bounds__(FTHREADS, 1) sweep_fwd_kernel(const SweepDev p) {
+    extern __shared__ __align__(128) uint8_t fsm[];
+    const uint32_t sb = m16::smem_u32(fsm);
+    float* Bias = reinterpret_cast<float*>(fsm + FW_BIAS);     // u | bv | bih | bhh
+    float* H32 = reinterpret_cast<float*>(fsm + FW_H32);
+    float* Ss = reinterpret_cast<float*>(fsm + FW_SS);
+    int* Ids = reinterpret_cast<int*>(fsm + FW_IDS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
     int code, rank, nct;
     find_role(p, code, rank, nct);
-    const float* W = p.weights + (size_t)(code < 0 ? 0 : code) * PACK;
-    const int col = tid & 63, rg = tid >> 6;
+    if (code >= 0) {
+        const float* W = p.weights + (size_t)code * PACK;
+        load_planes(fsm + FW_WV_HI, fsm + FW_WV_LO, W + O_WV, D, D2, LDXH, tid, FTHREADS);
+        load_planes(fsm + FW_WIH_HI, fsm + FW_WIH_LO, W + O_WIH, G3, D, LDMH, tid, FTHREADS);
+        load_planes(fsm + FW_WHH_HI, fsm + FW_WHH_LO, W + O_WHH, G3, D, LDMH, tid, FTHREADS);
+        for (int i = tid; i < 576; i += FTHREADS)
+            Bias[i] = __ldg(W + (i < 128 ? O_U + i : (i < 192 ? O_BV + i - 128 : (i < 384 ? O_BIH + i - 192 : O_BHH + i - 384))));
+    }
+    __syncthreads();
+    const float* Bu = Bias; const float* Bv = Bias + 128; const float* Bih = Bias + 192; const float* Bhh = Bias + 384;
+    float u8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u8[e] = Bu[8 * l16 + e];
+    const int mt = warp & 1, nt8 = (warp >> 1) * 8;
+    const int g = lane >> 2, t = lane & 3;
 
     for (int r = 0; r < p.R; ++r) {
         const float* hf_prev = r > 0 ? p.hf_all + (size_t)(r - 1) * p.N * D : nullptr;
         float* hf_cur = p.hf_all + (size_t)r * p.N * D;
         for (int lvl = 1; lvl < p.L; ++lvl) {
             if (code >= 0) {
-                const int sb = p.seg_ptr[lvl * MGV_NCODE + code], se = p.seg_ptr[lvl * MGV_NCODE + code + 1];
-                for (int t0 = sb + rank * FTM; t0 < se; t0 += nct * FTM) {
-                    const int rows = min(FTM, se - t0);
-                    // ---- phase A: gather + attention, one warp per node
-                    for (int row = warp; row < FTM; row += WARPS) {
-                        float4 xb = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int sbeg = p.seg_ptr[lvl * MGV_NCODE + code], send = p.seg_ptr[lvl * MGV_NCODE + code + 1];
+                for (int t0 = sbeg + rank * FTM; t0 < send; t0 += nct * FTM) {
+                    const int rows = min(FTM, send - t0);
+                    {   // ---- phase A: gather + attention, one half-warp per node
+                        const int row = warp * 2 + half;
+                        float xb[8], h8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { xb[e] = 0.f; h8[e] = 0.f; }
                         float S = 0.f;
                         int node = -1;
                         if (row < rows) {
                             node = p.order[t0 + row];
-                            gather_attend<false>(p, hf_cur, W, node, lane, xb, S);
-                            if (hf_prev != nullptr && lane < 16) h4 = mgv_ld4(hf_prev + (size_t)node * D + 4 * lane);
-                        }
-                        mgv_st4(Xs + row * LDX + 4 * lane, xb);
-                        if (lane < 16) mgv_st4(Hs + row * LDM + 4 * lane, h4);
-                        if (lane == 0) { Ss[row] = S; Ids[row] = node; }
-                    }
-                    __syncthreads();
-                    // ---- phase B: m = xbar Wv^T + bv S
-                    {
-                        float acc[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                        mgv_gemm_col<8, D2>(Xs + rg * 8 * LDX, LDX, W + O_WVT, D, col, acc);
-                        const float bv = __ldg(W + O_BV + col);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) Ms[(rg * 8 + i) * LDM + col] = fmaf(bv, Ss[rg * 8 + i], acc[i]);
-                    }
-                    __syncthreads();
-                    // ---- phase C: GRU
-                    {
-                        float ar[8], az[8], an[8], hr[8], hz[8], hn[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { ar[i] = az[i] = an[i] = 0.f; hr[i] = hz[i] = hn[i] = 0.f; }
-                        mgv_gemm_col3<8, D>(Ms + rg * 8 * LDM, LDM, W + O_WIHT, col, ar, az, an);
-                        if (hf_prev != nullptr) mgv_gemm_col3<8, D>(Hs + rg * 8 * LDM, LDM, W + O_WHHT, col, hr, hz, hn);
-                        const float bir = __ldg(W + O_BIH + col), biz = __ldg(W + O_BIH + D + col), bin = __ldg(W + O_BIH + 2 * D + col);
-                        const float bhr = __ldg(W + O_BHH + col), bhz = __ldg(W + O_BHH + D + col), bhn = __ldg(W + O_BHH + 2 * D + col);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int row = rg * 8 + i;
-                            const int node = Ids[row];
-                            if (node >= 0) {
-                                const float rr = mgv_sigmoid(ar[i] + bir + hr[i] + bhr);
-                                const float zz = mgv_sigmoid(az[i] + biz + hz[i] + bhz);
-                                const float nn = tanhf(an[i] + bin + rr * (hn[i] + bhn));
-                                const float hp = Hs[row * LDM + col];
-                                hf_cur[(size_t)node * D + col] = (1.0f - zz) * nn + zz * hp;
+                            gather_attend16<false>(p, hf_cur, u8, node, l16, hmask, xb, S);
+                            if (hf_prev != nullptr && l16 < 8) {
+                                const float4 a = mgv_ld4(hf_prev + (size_t)node * D + 8 * l16), b = mgv_ld4(hf_prev + (size_t)node * D + 8 * l16 + 4);
+                                h8[0] = a.x; h8[1] = a.y; h8[2] = a.z; h8[3] = a.w; h8[4] = b.x; h8[5] = b.y; h8[6] = b.z; h8[7] = b.w;
                             }
+                        }
+                        st_plane8(fsm + FW_XS_HI, fsm + FW_XS_LO, (uint32_t)(row * LDXH + 8 * l16), xb);
+                        if (l16 < 8) {
+                            st_plane8(fsm + FW_HS_HI, fsm + FW_HS_LO, (uint32_t)(row * LDMH + 8 * l16), h8);
+                            mgv_st4(H32 + row * LDF32 + 8 * l16, make_float4(h8[0], h8[1], h8[2], h8[3]));
+                            mgv_st4(H32 + row * LDF32 + 8 * l16 + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
+                        }
+                        if (l16 == 0) { Ss[row] = S; Ids[row] = node; }
+                    }
+                    __syncthreads();
+                    {   // ---- phase B: m = xbar Wv^T + bv S   (warp: 16 rows x 8 columns)
+                        const int n0[1] = {nt8};
+                        float c[1][1][4];
+                        m16::zero_frag(c);
+                        m16::warp_gemm<1, 1, D2 / 16, false, false>(c, sb + FW_XS_HI, sb + FW_XS_LO, LDXH, mt * 16, 0, sb + FW_WV_HI, sb + FW_WV_LO,
+                                                                    LDXH, n0, 0, lane);
+#pragma unroll
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            const int row = mt * 16 + g + 8 * hrow, col = nt8 + 2 * t;
+                            const float s = Ss[row];
+                            uint32_t hi, lo;
+                            m16::split2(fmaf(Bv[col], s, c[0][0][2 * hrow]), fmaf(Bv[col + 1], s, c[0][0][2 * hrow + 1]), hi, lo);
+                            *reinterpret_cast<uint32_t*>(fsm + FW_MS_HI + (row * LDMH + col) * 2) = hi;
+                            *reinterpret_cast<uint32_t*>(fsm + FW_MS_LO + (row * LDMH + col) * 2) = lo;
+                        }
+                    }
+                    __syncthreads();
+                    {   // ---- phase C: GRU (warp: 16 rows x 8 units, all three gates)
+                        const int n0[3] = {nt8, D + nt8, 2 * D + nt8};
+                        float ci[1][3][4], ch[1][3][4];
+                        m16::zero_frag(ci);
+                        m16::zero_frag(ch);
+                        m16::warp_gemm<1, 3, D / 16, false, false>(ci, sb + FW_MS_HI, sb + FW_MS_LO, LDMH, mt * 16, 0, sb + FW_WIH_HI, sb + FW_WIH_LO,
+                                                                   LDMH, n0, 0, lane);
+                        if (hf_prev != nullptr)
+                            m16::warp_gemm<1, 3, D / 16, false, false>(ch, sb + FW_HS_HI, sb + FW_HS_LO, LDMH, mt * 16, 0, sb + FW_WHH_HI, sb + FW_WHH_LO,
+                                                                       LDMH, n0, 0, lane);
+#pragma unroll
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            const int row = mt * 16 + g + 8 * hrow;
+                            const int node = Ids[row];
+                            float out[2];
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const int e = 2 * hrow + k, uu = nt8 + 2 * t + k;
+                                float rr, zz, nn;
+                                gru_gates(ci[0][0][e] + Bih[uu] + ch[0][0][e] + Bhh[uu], ci[0][1][e] + Bih[D + uu] + ch[0][1][e] + Bhh[D + uu],
+                                          ci[0][2][e] + Bih[2 * D + uu], ch[0][2][e] + Bhh[2 * D + uu], rr, zz, nn);
+                                const float hp = H32[row * LDF32 + uu];
+                                out[k] = fmaf(zz, hp - nn, nn);
+                            }
+                            if (node >= 0) *reinterpret_cast<float2*>(hf_cur + (size_t)node * D + nt8 + 2 * t) = make_float2(out[0], out[1]);
                         }
                     }
                     __syncthreads();
@@ -550,12 +694,12 @@ int fill_common(SweepDev& d, const mgv_schedule* sch, int rounds, unsigned handl
     return MGV_OK;
 }
 
-int coop_grid(const void* kernel, size_t smem, int* grid_out) {
+int coop_grid(const void* kernel, size_t smem, int threads, int* grid_out) {
     int dev = 0, sms = 0, occ = 0;
     MGV_CUDA(cudaGetDevice(&dev));
     MGV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MGV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, THREADS, smem));
+    MGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
     MGV_REQUIRE(occ >= 1, "level sweep: kernel does not fit on an SM (smem %zu)", smem);
     *grid_out = sms * occ;
     return MGV_OK;
@@ -573,21 +717,21 @@ extern "C" int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint
     d.hf_all = hf_all;
     if (sch->N == 0 || sch->L <= 1) return MGV_OK;          // no level >= 1: hf stays zero
     int grid = 0;
-    const size_t smem = (size_t)F_SMEM_FLOATS * sizeof(float);
-    rc = coop_grid((const void*)sweep_fwd_kernel, smem, &grid);
+    const size_t smem = (size_t)F_SMEM_BYTES;
+    rc = coop_grid((const void*)sweep_fwd_kernel, smem, FTHREADS, &grid);
     if (rc != MGV_OK) return rc;
     assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
     if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;          // nothing to propagate
     MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
     void* args[] = {&d};
-    MGV_CUDA(cudaLaunchCooperativeKernel((void*)sweep_fwd_kernel, dim3(grid), dim3(THREADS), args, smem, st));
+    MGV_CUDA(cudaLaunchCooperativeKernel((void*)sweep_fwd_kernel, dim3(grid), dim3(FTHREADS), args, smem, st));
     mgv_count_launches(1);
     return MGV_OK;
 }
 
 extern "C" int mgv_sweep_bwd_grid(void) {
     int grid = 0;
-    if (coop_grid((const void*)sweep_bwd_kernel, (size_t)B_SMEM_FLOATS * sizeof(float), &grid) != MGV_OK) return -1;
+    if (coop_grid((const void*)sweep_bwd_kernel, (size_t)B_SMEM_FLOATS * sizeof(float), THREADS, &grid) != MGV_OK) return -1;
     return grid;
 }
 
@@ -614,7 +758,7 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     if (sch->N == 0 || sch->L <= 1) return MGV_OK;
     int grid = 0;
     const size_t smem = (size_t)B_SMEM_FLOATS * sizeof(float);
-    rc = coop_grid((const void*)sweep_bwd_kernel, smem, &grid);
+    rc = coop_grid((const void*)sweep_bwd_kernel, smem, THREADS, &grid);
     if (rc != MGV_OK) return rc;
     assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
     if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;
