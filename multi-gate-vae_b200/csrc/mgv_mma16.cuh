@@ -186,4 +186,10 @@ __device__ __forceinline__ float pow2_scale_keep(float amax, float cur) {
     return (amax > 0.f) ? pow2_scale(amax) : cur;
 }
 
+__device__ __forceinline__ float pow2_scale_band(float amax, float cur, float lo, float hi) {
+    const float v = amax * cur;
+    if (v >= lo && v <= hi) return cur;
+    return (amax > 0.f) ? pow2_scale(amax) : cur;
+}
+
 }  // namespace m16

@@ -341,11 +341,34 @@ __global__ void __launch_bounds__(FTHREADS, 1) sweep_fwd_kernel(const SweepDev p
 }
 
 // ======================================================================================= backward
+// Reverse sweep on the same tensor-core tiles.  A tile is 16 nodes of one (level, code) segment; weight planes of the
+// CTA's gate code stay in shared memory and are read in both orientations (ldmatrix / ldmatrix.trans); weight
+// gradients are persistent register fragments, bias / attention-vector gradients shared-memory accumulators.
+//   P/A  pull d(hs, hf) over out-edges, recompute gather / attention (alphas kept)        half-warp per node
+//   B    m = xbar Wv^T + bv S                                                            C  GRU recompute + pointwise backward
+//   D    d m = d gi Wih,  d h = g z + d gh Whh        E  d xbar = d m Wv        F  attention backward (warp per node)
+//   G    d Wih += d gi^T m,  d Whh += d gh^T h,  d Wv += d m^T xbar
+// Gate gradients are scaled per tile by a power of two into fp16 range before the hi/lo split (mgv_mma16.cuh).
 constexpr int BTM = 16;                                        // nodes per tile
-constexpr int B_TILE_FLOATS = 2 * BTM * LDX + 4 * BTM * LDM + 2 * BTM * LDG + 3 * BTM;
-constexpr int B_SMEM_FLOATS = GRAD + B_TILE_FLOATS;
+constexpr int BTHREADS = 512;
+constexpr int LDGH = 264;                                      // d gate planes: dr | dz | dn_i | dn_h
+constexpr uint32_t BW_WV_HI = 0, BW_WV_LO = BW_WV_HI + D * LDXH * 2, BW_WIH_HI = BW_WV_LO + D * LDXH * 2,
+                   BW_WIH_LO = BW_WIH_HI + G3 * LDMH * 2, BW_WHH_HI = BW_WIH_LO + G3 * LDMH * 2, BW_WHH_LO = BW_WHH_HI + G3 * LDMH * 2;
+constexpr uint32_t BW_BIAS = BW_WHH_LO + G3 * LDMH * 2;        // u[128] bv[64] bih[192] bhh[192] fp32
+constexpr uint32_t BW_ACC = BW_BIAS + 576 * 4;                 // d u[128] d bv[64] d bih[192] d bhh[192] fp32
+constexpr uint32_t BW_XS_HI = BW_ACC + 576 * 4, BW_XS_LO = BW_XS_HI + BTM * LDXH * 2;
+constexpr uint32_t BW_X32 = BW_XS_LO + BTM * LDXH * 2, BW_DX32 = BW_X32 + BTM * LDX * 4;
+constexpr uint32_t BW_MS_HI = BW_DX32 + BTM * LDX * 4, BW_MS_LO = BW_MS_HI + BTM * LDMH * 2;
+constexpr uint32_t BW_HS_HI = BW_MS_LO + BTM * LDMH * 2, BW_HS_LO = BW_HS_HI + BTM * LDMH * 2;
+constexpr uint32_t BW_H32 = BW_HS_LO + BTM * LDMH * 2, BW_GS = BW_H32 + BTM * LDF32 * 4;
+constexpr uint32_t BW_DM_HI = BW_GS + BTM * LDF32 * 4, BW_DM_LO = BW_DM_HI + BTM * LDMH * 2, BW_DM32 = BW_DM_LO + BTM * LDMH * 2;
+constexpr uint32_t BW_DG_HI = BW_DM32 + BTM * LDF32 * 4, BW_DG_LO = BW_DG_HI + BTM * LDGH * 2;
+constexpr uint32_t BW_SS = BW_DG_LO + BTM * LDGH * 2, BW_IDS = BW_SS + BTM * 4, BW_MAX = BW_IDS + BTM * 4;
+constexpr uint32_t B_SMEM_BYTES = BW_MAX + 16;
+static_assert(B_SMEM_BYTES <= 227 * 1024 && BW_XS_HI % 16 == 0 && BW_MS_HI % 16 == 0 && BW_HS_HI % 16 == 0 && BW_DM_HI % 16 == 0 &&
+              BW_DG_HI % 16 == 0 && BW_DG_LO % 16 == 0 && BW_X32 % 16 == 0, "sweep backward smem");
 
-// Pull  sum over out-edges e=(v->k) of  alpha_e * dxbar_k + dscore_e * u_code(k)  (128-wide, lane chunk).
+// Pull  sum over out-edges e=(v->k) of  alpha_e * dxbar_k + dscore_e * u_code(k)  (128-wide, lane chunk of 4).
 __device__ __forceinline__ float4 pull_out_edges(const SweepDev& p, int v, int lane) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int beg = p.out_ptr[v], end = p.out_ptr[v + 1];
@@ -378,29 +401,90 @@ __device__ __forceinline__ float4 pull_out_edges(const SweepDev& p, int v, int l
     }
     return acc;
 }
+// The same for a half-warp: lane l16 owns columns 8 l16 .. 8 l16 + 7.
+__device__ __forceinline__ void pull_out_edges16(const SweepDev& p, int v, int l16, float (&acc)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    const int beg = p.out_ptr[v], end = p.out_ptr[v + 1];
+    for (int q0 = beg; q0 < end; q0 += 2) {
+        float4 dx[2][2], uu[2][2];
+        float a[2], ds[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            a[i] = 0.f; ds[i] = 0.f;
+            dx[i][0] = make_float4(0.f, 0.f, 0.f, 0.f); dx[i][1] = dx[i][0]; uu[i][0] = dx[i][0]; uu[i][1] = dx[i][0];
+            if (q0 + i < end) {
+                const int pk = p.out_pack[q0 + i];
+                const int c = (pk >> MGV_CODE_SHIFT) & 7;
+                if ((p.handled >> c) & 1u) {
+                    const int k = pk & NODE_MASK;
+                    const int slot = p.out_slot[q0 + i];
+                    a[i] = p.alpha[slot];
+                    ds[i] = p.dscore[slot];
+                    dx[i][0] = mgv_ld4(p.dxb + (size_t)k * D2 + 8 * l16);
+                    dx[i][1] = mgv_ld4(p.dxb + (size_t)k * D2 + 8 * l16 + 4);
+                    uu[i][0] = mgv_ldg4(p.weights + (size_t)c * PACK + O_U + 8 * l16);
+                    uu[i][1] = mgv_ldg4(p.weights + (size_t)c * PACK + O_U + 8 * l16 + 4);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            acc[0] = fmaf(a[i], dx[i][0].x, fmaf(ds[i], uu[i][0].x, acc[0])); acc[1] = fmaf(a[i], dx[i][0].y, fmaf(ds[i], uu[i][0].y, acc[1]));
+            acc[2] = fmaf(a[i], dx[i][0].z, fmaf(ds[i], uu[i][0].z, acc[2])); acc[3] = fmaf(a[i], dx[i][0].w, fmaf(ds[i], uu[i][0].w, acc[3]));
+            acc[4] = fmaf(a[i], dx[i][1].x, fmaf(ds[i], uu[i][1].x, acc[4])); acc[5] = fmaf(a[i], dx[i][1].y, fmaf(ds[i], uu[i][1].y, acc[5]));
+            acc[6] = fmaf(a[i], dx[i][1].z, fmaf(ds[i], uu[i][1].z, acc[6])); acc[7] = fmaf(a[i], dx[i][1].w, fmaf(ds[i], uu[i][1].w, acc[7]));
+        }
+    }
+}
 
-__global__ void __launch_bounds__(THREADS, 1) sweep_bwd_kernel(const SweepDev p) {
-    extern __shared__ __align__(16) float smem[];
-    float* ACC = smem;                       // [GRAD] this CTA's weight-gradient accumulators
-    float* Xs = ACC + GRAD;                  // [16][132] xbar
-    float* DXs = Xs + BTM * LDX;             // [16][132] d xbar
-    float* Ms = DXs + BTM * LDX;             // [16][68]  m
-    float* Hs = Ms + BTM * LDM;              // [16][68]  h
-    float* Gs = Hs + BTM * LDM;              // [16][68]  d hf (this round)
-    float* DMs = Gs + BTM * LDM;             // [16][68]  d m
-    float* DGI = DMs + BTM * LDM;            // [16][196] d gi (r,z,n)
-    float* DGH = DGI + BTM * LDG;            // [16][196] d gh
-    float* Ss = DGH + BTM * LDG;             // [16]
-    float* dSs = Ss + BTM;                   // [16]
-    int* Ids = reinterpret_cast<int*>(dSs + BTM);
+__global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p) {
+    extern __shared__ __align__(128) uint8_t bsm[];
+    const uint32_t sb = m16::smem_u32(bsm);
+    float* Bias = reinterpret_cast<float*>(bsm + BW_BIAS);
+    float* ACC = reinterpret_cast<float*>(bsm + BW_ACC);        // d u | d bv | d bih | d bhh
+    float* X32 = reinterpret_cast<float*>(bsm + BW_X32);
+    float* DX32 = reinterpret_cast<float*>(bsm + BW_DX32);
+    float* H32 = reinterpret_cast<float*>(bsm + BW_H32);
+    float* Gs = reinterpret_cast<float*>(bsm + BW_GS);          // d hf of the tile, then g z (direct path to h)
+    float* DM32 = reinterpret_cast<float*>(bsm + BW_DM32);
+    float* Ss = reinterpret_cast<float*>(bsm + BW_SS);
+    int* Ids = reinterpret_cast<int*>(bsm + BW_IDS);
+    unsigned* smax = reinterpret_cast<unsigned*>(bsm + BW_MAX);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+    const int g = lane >> 2, t = lane & 3;
     int code, rank, nct;
     find_role(p, code, rank, nct);
     const float* W = p.weights + (size_t)(code < 0 ? 0 : code) * PACK;
-    const int col = tid & 63, rg = tid >> 6;      // 64 columns x 4 row groups of 4 rows
-
-    for (int i = tid; i < GRAD; i += THREADS) ACC[i] = 0.f;
+    if (code >= 0) {
+        load_planes(bsm + BW_WV_HI, bsm + BW_WV_LO, W + O_WV, D, D2, LDXH, tid, BTHREADS);
+        load_planes(bsm + BW_WIH_HI, bsm + BW_WIH_LO, W + O_WIH, G3, D, LDMH, tid, BTHREADS);
+        load_planes(bsm + BW_WHH_HI, bsm + BW_WHH_LO, W + O_WHH, G3, D, LDMH, tid, BTHREADS);
+        for (int i = tid; i < 576; i += BTHREADS)
+            Bias[i] = __ldg(W + (i < 128 ? O_U + i : (i < 192 ? O_BV + i - 128 : (i < 384 ? O_BIH + i - 192 : O_BHH + i - 384))));
+    }
+    for (int i = tid; i < 576; i += BTHREADS) ACC[i] = 0.f;
+    if (tid < 2) smax[tid] = 0u;
+    const float* Bu = Bias; const float* Bv = Bias + 128; const float* Bih = Bias + 192; const float* Bhh = Bias + 384;
+    float* Au = ACC; float* Abv = ACC + 128; float* Abih = ACC + 192; float* Abhh = ACC + 384;
+    float u8[8];
     __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u8[e] = Bu[8 * l16 + e];
+
+    // persistent weight-gradient fragments (all scaled by acc_scale)
+    const int wh = warp >> 3, wn8 = 8 * (warp & 7);
+    const int wn0[1] = {wn8};
+    const int vn0[1] = {8 * warp};
+    float acc_ih[6][1][4], acc_ha[2][1][4], acc_hb[4][1][4], acc_v[4][1][4];
+    m16::zero_frag(acc_ih);
+    m16::zero_frag(acc_ha);
+    m16::zero_frag(acc_hb);
+    m16::zero_frag(acc_v);
+    float acc_scale = 1.0f;
+    int it = 0;
 
     for (int r = p.R - 1; r >= 0; --r) {
         const float* hf_prev = r > 0 ? p.hf_all + (size_t)(r - 1) * p.N * D : nullptr;
@@ -408,118 +492,209 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_bwd_kernel(const SweepDev p)
         for (int lvl = p.L - 1; lvl >= 0; --lvl) {
             // ------------------------------------------------ full backward tiles of my code
             if (code >= 0 && lvl >= 1) {
-                const int sb = p.seg_ptr[lvl * MGV_NCODE + code], se = p.seg_ptr[lvl * MGV_NCODE + code + 1];
-                for (int t0 = sb + rank * BTM; t0 < se; t0 += nct * BTM) {
-                    const int rows = min(BTM, se - t0);
-                    // ---- phase P/A: pull d(hs,hf), recompute gather/attention
-                    for (int row = warp; row < BTM; row += WARPS) {
-                        float4 xb = make_float4(0.f, 0.f, 0.f, 0.f), h4 = xb, g4 = xb;
+                const int sbeg = p.seg_ptr[lvl * MGV_NCODE + code], send = p.seg_ptr[lvl * MGV_NCODE + code + 1];
+                for (int t0 = sbeg + rank * BTM; t0 < send; t0 += nct * BTM, ++it) {
+                    const int rows = min(BTM, send - t0);
+                    // ---- phase P/A: pull d(hs, hf), recompute gather / attention  (warps 0-7, half-warp per node)
+                    if (warp < 8) {
+                        const int row = warp * 2 + half;
+                        float xb[8], h8[8], g8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { xb[e] = 0.f; h8[e] = 0.f; g8[e] = 0.f; }
                         float S = 0.f;
                         int node = -1;
                         if (row < rows) {
                             node = p.order[t0 + row];
-                            const float4 pl = pull_out_edges(p, node, lane);
-                            if (lane < 16) {
-                                float* gp = p.ghs + (size_t)node * D + 4 * lane;
-                                float4 cur = mgv_ld4(gp);
-                                cur.x += pl.x; cur.y += pl.y; cur.z += pl.z; cur.w += pl.w;
-                                mgv_st4(gp, cur);
+                            float pl[8];
+                            pull_out_edges16(p, node, l16, pl);
+                            if (l16 < 8) {
+                                float* gp = p.ghs + (size_t)node * D + 8 * l16;
+                                float4 c0 = mgv_ld4(gp), c1 = mgv_ld4(gp + 4);
+                                c0.x += pl[0]; c0.y += pl[1]; c0.z += pl[2]; c0.w += pl[3];
+                                c1.x += pl[4]; c1.y += pl[5]; c1.z += pl[6]; c1.w += pl[7];
+                                mgv_st4(gp, c0); mgv_st4(gp + 4, c1);
+                                if (hf_prev != nullptr) {
+                                    const float4 a = mgv_ld4(hf_prev + (size_t)node * D + 8 * l16), b2 = mgv_ld4(hf_prev + (size_t)node * D + 8 * l16 + 4);
+                                    h8[0] = a.x; h8[1] = a.y; h8[2] = a.z; h8[3] = a.w; h8[4] = b2.x; h8[5] = b2.y; h8[6] = b2.z; h8[7] = b2.w;
+                                }
                             } else {
-                                const float4 base = mgv_ld4(p.ghf + (size_t)node * D + 4 * (lane - 16));
-                                g4 = make_float4(base.x + pl.x, base.y + pl.y, base.z + pl.z, base.w + pl.w);
+                                const float* gq = p.ghf + (size_t)node * D + 8 * (l16 - 8);
+                                const float4 c0 = mgv_ld4(gq), c1 = mgv_ld4(gq + 4);
+                                g8[0] = c0.x + pl[0]; g8[1] = c0.y + pl[1]; g8[2] = c0.z + pl[2]; g8[3] = c0.w + pl[3];
+                                g8[4] = c1.x + pl[4]; g8[5] = c1.y + pl[5]; g8[6] = c1.z + pl[6]; g8[7] = c1.w + pl[7];
                             }
-                            gather_attend<true>(p, hf_cur, W, node, lane, xb, S);
-                            if (hf_prev != nullptr && lane < 16) h4 = mgv_ld4(hf_prev + (size_t)node * D + 4 * lane);
+                            gather_attend16<true>(p, hf_cur, u8, node, l16, hmask, xb, S);
                         }
-                        mgv_st4(Xs + row * LDX + 4 * lane, xb);
-                        if (lane < 16) mgv_st4(Hs + row * LDM + 4 * lane, h4);
-                        else mgv_st4(Gs + row * LDM + 4 * (lane - 16), g4);
-                        if (lane == 0) { Ss[row] = S; Ids[row] = node; }
+                        st_plane8(bsm + BW_XS_HI, bsm + BW_XS_LO, (uint32_t)(row * LDXH + 8 * l16), xb);
+                        mgv_st4(X32 + row * LDX + 8 * l16, make_float4(xb[0], xb[1], xb[2], xb[3]));
+                        mgv_st4(X32 + row * LDX + 8 * l16 + 4, make_float4(xb[4], xb[5], xb[6], xb[7]));
+                        if (l16 < 8) {
+                            st_plane8(bsm + BW_HS_HI, bsm + BW_HS_LO, (uint32_t)(row * LDMH + 8 * l16), h8);
+                            mgv_st4(H32 + row * LDF32 + 8 * l16, make_float4(h8[0], h8[1], h8[2], h8[3]));
+                            mgv_st4(H32 + row * LDF32 + 8 * l16 + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
+                        } else {
+                            mgv_st4(Gs + row * LDF32 + 8 * (l16 - 8), make_float4(g8[0], g8[1], g8[2], g8[3]));
+                            mgv_st4(Gs + row * LDF32 + 8 * (l16 - 8) + 4, make_float4(g8[4], g8[5], g8[6], g8[7]));
+                        }
+                        if (l16 == 0) { Ss[row] = S; Ids[row] = node; }
                     }
                     __syncthreads();
-                    // ---- phase B: m
-                    {
-                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                        mgv_gemm_col<4, D2>(Xs + rg * 4 * LDX, LDX, W + O_WVT, D, col, acc);
-                        const float bv = __ldg(W + O_BV + col);
+                    // ---- phase B: m = xbar Wv^T + bv S  (warps 0-7: 8 columns each)
+                    if (warp < 8) {
+                        float c[1][1][4];
+                        m16::zero_frag(c);
+                        m16::warp_gemm<1, 1, D2 / 16, false, false>(c, sb + BW_XS_HI, sb + BW_XS_LO, LDXH, 0, 0, sb + BW_WV_HI, sb + BW_WV_LO, LDXH,
+                                                                    wn0, 0, lane);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) Ms[(rg * 4 + i) * LDM + col] = fmaf(bv, Ss[rg * 4 + i], acc[i]);
-                    }
-                    __syncthreads();
-                    // ---- phase C: GRU recompute + elementwise backward
-                    float dh_direct[4];
-                    {
-                        float ar[4], az[4], an[4], hr[4], hz[4], hn[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { ar[i] = az[i] = an[i] = 0.f; hr[i] = hz[i] = hn[i] = 0.f; }
-                        mgv_gemm_col3<4, D>(Ms + rg * 4 * LDM, LDM, W + O_WIHT, col, ar, az, an);
-                        if (hf_prev != nullptr) mgv_gemm_col3<4, D>(Hs + rg * 4 * LDM, LDM, W + O_WHHT, col, hr, hz, hn);
-                        const float bir = __ldg(W + O_BIH + col), biz = __ldg(W + O_BIH + D + col), bin = __ldg(W + O_BIH + 2 * D + col);
-                        const float bhr = __ldg(W + O_BHH + col), bhz = __ldg(W + O_BHH + D + col), bhn = __ldg(W + O_BHH + 2 * D + col);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int row = rg * 4 + i;
-                            const float g = Gs[row * LDM + col];
-                            const float hp = Hs[row * LDM + col];
-                            const float rr = mgv_sigmoid(ar[i] + bir + hr[i] + bhr);
-                            const float zz = mgv_sigmoid(az[i] + biz + hz[i] + bhz);
-                            const float hnb = hn[i] + bhn;
-                            const float nn = tanhf(an[i] + bin + rr * hnb);
-                            const float dn = g * (1.0f - zz);
-                            const float dz = g * (hp - nn);
-                            const float dnpre = dn * (1.0f - nn * nn);
-                            const float drpre = dnpre * hnb * rr * (1.0f - rr);
-                            const float dzpre = dz * zz * (1.0f - zz);
-                            dh_direct[i] = g * zz;
-                            DGI[row * LDG + col] = drpre;
-                            DGI[row * LDG + D + col] = dzpre;
-                            DGI[row * LDG + 2 * D + col] = dnpre;
-                            DGH[row * LDG + col] = drpre;
-                            DGH[row * LDG + D + col] = dzpre;
-                            DGH[row * LDG + 2 * D + col] = dnpre * rr;
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            const int row = g + 8 * hrow, col = wn8 + 2 * t;
+                            const float sv = Ss[row];
+                            uint32_t hi, lo;
+                            m16::split2(fmaf(Bv[col], sv, c[0][0][2 * hrow]), fmaf(Bv[col + 1], sv, c[0][0][2 * hrow + 1]), hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + BW_MS_HI + (row * LDMH + col) * 2) = hi;
+                            *reinterpret_cast<uint32_t*>(bsm + BW_MS_LO + (row * LDMH + col) * 2) = lo;
                         }
                     }
                     __syncthreads();
-                    // ---- phase D: d m = d gi . Wih ;  d h = g z + d gh . Whh
-                    {
-                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                        mgv_gemm_col<4, G3>(DGI + rg * 4 * LDG, LDG, W + O_WIH, D, col, acc);
+                    // ---- phase C: GRU recompute + pointwise backward  (warps 0-7: 8 units each)
+                    float dr[4], dz[4], dni[4], dnh[4];
+                    if (warp < 8) {
+                        const int n0[3] = {wn8, D + wn8, 2 * D + wn8};
+                        float ci[1][3][4], ch[1][3][4];
+                        m16::zero_frag(ci);
+                        m16::zero_frag(ch);
+                        m16::warp_gemm<1, 3, D / 16, false, false>(ci, sb + BW_MS_HI, sb + BW_MS_LO, LDMH, 0, 0, sb + BW_WIH_HI, sb + BW_WIH_LO, LDMH,
+                                                                   n0, 0, lane);
+                        if (hf_prev != nullptr)
+                            m16::warp_gemm<1, 3, D / 16, false, false>(ch, sb + BW_HS_HI, sb + BW_HS_LO, LDMH, 0, 0, sb + BW_WHH_HI, sb + BW_WHH_LO,
+                                                                       LDMH, n0, 0, lane);
+                        float amax = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) DMs[(rg * 4 + i) * LDM + col] = acc[i];
-                        if (hf_prev != nullptr) {
-                            float acch[4] = {0.f, 0.f, 0.f, 0.f};
-                            mgv_gemm_col<4, G3>(DGH + rg * 4 * LDG, LDG, W + O_WHH, D, col, acch);
+                        for (int e = 0; e < 4; ++e) {
+                            const int row = g + ((e & 2) ? 8 : 0), uu = wn8 + 2 * t + (e & 1);
+                            const float hnb = ch[0][2][e] + Bhh[2 * D + uu];
+                            float rr, zz, nn;
+                            gru_gates(ci[0][0][e] + Bih[uu] + ch[0][0][e] + Bhh[uu], ci[0][1][e] + Bih[D + uu] + ch[0][1][e] + Bhh[D + uu],
+                                      ci[0][2][e] + Bih[2 * D + uu], hnb, rr, zz, nn);
+                            const float gg = Gs[row * LDF32 + uu];
+                            const float hp = H32[row * LDF32 + uu];
+                            dni[e] = gg * (1.0f - zz) * (1.0f - nn * nn);
+                            dr[e] = dni[e] * hnb * rr * (1.0f - rr);
+                            dz[e] = gg * (hp - nn) * zz * (1.0f - zz);
+                            dnh[e] = dni[e] * rr;
+                            Gs[row * LDF32 + uu] = gg * zz;                                  // direct path to h
+                            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dr[e]), fabsf(dz[e])), fabsf(dni[e])));
+                        }
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int node = Ids[rg * 4 + i];
-                                if (node >= 0) p.ghf[(size_t)node * D + col] = dh_direct[i] + acch[i];
+                        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                        if (lane == 0) atomicMax(smax + (it & 1), __float_as_uint(amax));
+                        // bias gradients: column sums over the 16 rows (lanes with equal t), then one atomic per column
+                        float sums[8] = {dr[0] + dr[2], dr[1] + dr[3], dz[0] + dz[2], dz[1] + dz[3],
+                                         dni[0] + dni[2], dni[1] + dni[3], dnh[0] + dnh[2], dnh[1] + dnh[3]};
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            sums[k] += __shfl_xor_sync(0xffffffffu, sums[k], 4);
+                            sums[k] += __shfl_xor_sync(0xffffffffu, sums[k], 8);
+                            sums[k] += __shfl_xor_sync(0xffffffffu, sums[k], 16);
+                        }
+                        if (g == 0) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const int uu = wn8 + 2 * t + k;
+                                atomicAdd(Abih + uu, sums[k]); atomicAdd(Abih + D + uu, sums[2 + k]); atomicAdd(Abih + 2 * D + uu, sums[4 + k]);
+                                atomicAdd(Abhh + uu, sums[k]); atomicAdd(Abhh + D + uu, sums[2 + k]); atomicAdd(Abhh + 2 * D + uu, sums[6 + k]);
                             }
                         }
                     }
+                    if (tid == 0) smax[(it + 1) & 1] = 0u;
                     __syncthreads();
-                    // ---- phase E: d xbar = d m . Wv   (128 columns x 2 row groups of 8)
-                    {
-                        const int k = tid & 127, rg2 = tid >> 7;
-                        float acc[8];
+                    const float scale = m16::pow2_scale_band(__uint_as_float(smax[it & 1]), acc_scale, 1.0f, 512.0f);
+                    const float inv_scale = 1.0f / scale;
+                    if (warp < 8) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                        mgv_gemm_col<8, D>(DMs + rg2 * 8 * LDM, LDM, W + O_WV, D2, k, acc);
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            const int row = g + 8 * hrow, e0 = 2 * hrow;
+                            const uint32_t off = (uint32_t)(row * LDGH + wn8 + 2 * t) * 2;
+                            uint32_t hi, lo;
+                            m16::split2(dr[e0] * scale, dr[e0 + 1] * scale, hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + BW_DG_HI + off) = hi; *reinterpret_cast<uint32_t*>(bsm + BW_DG_LO + off) = lo;
+                            m16::split2(dz[e0] * scale, dz[e0 + 1] * scale, hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + BW_DG_HI + off + 2 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + BW_DG_LO + off + 2 * D) = lo;
+                            m16::split2(dni[e0] * scale, dni[e0 + 1] * scale, hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + BW_DG_HI + off + 4 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + BW_DG_LO + off + 4 * D) = lo;
+                            m16::split2(dnh[e0] * scale, dnh[e0 + 1] * scale, hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + BW_DG_HI + off + 6 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + BW_DG_LO + off + 6 * D) = lo;
+                        }
+                    }
+                    __syncthreads();
+                    // ---- phase D: d m = d gi . Wih (warps 0-7);  d h = g z + d gh . Whh (warps 8-15)
+                    if (warp < 8) {
+                        float c[1][1][4];
+                        m16::zero_frag(c);
+                        m16::warp_gemm<1, 1, G3 / 16, false, true>(c, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, 0, 0, sb + BW_WIH_HI, sb + BW_WIH_LO, LDMH,
+                                                                   wn0, 0, lane);
+                        float sbv[2] = {0.f, 0.f};
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int row = rg2 * 8 + i;
-                            DXs[row * LDX + k] = acc[i];
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            const int row = g + 8 * hrow, col = wn8 + 2 * t;
+                            uint32_t hi, lo;
+                            m16::split2(c[0][0][2 * hrow], c[0][0][2 * hrow + 1], hi, lo);              // stays scaled
+                            *reinterpret_cast<uint32_t*>(bsm + BW_DM_HI + (row * LDMH + col) * 2) = hi;
+                            *reinterpret_cast<uint32_t*>(bsm + BW_DM_LO + (row * LDMH + col) * 2) = lo;
+                            const float d0 = c[0][0][2 * hrow] * inv_scale, d1 = c[0][0][2 * hrow + 1] * inv_scale;
+                            DM32[row * LDF32 + col] = d0;
+                            DM32[row * LDF32 + col + 1] = d1;
+                            sbv[0] = fmaf(d0, Ss[row], sbv[0]);
+                            sbv[1] = fmaf(d1, Ss[row], sbv[1]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            sbv[k] += __shfl_xor_sync(0xffffffffu, sbv[k], 4);
+                            sbv[k] += __shfl_xor_sync(0xffffffffu, sbv[k], 8);
+                            sbv[k] += __shfl_xor_sync(0xffffffffu, sbv[k], 16);
+                        }
+                        if (g == 0) { atomicAdd(Abv + wn8 + 2 * t, sbv[0]); atomicAdd(Abv + wn8 + 2 * t + 1, sbv[1]); }
+                    } else if (hf_prev != nullptr) {
+                        float c[1][1][4];
+                        m16::zero_frag(c);
+                        m16::warp_gemm<1, 1, 2 * D / 16, false, true>(c, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, 0, 0, sb + BW_WHH_HI, sb + BW_WHH_LO, LDMH,
+                                                                      wn0, 0, lane);
+                        m16::warp_gemm<1, 1, D / 16, false, true>(c, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, 0, 3 * D, sb + BW_WHH_HI, sb + BW_WHH_LO, LDMH,
+                                                                  wn0, 2 * D, lane);
+#pragma unroll
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            const int row = g + 8 * hrow, col = wn8 + 2 * t;
                             const int node = Ids[row];
-                            if (node >= 0) p.dxb[(size_t)node * D2 + k] = acc[i];
+                            if (node >= 0)
+                                *reinterpret_cast<float2*>(p.ghf + (size_t)node * D + col) =
+                                    make_float2(fmaf(c[0][0][2 * hrow], inv_scale, Gs[row * LDF32 + col]),
+                                                fmaf(c[0][0][2 * hrow + 1], inv_scale, Gs[row * LDF32 + col + 1]));
+                        }
+                    }
+                    __syncthreads();
+                    // ---- phase E: d xbar = d m . Wv   (16 warps x 8 of the 128 columns)
+                    {
+                        float c[1][1][4];
+                        m16::zero_frag(c);
+                        m16::warp_gemm<1, 1, D / 16, false, true>(c, sb + BW_DM_HI, sb + BW_DM_LO, LDMH, 0, 0, sb + BW_WV_HI, sb + BW_WV_LO, LDXH,
+                                                                  vn0, 0, lane);
+#pragma unroll
+                        for (int hrow = 0; hrow < 2; ++hrow) {
+                            const int row = g + 8 * hrow, col = 8 * warp + 2 * t;
+                            const float2 v = make_float2(c[0][0][2 * hrow] * inv_scale, c[0][0][2 * hrow + 1] * inv_scale);
+                            *reinterpret_cast<float2*>(DX32 + row * LDX + col) = v;
+                            const int node = Ids[row];
+                            if (node >= 0) *reinterpret_cast<float2*>(p.dxb + (size_t)node * D2 + col) = v;
                         }
                     }
                     __syncthreads();
                     // ---- phase F: attention backward per node (one warp per node)
-                    for (int row = warp; row < rows; row += WARPS) {
+                    if (warp < rows) {
+                        const int row = warp;
                         const int node = Ids[row];
-                        const float dS = mgv_warp_sum(__ldg(W + O_BV + lane) * DMs[row * LDM + lane] +
-                                                      __ldg(W + O_BV + 32 + lane) * DMs[row * LDM + 32 + lane]);
-                        const float4 dxb4 = mgv_ld4(DXs + row * LDX + 4 * lane);
-                        const float4 xb4 = mgv_ld4(Xs + row * LDX + 4 * lane);
+                        const float dS = mgv_warp_sum(Bv[lane] * DM32[row * LDF32 + lane] + Bv[32 + lane] * DM32[row * LDF32 + 32 + lane]);
+                        const float4 dxb4 = mgv_ld4(DX32 + row * LDX + 4 * lane);
+                        const float4 xb4 = mgv_ld4(X32 + row * LDX + 4 * lane);
                         const int beg = p.in_ptr[node], end = p.in_ptr[node + 1];
                         const int off = (lane < 16) ? 4 * lane : 4 * (lane - 16);
                         float A = 0.f;
@@ -537,85 +712,37 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_bwd_kernel(const SweepDev p)
                         __syncwarp();
                         for (int q = beg + lane; q < end; q += 32) p.dscore[q] = p.alpha[q] * (p.dscore[q] - A);
                         // d u += sum_j dscore_j x_j = v - A xbar
-                        atomicAdd(ACC + G_U + 4 * lane + 0, v4.x - A * xb4.x);
-                        atomicAdd(ACC + G_U + 4 * lane + 1, v4.y - A * xb4.y);
-                        atomicAdd(ACC + G_U + 4 * lane + 2, v4.z - A * xb4.z);
-                        atomicAdd(ACC + G_U + 4 * lane + 3, v4.w - A * xb4.w);
+                        atomicAdd(Au + 4 * lane + 0, v4.x - A * xb4.x);
+                        atomicAdd(Au + 4 * lane + 1, v4.y - A * xb4.y);
+                        atomicAdd(Au + 4 * lane + 2, v4.z - A * xb4.z);
+                        atomicAdd(Au + 4 * lane + 3, v4.w - A * xb4.w);
                     }
-                    // ---- phase G: weight-gradient accumulation (reads tile buffers only)
-                    {
-                        // dWih[o][c] += sum_row dgi[row][o] m[row][c]   (o in [48 og, 48 og + 48), c = col)
-                        const int og = rg * 48;
-                        float acc[48];
-#pragma unroll
-                        for (int i = 0; i < 48; ++i) acc[i] = 0.f;
-                        for (int row = 0; row < BTM; ++row) {
-                            const float mv = Ms[row * LDM + col];
-#pragma unroll
-                            for (int i = 0; i < 48; i += 4) {
-                                const float4 d4 = mgv_ld4(DGI + row * LDG + og + i);
-                                acc[i] = fmaf(d4.x, mv, acc[i]); acc[i + 1] = fmaf(d4.y, mv, acc[i + 1]);
-                                acc[i + 2] = fmaf(d4.z, mv, acc[i + 2]); acc[i + 3] = fmaf(d4.w, mv, acc[i + 3]);
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 48; ++i) ACC[G_WIH + (og + i) * D + col] += acc[i];
-                        if (hf_prev != nullptr) {
-#pragma unroll
-                            for (int i = 0; i < 48; ++i) acc[i] = 0.f;
-                            for (int row = 0; row < BTM; ++row) {
-                                const float hv = Hs[row * LDM + col];
-#pragma unroll
-                                for (int i = 0; i < 48; i += 4) {
-                                    const float4 d4 = mgv_ld4(DGH + row * LDG + og + i);
-                                    acc[i] = fmaf(d4.x, hv, acc[i]); acc[i + 1] = fmaf(d4.y, hv, acc[i + 1]);
-                                    acc[i + 2] = fmaf(d4.z, hv, acc[i + 2]); acc[i + 3] = fmaf(d4.w, hv, acc[i + 3]);
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 48; ++i) ACC[G_WHH + (og + i) * D + col] += acc[i];
-                        }
+                    // ---- phase G: weight gradients (tile buffers are read-only here)
+                    if (scale != acc_scale) {
+                        const float f = scale / acc_scale;
+                        m16::scale_frag(acc_ih, f);
+                        m16::scale_frag(acc_ha, f);
+                        m16::scale_frag(acc_hb, f);
+                        m16::scale_frag(acc_v, f);
+                        acc_scale = scale;
                     }
-                    {
-                        // dWv[c][k] += sum_row dm[row][c] xbar[row][k]   (c in [32 cg, 32 cg + 32), k = tid & 127)
-                        const int k = tid & 127, cg = (tid >> 7) * 32;
-                        float acc[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-                        for (int row = 0; row < BTM; ++row) {
-                            const float xv = Xs[row * LDX + k];
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const float4 d4 = mgv_ld4(DMs + row * LDM + cg + i);
-                                acc[i] = fmaf(d4.x, xv, acc[i]); acc[i + 1] = fmaf(d4.y, xv, acc[i + 1]);
-                                acc[i + 2] = fmaf(d4.z, xv, acc[i + 2]); acc[i + 3] = fmaf(d4.w, xv, acc[i + 3]);
-                            }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) ACC[G_WV + (cg + i) * D2 + k] += acc[i];
+                    m16::warp_gemm<6, 1, 1, true, true>(acc_ih, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, wh * 96, 0, sb + BW_MS_HI, sb + BW_MS_LO, LDMH, wn0, 0, lane);
+                    if (hf_prev != nullptr) {
+                        m16::warp_gemm<2, 1, 1, true, true>(acc_ha, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, wh * 96, 0, sb + BW_HS_HI, sb + BW_HS_LO, LDMH, wn0, 0, lane);
+                        m16::warp_gemm<4, 1, 1, true, true>(acc_hb, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, wh ? 3 * D : 32, 0, sb + BW_HS_HI, sb + BW_HS_LO, LDMH, wn0, 0, lane);
                     }
-                    if (tid < G3) {
-                        float sgi = 0.f, sgh = 0.f;
-                        for (int row = 0; row < BTM; ++row) { sgi += DGI[row * LDG + tid]; sgh += DGH[row * LDG + tid]; }
-                        ACC[G_BIH + tid] += sgi;
-                        ACC[G_BHH + tid] += sgh;
-                    } else {
-                        const int c = tid - G3;          // 64 threads: d bv
-                        float s = 0.f;
-                        for (int row = 0; row < BTM; ++row) s = fmaf(DMs[row * LDM + c], Ss[row], s);
-                        ACC[G_BV + c] += s;
-                    }
+                    m16::warp_gemm<4, 1, 1, true, true>(acc_v, sb + BW_DM_HI, sb + BW_DM_LO, LDMH, 0, 0, sb + BW_XS_HI, sb + BW_XS_LO, LDXH, vn0, 0, lane);
                     __syncthreads();
                 }
             }
             // ------------------------------------------------ pull-only nodes (level 0 / codes without a module)
             {
-                const int gw = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+                const int gw = blockIdx.x * (BTHREADS / 32) + warp, nw = gridDim.x * (BTHREADS / 32);
                 for (int c = 0; c < MGV_NCODE; ++c) {
                     if (lvl >= 1 && ((p.handled >> c) & 1u)) continue;
-                    const int sb = p.seg_ptr[lvl * MGV_NCODE + c], se = p.seg_ptr[lvl * MGV_NCODE + c + 1];
-                    for (int t = sb + gw; t < se; t += nw) {
-                        const int node = p.order[t];
+                    const int sbeg = p.seg_ptr[lvl * MGV_NCODE + c], send = p.seg_ptr[lvl * MGV_NCODE + c + 1];
+                    for (int tt = sbeg + gw; tt < send; tt += nw) {
+                        const int node = p.order[tt];
                         const float4 pl = pull_out_edges(p, node, lane);
                         if (lane < 16) {
                             float* gp = p.ghs + (size_t)node * D + 4 * lane;
@@ -630,14 +757,38 @@ __global__ void __launch_bounds__(THREADS, 1) sweep_bwd_kernel(const SweepDev p)
         }
     }
     // ---------------------------------------------------- flush accumulators, reduce over the CTAs of a code
-    for (int i = tid; i < GRAD; i += THREADS) p.partial[(size_t)blockIdx.x * GRAD + i] = ACC[i];
+    {
+        float* part = p.partial + (size_t)blockIdx.x * GRAD;
+        for (int i = tid; i < GRAD; i += BTHREADS) part[i] = 0.f;
+        __syncthreads();
+        const float un = 1.0f / acc_scale;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int o = wh * 96 + 16 * m + g + ((e & 2) ? 8 : 0), c = wn8 + 2 * t + (e & 1);
+                part[G_WIH + o * D + c] = acc_ih[m][0][e] * un;
+                part[G_WHH + o * D + c] = (m < 2 ? acc_ha[m][0][e] : acc_hb[m - 2][0][e]) * un;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int o = 16 * m + g + ((e & 2) ? 8 : 0), k = 8 * warp + 2 * t + (e & 1);
+                part[G_WV + o * D2 + k] = acc_v[m][0][e] * un;
+            }
+        }
+        for (int i = tid; i < 576; i += BTHREADS)
+            part[i < 128 ? G_U + i : (i < 192 ? G_BV + i - 128 : (i < 384 ? G_BIH + i - 192 : G_BHH + i - 384))] = ACC[i];
+    }
     mgv_grid_sync(p.bar, gridDim.x);
     const size_t total = (size_t)MGV_NCODE * GRAD;
-    for (size_t idx = (size_t)blockIdx.x * THREADS + tid; idx < total; idx += (size_t)gridDim.x * THREADS) {
+    for (size_t idx = (size_t)blockIdx.x * BTHREADS + tid; idx < total; idx += (size_t)gridDim.x * BTHREADS) {
         const int c = (int)(idx / GRAD), e = (int)(idx % GRAD);
-        float s = 0.f;
-        for (int b = p.cta_start[c]; b < p.cta_start[c + 1]; ++b) s += p.partial[(size_t)b * GRAD + e];
-        p.grads[idx] = s;
+        float sacc = 0.f;
+        for (int bb = p.cta_start[c]; bb < p.cta_start[c + 1]; ++bb) sacc += p.partial[(size_t)bb * GRAD + e];
+        p.grads[idx] = sacc;
     }
 }
 
@@ -731,7 +882,7 @@ extern "C" int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint
 
 extern "C" int mgv_sweep_bwd_grid(void) {
     int grid = 0;
-    if (coop_grid((const void*)sweep_bwd_kernel, (size_t)B_SMEM_FLOATS * sizeof(float), THREADS, &grid) != MGV_OK) return -1;
+    if (coop_grid((const void*)sweep_bwd_kernel, (size_t)B_SMEM_BYTES, BTHREADS, &grid) != MGV_OK) return -1;
     return grid;
 }
 
@@ -757,8 +908,8 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     MGV_CUDA(cudaMemsetAsync(grads, 0, (size_t)MGV_NCODE * GRAD * sizeof(float), st));
     if (sch->N == 0 || sch->L <= 1) return MGV_OK;
     int grid = 0;
-    const size_t smem = (size_t)B_SMEM_FLOATS * sizeof(float);
-    rc = coop_grid((const void*)sweep_bwd_kernel, smem, THREADS, &grid);
+    const size_t smem = (size_t)B_SMEM_BYTES;
+    rc = coop_grid((const void*)sweep_bwd_kernel, smem, BTHREADS, &grid);
     if (rc != MGV_OK) return rc;
     assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
     if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;
@@ -775,7 +926,7 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     d.ghs = ghs; d.ghf = ghf; d.grads = grads;
     MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
     void* args[] = {&d};
-    MGV_CUDA(cudaLaunchCooperativeKernel((void*)sweep_bwd_kernel, dim3(grid), dim3(THREADS), args, smem, st));
+    MGV_CUDA(cudaLaunchCooperativeKernel((void*)sweep_bwd_kernel, dim3(grid), dim3(BTHREADS), args, smem, st));
     mgv_count_launches(1);
     return MGV_OK;
 }
