@@ -207,6 +207,24 @@ int mgv_vae_func_loss_bwd(const float* g_out, const float* gz, const float* mu, 
                           const float* hf, const int64_t* pair, const float* tt_sim, int64_t P,
                           const float* out, const void* ws, float* ghf, mgv_stream_t stream);
 
+/* ------------------------------------------------------------------ parameter packing (host pointer tables -> weight blocks)
+ * `params` are HOST arrays of DEVICE pointers to the reference modules' fp32 parameters (contiguous, natural shapes).
+ * struct encoder, per encoder: [aggr.msg.weight, aggr.msg.bias, update.weight_ih_l0, update.weight_hh_l0, update.bias_ih_l0,
+ *   update.bias_hh_l0, the same six of aggr_r / update_r, (ln.weight, ln.bias if layernorm)]  ->  pack [num_enc][2][MGV_STRUCT_PACK_FLOATS].
+ * mgv_struct_unpack_grads applies the chain rule of the composition (Wc = W_ih[:, :64] W_msg, bc = W_ih[:, :64] b_msg) to the gradient
+ * blocks and writes, per encoder, d(those parameters) back to back in the same order and natural shapes.
+ * level sweep, per listed gate code: [attn_lin.weight, msg_k.weight, msg_v.weight, msg_v.bias, weight_ih_l0, weight_hh_l0,
+ *   bias_ih_l0, bias_hh_l0]  ->  pack [MGV_NCODE][MGV_SWEEP_PACK_FLOATS] (blocks of unlisted codes untouched).
+ * mgv_sweep_unpack_grads writes per listed code d attn_lin.weight [128] then d msg_k.weight [64][128]; the other gradients are
+ * read in place from the gradient block (natural layouts).
+ */
+int mgv_struct_pack(const void* const* params, int32_t num_enc, int32_t layernorm, int32_t feat, float* pack, mgv_stream_t stream);
+int mgv_struct_unpack_grads(const void* const* params, int32_t num_enc, int32_t layernorm, int32_t feat,
+                            const float* grads, float* out, mgv_stream_t stream);
+int mgv_sweep_pack(const void* const* params, const int32_t* codes, int32_t n, float* pack, mgv_stream_t stream);
+int mgv_sweep_unpack_grads(const void* const* params, const int32_t* codes, int32_t n, const float* grads, float* out,
+                           mgv_stream_t stream);
+
 /* ------------------------------------------------------------------ reconstruction loss + negative sampler
  * Replaces Model.recon_loss (dg_ae_model_mig.py:169-191) around the directed inner-product decoder
  * (digae_layer.py:26-33): st = hs_decompose(hs) = [s | t] float [N][128]; value(u -> v) = sigmoid(s_u . t_v);

@@ -7,6 +7,8 @@
 Every function fails loudly when its inputs are not on a CUDA device or the library is
 missing; nothing here falls back to PyTorch ops for the arithmetic.
 """
+import ctypes
+
 import torch
 
 from . import _native as nat
@@ -49,18 +51,33 @@ def _f32(t, name):
 
 
 # =========================================================================== level sweep
-def _sweep_pack(params, codes, device):
-    """[8][66112] weight blocks in the kernel layout (include/mgv_b200.h)."""
+def _ptr_table(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _code_table(codes):
+    return (ctypes.c_int32 * len(codes))(*codes)
+
+
+def _sweep_tables(params, codes):
+    """Pointer table of the parameters mgv_sweep_pack / mgv_sweep_unpack_grads read, per listed gate code."""
     D = nat.D
-    pack = torch.zeros(nat.NCODE, nat.SWEEP_PACK_FLOATS, dtype=torch.float32, device=device)
-    for i, c in enumerate(codes):
-        aw, ab, qw, qb, kw, kb, vw, vb, wih, whh, bih, bhh = [p.detach() for p in
-                                                              params[i * PARAMS_PER_CODE:(i + 1) * PARAMS_PER_CODE]]
+    sel = []
+    for i in range(len(codes)):
+        aw, ab, qw, qb, kw, kb, vw, vb, wih, whh, bih, bhh = params[i * PARAMS_PER_CODE:(i + 1) * PARAMS_PER_CODE]
         if tuple(vw.shape) != (D, 2 * D) or tuple(wih.shape) != (3 * D, D):
             raise RuntimeError("mgv_b200: level sweep kernels are built for dim_hidden=%d" % D)
-        u = aw[0, D:] @ kw                                   # [128] = W_k^T w_a[64:]
-        pack[c] = torch.cat([u, vw.t().reshape(-1), vb, wih.t().reshape(-1), whh.t().reshape(-1), bih, bhh,
-                             vw.reshape(-1), wih.reshape(-1), whh.reshape(-1)])
+        sel += [_f32(t, "sweep parameter") for t in (aw, kw, vw, vb, wih, whh, bih, bhh)]
+    return sel
+
+
+def _sweep_pack(params, codes, device):
+    """[8][66112] weight blocks in the kernel layout (include/mgv_b200.h), one launch."""
+    pack = torch.zeros(nat.NCODE, nat.SWEEP_PACK_FLOATS, dtype=torch.float32, device=device)
+    sel = _sweep_tables(params, codes)
+    with torch.cuda.device(device):
+        nat.check(nat.lib().mgv_sweep_pack(_ptr_table(sel), _code_table(codes), len(codes), nat.ptr(pack),
+                                           nat.stream_of(device)), "mgv_sweep_pack")
     return pack
 
 
@@ -110,16 +127,16 @@ class LevelSweepFunction(torch.autograd.Function):
                                               nat.ptr(hf_all), nat.ptr(ghs), nat.ptr(ghf), nat.ptr(grads),
                                               nat.ptr(ws), nb, nat.ptr(sync), nat.stream_of(dev)),
                       "mgv_level_sweep_bwd")
+        sel = _sweep_tables(params, codes)
+        extra = torch.empty(max(len(codes), 1), 128 + D * 2 * D, dtype=torch.float32, device=dev)
+        zero = torch.zeros(D * 2 * D, dtype=torch.float32, device=dev)     # query / key-bias / attn-bias cancel in the softmax
+        with torch.cuda.device(dev):
+            nat.check(lib.mgv_sweep_unpack_grads(_ptr_table(sel), _code_table(list(codes)), len(codes), nat.ptr(grads),
+                                                 nat.ptr(extra), nat.stream_of(dev)), "mgv_sweep_unpack_grads")
         out = []
         for i, c in enumerate(codes):
-            aw, ab, qw, qb, kw, kb, vw, vb, wih, whh, bih, bhh = params[i * PARAMS_PER_CODE:(i + 1) * PARAMS_PER_CODE]
             g = grads[c]
-            du = g[0:128]
-            d_aw = torch.zeros_like(aw)
-            d_aw[0, D:] = kw.detach() @ du                    # u = W_k^T w_a[64:]
-            d_kw = torch.outer(aw.detach()[0, D:], du)
-            out += [d_aw, torch.zeros_like(ab), torch.zeros_like(qw), torch.zeros_like(qb), d_kw,
-                    torch.zeros_like(kb),                     # query / key-bias / attn-bias cancel in the softmax
+            out += [extra[i, :128].view(1, 2 * D), zero[:1], zero.view(D, 2 * D), zero[:D], extra[i, 128:].view(D, 2 * D), zero[:D],
                     g[128:8320].view(D, 2 * D), g[8320:8384],
                     g[8384:20672].view(3 * D, D), g[20672:32960].view(3 * D, D), g[32960:33152], g[33152:33344]]
         return (ghs[:N], None, None, None) + tuple(out)
@@ -142,32 +159,24 @@ _LDC, _LDM = 76, 68
 
 
 def _struct_pack(enc_params, layernorm, device):
-    """[num_enc][2][28416] weight blocks (include/mgv_b200.h).  enc_params[e] = (aggr.w, aggr.b, upd.wih, upd.whh,
+    """[num_enc][2][28416] weight blocks (include/mgv_b200.h), one launch.  enc_params[e] = (aggr.w, aggr.b, upd.wih, upd.whh,
     upd.bih, upd.bhh, aggr_r.w, aggr_r.b, upd_r.wih, upd_r.whh, upd_r.bih, upd_r.bhh[, ln.w, ln.b]).
     The AggConv linear is pre-composed into the GRU input weights: Wc = wih[:, :64] @ w, bc = wih[:, :64] @ b."""
     D = nat.D
-    pack = torch.zeros(len(enc_params), 2, nat.STRUCT_PACK_FLOATS, dtype=torch.float32, device=device)
-    for e, ps in enumerate(enc_params):
-        ps = [p.detach() for p in ps]
+    flat = []
+    feat = None
+    for ps in enc_params:
         for d in range(2):
-            w, b, wih, whh, bih, bhh = ps[6 * d:6 * d + 6]
-            feat = wih.shape[1] - D
-            if tuple(w.shape) != (D, D) or feat < 0 or feat > nat.MAX_FEAT:
-                raise RuntimeError("mgv_b200: struct encoder kernels need dim_hidden=%d, dim_feature<=%d"
-                                   % (D, nat.MAX_FEAT))
-            blk = pack[e, d]
-            wcx = blk[_S_WCX:_S_WHH].view(3 * D, _LDC)
-            wcx[:, :D] = wih[:, :D] @ w
-            wcx[:, D:D + feat] = wih[:, D:]
-            blk[_S_WHH:_S_BC].view(3 * D, _LDM)[:, :D] = whh
-            blk[_S_BC:_S_BIH] = wih[:, :D] @ b
-            blk[_S_BIH:_S_BHH] = bih
-            blk[_S_BHH:_S_LNW] = bhh
-            if layernorm:
-                blk[_S_LNW:_S_LNB] = ps[12]
-                blk[_S_LNB:_S_LNB + D] = ps[13]
-            else:
-                blk[_S_LNW:_S_LNB] = 1.0
+            w, wih = ps[6 * d], ps[6 * d + 2]
+            f = wih.shape[1] - D
+            if tuple(w.shape) != (D, D) or f < 0 or f > nat.MAX_FEAT or (feat is not None and f != feat):
+                raise RuntimeError("mgv_b200: struct encoder kernels need dim_hidden=%d, dim_feature<=%d" % (D, nat.MAX_FEAT))
+            feat = f
+        flat += [_f32(t, "struct encoder parameter") for t in ps]
+    pack = torch.empty(len(enc_params), 2, nat.STRUCT_PACK_FLOATS, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        nat.check(nat.lib().mgv_struct_pack(_ptr_table(flat), len(enc_params), int(bool(layernorm)), feat, nat.ptr(pack),
+                                            nat.stream_of(device)), "mgv_struct_pack")
     return pack
 
 
@@ -214,23 +223,28 @@ class StructEncoderFunction(torch.autograd.Function):
                                                  nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(g),
                                                  nat.ptr(grads), nat.ptr(ws), nb, nat.stream_of(dev)),
                       "mgv_struct_encoder_bwd")
-        out = []
         params = ctx.saved_params
+        ldw = D + feat
+        per_dir = D * D + D + 3 * D * ldw + 3 * D * D + 6 * D
+        per_enc = 2 * per_dir + (2 * D if ctx.layernorm else 0)
+        flat = [_f32(t, "struct encoder parameter") for t in params]
+        buf = torch.empty(num_enc, per_enc, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nat.check(lib.mgv_struct_unpack_grads(_ptr_table(flat), num_enc, int(bool(ctx.layernorm)), feat, nat.ptr(grads),
+                                                  nat.ptr(buf), nat.stream_of(dev)), "mgv_struct_unpack_grads")
+        out = []
         for e in range(num_enc):
-            ps = params[e * per:(e + 1) * per]
             for d in range(2):
-                w, b, wih = ps[6 * d].detach(), ps[6 * d + 1].detach(), ps[6 * d + 2].detach()
-                gd = grads[e, d]
-                g_wcx = gd[_S_WCX:_S_WHH].view(3 * D, _LDC)
-                g_wc, g_bc = g_wcx[:, :D], gd[_S_BC:_S_BIH]
-                wih_m = wih[:, :D]
-                # Wc = wih_m @ w, bc = wih_m @ b  ->  chain rule back to the reference's parameters
-                g_wih = torch.cat([g_wc @ w.t() + torch.outer(g_bc, b), g_wcx[:, D:D + feat]], dim=1)
-                out += [wih_m.t() @ g_wc, wih_m.t() @ g_bc, g_wih,
-                        gd[_S_WHH:_S_BC].view(3 * D, _LDM)[:, :D], gd[_S_BIH:_S_BHH], gd[_S_BHH:_S_LNW]]
+                o = d * per_dir
+                sizes = ((D, D), (D,), (3 * D, ldw), (3 * D, D), (3 * D,), (3 * D,))
+                for shp in sizes:
+                    n = 1
+                    for v in shp:
+                        n *= v
+                    out.append(buf[e, o:o + n].view(*shp))
+                    o += n
             if ctx.layernorm:
-                out += [grads[e, 0, _S_LNW:_S_LNB] + grads[e, 1, _S_LNW:_S_LNB],
-                        grads[e, 0, _S_LNB:_S_LNB + D] + grads[e, 1, _S_LNB:_S_LNB + D]]
+                out += [buf[e, 2 * per_dir:2 * per_dir + D], buf[e, 2 * per_dir + D:2 * per_dir + 2 * D]]
         return (None, None, None, None, None) + tuple(out)
 
 
