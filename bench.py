@@ -283,7 +283,7 @@ def run_ours(args, w):
     per_launch = {
         "level_sweep_fwd": ("sweep_fwd_kernel", 1, "sweep_fwd_bytes"),
         "level_sweep_bwd": ("sweep_bwd_kernel", 1, "sweep_bwd_bytes"),
-        "struct_encoder_fwd": ("struct_fwd_kernel", 8, "struct_fwd_bytes"),      # 2 * s_rounds step launches per call
+        "struct_encoder_fwd": ("struct_fwd_tc_kernel", 8, "struct_fwd_bytes"),   # 2 * s_rounds step launches per call
         "struct_encoder_bwd": ("struct_bwd_kernel", 8, "struct_bwd_bytes"),
     }
     mean_stats = {k: sum(s[k] for s in stats) / len(stats) for k in stats[0]}
@@ -298,8 +298,18 @@ def run_ours(args, w):
     top = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     roofline = None
     if top:
+        # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this workload (else null)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            ent = tj.get(args.workload, {}).get(top)
+            if ent:
+                traffic = ent["dram_read_bytes"] + ent["dram_write_bytes"]
+        except Exception:
+            pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": None,
+                    "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": traffic,
+                    "algorithmic_bytes_per_launch": mean_stats[per_launch[[k for k, v in per_launch.items() if v[0] == top][0]][2]],
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                     "share_of_step": kernels[top]["ms_per_step"] / (ms / args.steps)}
     sweep_ms = sum(kernels[k]["ms_per_step"] for k in ("sweep_fwd_kernel", "sweep_bwd_kernel") if k in kernels)

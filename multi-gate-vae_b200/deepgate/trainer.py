@@ -41,28 +41,20 @@ class FlatGradAllReduce(object):
         world = torch.distributed.get_world_size()
         if world == 1:
             return
-        total = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        if self.flat is None or self.flat.numel() != total or self.flat.device != dev:
-            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        off = 0
+        # one cat, one all-reduce, one scale, one multi-tensor copy back (instead of two small ops per parameter)
         for p in self.params:
-            n = p.numel()
             if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in self.params]
+        self.flat = torch.cat([g.reshape(-1) for g in grads])
         torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM)
         self.flat.div_(world)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = self.flat[off:off + n].view_as(p).clone()
-            else:
-                p.grad.copy_(self.flat[off:off + n].view_as(p))
+        views, off = [], 0
+        for g in grads:
+            n = g.numel()
+            views.append(self.flat[off:off + n].view_as(g))
             off += n
+        torch._foreach_copy_(grads, views)
 
 
 class Logger(object):
