@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
     m16::zero_frag(acc_hb);
     m16::zero_frag(acc_fb);
     float acc_scale = 1.0f;
+    float lnw_acc[2] = {0.f, 0.f}, lnb_acc[2] = {0.f, 0.f};     // d ln_w / d ln_b of columns lane, lane + 32 (rows of this warp)
     __syncthreads();
 
     int it = 0;
@@ -237,10 +238,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
                 const float rstd = rsqrtf(var + LN_EPS);
                 const float x0 = d0 * rstd, x1 = d1 * rstd;
                 const float gy0 = Gs[row * LDF + lane], gy1 = Gs[row * LDF + 32 + lane];
-                atomicAdd(LNA + lane, gy0 * x0);
-                atomicAdd(LNA + 32 + lane, gy1 * x1);
-                atomicAdd(LNA + D + lane, gy0);
-                atomicAdd(LNA + D + 32 + lane, gy1);
+                lnw_acc[0] = fmaf(gy0, x0, lnw_acc[0]); lnw_acc[1] = fmaf(gy1, x1, lnw_acc[1]);
+                lnb_acc[0] += gy0; lnb_acc[1] += gy1;
                 const float dx0 = gy0 * Ln[lane], dx1 = gy1 * Ln[32 + lane];
                 const float c1 = mgv_warp_sum(dx0 + dx1) * (1.0f / D);
                 const float c2 = mgv_warp_sum(dx0 * x0 + dx1 * x1) * (1.0f / D);
@@ -357,6 +356,10 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             part[O_BHH + oc - D] += acc_fb[0][1][e] * un;                      // n: sum of d gh_n
         }
     }
+    atomicAdd(LNA + lane, lnw_acc[0]);
+    atomicAdd(LNA + 32 + lane, lnw_acc[1]);
+    atomicAdd(LNA + D + lane, lnb_acc[0]);
+    atomicAdd(LNA + D + 32 + lane, lnb_acc[1]);
     __syncthreads();
     if (tid < 2 * D) part[O_LNW + tid] += LNA[tid];
 }

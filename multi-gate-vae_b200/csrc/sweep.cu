@@ -484,6 +484,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
     m16::zero_frag(acc_hb);
     m16::zero_frag(acc_v);
     float acc_scale = 1.0f;
+    float du_acc[4] = {0.f, 0.f, 0.f, 0.f};                    // d u of columns 4 lane .. 4 lane + 3 (nodes of this warp)
     int it = 0;
 
     for (int r = p.R - 1; r >= 0; --r) {
@@ -712,10 +713,8 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         __syncwarp();
                         for (int q = beg + lane; q < end; q += 32) p.dscore[q] = p.alpha[q] * (p.dscore[q] - A);
                         // d u += sum_j dscore_j x_j = v - A xbar
-                        atomicAdd(Au + 4 * lane + 0, v4.x - A * xb4.x);
-                        atomicAdd(Au + 4 * lane + 1, v4.y - A * xb4.y);
-                        atomicAdd(Au + 4 * lane + 2, v4.z - A * xb4.z);
-                        atomicAdd(Au + 4 * lane + 3, v4.w - A * xb4.w);
+                        du_acc[0] += v4.x - A * xb4.x; du_acc[1] += v4.y - A * xb4.y;
+                        du_acc[2] += v4.z - A * xb4.z; du_acc[3] += v4.w - A * xb4.w;
                     }
                     // ---- phase G: weight gradients (tile buffers are read-only here)
                     if (scale != acc_scale) {
@@ -760,6 +759,8 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
     {
         float* part = p.partial + (size_t)blockIdx.x * GRAD;
         for (int i = tid; i < GRAD; i += BTHREADS) part[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(Au + 4 * lane + k, du_acc[k]);
         __syncthreads();
         const float un = 1.0f / acc_scale;
 #pragma unroll
