@@ -11,6 +11,8 @@
 // d b_hh fall out of the weight-gradient product.
 #include "mgv_mma16.cuh"
 
+long long* mgv_debug_trace();
+
 namespace {
 
 constexpr int D = MGV_D;              // 64
@@ -51,7 +53,9 @@ struct StepDev {
     const float* in_part; const float* in_agg;
     float* out_part; float* out_agg;     // [enc][N][64]
     float* partial;            // [enc][gx][2][SGRAD]
+    long long* trace;          // optional [CTA][16 tiles][16] clock64 samples (dev tool)
 };
+#define BTRACE(slot) do { if (p.trace && tid == 0 && it < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + it) * 16 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int t0 = tile * TM;
+        BTRACE(0);
         {   // ---- gathers: neighbour sum of state_{k-1}; d state_k = part + sum of neighbours' d agg_{k+1}
             const int row = warp * 2 + half, node = t0 + row;
             float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sbv = sa, h4 = sa, g4 = sa, x4 = sa;
@@ -202,6 +207,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             mgv_st4(Gs + row * LDF + 4 * l16, g4);
         }
         __syncthreads();
+        BTRACE(1);
         // ---- recompute the step (gates stay in registers)
         float gr[4], gz[4], gn[4], hnb[4];
         {
@@ -219,6 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
                           gr[e], gz[e], gn[e]);
             }
         }
+        BTRACE(2);
         if (p.layernorm) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -248,6 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             }
             __syncthreads();
         }
+        BTRACE(3);
         // ---- GRU backward on the owned elements; tile-wide power-of-two scale for the fp16 planes
         float dr[4], dz[4], dni[4], dnh[4], dh_direct[4];
         {
@@ -292,6 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             }
         }
         __syncthreads();
+        BTRACE(4);
         // ---- data gradients: d agg = d gi . Wc ;  d part = g z + d gh . Whh   (both 32 x 64, K = 192)
         if (!p.first) {
             const int n0[1] = {u0};
@@ -313,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
                 }
             }
         }
+        BTRACE(5);
         // ---- weight gradients (tile buffers are read-only here)
         if (scale != acc_scale) {
             const float f = scale / acc_scale;
@@ -326,7 +336,9 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
         m16::warp_gemm<2, 1, TM / 16, true, true>(acc_ha, sb + DG_HI, sb + DG_LO, LDG, wh * 96, 0, sb + HS_HI, sb + HS_LO, LDW, wn0, 0, lane);
         m16::warp_gemm<4, 1, TM / 16, true, true>(acc_hb, sb + DG_HI, sb + DG_LO, LDG, wh ? 3 * D : 32, 0, sb + HS_HI, sb + HS_LO, LDW, wn0, 0, lane);
         m16::warp_gemm<1, 2, TM / 16, true, true>(acc_fb, sb + DG_HI, sb + DG_LO, LDG, 16 * warp, 0, sb + AS_HI, sb + AS_LO, LDC, fn0, 0, lane);
+        BTRACE(6);
         __syncthreads();
+        BTRACE(7);
     }
     // ---- flush this CTA's accumulators into its private partial block (summed over the launches of a call)
     float* part = p.partial + (((size_t)enc * gridDim.x + blockIdx.x) * 2 + p.dir) * SGRAD;
@@ -461,6 +473,7 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
         p.in_part = part[k & 1]; p.in_agg = agg[k & 1];
         p.out_part = part[(k - 1) & 1]; p.out_agg = agg[(k - 1) & 1];
         p.partial = partial;
+        p.trace = (k == 2) ? mgv_debug_trace() : nullptr;
         struct_bwd_kernel<<<dim3(gx, num_enc), THREADS, smem, st>>>(p);
         mgv_count_launches(1);
     }

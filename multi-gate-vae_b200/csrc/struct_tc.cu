@@ -433,6 +433,7 @@ __global__ void fill_ones_kernel(float* p, size_t n) {
 
 static long long* g_trace = nullptr;
 extern "C" void mgv_debug_set_trace(void* p) { g_trace = (long long*)p; }
+long long* mgv_debug_trace() { return g_trace; }
 
 size_t mgv_struct_image_bytes(int num_enc) { return mgv_align_up((size_t)num_enc * 2 * IMG_BYTES, 256); }
 
