@@ -349,24 +349,29 @@ __global__ void __launch_bounds__(FTHREADS, 1) sweep_fwd_kernel(const SweepDev p
 //   D    d m = d gi Wih,  d h = g z + d gh Whh        E  d xbar = d m Wv        F  attention backward (warp per node)
 //   G    d Wih += d gi^T m,  d Whh += d gh^T h,  d Wv += d m^T xbar
 // Gate gradients are scaled per tile by a power of two into fp16 range before the hi/lo split (mgv_mma16.cuh).
-constexpr int BTM = 16;                                        // nodes per tile
 constexpr int BTHREADS = 512;
 constexpr int LDGH = 264;                                      // d gate planes: dr | dz | dn_i | dn_h
-constexpr uint32_t BW_WV_HI = 0, BW_WV_LO = BW_WV_HI + D * LDXH * 2, BW_WIH_HI = BW_WV_LO + D * LDXH * 2,
-                   BW_WIH_LO = BW_WIH_HI + G3 * LDMH * 2, BW_WHH_HI = BW_WIH_LO + G3 * LDMH * 2, BW_WHH_LO = BW_WHH_HI + G3 * LDMH * 2;
-constexpr uint32_t BW_BIAS = BW_WHH_LO + G3 * LDMH * 2;        // u[128] bv[64] bih[192] bhh[192] fp32
-constexpr uint32_t BW_ACC = BW_BIAS + 576 * 4;                 // d u[128] d bv[64] d bih[192] d bhh[192] fp32
-constexpr uint32_t BW_XS_HI = BW_ACC + 576 * 4, BW_XS_LO = BW_XS_HI + BTM * LDXH * 2;
-constexpr uint32_t BW_X32 = BW_XS_LO + BTM * LDXH * 2, BW_DX32 = BW_X32 + BTM * LDX * 4;
-constexpr uint32_t BW_MS_HI = BW_DX32 + BTM * LDX * 4, BW_MS_LO = BW_MS_HI + BTM * LDMH * 2;
-constexpr uint32_t BW_HS_HI = BW_MS_LO + BTM * LDMH * 2, BW_HS_LO = BW_HS_HI + BTM * LDMH * 2;
-constexpr uint32_t BW_H32 = BW_HS_LO + BTM * LDMH * 2, BW_GS = BW_H32 + BTM * LDF32 * 4;
-constexpr uint32_t BW_DM_HI = BW_GS + BTM * LDF32 * 4, BW_DM_LO = BW_DM_HI + BTM * LDMH * 2, BW_DM32 = BW_DM_LO + BTM * LDMH * 2;
-constexpr uint32_t BW_DG_HI = BW_DM32 + BTM * LDF32 * 4, BW_DG_LO = BW_DG_HI + BTM * LDGH * 2;
-constexpr uint32_t BW_SS = BW_DG_LO + BTM * LDGH * 2, BW_IDS = BW_SS + BTM * 4, BW_MAX = BW_IDS + BTM * 4;
-constexpr uint32_t B_SMEM_BYTES = BW_MAX + 16;
-static_assert(B_SMEM_BYTES <= 227 * 1024 && BW_XS_HI % 16 == 0 && BW_MS_HI % 16 == 0 && BW_HS_HI % 16 == 0 && BW_DM_HI % 16 == 0 &&
-              BW_DG_HI % 16 == 0 && BW_DG_LO % 16 == 0 && BW_X32 % 16 == 0, "sweep backward smem");
+// Two instantiations: <16 nodes per tile, with the hidden-state products> for multi-round sweeps, and
+// <32 nodes per tile, no W_hh / h tiles> for the common single-round sweep (h = 0: gh = b_hh), where the freed
+// shared memory doubles the tile and every phase runs on all 16 warps.
+template <int BTM, bool HAS_H>
+struct BwdSmem {
+    static constexpr uint32_t WV_HI = 0, WV_LO = WV_HI + D * LDXH * 2, WIH_HI = WV_LO + D * LDXH * 2, WIH_LO = WIH_HI + G3 * LDMH * 2;
+    static constexpr uint32_t WHH_HI = WIH_LO + G3 * LDMH * 2, WHH_LO = WHH_HI + (HAS_H ? G3 * LDMH * 2 : 0);
+    static constexpr uint32_t BIAS = WHH_LO + (HAS_H ? G3 * LDMH * 2 : 0);          // u[128] bv[64] bih[192] bhh[192] fp32
+    static constexpr uint32_t ACC = BIAS + 576 * 4;                                  // d u[128] d bv[64] d bih[192] d bhh[192] fp32
+    static constexpr uint32_t XS_HI = ACC + 576 * 4, XS_LO = XS_HI + BTM * LDXH * 2;
+    static constexpr uint32_t X32 = XS_LO + BTM * LDXH * 2, DX32 = X32 + BTM * LDX * 4;
+    static constexpr uint32_t MS_HI = DX32 + BTM * LDX * 4, MS_LO = MS_HI + BTM * LDMH * 2;
+    static constexpr uint32_t HS_HI = MS_LO + BTM * LDMH * 2, HS_LO = HS_HI + (HAS_H ? BTM * LDMH * 2 : 0);
+    static constexpr uint32_t H32 = HS_LO + (HAS_H ? BTM * LDMH * 2 : 0), GS = H32 + (HAS_H ? BTM * LDF32 * 4 : 0);
+    static constexpr uint32_t DM_HI = GS + BTM * LDF32 * 4, DM_LO = DM_HI + BTM * LDMH * 2, DM32 = DM_LO + BTM * LDMH * 2;
+    static constexpr uint32_t DG_HI = DM32 + BTM * LDF32 * 4, DG_LO = DG_HI + BTM * LDGH * 2;
+    static constexpr uint32_t SS = DG_LO + BTM * LDGH * 2, IDS = SS + BTM * 4, MAX = IDS + BTM * 4;
+    static constexpr uint32_t BYTES = MAX + 16;
+    static_assert(BYTES <= 227 * 1024 && XS_HI % 16 == 0 && MS_HI % 16 == 0 && HS_HI % 16 == 0 && DM_HI % 16 == 0 && DG_HI % 16 == 0 &&
+                  DG_LO % 16 == 0 && X32 % 16 == 0, "sweep backward smem");
+};
 
 // Pull  sum over out-edges e=(v->k) of  alpha_e * dxbar_k + dscore_e * u_code(k)  (128-wide, lane chunk of 4).
 __device__ __forceinline__ float4 pull_out_edges(const SweepDev& p, int v, int lane) {
@@ -438,19 +443,23 @@ __device__ __forceinline__ void pull_out_edges16(const SweepDev& p, int v, int l
     }
 }
 
+template <int BTM, bool HAS_H>
 __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p) {
+    using S = BwdSmem<BTM, HAS_H>;
+    constexpr int MT = BTM / 16;
+    static_assert(!HAS_H || MT == 1, "the multi-round variant uses 16-node tiles");
     extern __shared__ __align__(128) uint8_t bsm[];
     const uint32_t sb = m16::smem_u32(bsm);
-    float* Bias = reinterpret_cast<float*>(bsm + BW_BIAS);
-    float* ACC = reinterpret_cast<float*>(bsm + BW_ACC);        // d u | d bv | d bih | d bhh
-    float* X32 = reinterpret_cast<float*>(bsm + BW_X32);
-    float* DX32 = reinterpret_cast<float*>(bsm + BW_DX32);
-    float* H32 = reinterpret_cast<float*>(bsm + BW_H32);
-    float* Gs = reinterpret_cast<float*>(bsm + BW_GS);          // d hf of the tile, then g z (direct path to h)
-    float* DM32 = reinterpret_cast<float*>(bsm + BW_DM32);
-    float* Ss = reinterpret_cast<float*>(bsm + BW_SS);
-    int* Ids = reinterpret_cast<int*>(bsm + BW_IDS);
-    unsigned* smax = reinterpret_cast<unsigned*>(bsm + BW_MAX);
+    float* Bias = reinterpret_cast<float*>(bsm + S::BIAS);
+    float* ACC = reinterpret_cast<float*>(bsm + S::ACC);        // d u | d bv | d bih | d bhh
+    float* X32 = reinterpret_cast<float*>(bsm + S::X32);
+    float* DX32 = reinterpret_cast<float*>(bsm + S::DX32);
+    float* H32 = reinterpret_cast<float*>(bsm + S::H32);
+    float* Gs = reinterpret_cast<float*>(bsm + S::GS);          // d hf of the tile, then g z (direct path to h)
+    float* DM32 = reinterpret_cast<float*>(bsm + S::DM32);
+    float* Ss = reinterpret_cast<float*>(bsm + S::SS);
+    int* Ids = reinterpret_cast<int*>(bsm + S::IDS);
+    unsigned* smax = reinterpret_cast<unsigned*>(bsm + S::MAX);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, l16 = lane & 15;
     const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
@@ -459,9 +468,9 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
     find_role(p, code, rank, nct);
     const float* W = p.weights + (size_t)(code < 0 ? 0 : code) * PACK;
     if (code >= 0) {
-        load_planes(bsm + BW_WV_HI, bsm + BW_WV_LO, W + O_WV, D, D2, LDXH, tid, BTHREADS);
-        load_planes(bsm + BW_WIH_HI, bsm + BW_WIH_LO, W + O_WIH, G3, D, LDMH, tid, BTHREADS);
-        load_planes(bsm + BW_WHH_HI, bsm + BW_WHH_LO, W + O_WHH, G3, D, LDMH, tid, BTHREADS);
+        load_planes(bsm + S::WV_HI, bsm + S::WV_LO, W + O_WV, D, D2, LDXH, tid, BTHREADS);
+        load_planes(bsm + S::WIH_HI, bsm + S::WIH_LO, W + O_WIH, G3, D, LDMH, tid, BTHREADS);
+        if (HAS_H) load_planes(bsm + S::WHH_HI, bsm + S::WHH_LO, W + O_WHH, G3, D, LDMH, tid, BTHREADS);
         for (int i = tid; i < 576; i += BTHREADS)
             Bias[i] = __ldg(W + (i < 128 ? O_U + i : (i < 192 ? O_BV + i - 128 : (i < 384 ? O_BIH + i - 192 : O_BHH + i - 384))));
     }
@@ -476,6 +485,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
 
     // persistent weight-gradient fragments (all scaled by acc_scale)
     const int wh = warp >> 3, wn8 = 8 * (warp & 7);
+    const int mt = (MT == 2) ? wh : 0, mrow = mt * 16;
     const int wn0[1] = {wn8};
     const int vn0[1] = {8 * warp};
     float acc_ih[6][1][4], acc_ha[2][1][4], acc_hb[4][1][4], acc_v[4][1][4];
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
     int it = 0;
 
     for (int r = p.R - 1; r >= 0; --r) {
-        const float* hf_prev = r > 0 ? p.hf_all + (size_t)(r - 1) * p.N * D : nullptr;
+        const float* hf_prev = (HAS_H && r > 0) ? p.hf_all + (size_t)(r - 1) * p.N * D : nullptr;
         const float* hf_cur = p.hf_all + (size_t)r * p.N * D;
         for (int lvl = p.L - 1; lvl >= 0; --lvl) {
             // ------------------------------------------------ full backward tiles of my code
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                 for (int t0 = sbeg + rank * BTM; t0 < send; t0 += nct * BTM, ++it) {
                     const int rows = min(BTM, send - t0);
                     // ---- phase P/A: pull d(hs, hf), recompute gather / attention  (warps 0-7, half-warp per node)
-                    if (warp < 8) {
+                    if (warp < BTM / 2) {
                         const int row = warp * 2 + half;
                         float xb[8], h8[8], g8[8];
 #pragma unroll
@@ -526,13 +536,15 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                             }
                             gather_attend16<true>(p, hf_cur, u8, node, l16, hmask, xb, S);
                         }
-                        st_plane8(bsm + BW_XS_HI, bsm + BW_XS_LO, (uint32_t)(row * LDXH + 8 * l16), xb);
+                        st_plane8(bsm + S::XS_HI, bsm + S::XS_LO, (uint32_t)(row * LDXH + 8 * l16), xb);
                         mgv_st4(X32 + row * LDX + 8 * l16, make_float4(xb[0], xb[1], xb[2], xb[3]));
                         mgv_st4(X32 + row * LDX + 8 * l16 + 4, make_float4(xb[4], xb[5], xb[6], xb[7]));
                         if (l16 < 8) {
-                            st_plane8(bsm + BW_HS_HI, bsm + BW_HS_LO, (uint32_t)(row * LDMH + 8 * l16), h8);
-                            mgv_st4(H32 + row * LDF32 + 8 * l16, make_float4(h8[0], h8[1], h8[2], h8[3]));
-                            mgv_st4(H32 + row * LDF32 + 8 * l16 + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
+                            if (HAS_H) {
+                                st_plane8(bsm + S::HS_HI, bsm + S::HS_LO, (uint32_t)(row * LDMH + 8 * l16), h8);
+                                mgv_st4(H32 + row * LDF32 + 8 * l16, make_float4(h8[0], h8[1], h8[2], h8[3]));
+                                mgv_st4(H32 + row * LDF32 + 8 * l16 + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
+                            }
                         } else {
                             mgv_st4(Gs + row * LDF32 + 8 * (l16 - 8), make_float4(g8[0], g8[1], g8[2], g8[3]));
                             mgv_st4(Gs + row * LDF32 + 8 * (l16 - 8) + 4, make_float4(g8[4], g8[5], g8[6], g8[7]));
@@ -541,44 +553,44 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     }
                     __syncthreads();
                     // ---- phase B: m = xbar Wv^T + bv S  (warps 0-7: 8 columns each)
-                    if (warp < 8) {
+                    if (warp < 8 * MT) {
                         float c[1][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<1, 1, D2 / 16, false, false>(c, sb + BW_XS_HI, sb + BW_XS_LO, LDXH, 0, 0, sb + BW_WV_HI, sb + BW_WV_LO, LDXH,
+                        m16::warp_gemm<1, 1, D2 / 16, false, false>(c, sb + S::XS_HI, sb + S::XS_LO, LDXH, mrow, 0, sb + S::WV_HI, sb + S::WV_LO, LDXH,
                                                                     wn0, 0, lane);
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
-                            const int row = g + 8 * hrow, col = wn8 + 2 * t;
+                            const int row = mrow + g + 8 * hrow, col = wn8 + 2 * t;
                             const float sv = Ss[row];
                             uint32_t hi, lo;
                             m16::split2(fmaf(Bv[col], sv, c[0][0][2 * hrow]), fmaf(Bv[col + 1], sv, c[0][0][2 * hrow + 1]), hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + BW_MS_HI + (row * LDMH + col) * 2) = hi;
-                            *reinterpret_cast<uint32_t*>(bsm + BW_MS_LO + (row * LDMH + col) * 2) = lo;
+                            *reinterpret_cast<uint32_t*>(bsm + S::MS_HI + (row * LDMH + col) * 2) = hi;
+                            *reinterpret_cast<uint32_t*>(bsm + S::MS_LO + (row * LDMH + col) * 2) = lo;
                         }
                     }
                     __syncthreads();
                     // ---- phase C: GRU recompute + pointwise backward  (warps 0-7: 8 units each)
                     float dr[4], dz[4], dni[4], dnh[4];
-                    if (warp < 8) {
+                    if (warp < 8 * MT) {
                         const int n0[3] = {wn8, D + wn8, 2 * D + wn8};
                         float ci[1][3][4], ch[1][3][4];
                         m16::zero_frag(ci);
                         m16::zero_frag(ch);
-                        m16::warp_gemm<1, 3, D / 16, false, false>(ci, sb + BW_MS_HI, sb + BW_MS_LO, LDMH, 0, 0, sb + BW_WIH_HI, sb + BW_WIH_LO, LDMH,
+                        m16::warp_gemm<1, 3, D / 16, false, false>(ci, sb + S::MS_HI, sb + S::MS_LO, LDMH, mrow, 0, sb + S::WIH_HI, sb + S::WIH_LO, LDMH,
                                                                    n0, 0, lane);
-                        if (hf_prev != nullptr)
-                            m16::warp_gemm<1, 3, D / 16, false, false>(ch, sb + BW_HS_HI, sb + BW_HS_LO, LDMH, 0, 0, sb + BW_WHH_HI, sb + BW_WHH_LO,
+                        if (HAS_H && hf_prev != nullptr)
+                            m16::warp_gemm<1, 3, D / 16, false, false>(ch, sb + S::HS_HI, sb + S::HS_LO, LDMH, mrow, 0, sb + S::WHH_HI, sb + S::WHH_LO,
                                                                        LDMH, n0, 0, lane);
                         float amax = 0.f;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int row = g + ((e & 2) ? 8 : 0), uu = wn8 + 2 * t + (e & 1);
+                            const int row = mrow + g + ((e & 2) ? 8 : 0), uu = wn8 + 2 * t + (e & 1);
                             const float hnb = ch[0][2][e] + Bhh[2 * D + uu];
                             float rr, zz, nn;
                             gru_gates(ci[0][0][e] + Bih[uu] + ch[0][0][e] + Bhh[uu], ci[0][1][e] + Bih[D + uu] + ch[0][1][e] + Bhh[D + uu],
                                       ci[0][2][e] + Bih[2 * D + uu], hnb, rr, zz, nn);
                             const float gg = Gs[row * LDF32 + uu];
-                            const float hp = H32[row * LDF32 + uu];
+                            const float hp = HAS_H ? H32[row * LDF32 + uu] : 0.f;
                             dni[e] = gg * (1.0f - zz) * (1.0f - nn * nn);
                             dr[e] = dni[e] * hnb * rr * (1.0f - rr);
                             dz[e] = gg * (hp - nn) * zz * (1.0f - zz);
@@ -611,37 +623,37 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     __syncthreads();
                     const float scale = m16::pow2_scale_band(__uint_as_float(smax[it & 1]), acc_scale, 1.0f, 512.0f);
                     const float inv_scale = 1.0f / scale;
-                    if (warp < 8) {
+                    if (warp < 8 * MT) {
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
-                            const int row = g + 8 * hrow, e0 = 2 * hrow;
+                            const int row = mrow + g + 8 * hrow, e0 = 2 * hrow;
                             const uint32_t off = (uint32_t)(row * LDGH + wn8 + 2 * t) * 2;
                             uint32_t hi, lo;
                             m16::split2(dr[e0] * scale, dr[e0 + 1] * scale, hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + BW_DG_HI + off) = hi; *reinterpret_cast<uint32_t*>(bsm + BW_DG_LO + off) = lo;
+                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off) = hi; *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off) = lo;
                             m16::split2(dz[e0] * scale, dz[e0 + 1] * scale, hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + BW_DG_HI + off + 2 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + BW_DG_LO + off + 2 * D) = lo;
+                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 2 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 2 * D) = lo;
                             m16::split2(dni[e0] * scale, dni[e0 + 1] * scale, hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + BW_DG_HI + off + 4 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + BW_DG_LO + off + 4 * D) = lo;
+                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 4 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 4 * D) = lo;
                             m16::split2(dnh[e0] * scale, dnh[e0 + 1] * scale, hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + BW_DG_HI + off + 6 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + BW_DG_LO + off + 6 * D) = lo;
+                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 6 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 6 * D) = lo;
                         }
                     }
                     __syncthreads();
                     // ---- phase D: d m = d gi . Wih (warps 0-7);  d h = g z + d gh . Whh (warps 8-15)
-                    if (warp < 8) {
+                    if (warp < 8 * MT) {
                         float c[1][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<1, 1, G3 / 16, false, true>(c, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, 0, 0, sb + BW_WIH_HI, sb + BW_WIH_LO, LDMH,
+                        m16::warp_gemm<1, 1, G3 / 16, false, true>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, mrow, 0, sb + S::WIH_HI, sb + S::WIH_LO, LDMH,
                                                                    wn0, 0, lane);
                         float sbv[2] = {0.f, 0.f};
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
-                            const int row = g + 8 * hrow, col = wn8 + 2 * t;
+                            const int row = mrow + g + 8 * hrow, col = wn8 + 2 * t;
                             uint32_t hi, lo;
                             m16::split2(c[0][0][2 * hrow], c[0][0][2 * hrow + 1], hi, lo);              // stays scaled
-                            *reinterpret_cast<uint32_t*>(bsm + BW_DM_HI + (row * LDMH + col) * 2) = hi;
-                            *reinterpret_cast<uint32_t*>(bsm + BW_DM_LO + (row * LDMH + col) * 2) = lo;
+                            *reinterpret_cast<uint32_t*>(bsm + S::DM_HI + (row * LDMH + col) * 2) = hi;
+                            *reinterpret_cast<uint32_t*>(bsm + S::DM_LO + (row * LDMH + col) * 2) = lo;
                             const float d0 = c[0][0][2 * hrow] * inv_scale, d1 = c[0][0][2 * hrow + 1] * inv_scale;
                             DM32[row * LDF32 + col] = d0;
                             DM32[row * LDF32 + col + 1] = d1;
@@ -655,12 +667,12 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                             sbv[k] += __shfl_xor_sync(0xffffffffu, sbv[k], 16);
                         }
                         if (g == 0) { atomicAdd(Abv + wn8 + 2 * t, sbv[0]); atomicAdd(Abv + wn8 + 2 * t + 1, sbv[1]); }
-                    } else if (hf_prev != nullptr) {
+                    } else if (HAS_H && hf_prev != nullptr) {
                         float c[1][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<1, 1, 2 * D / 16, false, true>(c, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, 0, 0, sb + BW_WHH_HI, sb + BW_WHH_LO, LDMH,
+                        m16::warp_gemm<1, 1, 2 * D / 16, false, true>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, 0, 0, sb + S::WHH_HI, sb + S::WHH_LO, LDMH,
                                                                       wn0, 0, lane);
-                        m16::warp_gemm<1, 1, D / 16, false, true>(c, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, 0, 3 * D, sb + BW_WHH_HI, sb + BW_WHH_LO, LDMH,
+                        m16::warp_gemm<1, 1, D / 16, false, true>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, 0, 3 * D, sb + S::WHH_HI, sb + S::WHH_LO, LDMH,
                                                                   wn0, 2 * D, lane);
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
@@ -675,23 +687,24 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     __syncthreads();
                     // ---- phase E: d xbar = d m . Wv   (16 warps x 8 of the 128 columns)
                     {
-                        float c[1][1][4];
+                        float c[MT][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<1, 1, D / 16, false, true>(c, sb + BW_DM_HI, sb + BW_DM_LO, LDMH, 0, 0, sb + BW_WV_HI, sb + BW_WV_LO, LDXH,
-                                                                  vn0, 0, lane);
+                        m16::warp_gemm<MT, 1, D / 16, false, true>(c, sb + S::DM_HI, sb + S::DM_LO, LDMH, 0, 0, sb + S::WV_HI, sb + S::WV_LO, LDXH,
+                                                                   vn0, 0, lane);
 #pragma unroll
-                        for (int hrow = 0; hrow < 2; ++hrow) {
-                            const int row = g + 8 * hrow, col = 8 * warp + 2 * t;
-                            const float2 v = make_float2(c[0][0][2 * hrow] * inv_scale, c[0][0][2 * hrow + 1] * inv_scale);
-                            *reinterpret_cast<float2*>(DX32 + row * LDX + col) = v;
-                            const int node = Ids[row];
-                            if (node >= 0) *reinterpret_cast<float2*>(p.dxb + (size_t)node * D2 + col) = v;
-                        }
+                        for (int m = 0; m < MT; ++m)
+#pragma unroll
+                            for (int hrow = 0; hrow < 2; ++hrow) {
+                                const int row = 16 * m + g + 8 * hrow, col = 8 * warp + 2 * t;
+                                const float2 v = make_float2(c[m][0][2 * hrow] * inv_scale, c[m][0][2 * hrow + 1] * inv_scale);
+                                *reinterpret_cast<float2*>(DX32 + row * LDX + col) = v;
+                                const int node = Ids[row];
+                                if (node >= 0) *reinterpret_cast<float2*>(p.dxb + (size_t)node * D2 + col) = v;
+                            }
                     }
                     __syncthreads();
                     // ---- phase F: attention backward per node (one warp per node)
-                    if (warp < rows) {
-                        const int row = warp;
+                    for (int row = warp; row < rows; row += BTHREADS / 32) {
                         const int node = Ids[row];
                         const float dS = mgv_warp_sum(Bv[lane] * DM32[row * LDF32 + lane] + Bv[32 + lane] * DM32[row * LDF32 + 32 + lane]);
                         const float4 dxb4 = mgv_ld4(DX32 + row * LDX + 4 * lane);
@@ -725,12 +738,12 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         m16::scale_frag(acc_v, f);
                         acc_scale = scale;
                     }
-                    m16::warp_gemm<6, 1, 1, true, true>(acc_ih, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, wh * 96, 0, sb + BW_MS_HI, sb + BW_MS_LO, LDMH, wn0, 0, lane);
-                    if (hf_prev != nullptr) {
-                        m16::warp_gemm<2, 1, 1, true, true>(acc_ha, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, wh * 96, 0, sb + BW_HS_HI, sb + BW_HS_LO, LDMH, wn0, 0, lane);
-                        m16::warp_gemm<4, 1, 1, true, true>(acc_hb, sb + BW_DG_HI, sb + BW_DG_LO, LDGH, wh ? 3 * D : 32, 0, sb + BW_HS_HI, sb + BW_HS_LO, LDMH, wn0, 0, lane);
+                    m16::warp_gemm<6, 1, MT, true, true>(acc_ih, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh * 96, 0, sb + S::MS_HI, sb + S::MS_LO, LDMH, wn0, 0, lane);
+                    if (HAS_H && hf_prev != nullptr) {
+                        m16::warp_gemm<2, 1, MT, true, true>(acc_ha, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh * 96, 0, sb + S::HS_HI, sb + S::HS_LO, LDMH, wn0, 0, lane);
+                        m16::warp_gemm<4, 1, MT, true, true>(acc_hb, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh ? 3 * D : 32, 0, sb + S::HS_HI, sb + S::HS_LO, LDMH, wn0, 0, lane);
                     }
-                    m16::warp_gemm<4, 1, 1, true, true>(acc_v, sb + BW_DM_HI, sb + BW_DM_LO, LDMH, 0, 0, sb + BW_XS_HI, sb + BW_XS_LO, LDXH, vn0, 0, lane);
+                    m16::warp_gemm<4, 1, MT, true, true>(acc_v, sb + S::DM_HI, sb + S::DM_LO, LDMH, 0, 0, sb + S::XS_HI, sb + S::XS_LO, LDXH, vn0, 0, lane);
                     __syncthreads();
                 }
             }
@@ -882,9 +895,10 @@ extern "C" int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint
 }
 
 extern "C" int mgv_sweep_bwd_grid(void) {
-    int grid = 0;
-    if (coop_grid((const void*)sweep_bwd_kernel, (size_t)B_SMEM_BYTES, BTHREADS, &grid) != MGV_OK) return -1;
-    return grid;
+    int g1 = 0, g2 = 0;
+    if (coop_grid((const void*)sweep_bwd_kernel<16, true>, (size_t)BwdSmem<16, true>::BYTES, BTHREADS, &g1) != MGV_OK) return -1;
+    if (coop_grid((const void*)sweep_bwd_kernel<32, false>, (size_t)BwdSmem<32, false>::BYTES, BTHREADS, &g2) != MGV_OK) return -1;
+    return g1 > g2 ? g1 : g2;
 }
 
 extern "C" size_t mgv_sweep_bwd_workspace_bytes(int64_t N, int64_t E) {
@@ -909,8 +923,10 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     MGV_CUDA(cudaMemsetAsync(grads, 0, (size_t)MGV_NCODE * GRAD * sizeof(float), st));
     if (sch->N == 0 || sch->L <= 1) return MGV_OK;
     int grid = 0;
-    const size_t smem = (size_t)B_SMEM_BYTES;
-    rc = coop_grid((const void*)sweep_bwd_kernel, smem, BTHREADS, &grid);
+    const bool single = rounds == 1;                          // h = 0 everywhere: the 32-node variant without W_hh
+    const void* kern = single ? (const void*)sweep_bwd_kernel<32, false> : (const void*)sweep_bwd_kernel<16, true>;
+    const size_t smem = single ? (size_t)BwdSmem<32, false>::BYTES : (size_t)BwdSmem<16, true>::BYTES;
+    rc = coop_grid(kern, smem, BTHREADS, &grid);
     if (rc != MGV_OK) return rc;
     assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
     if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;
@@ -927,7 +943,7 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     d.ghs = ghs; d.ghf = ghf; d.grads = grads;
     MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
     void* args[] = {&d};
-    MGV_CUDA(cudaLaunchCooperativeKernel((void*)sweep_bwd_kernel, dim3(grid), dim3(BTHREADS), args, smem, st));
+    MGV_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(BTHREADS), args, smem, st));
     mgv_count_launches(1);
     return MGV_OK;
 }
