@@ -15,6 +15,8 @@
 // weight-gradient accumulators in shared memory for the whole sweep.
 #include "mgv_mma16.cuh"
 
+long long* mgv_debug_trace();
+
 namespace {
 
 constexpr int D = MGV_D;              // 64
@@ -47,7 +49,9 @@ struct SweepDev {
     unsigned* bar;
     // backward only
     float* ghs; float* ghf; float* dxb; float* alpha; float* dscore; float* partial; float* grads;
+    long long* trace;          // optional [CTA][16] accumulated clock64 cycles per phase (dev tool)
 };
+#define SWTRACE(slot) do { if (p.trace && tid == 0) { const long long now_ = clock64(); tr_acc[slot] += now_ - tr_last; tr_last = now_; } } while (0)
 
 // Gather + additive attention of one node by one warp.  Lane l owns elements 4l..4l+3 of the
 // 128-wide row [hs || hf].  Returns xbar chunk and S; optionally stores raw scores / alphas.
@@ -493,6 +497,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
     m16::zero_frag(acc_ha);
     m16::zero_frag(acc_hb);
     m16::zero_frag(acc_v);
+    long long tr_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tr_last = clock64();
     float acc_scale = 1.0f;
     float du_acc[4] = {0.f, 0.f, 0.f, 0.f};                    // d u of columns 4 lane .. 4 lane + 3 (nodes of this warp)
     int it = 0;
@@ -506,6 +511,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                 const int sbeg = p.seg_ptr[lvl * MGV_NCODE + code], send = p.seg_ptr[lvl * MGV_NCODE + code + 1];
                 for (int t0 = sbeg + rank * BTM; t0 < send; t0 += nct * BTM, ++it) {
                     const int rows = min(BTM, send - t0);
+                    SWTRACE(9);
                     // ---- phase P/A: pull d(hs, hf), recompute gather / attention  (warps 0-7, half-warp per node)
                     if (warp < BTM / 2) {
                         const int row = warp * 2 + half;
@@ -552,6 +558,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         if (l16 == 0) { Ss[row] = S; Ids[row] = node; }
                     }
                     __syncthreads();
+                    SWTRACE(0);
                     // ---- phase B: m = xbar Wv^T + bv S  (warps 0-7: 8 columns each)
                     if (warp < 8 * MT) {
                         float c[1][1][4];
@@ -569,6 +576,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         }
                     }
                     __syncthreads();
+                    SWTRACE(1);
                     // ---- phase C: GRU recompute + pointwise backward  (warps 0-7: 8 units each)
                     float dr[4], dz[4], dni[4], dnh[4];
                     if (warp < 8 * MT) {
@@ -640,6 +648,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         }
                     }
                     __syncthreads();
+                    SWTRACE(2);
                     // ---- phase D: d m = d gi . Wih (warps 0-7);  d h = g z + d gh . Whh (warps 8-15)
                     if (warp < 8 * MT) {
                         float c[1][1][4];
@@ -685,6 +694,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         }
                     }
                     __syncthreads();
+                    SWTRACE(3);
                     // ---- phase E: d xbar = d m . Wv   (16 warps x 8 of the 128 columns)
                     {
                         float c[MT][1][4];
@@ -703,6 +713,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                             }
                     }
                     __syncthreads();
+                    SWTRACE(4);
                     // ---- phase F: attention backward per node (one warp per node)
                     for (int row = warp; row < rows; row += BTHREADS / 32) {
                         const int node = Ids[row];
@@ -729,6 +740,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         du_acc[0] += v4.x - A * xb4.x; du_acc[1] += v4.y - A * xb4.y;
                         du_acc[2] += v4.z - A * xb4.z; du_acc[3] += v4.w - A * xb4.w;
                     }
+                    SWTRACE(5);
                     // ---- phase G: weight gradients (tile buffers are read-only here)
                     if (scale != acc_scale) {
                         const float f = scale / acc_scale;
@@ -745,8 +757,10 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     }
                     m16::warp_gemm<4, 1, MT, true, true>(acc_v, sb + S::DM_HI, sb + S::DM_LO, LDMH, 0, 0, sb + S::XS_HI, sb + S::XS_LO, LDXH, vn0, 0, lane);
                     __syncthreads();
+                    SWTRACE(6);
                 }
             }
+            SWTRACE(9);
             // ------------------------------------------------ pull-only nodes (level 0 / codes without a module)
             {
                 const int gw = blockIdx.x * (BTHREADS / 32) + warp, nw = gridDim.x * (BTHREADS / 32);
@@ -765,9 +779,13 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     }
                 }
             }
+            SWTRACE(7);
             mgv_grid_sync(p.bar, gridDim.x);
+            SWTRACE(8);
         }
     }
+    if (p.trace && tid == 0)
+        for (int i = 0; i < 10; ++i) p.trace[(size_t)blockIdx.x * 16 + i] = tr_acc[i];
     // ---------------------------------------------------- flush accumulators, reduce over the CTAs of a code
     {
         float* part = p.partial + (size_t)blockIdx.x * GRAD;
@@ -856,6 +874,7 @@ int fill_common(SweepDev& d, const mgv_schedule* sch, int rounds, unsigned handl
     d.out_ptr = sch->out_ptr; d.out_pack = sch->out_pack; d.out_slot = sch->out_slot;
     d.weights = weights; d.hs = hs; d.bar = reinterpret_cast<unsigned*>(sync);
     d.ghs = d.ghf = d.dxb = d.alpha = d.dscore = d.partial = d.grads = nullptr;
+    d.trace = nullptr;
     return MGV_OK;
 }
 
@@ -941,6 +960,7 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     d.dscore = a.take<float>((size_t)sch->E + 1);
     d.partial = a.take<float>((size_t)grid * GRAD);
     d.ghs = ghs; d.ghf = ghf; d.grads = grads;
+    d.trace = mgv_debug_trace();
     MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
     void* args[] = {&d};
     MGV_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(BTHREADS), args, smem, st));
