@@ -142,9 +142,15 @@ typedef struct mgv_schedule {
     const int32_t* gdesc_out;
 } mgv_schedule;
 
+/* precision (all compute entry points): MGV_PRECISION_FP32 = fp32-accurate tensor-core products (fp16 hi/lo planes, three
+ * products, see csrc/mgv_tc.cuh), MGV_PRECISION_BF16 = one plane of bf16 operands with fp32 accumulation (tolerance 2e-2,
+ * tests/test_gpu_parity.py::test_bf16_mode_within_stated_tolerance).  Storage stays fp32 in both.
+ */
+#define MGV_PRECISION_FP32 0
+#define MGV_PRECISION_BF16 1
 int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,
                         const float* weights, const float* hs, float* hf_all,
-                        int32_t* sync, mgv_stream_t stream);
+                        int32_t* sync, int32_t precision, mgv_stream_t stream);
 
 /* Backward of the sweep.  ghs [N][64] in/out: += d loss / d hs through every gather of every
  * round.  ghf [N][64] in/out: in = d loss / d hf (final round); clobbered.  grads: float
@@ -158,7 +164,7 @@ size_t mgv_sweep_bwd_workspace_bytes(int64_t N, int64_t E);
 int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,
                         const float* weights, const float* hs, const float* hf_all,
                         float* ghs, float* ghf, float* grads,
-                        void* ws, size_t ws_bytes, int32_t* sync, mgv_stream_t stream);
+                        void* ws, size_t ws_bytes, int32_t* sync, int32_t precision, mgv_stream_t stream);
 
 /* ------------------------------------------------------------------ struct encoder (fp32)
  * Replaces MultiGCNEncoder.forward (digae_layer.py:257-277) with AggConv (arch/gcn_conv.py:30-42):
@@ -177,7 +183,7 @@ int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint32_t handle
 size_t mgv_struct_fwd_workspace_bytes(int64_t N, int32_t num_enc);
 int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
                            int32_t feat, const float* x, const float* weights, float* states,
-                           void* ws, size_t ws_bytes, mgv_stream_t stream);
+                           void* ws, size_t ws_bytes, int32_t precision, mgv_stream_t stream);
 /* gout: float [num_enc][N][64] = d loss / d (encoder output).  grads: float
  * [num_enc][2][MGV_STRUCT_GRAD_FLOATS] out, SAME layout as the weight block (d Wcx, d Whh, d bc, d bih, d bhh,
  * d ln_w, d ln_b; padding columns are zero).  The host maps d Wc / d bc back to msg.* and weight_ih_l0. */
@@ -185,7 +191,8 @@ int mgv_struct_bwd_grid(void);
 size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc);
 int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
                            int32_t feat, const float* x, const float* weights, const float* states,
-                           const float* gout, float* grads, void* ws, size_t ws_bytes, mgv_stream_t stream);
+                           const float* gout, float* grads, void* ws, size_t ws_bytes, int32_t precision,
+                           mgv_stream_t stream);
 
 /* ------------------------------------------------------------------ fused reparam + KL + func loss
  * Replaces DirectedGVAE.sample's elementwise part (digvae_model.py:138-141), the KL of

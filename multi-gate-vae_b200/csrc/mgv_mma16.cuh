@@ -31,6 +31,17 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
     lo = pack_f16x2_sat(a - hf.x, b - hf.y);
 }
+// bf16 mode (precision = 1): ONE plane, bf16 operands, fp32 accumulate -- the "stated tolerance" configuration.
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+template <bool LOWP>
+__device__ __forceinline__ void split2p(float a, float b, uint32_t& hi, uint32_t& lo) {
+    if (LOWP) { hi = pack_bf16x2(a, b); lo = 0u; }
+    else split2(a, b, hi, lo);
+}
 __device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo) {
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi));
     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lo));
@@ -58,6 +69,13 @@ __device__ __forceinline__ void mma(float (&c)[4], const uint32_t (&a)[4], const
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 // Per-lane byte offset (inside a plane) of the ldmatrix row this lane addresses.
 //   A, not transposed: storage S[m][k] (k contiguous)      A(m, k) = S[m0 + m][k0 + k]
 //   A, transposed    : storage S[k][m] (m contiguous)      A(m, k) = S[k0 + k][m0 + m]
@@ -79,10 +97,10 @@ __device__ __forceinline__ uint32_t b_lane_off(int ld, int k0, int n0, int lane)
 // c[mt][nt] += A[16 mt .., 16 KSTEPS) * B[.., n0[nt] ..)  for one warp; planes given as shared-memory byte addresses.
 // A rows (or storage columns when A_TRANS) start at am0 + 16 mt; its K range starts at ak0; B's K range at bk0.
 // The three products go to separate accumulator chains when MT * NT is small (more independent MMAs in flight).
-template <int MT, int NT, int KSTEPS, bool A_TRANS, bool B_KN>
+template <int MT, int NT, int KSTEPS, bool A_TRANS, bool B_KN, bool LOWP = false>
 __device__ __forceinline__ void warp_gemm(float (&c)[MT][NT][4], uint32_t a_hi, uint32_t a_lo, int lda, int am0, int ak0,
                                           uint32_t b_hi, uint32_t b_lo, int ldb, const int (&n0)[NT], int bk0, int lane) {
-    constexpr bool SPLIT = (MT * NT <= 2);
+    constexpr bool SPLIT = !LOWP && (MT * NT <= 2);
     uint32_t aoff[MT], boff[NT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) aoff[mt] = a_lane_off<A_TRANS>(lda, am0 + 16 * mt, ak0, lane);
@@ -105,13 +123,14 @@ __device__ __forceinline__ void warp_gemm(float (&c)[MT][NT][4], uint32_t a_hi, 
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             if (2 * kp + 1 < KSTEPS) {
-                if (B_KN) { ldsm_x4_t(b_hi + boff[nt] + 2 * kp * bstep, bhi[nt]); ldsm_x4_t(b_lo + boff[nt] + 2 * kp * bstep, blo[nt]); }
-                else { ldsm_x4(b_hi + boff[nt] + 2 * kp * bstep, bhi[nt]); ldsm_x4(b_lo + boff[nt] + 2 * kp * bstep, blo[nt]); }
+                if (B_KN) { ldsm_x4_t(b_hi + boff[nt] + 2 * kp * bstep, bhi[nt]); if (!LOWP) ldsm_x4_t(b_lo + boff[nt] + 2 * kp * bstep, blo[nt]); }
+                else { ldsm_x4(b_hi + boff[nt] + 2 * kp * bstep, bhi[nt]); if (!LOWP) ldsm_x4(b_lo + boff[nt] + 2 * kp * bstep, blo[nt]); }
             } else {                                   // odd tail: one k-step (lanes 16..31 re-address rows of the first half)
                 uint32_t t2[2];
                 const uint32_t o = boff[nt] - (B_KN ? (uint32_t)(((lane >> 4) * 16) * ldb * 2) : (uint32_t)((lane >> 4) * 32));
-                if (B_KN) { ldsm_x2_t(b_hi + o + 2 * kp * bstep, t2); bhi[nt][0] = t2[0]; bhi[nt][1] = t2[1]; ldsm_x2_t(b_lo + o + 2 * kp * bstep, t2); blo[nt][0] = t2[0]; blo[nt][1] = t2[1]; }
-                else { ldsm_x2(b_hi + o + 2 * kp * bstep, t2); bhi[nt][0] = t2[0]; bhi[nt][1] = t2[1]; ldsm_x2(b_lo + o + 2 * kp * bstep, t2); blo[nt][0] = t2[0]; blo[nt][1] = t2[1]; }
+                blo[nt][0] = blo[nt][1] = 0u;
+                if (B_KN) { ldsm_x2_t(b_hi + o + 2 * kp * bstep, t2); bhi[nt][0] = t2[0]; bhi[nt][1] = t2[1]; if (!LOWP) { ldsm_x2_t(b_lo + o + 2 * kp * bstep, t2); blo[nt][0] = t2[0]; blo[nt][1] = t2[1]; } }
+                else { ldsm_x2(b_hi + o + 2 * kp * bstep, t2); bhi[nt][0] = t2[0]; bhi[nt][1] = t2[1]; if (!LOWP) { ldsm_x2(b_lo + o + 2 * kp * bstep, t2); blo[nt][0] = t2[0]; blo[nt][1] = t2[1]; } }
                 bhi[nt][2] = bhi[nt][3] = blo[nt][2] = blo[nt][3] = 0u;
             }
         }
@@ -122,22 +141,26 @@ __device__ __forceinline__ void warp_gemm(float (&c)[MT][NT][4], uint32_t a_hi, 
                 uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    if (A_TRANS) { ldsm_x4_t(a_hi + aoff[mt] + ks * astep, ahi[mt]); ldsm_x4_t(a_lo + aoff[mt] + ks * astep, alo[mt]); }
-                    else { ldsm_x4(a_hi + aoff[mt] + ks * astep, ahi[mt]); ldsm_x4(a_lo + aoff[mt] + ks * astep, alo[mt]); }
+                    if (A_TRANS) { ldsm_x4_t(a_hi + aoff[mt] + ks * astep, ahi[mt]); if (!LOWP) ldsm_x4_t(a_lo + aoff[mt] + ks * astep, alo[mt]); }
+                    else { ldsm_x4(a_hi + aoff[mt] + ks * astep, ahi[mt]); if (!LOWP) ldsm_x4(a_lo + aoff[mt] + ks * astep, alo[mt]); }
                 }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const uint32_t bh[2] = {bhi[nt][2 * kk], bhi[nt][2 * kk + 1]}, bl[2] = {blo[nt][2 * kk], blo[nt][2 * kk + 1]};
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        if (SPLIT) {
-                            mma(c1[mt][nt], alo[mt], bh);
-                            mma(c2[mt][nt], ahi[mt], bl);
+                        if (LOWP) {
+                            mma_bf16(c[mt][nt], ahi[mt], bh);
                         } else {
-                            mma(c[mt][nt], alo[mt], bh);
-                            mma(c[mt][nt], ahi[mt], bl);
+                            if (SPLIT) {
+                                mma(c1[mt][nt], alo[mt], bh);
+                                mma(c2[mt][nt], ahi[mt], bl);
+                            } else {
+                                mma(c[mt][nt], alo[mt], bh);
+                                mma(c[mt][nt], ahi[mt], bl);
+                            }
+                            mma(c[mt][nt], ahi[mt], bh);
                         }
-                        mma(c[mt][nt], ahi[mt], bh);
                     }
                 }
             }

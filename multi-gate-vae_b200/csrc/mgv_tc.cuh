@@ -49,6 +49,21 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
     lo = pack_f16x2_sat(a - hf.x, b - hf.y);
 }
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+// bf16 mode: one plane of bf16 operands (the lo plane is not written / not multiplied).
+template <bool LOWP>
+__device__ __forceinline__ void split8p(const float (&v)[8], uint4& hi, uint4& lo) {
+    if (LOWP) {
+        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]); hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+        lo = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y); split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
+    }
+}
 // 8 consecutive K elements -> one 16-byte chunk in each plane.
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
     split2(v[0], v[1], hi.x, lo.x);
@@ -154,10 +169,10 @@ __device__ __forceinline__ uint64_t desc_k_plain16(uint32_t saddr) { return make
 // ... read MN-major (rows = K index): 8-element M/N chunks 128 bytes apart (SBO), 8-row K groups 256 bytes apart (LBO).
 __device__ __forceinline__ uint64_t desc_mn_plain16(uint32_t saddr) { return make_desc(saddr, 256, 128, LAYOUT_NONE); }
 
-// Instruction descriptor, kind::f16, fp16 operands, fp32 accumulate.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
+// Instruction descriptor, kind::f16, fp16 (or bf16) operands, fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major, bool bf16 = false) {
     return (1u << 4)                                  // D format f32
-           | (0u << 7) | (0u << 10)                   // A, B format f16
+           | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10)      // A, B format: 0 = f16, 1 = bf16
            | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
            | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -176,6 +191,12 @@ __device__ __forceinline__ void mma3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_
     mma(d_tmem, a_hi, b_hi, idesc, accumulate);
     mma(d_tmem, a_lo, b_hi, idesc, 1u);
     mma(d_tmem, a_hi, b_lo, idesc, 1u);
+}
+template <bool LOWP>
+__device__ __forceinline__ void mma3p(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                      uint32_t idesc, uint32_t accumulate) {
+    if (LOWP) mma(d_tmem, a_hi, b_hi, idesc, accumulate);
+    else mma3(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, accumulate);
 }
 __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 

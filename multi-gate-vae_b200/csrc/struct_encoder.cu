@@ -98,15 +98,17 @@ __device__ __forceinline__ void gru_gates(float gr, float gz, float gi, float gh
     n = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y));
 }
 
+template <bool LOWP>
 __device__ __forceinline__ void st_plane4(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t half_off, float a, float b, float c, float d) {
     uint2 hi, lo;
-    m16::split2(a, b, hi.x, lo.x);
-    m16::split2(c, d, hi.y, lo.y);
+    m16::split2p<LOWP>(a, b, hi.x, lo.x);
+    m16::split2p<LOWP>(c, d, hi.y, lo.y);
     *reinterpret_cast<uint2*>(hi_plane + half_off * 2) = hi;
-    *reinterpret_cast<uint2*>(lo_plane + half_off * 2) = lo;
+    if (!LOWP) *reinterpret_cast<uint2*>(lo_plane + half_off * 2) = lo;
 }
 
 // ======================================================================================= backward step
+template <bool LOWP>
 __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sb = m16::smem_u32(smem);
@@ -137,8 +139,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             v[1] = __ldg(W + O_BIH + o);
         }
         const uint32_t off = (uint32_t)(o * LDC + c * 8);
-        st_plane4(smem + WCX_HI, smem + WCX_LO, off, v[0], v[1], v[2], v[3]);
-        st_plane4(smem + WCX_HI, smem + WCX_LO, off + 4, v[4], v[5], v[6], v[7]);
+        st_plane4<LOWP>(smem + WCX_HI, smem + WCX_LO, off, v[0], v[1], v[2], v[3]);
+        st_plane4<LOWP>(smem + WCX_HI, smem + WCX_LO, off + 4, v[4], v[5], v[6], v[7]);
     }
     for (int i = tid; i < G3 * 8; i += THREADS) {
         const int o = i >> 3, c = i & 7;
@@ -146,8 +148,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = __ldg(W + O_WHH + o * NLDM + c * 8 + e);
         const uint32_t off = (uint32_t)(o * LDW + c * 8);
-        st_plane4(smem + WHH_HI, smem + WHH_LO, off, v[0], v[1], v[2], v[3]);
-        st_plane4(smem + WHH_HI, smem + WHH_LO, off + 4, v[4], v[5], v[6], v[7]);
+        st_plane4<LOWP>(smem + WHH_HI, smem + WHH_LO, off, v[0], v[1], v[2], v[3]);
+        st_plane4<LOWP>(smem + WHH_HI, smem + WHH_LO, off + 4, v[4], v[5], v[6], v[7]);
     }
     if (tid < G3) Bhh[tid] = __ldg(W + O_BHH + tid);
     if (tid < 2 * D) { Ln[tid] = __ldg(W + O_LNW + tid); LNA[tid] = 0.f; }
@@ -200,9 +202,9 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
                     x4 = make_float4((float)deg, 1.0f, 0.f, 0.f);
                 }
             }
-            st_plane4(smem + AS_HI, smem + AS_LO, (uint32_t)(row * LDC + 4 * l16), sa.x, sa.y, sa.z, sa.w);
-            if (l16 < 4) st_plane4(smem + AS_HI, smem + AS_LO, (uint32_t)(row * LDC + D + 4 * l16), x4.x, x4.y, x4.z, x4.w);
-            st_plane4(smem + HS_HI, smem + HS_LO, (uint32_t)(row * LDW + 4 * l16), h4.x, h4.y, h4.z, h4.w);
+            st_plane4<LOWP>(smem + AS_HI, smem + AS_LO, (uint32_t)(row * LDC + 4 * l16), sa.x, sa.y, sa.z, sa.w);
+            if (l16 < 4) st_plane4<LOWP>(smem + AS_HI, smem + AS_LO, (uint32_t)(row * LDC + D + 4 * l16), x4.x, x4.y, x4.z, x4.w);
+            st_plane4<LOWP>(smem + HS_HI, smem + HS_LO, (uint32_t)(row * LDW + 4 * l16), h4.x, h4.y, h4.z, h4.w);
             mgv_st4(H32 + row * LDF + 4 * l16, h4);
             mgv_st4(Gs + row * LDF + 4 * l16, g4);
         }
@@ -215,8 +217,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             float ci[1][3][4], ch[1][3][4];
             m16::zero_frag(ci);
             m16::zero_frag(ch);
-            m16::warp_gemm<1, 3, KX / 16, false, false>(ci, sb + AS_HI, sb + AS_LO, LDC, mt * 16, 0, sb + WCX_HI, sb + WCX_LO, LDC, n0, 0, lane);
-            m16::warp_gemm<1, 3, D / 16, false, false>(ch, sb + HS_HI, sb + HS_LO, LDW, mt * 16, 0, sb + WHH_HI, sb + WHH_LO, LDW, n0, 0, lane);
+            m16::warp_gemm<1, 3, KX / 16, false, false, LOWP>(ci, sb + AS_HI, sb + AS_LO, LDC, mt * 16, 0, sb + WCX_HI, sb + WCX_LO, LDC, n0, 0, lane);
+            m16::warp_gemm<1, 3, D / 16, false, false, LOWP>(ch, sb + HS_HI, sb + HS_LO, LDW, mt * 16, 0, sb + WHH_HI, sb + WHH_LO, LDW, n0, 0, lane);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int u = u0 + 2 * t + (e & 1);
@@ -289,14 +291,14 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
                 const int row = mt * 16 + g + 8 * hrow, e0 = 2 * hrow;
                 const uint32_t off = (uint32_t)(row * LDG + u0 + 2 * t) * 2;
                 uint32_t hi, lo;
-                m16::split2(dr[e0] * scale, dr[e0 + 1] * scale, hi, lo);
-                *reinterpret_cast<uint32_t*>(smem + DG_HI + off) = hi; *reinterpret_cast<uint32_t*>(smem + DG_LO + off) = lo;
-                m16::split2(dz[e0] * scale, dz[e0 + 1] * scale, hi, lo);
-                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 2 * D) = hi; *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 2 * D) = lo;
-                m16::split2(dni[e0] * scale, dni[e0 + 1] * scale, hi, lo);
-                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 4 * D) = hi; *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 4 * D) = lo;
-                m16::split2(dnh[e0] * scale, dnh[e0 + 1] * scale, hi, lo);
-                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 6 * D) = hi; *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 6 * D) = lo;
+                m16::split2p<LOWP>(dr[e0] * scale, dr[e0 + 1] * scale, hi, lo);
+                *reinterpret_cast<uint32_t*>(smem + DG_HI + off) = hi; if (!LOWP) *reinterpret_cast<uint32_t*>(smem + DG_LO + off) = lo;
+                m16::split2p<LOWP>(dz[e0] * scale, dz[e0 + 1] * scale, hi, lo);
+                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 2 * D) = hi; if (!LOWP) *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 2 * D) = lo;
+                m16::split2p<LOWP>(dni[e0] * scale, dni[e0 + 1] * scale, hi, lo);
+                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 4 * D) = hi; if (!LOWP) *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 4 * D) = lo;
+                m16::split2p<LOWP>(dnh[e0] * scale, dnh[e0 + 1] * scale, hi, lo);
+                *reinterpret_cast<uint32_t*>(smem + DG_HI + off + 6 * D) = hi; if (!LOWP) *reinterpret_cast<uint32_t*>(smem + DG_LO + off + 6 * D) = lo;
             }
         }
         __syncthreads();
@@ -307,9 +309,9 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             float ca[1][1][4], cp[1][1][4];
             m16::zero_frag(ca);
             m16::zero_frag(cp);
-            m16::warp_gemm<1, 1, G3 / 16, false, true>(ca, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 0, sb + WCX_HI, sb + WCX_LO, LDC, n0, 0, lane);
-            m16::warp_gemm<1, 1, 2 * D / 16, false, true>(cp, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 0, sb + WHH_HI, sb + WHH_LO, LDW, n0, 0, lane);
-            m16::warp_gemm<1, 1, D / 16, false, true>(cp, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 3 * D, sb + WHH_HI, sb + WHH_LO, LDW, n0, 2 * D, lane);
+            m16::warp_gemm<1, 1, G3 / 16, false, true, LOWP>(ca, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 0, sb + WCX_HI, sb + WCX_LO, LDC, n0, 0, lane);
+            m16::warp_gemm<1, 1, 2 * D / 16, false, true, LOWP>(cp, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 0, sb + WHH_HI, sb + WHH_LO, LDW, n0, 0, lane);
+            m16::warp_gemm<1, 1, D / 16, false, true, LOWP>(cp, sb + DG_HI, sb + DG_LO, LDG, mt * 16, 3 * D, sb + WHH_HI, sb + WHH_LO, LDW, n0, 2 * D, lane);
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
                 const int node = t0 + mt * 16 + g + 8 * hrow;
@@ -332,10 +334,10 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_kernel(const StepDev p)
             m16::scale_frag(acc_fb, f);
             acc_scale = scale;
         }
-        m16::warp_gemm<6, 1, TM / 16, true, true>(acc_cx, sb + DG_HI, sb + DG_LO, LDG, wh * 96, 0, sb + AS_HI, sb + AS_LO, LDC, wn0, 0, lane);
-        m16::warp_gemm<2, 1, TM / 16, true, true>(acc_ha, sb + DG_HI, sb + DG_LO, LDG, wh * 96, 0, sb + HS_HI, sb + HS_LO, LDW, wn0, 0, lane);
-        m16::warp_gemm<4, 1, TM / 16, true, true>(acc_hb, sb + DG_HI, sb + DG_LO, LDG, wh ? 3 * D : 32, 0, sb + HS_HI, sb + HS_LO, LDW, wn0, 0, lane);
-        m16::warp_gemm<1, 2, TM / 16, true, true>(acc_fb, sb + DG_HI, sb + DG_LO, LDG, 16 * warp, 0, sb + AS_HI, sb + AS_LO, LDC, fn0, 0, lane);
+        m16::warp_gemm<6, 1, TM / 16, true, true, LOWP>(acc_cx, sb + DG_HI, sb + DG_LO, LDG, wh * 96, 0, sb + AS_HI, sb + AS_LO, LDC, wn0, 0, lane);
+        m16::warp_gemm<2, 1, TM / 16, true, true, LOWP>(acc_ha, sb + DG_HI, sb + DG_LO, LDG, wh * 96, 0, sb + HS_HI, sb + HS_LO, LDW, wn0, 0, lane);
+        m16::warp_gemm<4, 1, TM / 16, true, true, LOWP>(acc_hb, sb + DG_HI, sb + DG_LO, LDG, wh ? 3 * D : 32, 0, sb + HS_HI, sb + HS_LO, LDW, wn0, 0, lane);
+        m16::warp_gemm<1, 2, TM / 16, true, true, LOWP>(acc_fb, sb + DG_HI, sb + DG_LO, LDG, 16 * warp, 0, sb + AS_HI, sb + AS_LO, LDC, fn0, 0, lane);
         BTRACE(6);
         __syncthreads();
         BTRACE(7);
@@ -439,7 +441,7 @@ extern "C" size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc) {
 extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
                                       int32_t feat, const float* x, const float* weights, const float* states,
                                       const float* gout, float* grads, void* ws, size_t ws_bytes,
-                                      mgv_stream_t stream) {
+                                      int32_t precision, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_args(sch, num_enc, rounds, feat);
     if (rc != MGV_OK) return rc;
@@ -465,7 +467,9 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     float* partial = a.take<float>((size_t)num_enc * gx * 2 * SGRAD);
     MGV_CUDA(cudaMemsetAsync(partial, 0, (size_t)num_enc * gx * 2 * SGRAD * sizeof(float), st));
     const size_t smem = (size_t)B_SMEM;
-    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGV_REQUIRE(precision == 0 || precision == 1, "struct encoder: precision must be 0 (fp32-accurate) or 1 (bf16)");
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int k = steps; k >= 1; --k) {
         StepDev p{};
         fill_step(p, sch, k, steps, layernorm, feat, x, weights, states, slot, enc_stride);
@@ -474,7 +478,8 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
         p.out_part = part[(k - 1) & 1]; p.out_agg = agg[(k - 1) & 1];
         p.partial = partial;
         p.trace = (k == 2) ? mgv_debug_trace() : nullptr;
-        struct_bwd_kernel<<<dim3(gx, num_enc), THREADS, smem, st>>>(p);
+        if (precision == 1) struct_bwd_kernel<true><<<dim3(gx, num_enc), THREADS, smem, st>>>(p);
+        else struct_bwd_kernel<false><<<dim3(gx, num_enc), THREADS, smem, st>>>(p);
         mgv_count_launches(1);
     }
     const size_t total = (size_t)num_enc * 2 * SGRAD;

@@ -86,16 +86,18 @@ __device__ __forceinline__ void tmem_ld4x4(uint32_t taddr, float (&v)[16]) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(r[4 * k]), "=r"(r[4 * k + 1]), "=r"(r[4 * k + 2]), "=r"(r[4 * k + 3]) : "r"(taddr + 64u * k) : "memory");
 }
+template <bool LOWP>
 __device__ __forceinline__ void split_store_sw128(uint32_t hi_base, uint32_t lo_base, int row, int c, const float (&v)[8]) {
     uint4 hi, lo;
-    tc::split8(v, hi, lo);
+    tc::split8p<LOWP>(v, hi, lo);
     const uint32_t off = tc::sw128_off(row, c);
     tc::st_shared_v4(hi_base + off, hi);
-    tc::st_shared_v4(lo_base + off, lo);
+    if (!LOWP) tc::st_shared_v4(lo_base + off, lo);
 }
 
 // ======================================================================================= weight image
 // natural fp32 block -> fp16 hi/lo planes in the UMMA layouts the step kernels consume.
+template <bool LOWP>
 __global__ void struct_image_kernel(const float* __restrict__ pack, uint8_t* __restrict__ image, int blocks) {
     const int blk = blockIdx.y;
     if (blk >= blocks) return;
@@ -108,7 +110,7 @@ __global__ void struct_image_kernel(const float* __restrict__ pack, uint8_t* __r
         const int o = i >> 3, c = i & 7;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = W[O_WCX + o * LDC + c * 8 + e];
-        tc::split8(v, hi, lo);
+        tc::split8p<LOWP>(v, hi, lo);
         const uint32_t off = tc::sw128_off(o, c);
         *reinterpret_cast<uint4*>(img + WC_HI + off) = hi;
         *reinterpret_cast<uint4*>(img + WC_LO + off) = lo;
@@ -116,7 +118,7 @@ __global__ void struct_image_kernel(const float* __restrict__ pack, uint8_t* __r
         const int j = i - G3 * 8, o = j >> 3, c = j & 7;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = W[O_WHH + o * LDM + c * 8 + e];
-        tc::split8(v, hi, lo);
+        tc::split8p<LOWP>(v, hi, lo);
         const uint32_t off = tc::sw128_off(o, c);
         *reinterpret_cast<uint4*>(img + WHH_HI + off) = hi;
         *reinterpret_cast<uint4*>(img + WHH_LO + off) = lo;
@@ -134,7 +136,7 @@ __global__ void struct_image_kernel(const float* __restrict__ pack, uint8_t* __r
             else if (n < G3) { v[0] = W[O_BC + n]; v[1] = W[O_BIH + n]; }                   // gi_n
             else { v[1] = W[O_BHH + n - D]; }                                               // gh_n
         }
-        tc::split8(v, hi, lo);
+        tc::split8p<LOWP>(v, hi, lo);
         const uint32_t off = tc::plain16_off(n, c);
         *reinterpret_cast<uint4*>(img + WX_HI + off) = hi;
         *reinterpret_cast<uint4*>(img + WX_LO + off) = lo;
@@ -158,6 +160,7 @@ __device__ __forceinline__ void gru_gates(float gr, float gz, float gi, float gh
     n = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y));
 }
 
+template <bool LOWP>
 __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             for (int ps = 0; ps < 4; ++ps) {
                 const int row = gw * 16 + ps * 4 + rg;
                 const float h8[8] = {ha[ps].x, ha[ps].y, ha[ps].z, ha[ps].w, hb[ps].x, hb[ps].y, hb[ps].z, hb[ps].w};
-                split_store_sw128(sbase + A_H_HI, sbase + A_H_LO, row, c, h8);
+                split_store_sw128<LOWP>(sbase + A_H_HI, sbase + A_H_LO, row, c, h8);
                 float xv[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) xv[e] = __shfl_sync(0xffffffffu, xe[ps], (lane & 24) + e);   // features of this row
@@ -266,10 +269,10 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                 }
                 if (c < 2) {
                     uint4 hi, lo;
-                    tc::split8(xv, hi, lo);
+                    tc::split8p<LOWP>(xv, hi, lo);
                     const uint32_t off = tc::plain16_off(row, c);
                     tc::st_shared_v4(sbase + A_X_HI + off, hi);
-                    tc::st_shared_v4(sbase + A_X_LO + off, lo);
+                    if (!LOWP) tc::st_shared_v4(sbase + A_X_LO + off, lo);
                 }
             }
             if (warp == EPI_WARPS && lane == 0) TRACE(3);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             }
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps)
-                split_store_sw128(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps]);
+                split_store_sw128<LOWP>(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps]);
             if (warp == EPI_WARPS && lane == 0) TRACE(4);
             tc::fence_async_smem();
             tc::mbar_arrive(bar_a_full);
@@ -323,23 +326,23 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                 TRACE(6);
                 const uint32_t d = tmem + (uint32_t)b * 256u;
                 // [x deg 1] block first: initialises all 256 columns (biases, degree term, feature term)
-                tc::mma3(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
-                         tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false), 0u);
+                tc::mma3p<LOWP>(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
+                         tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false, LOWP), 0u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)      // h . Whh[r, z]^T -> r, z
-                    tc::mma3(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                    tc::mma3p<LOWP>(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
                              tc::desc_k_sw128(sbase + WHH_HI + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 32 * j),
-                             tc::make_idesc(128, 128, false, false), 1u);
+                             tc::make_idesc(128, 128, false, false, LOWP), 1u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)      // h . Whh[n]^T -> gh_n
-                    tc::mma3(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                    tc::mma3p<LOWP>(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
                              tc::desc_k_sw128(sbase + WHH_HI + 16384 + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 16384 + 32 * j),
-                             tc::make_idesc(128, 64, false, false), 1u);
+                             tc::make_idesc(128, 64, false, false, LOWP), 1u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)      // agg . Wc^T -> r, z, gi_n
-                    tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
+                    tc::mma3p<LOWP>(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
                              tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
-                             tc::make_idesc(128, 192, false, false), 1u);
+                             tc::make_idesc(128, 192, false, false, LOWP), 1u);
                 tc::mma_commit(bar_a_empty);
                 tc::mma_commit(bar_acc_full + 8 * b);
                 TRACE(7);
@@ -437,9 +440,10 @@ long long* mgv_debug_trace() { return g_trace; }
 
 size_t mgv_struct_image_bytes(int num_enc) { return mgv_align_up((size_t)num_enc * 2 * IMG_BYTES, 256); }
 
-int mgv_struct_build_image(const float* weights, int num_enc, uint8_t* image, cudaStream_t st) {
+int mgv_struct_build_image(const float* weights, int num_enc, uint8_t* image, int precision, cudaStream_t st) {
     const int items = 2 * G3 * 8 + 256 * 2 + 2 * D;
-    struct_image_kernel<<<dim3((items + 255) / 256, num_enc * 2), 256, 0, st>>>(weights, image, num_enc * 2);
+    if (precision == 1) struct_image_kernel<true><<<dim3((items + 255) / 256, num_enc * 2), 256, 0, st>>>(weights, image, num_enc * 2);
+    else struct_image_kernel<false><<<dim3((items + 255) / 256, num_enc * 2), 256, 0, st>>>(weights, image, num_enc * 2);
     mgv_count_launches(1);
     return mgv_check_cuda(cudaGetLastError(), "struct_image_kernel");
 }
@@ -451,9 +455,10 @@ extern "C" size_t mgv_struct_fwd_workspace_bytes(int64_t N, int32_t num_enc) {
 
 extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
                                       int32_t feat, const float* x, const float* weights, float* states,
-                                      void* ws, size_t ws_bytes, mgv_stream_t stream) {
+                                      void* ws, size_t ws_bytes, int32_t precision, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MGV_REQUIRE(sch != nullptr, "struct encoder: null schedule");
+    MGV_REQUIRE(precision == 0 || precision == 1, "struct encoder: precision must be 0 (fp32-accurate) or 1 (bf16)");
     MGV_REQUIRE(num_enc >= 1 && num_enc <= 2, "struct encoder: num_enc must be 1 or 2");
     MGV_REQUIRE(rounds >= 1, "struct encoder: rounds must be >= 1");
     MGV_REQUIRE(feat >= 0 && feat <= MGV_MAX_FEAT, "struct encoder: dim_feature %d > %d", feat, MGV_MAX_FEAT);
@@ -467,12 +472,13 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
     }
     MgvArena a(ws, ws_bytes);
     uint8_t* image = a.take<uint8_t>((size_t)num_enc * 2 * IMG_BYTES);
-    int rc = mgv_struct_build_image(weights, num_enc, image, st);
+    int rc = mgv_struct_build_image(weights, num_enc, image, precision, st);
     if (rc != MGV_OK) return rc;
     const int steps = 2 * rounds;
     const size_t slot = (size_t)N * D;
     const size_t enc_stride = (size_t)(steps + 1) * slot;
-    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
     int dev = 0, sms = 0;
     MGV_CUDA(cudaGetDevice(&dev));
     MGV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -499,7 +505,8 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         p.next = states + (size_t)k * slot;
         p.enc_stride = enc_stride;
         p.trace = (k == steps) ? g_trace : nullptr;
-        struct_fwd_tc_kernel<<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
+        if (precision == 1) struct_fwd_tc_kernel<true><<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
+        else struct_fwd_tc_kernel<false><<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
         mgv_count_launches(1);
     }
     return mgv_check_cuda(cudaGetLastError(), "mgv_struct_encoder_fwd");

@@ -136,16 +136,18 @@ constexpr uint32_t FW_H32 = FW_HS_LO + FTM * LDMH * 2, FW_SS = FW_H32 + FTM * LD
 constexpr uint32_t F_SMEM_BYTES = FW_IDS + FTM * 4;
 static_assert(F_SMEM_BYTES <= 227 * 1024 && FW_XS_HI % 16 == 0 && FW_MS_HI % 16 == 0 && FW_HS_HI % 16 == 0, "sweep forward smem");
 
+template <bool LOWP>
 __device__ __forceinline__ void st_plane8(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t half_off, const float (&v)[8]) {
     uint4 hi, lo;
-    m16::split2(v[0], v[1], hi.x, lo.x);
-    m16::split2(v[2], v[3], hi.y, lo.y);
-    m16::split2(v[4], v[5], hi.z, lo.z);
-    m16::split2(v[6], v[7], hi.w, lo.w);
+    m16::split2p<LOWP>(v[0], v[1], hi.x, lo.x);
+    m16::split2p<LOWP>(v[2], v[3], hi.y, lo.y);
+    m16::split2p<LOWP>(v[4], v[5], hi.z, lo.z);
+    m16::split2p<LOWP>(v[6], v[7], hi.w, lo.w);
     *reinterpret_cast<uint4*>(hi_plane + half_off * 2) = hi;
-    *reinterpret_cast<uint4*>(lo_plane + half_off * 2) = lo;
+    if (!LOWP) *reinterpret_cast<uint4*>(lo_plane + half_off * 2) = lo;
 }
 // [rows][cols] fp32 row-major (global) -> hi/lo planes with row stride ld (halves)
+template <bool LOWP>
 __device__ __forceinline__ void load_planes(uint8_t* hi_plane, uint8_t* lo_plane, const float* __restrict__ W, int rows, int cols, int ld,
                                             int tid, int nthr) {
     const int chunks = cols / 8;
@@ -154,7 +156,7 @@ __device__ __forceinline__ void load_planes(uint8_t* hi_plane, uint8_t* lo_plane
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = __ldg(W + (size_t)r * cols + c * 8 + e);
-        st_plane8(hi_plane, lo_plane, (uint32_t)(r * ld + c * 8), v);
+        st_plane8<LOWP>(hi_plane, lo_plane, (uint32_t)(r * ld + c * 8), v);
     }
 }
 __device__ __forceinline__ void gru_gates(float gr, float gz, float gi, float gh, float& r, float& z, float& n) {
@@ -232,6 +234,7 @@ __device__ __forceinline__ void gather_attend16(const SweepDev& p, const float* 
     }
 }
 
+template <bool LOWP>
 __global__ void __launch_bounds__(FTHREADS, 1) sweep_fwd_kernel(const SweepDev p) {
     extern __shared__ __align__(128) uint8_t fsm[];
     const uint32_t sb = m16::smem_u32(fsm);
@@ -246,9 +249,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) sweep_fwd_kernel(const SweepDev p
     find_role(p, code, rank, nct);
     if (code >= 0) {
         const float* W = p.weights + (size_t)code * PACK;
-        load_planes(fsm + FW_WV_HI, fsm + FW_WV_LO, W + O_WV, D, D2, LDXH, tid, FTHREADS);
-        load_planes(fsm + FW_WIH_HI, fsm + FW_WIH_LO, W + O_WIH, G3, D, LDMH, tid, FTHREADS);
-        load_planes(fsm + FW_WHH_HI, fsm + FW_WHH_LO, W + O_WHH, G3, D, LDMH, tid, FTHREADS);
+        load_planes<LOWP>(fsm + FW_WV_HI, fsm + FW_WV_LO, W + O_WV, D, D2, LDXH, tid, FTHREADS);
+        load_planes<LOWP>(fsm + FW_WIH_HI, fsm + FW_WIH_LO, W + O_WIH, G3, D, LDMH, tid, FTHREADS);
+        load_planes<LOWP>(fsm + FW_WHH_HI, fsm + FW_WHH_LO, W + O_WHH, G3, D, LDMH, tid, FTHREADS);
         for (int i = tid; i < 576; i += FTHREADS)
             Bias[i] = __ldg(W + (i < 128 ? O_U + i : (i < 192 ? O_BV + i - 128 : (i < 384 ? O_BIH + i - 192 : O_BHH + i - 384))));
     }
@@ -283,9 +286,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) sweep_fwd_kernel(const SweepDev p
                                 h8[0] = a.x; h8[1] = a.y; h8[2] = a.z; h8[3] = a.w; h8[4] = b.x; h8[5] = b.y; h8[6] = b.z; h8[7] = b.w;
                             }
                         }
-                        st_plane8(fsm + FW_XS_HI, fsm + FW_XS_LO, (uint32_t)(row * LDXH + 8 * l16), xb);
+                        st_plane8<LOWP>(fsm + FW_XS_HI, fsm + FW_XS_LO, (uint32_t)(row * LDXH + 8 * l16), xb);
                         if (l16 < 8) {
-                            st_plane8(fsm + FW_HS_HI, fsm + FW_HS_LO, (uint32_t)(row * LDMH + 8 * l16), h8);
+                            st_plane8<LOWP>(fsm + FW_HS_HI, fsm + FW_HS_LO, (uint32_t)(row * LDMH + 8 * l16), h8);
                             mgv_st4(H32 + row * LDF32 + 8 * l16, make_float4(h8[0], h8[1], h8[2], h8[3]));
                             mgv_st4(H32 + row * LDF32 + 8 * l16 + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
                         }
@@ -296,16 +299,16 @@ __global__ void __launch_bounds__(FTHREADS, 1) sweep_fwd_kernel(const SweepDev p
                         const int n0[1] = {nt8};
                         float c[1][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<1, 1, D2 / 16, false, false>(c, sb + FW_XS_HI, sb + FW_XS_LO, LDXH, mt * 16, 0, sb + FW_WV_HI, sb + FW_WV_LO,
+                        m16::warp_gemm<1, 1, D2 / 16, false, false, LOWP>(c, sb + FW_XS_HI, sb + FW_XS_LO, LDXH, mt * 16, 0, sb + FW_WV_HI, sb + FW_WV_LO,
                                                                     LDXH, n0, 0, lane);
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
                             const int row = mt * 16 + g + 8 * hrow, col = nt8 + 2 * t;
                             const float s = Ss[row];
                             uint32_t hi, lo;
-                            m16::split2(fmaf(Bv[col], s, c[0][0][2 * hrow]), fmaf(Bv[col + 1], s, c[0][0][2 * hrow + 1]), hi, lo);
+                            m16::split2p<LOWP>(fmaf(Bv[col], s, c[0][0][2 * hrow]), fmaf(Bv[col + 1], s, c[0][0][2 * hrow + 1]), hi, lo);
                             *reinterpret_cast<uint32_t*>(fsm + FW_MS_HI + (row * LDMH + col) * 2) = hi;
-                            *reinterpret_cast<uint32_t*>(fsm + FW_MS_LO + (row * LDMH + col) * 2) = lo;
+                            if (!LOWP) *reinterpret_cast<uint32_t*>(fsm + FW_MS_LO + (row * LDMH + col) * 2) = lo;
                         }
                     }
                     __syncthreads();
@@ -314,10 +317,10 @@ __global__ void __launch_bounds__(FTHREADS, 1) sweep_fwd_kernel(const SweepDev p
                         float ci[1][3][4], ch[1][3][4];
                         m16::zero_frag(ci);
                         m16::zero_frag(ch);
-                        m16::warp_gemm<1, 3, D / 16, false, false>(ci, sb + FW_MS_HI, sb + FW_MS_LO, LDMH, mt * 16, 0, sb + FW_WIH_HI, sb + FW_WIH_LO,
+                        m16::warp_gemm<1, 3, D / 16, false, false, LOWP>(ci, sb + FW_MS_HI, sb + FW_MS_LO, LDMH, mt * 16, 0, sb + FW_WIH_HI, sb + FW_WIH_LO,
                                                                    LDMH, n0, 0, lane);
                         if (hf_prev != nullptr)
-                            m16::warp_gemm<1, 3, D / 16, false, false>(ch, sb + FW_HS_HI, sb + FW_HS_LO, LDMH, mt * 16, 0, sb + FW_WHH_HI, sb + FW_WHH_LO,
+                            m16::warp_gemm<1, 3, D / 16, false, false, LOWP>(ch, sb + FW_HS_HI, sb + FW_HS_LO, LDMH, mt * 16, 0, sb + FW_WHH_HI, sb + FW_WHH_LO,
                                                                        LDMH, n0, 0, lane);
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
@@ -447,7 +450,7 @@ __device__ __forceinline__ void pull_out_edges16(const SweepDev& p, int v, int l
     }
 }
 
-template <int BTM, bool HAS_H>
+template <int BTM, bool HAS_H, bool LOWP>
 __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p) {
     using S = BwdSmem<BTM, HAS_H>;
     constexpr int MT = BTM / 16;
@@ -472,9 +475,9 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
     find_role(p, code, rank, nct);
     const float* W = p.weights + (size_t)(code < 0 ? 0 : code) * PACK;
     if (code >= 0) {
-        load_planes(bsm + S::WV_HI, bsm + S::WV_LO, W + O_WV, D, D2, LDXH, tid, BTHREADS);
-        load_planes(bsm + S::WIH_HI, bsm + S::WIH_LO, W + O_WIH, G3, D, LDMH, tid, BTHREADS);
-        if (HAS_H) load_planes(bsm + S::WHH_HI, bsm + S::WHH_LO, W + O_WHH, G3, D, LDMH, tid, BTHREADS);
+        load_planes<LOWP>(bsm + S::WV_HI, bsm + S::WV_LO, W + O_WV, D, D2, LDXH, tid, BTHREADS);
+        load_planes<LOWP>(bsm + S::WIH_HI, bsm + S::WIH_LO, W + O_WIH, G3, D, LDMH, tid, BTHREADS);
+        if (HAS_H) load_planes<LOWP>(bsm + S::WHH_HI, bsm + S::WHH_LO, W + O_WHH, G3, D, LDMH, tid, BTHREADS);
         for (int i = tid; i < 576; i += BTHREADS)
             Bias[i] = __ldg(W + (i < 128 ? O_U + i : (i < 192 ? O_BV + i - 128 : (i < 384 ? O_BIH + i - 192 : O_BHH + i - 384))));
     }
@@ -542,12 +545,12 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                             }
                             gather_attend16<true>(p, hf_cur, u8, node, l16, hmask, xb, S);
                         }
-                        st_plane8(bsm + S::XS_HI, bsm + S::XS_LO, (uint32_t)(row * LDXH + 8 * l16), xb);
+                        st_plane8<LOWP>(bsm + S::XS_HI, bsm + S::XS_LO, (uint32_t)(row * LDXH + 8 * l16), xb);
                         mgv_st4(X32 + row * LDX + 8 * l16, make_float4(xb[0], xb[1], xb[2], xb[3]));
                         mgv_st4(X32 + row * LDX + 8 * l16 + 4, make_float4(xb[4], xb[5], xb[6], xb[7]));
                         if (l16 < 8) {
                             if (HAS_H) {
-                                st_plane8(bsm + S::HS_HI, bsm + S::HS_LO, (uint32_t)(row * LDMH + 8 * l16), h8);
+                                st_plane8<LOWP>(bsm + S::HS_HI, bsm + S::HS_LO, (uint32_t)(row * LDMH + 8 * l16), h8);
                                 mgv_st4(H32 + row * LDF32 + 8 * l16, make_float4(h8[0], h8[1], h8[2], h8[3]));
                                 mgv_st4(H32 + row * LDF32 + 8 * l16 + 4, make_float4(h8[4], h8[5], h8[6], h8[7]));
                             }
@@ -563,16 +566,16 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     if (warp < 8 * MT) {
                         float c[1][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<1, 1, D2 / 16, false, false>(c, sb + S::XS_HI, sb + S::XS_LO, LDXH, mrow, 0, sb + S::WV_HI, sb + S::WV_LO, LDXH,
+                        m16::warp_gemm<1, 1, D2 / 16, false, false, LOWP>(c, sb + S::XS_HI, sb + S::XS_LO, LDXH, mrow, 0, sb + S::WV_HI, sb + S::WV_LO, LDXH,
                                                                     wn0, 0, lane);
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
                             const int row = mrow + g + 8 * hrow, col = wn8 + 2 * t;
                             const float sv = Ss[row];
                             uint32_t hi, lo;
-                            m16::split2(fmaf(Bv[col], sv, c[0][0][2 * hrow]), fmaf(Bv[col + 1], sv, c[0][0][2 * hrow + 1]), hi, lo);
+                            m16::split2p<LOWP>(fmaf(Bv[col], sv, c[0][0][2 * hrow]), fmaf(Bv[col + 1], sv, c[0][0][2 * hrow + 1]), hi, lo);
                             *reinterpret_cast<uint32_t*>(bsm + S::MS_HI + (row * LDMH + col) * 2) = hi;
-                            *reinterpret_cast<uint32_t*>(bsm + S::MS_LO + (row * LDMH + col) * 2) = lo;
+                            if (!LOWP) *reinterpret_cast<uint32_t*>(bsm + S::MS_LO + (row * LDMH + col) * 2) = lo;
                         }
                     }
                     __syncthreads();
@@ -584,10 +587,10 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         float ci[1][3][4], ch[1][3][4];
                         m16::zero_frag(ci);
                         m16::zero_frag(ch);
-                        m16::warp_gemm<1, 3, D / 16, false, false>(ci, sb + S::MS_HI, sb + S::MS_LO, LDMH, mrow, 0, sb + S::WIH_HI, sb + S::WIH_LO, LDMH,
+                        m16::warp_gemm<1, 3, D / 16, false, false, LOWP>(ci, sb + S::MS_HI, sb + S::MS_LO, LDMH, mrow, 0, sb + S::WIH_HI, sb + S::WIH_LO, LDMH,
                                                                    n0, 0, lane);
                         if (HAS_H && hf_prev != nullptr)
-                            m16::warp_gemm<1, 3, D / 16, false, false>(ch, sb + S::HS_HI, sb + S::HS_LO, LDMH, mrow, 0, sb + S::WHH_HI, sb + S::WHH_LO,
+                            m16::warp_gemm<1, 3, D / 16, false, false, LOWP>(ch, sb + S::HS_HI, sb + S::HS_LO, LDMH, mrow, 0, sb + S::WHH_HI, sb + S::WHH_LO,
                                                                        LDMH, n0, 0, lane);
                         float amax = 0.f;
 #pragma unroll
@@ -637,14 +640,14 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                             const int row = mrow + g + 8 * hrow, e0 = 2 * hrow;
                             const uint32_t off = (uint32_t)(row * LDGH + wn8 + 2 * t) * 2;
                             uint32_t hi, lo;
-                            m16::split2(dr[e0] * scale, dr[e0 + 1] * scale, hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off) = hi; *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off) = lo;
-                            m16::split2(dz[e0] * scale, dz[e0 + 1] * scale, hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 2 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 2 * D) = lo;
-                            m16::split2(dni[e0] * scale, dni[e0 + 1] * scale, hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 4 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 4 * D) = lo;
-                            m16::split2(dnh[e0] * scale, dnh[e0 + 1] * scale, hi, lo);
-                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 6 * D) = hi; *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 6 * D) = lo;
+                            m16::split2p<LOWP>(dr[e0] * scale, dr[e0 + 1] * scale, hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off) = hi; if (!LOWP) *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off) = lo;
+                            m16::split2p<LOWP>(dz[e0] * scale, dz[e0 + 1] * scale, hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 2 * D) = hi; if (!LOWP) *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 2 * D) = lo;
+                            m16::split2p<LOWP>(dni[e0] * scale, dni[e0 + 1] * scale, hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 4 * D) = hi; if (!LOWP) *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 4 * D) = lo;
+                            m16::split2p<LOWP>(dnh[e0] * scale, dnh[e0 + 1] * scale, hi, lo);
+                            *reinterpret_cast<uint32_t*>(bsm + S::DG_HI + off + 6 * D) = hi; if (!LOWP) *reinterpret_cast<uint32_t*>(bsm + S::DG_LO + off + 6 * D) = lo;
                         }
                     }
                     __syncthreads();
@@ -653,16 +656,16 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     if (warp < 8 * MT) {
                         float c[1][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<1, 1, G3 / 16, false, true>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, mrow, 0, sb + S::WIH_HI, sb + S::WIH_LO, LDMH,
+                        m16::warp_gemm<1, 1, G3 / 16, false, true, LOWP>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, mrow, 0, sb + S::WIH_HI, sb + S::WIH_LO, LDMH,
                                                                    wn0, 0, lane);
                         float sbv[2] = {0.f, 0.f};
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
                             const int row = mrow + g + 8 * hrow, col = wn8 + 2 * t;
                             uint32_t hi, lo;
-                            m16::split2(c[0][0][2 * hrow], c[0][0][2 * hrow + 1], hi, lo);              // stays scaled
+                            m16::split2p<LOWP>(c[0][0][2 * hrow], c[0][0][2 * hrow + 1], hi, lo);              // stays scaled
                             *reinterpret_cast<uint32_t*>(bsm + S::DM_HI + (row * LDMH + col) * 2) = hi;
-                            *reinterpret_cast<uint32_t*>(bsm + S::DM_LO + (row * LDMH + col) * 2) = lo;
+                            if (!LOWP) *reinterpret_cast<uint32_t*>(bsm + S::DM_LO + (row * LDMH + col) * 2) = lo;
                             const float d0 = c[0][0][2 * hrow] * inv_scale, d1 = c[0][0][2 * hrow + 1] * inv_scale;
                             DM32[row * LDF32 + col] = d0;
                             DM32[row * LDF32 + col + 1] = d1;
@@ -679,9 +682,9 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     } else if (HAS_H && hf_prev != nullptr) {
                         float c[1][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<1, 1, 2 * D / 16, false, true>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, 0, 0, sb + S::WHH_HI, sb + S::WHH_LO, LDMH,
+                        m16::warp_gemm<1, 1, 2 * D / 16, false, true, LOWP>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, 0, 0, sb + S::WHH_HI, sb + S::WHH_LO, LDMH,
                                                                       wn0, 0, lane);
-                        m16::warp_gemm<1, 1, D / 16, false, true>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, 0, 3 * D, sb + S::WHH_HI, sb + S::WHH_LO, LDMH,
+                        m16::warp_gemm<1, 1, D / 16, false, true, LOWP>(c, sb + S::DG_HI, sb + S::DG_LO, LDGH, 0, 3 * D, sb + S::WHH_HI, sb + S::WHH_LO, LDMH,
                                                                   wn0, 2 * D, lane);
 #pragma unroll
                         for (int hrow = 0; hrow < 2; ++hrow) {
@@ -699,7 +702,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                     {
                         float c[MT][1][4];
                         m16::zero_frag(c);
-                        m16::warp_gemm<MT, 1, D / 16, false, true>(c, sb + S::DM_HI, sb + S::DM_LO, LDMH, 0, 0, sb + S::WV_HI, sb + S::WV_LO, LDXH,
+                        m16::warp_gemm<MT, 1, D / 16, false, true, LOWP>(c, sb + S::DM_HI, sb + S::DM_LO, LDMH, 0, 0, sb + S::WV_HI, sb + S::WV_LO, LDXH,
                                                                    vn0, 0, lane);
 #pragma unroll
                         for (int m = 0; m < MT; ++m)
@@ -750,12 +753,12 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         m16::scale_frag(acc_v, f);
                         acc_scale = scale;
                     }
-                    m16::warp_gemm<6, 1, MT, true, true>(acc_ih, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh * 96, 0, sb + S::MS_HI, sb + S::MS_LO, LDMH, wn0, 0, lane);
+                    m16::warp_gemm<6, 1, MT, true, true, LOWP>(acc_ih, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh * 96, 0, sb + S::MS_HI, sb + S::MS_LO, LDMH, wn0, 0, lane);
                     if (HAS_H && hf_prev != nullptr) {
-                        m16::warp_gemm<2, 1, MT, true, true>(acc_ha, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh * 96, 0, sb + S::HS_HI, sb + S::HS_LO, LDMH, wn0, 0, lane);
-                        m16::warp_gemm<4, 1, MT, true, true>(acc_hb, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh ? 3 * D : 32, 0, sb + S::HS_HI, sb + S::HS_LO, LDMH, wn0, 0, lane);
+                        m16::warp_gemm<2, 1, MT, true, true, LOWP>(acc_ha, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh * 96, 0, sb + S::HS_HI, sb + S::HS_LO, LDMH, wn0, 0, lane);
+                        m16::warp_gemm<4, 1, MT, true, true, LOWP>(acc_hb, sb + S::DG_HI, sb + S::DG_LO, LDGH, wh ? 3 * D : 32, 0, sb + S::HS_HI, sb + S::HS_LO, LDMH, wn0, 0, lane);
                     }
-                    m16::warp_gemm<4, 1, MT, true, true>(acc_v, sb + S::DM_HI, sb + S::DM_LO, LDMH, 0, 0, sb + S::XS_HI, sb + S::XS_LO, LDXH, vn0, 0, lane);
+                    m16::warp_gemm<4, 1, MT, true, true, LOWP>(acc_v, sb + S::DM_HI, sb + S::DM_LO, LDMH, 0, 0, sb + S::XS_HI, sb + S::XS_LO, LDXH, vn0, 0, lane);
                     __syncthreads();
                     SWTRACE(6);
                 }
@@ -893,7 +896,7 @@ int coop_grid(const void* kernel, size_t smem, int threads, int* grid_out) {
 
 extern "C" int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,
                                    const float* weights, const float* hs, float* hf_all,
-                                   int32_t* sync, mgv_stream_t stream) {
+                                   int32_t* sync, int32_t precision, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     SweepDev d;
     int rc = fill_common(d, sch, rounds, handled_mask, weights, hs, sync);
@@ -902,21 +905,23 @@ extern "C" int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint
     if (sch->N == 0 || sch->L <= 1) return MGV_OK;          // no level >= 1: hf stays zero
     int grid = 0;
     const size_t smem = (size_t)F_SMEM_BYTES;
-    rc = coop_grid((const void*)sweep_fwd_kernel, smem, FTHREADS, &grid);
+    MGV_REQUIRE(precision == 0 || precision == 1, "level sweep: precision must be 0 (fp32-accurate) or 1 (bf16)");
+    const void* fkern = precision == 1 ? (const void*)sweep_fwd_kernel<true> : (const void*)sweep_fwd_kernel<false>;
+    rc = coop_grid(fkern, smem, FTHREADS, &grid);
     if (rc != MGV_OK) return rc;
     assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
     if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;          // nothing to propagate
     MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
     void* args[] = {&d};
-    MGV_CUDA(cudaLaunchCooperativeKernel((void*)sweep_fwd_kernel, dim3(grid), dim3(FTHREADS), args, smem, st));
+    MGV_CUDA(cudaLaunchCooperativeKernel((void*)fkern, dim3(grid), dim3(FTHREADS), args, smem, st));
     mgv_count_launches(1);
     return MGV_OK;
 }
 
 extern "C" int mgv_sweep_bwd_grid(void) {
     int g1 = 0, g2 = 0;
-    if (coop_grid((const void*)sweep_bwd_kernel<16, true>, (size_t)BwdSmem<16, true>::BYTES, BTHREADS, &g1) != MGV_OK) return -1;
-    if (coop_grid((const void*)sweep_bwd_kernel<32, false>, (size_t)BwdSmem<32, false>::BYTES, BTHREADS, &g2) != MGV_OK) return -1;
+    if (coop_grid((const void*)sweep_bwd_kernel<16, true, false>, (size_t)BwdSmem<16, true>::BYTES, BTHREADS, &g1) != MGV_OK) return -1;
+    if (coop_grid((const void*)sweep_bwd_kernel<32, false, false>, (size_t)BwdSmem<32, false>::BYTES, BTHREADS, &g2) != MGV_OK) return -1;
     return g1 > g2 ? g1 : g2;
 }
 
@@ -933,7 +938,7 @@ extern "C" size_t mgv_sweep_bwd_workspace_bytes(int64_t N, int64_t E) {
 extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,
                                    const float* weights, const float* hs, const float* hf_all,
                                    float* ghs, float* ghf, float* grads,
-                                   void* ws, size_t ws_bytes, int32_t* sync, mgv_stream_t stream) {
+                                   void* ws, size_t ws_bytes, int32_t* sync, int32_t precision, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     SweepDev d;
     int rc = fill_common(d, sch, rounds, handled_mask, weights, hs, sync);
@@ -943,7 +948,9 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     if (sch->N == 0 || sch->L <= 1) return MGV_OK;
     int grid = 0;
     const bool single = rounds == 1;                          // h = 0 everywhere: the 32-node variant without W_hh
-    const void* kern = single ? (const void*)sweep_bwd_kernel<32, false> : (const void*)sweep_bwd_kernel<16, true>;
+    MGV_REQUIRE(precision == 0 || precision == 1, "level sweep: precision must be 0 (fp32-accurate) or 1 (bf16)");
+    const void* kern = single ? (precision == 1 ? (const void*)sweep_bwd_kernel<32, false, true> : (const void*)sweep_bwd_kernel<32, false, false>)
+                              : (precision == 1 ? (const void*)sweep_bwd_kernel<16, true, true> : (const void*)sweep_bwd_kernel<16, true, false>);
     const size_t smem = single ? (size_t)BwdSmem<32, false>::BYTES : (size_t)BwdSmem<16, true>::BYTES;
     rc = coop_grid(kern, smem, BTHREADS, &grid);
     if (rc != MGV_OK) return rc;

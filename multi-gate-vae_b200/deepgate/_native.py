@@ -17,6 +17,7 @@ NCODE = 8
 CODE_SHIFT = 28
 MAX_FEAT = 8
 TILE_ROWS = 128
+PRECISION_FP32, PRECISION_BF16 = 0, 1
 SWEEP_PACK_FLOATS = 66112
 SWEEP_GRAD_FLOATS = 33344
 STRUCT_PACK_FLOATS = 28416
@@ -52,15 +53,15 @@ _PROTOTYPES = {
     "mgv_build_level_lists": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _vp, _vp]),
     "mgv_degree_order_workspace_bytes": (_sz, [_i64]),
     "mgv_build_degree_order": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "mgv_level_sweep_fwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "mgv_level_sweep_fwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mgv_sweep_bwd_grid": (ctypes.c_int, []),
     "mgv_sweep_bwd_workspace_bytes": (_sz, [_i64, _i64]),
-    "mgv_level_sweep_bwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "mgv_level_sweep_bwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i32, _vp]),
     "mgv_struct_fwd_workspace_bytes": (_sz, [_i64, _i32]),
-    "mgv_struct_encoder_fwd": (ctypes.c_int, [_SP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mgv_struct_encoder_fwd": (ctypes.c_int, [_SP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "mgv_struct_bwd_grid": (ctypes.c_int, []),
     "mgv_struct_bwd_workspace_bytes": (_sz, [_i64, _i32]),
-    "mgv_struct_encoder_bwd": (ctypes.c_int, [_SP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mgv_struct_encoder_bwd": (ctypes.c_int, [_SP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "mgv_vae_func_workspace_bytes": (_sz, [_i64]),
     "mgv_vae_func_loss_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "mgv_vae_func_loss_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64,

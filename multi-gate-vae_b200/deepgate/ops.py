@@ -19,6 +19,23 @@ _GRU_KEYS = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")
 PARAMS_PER_CODE = len(_AGGR_KEYS) + len(_GRU_KEYS)      # 12
 
 
+# Arithmetic of the tensor-core products: "fp32" (default; fp16 hi/lo planes, fp32-accurate) or "bf16" (one bf16 plane,
+# fp32 accumulation; embeddings / gradients within 2e-2 -- the stated tolerance of the bf16 configuration).  Read at
+# forward time; the backward of a graph uses the precision of its forward.
+PRECISION = "fp32"
+
+
+def set_precision(name):
+    global PRECISION
+    if name not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    PRECISION = name
+
+
+def _prec():
+    return nat.PRECISION_BF16 if PRECISION == "bf16" else nat.PRECISION_FP32
+
+
 # Optional per-kernel timing (bench.py): PROFILE = {} enables CUDA-event brackets around each
 # library call on the launching stream; entries are name -> [(start_event, end_event), ...].
 PROFILE = None
@@ -93,15 +110,16 @@ class LevelSweepFunction(torch.autograd.Function):
         mask = 0
         for c in codes:
             mask |= 1 << c
+        prec = _prec()
         pack = _sweep_pack(params, codes, dev)
         hf_all = torch.zeros(rounds, max(N, 1), nat.D, dtype=torch.float32, device=dev)
         sync = torch.zeros(64, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             with _timed("level_sweep_fwd", dev):
               nat.check(lib.mgv_level_sweep_fwd(sched.c_struct(), rounds, mask, nat.ptr(pack), nat.ptr(hs_c),
-                                              nat.ptr(hf_all), nat.ptr(sync), nat.stream_of(dev)),
+                                              nat.ptr(hf_all), nat.ptr(sync), prec, nat.stream_of(dev)),
                       "mgv_level_sweep_fwd")
-        ctx.sched, ctx.rounds, ctx.codes, ctx.mask = sched, rounds, tuple(codes), mask
+        ctx.sched, ctx.rounds, ctx.codes, ctx.mask, ctx.prec = sched, rounds, tuple(codes), mask, prec
         ctx.save_for_backward(hs_c, hf_all, pack, *params)
         ctx.launches = 1
         return hf_all[rounds - 1][:N]
@@ -125,7 +143,7 @@ class LevelSweepFunction(torch.autograd.Function):
             with _timed("level_sweep_bwd", dev):
               nat.check(lib.mgv_level_sweep_bwd(sched.c_struct(), rounds, ctx.mask, nat.ptr(pack), nat.ptr(hs_c),
                                               nat.ptr(hf_all), nat.ptr(ghs), nat.ptr(ghf), nat.ptr(grads),
-                                              nat.ptr(ws), nb, nat.ptr(sync), nat.stream_of(dev)),
+                                              nat.ptr(ws), nb, nat.ptr(sync), ctx.prec, nat.stream_of(dev)),
                       "mgv_level_sweep_bwd")
         sel = _sweep_tables(params, codes)
         extra = torch.empty(max(len(codes), 1), 128 + D * 2 * D, dtype=torch.float32, device=dev)
@@ -190,6 +208,7 @@ class StructEncoderFunction(torch.autograd.Function):
         feat = int(x_c.shape[1])
         per = len(params) // num_enc
         enc_params = [params[e * per:(e + 1) * per] for e in range(num_enc)]
+        prec = _prec()
         pack = _struct_pack(enc_params, layernorm, dev)
         states = torch.empty(num_enc, 2 * rounds + 1, max(N, 1), nat.D, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
@@ -198,9 +217,10 @@ class StructEncoderFunction(torch.autograd.Function):
             with _timed("struct_encoder_fwd", dev):
               nat.check(lib.mgv_struct_encoder_fwd(csr.c_struct(), num_enc, rounds, int(layernorm), feat,
                                                  nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(ws), nb,
-                                                 nat.stream_of(dev)),
+                                                 prec, nat.stream_of(dev)),
                       "mgv_struct_encoder_fwd")
         ctx.csr, ctx.rounds, ctx.layernorm, ctx.num_enc, ctx.feat, ctx.per = csr, rounds, layernorm, num_enc, feat, per
+        ctx.prec = prec
         ctx.save_for_backward(x_c, pack, states)
         ctx.saved_params = params
         return states[:, 2 * rounds, :N]
@@ -221,7 +241,7 @@ class StructEncoderFunction(torch.autograd.Function):
             with _timed("struct_encoder_bwd", dev):
               nat.check(lib.mgv_struct_encoder_bwd(csr.c_struct(), num_enc, rounds, int(ctx.layernorm), feat,
                                                  nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(g),
-                                                 nat.ptr(grads), nat.ptr(ws), nb, nat.stream_of(dev)),
+                                                 nat.ptr(grads), nat.ptr(ws), nb, ctx.prec, nat.stream_of(dev)),
                       "mgv_struct_encoder_bwd")
         params = ctx.saved_params
         ldw = D + feat

@@ -7,7 +7,8 @@ import pytest
 import torch
 
 from oracle import dg_oracle as O
-from util import (batch_from_arrays, build_model, check_grads, load_golden, oracle_inputs, oracle_train_grads, rel)
+from util import (ZERO_GRAD_TAGS as ZERO_TAGS, batch_from_arrays, build_model, check_grads, load_golden, oracle_inputs,
+                  oracle_train_grads, rel)
 
 pytestmark = pytest.mark.gpu
 CASES = ["mig_b4_r1", "aig_b4_r1", "xmg_b3_r2", "xag_b3_r1"]
@@ -288,3 +289,45 @@ def test_async_schedule_equals_sync_schedule_and_flags_bad_input():
     check_deferred_errors()                                         # flag was cleared
     with pytest.raises(RuntimeError):
         GraphCSR(bad, G.x.size(0), code=G.gate.reshape(-1), validate=True)
+
+
+# --------------------------------------------------------------------------- bf16 configuration (stated tolerance)
+BF16_TOL = 2e-2          # embeddings / losses, max-norm relative; gradients 5e-2 (one bf16 plane, fp32 accumulate)
+
+
+def test_bf16_mode_within_stated_tolerance():
+    """cfg4's bf16 configuration: tensor-core operands rounded to ONE bf16 plane (fp32 accumulation and fp32
+    storage); the reference has no bf16 path, so the bar is the fp32 oracle within the stated tolerance."""
+    import deepgate
+    from deepgate import ops, synth
+    circuits = synth.make_circuits("xmg", 4, 12, 300, cfg=24, window=40, n_pairs=40)
+    G = deepgate.circuits_to_batch(circuits, "cuda")
+    sd = O.synth_state_dict("xmg", 6)
+    model = build_model("xmg", sd, 2)
+    gen = torch.Generator().manual_seed(3)
+    E, n = G.edge_index.size(1), G.x.size(0)
+    pos = G.edge_index.cpu()[:, torch.randperm(E, generator=gen)]
+    neg = torch.randint(0, n, (2, E), generator=gen)
+    weights = (1.0, 4.0, 4.0)
+    ops.set_precision("bf16")
+    try:
+        hs, hf = model(G)
+        rec, _, _ = model.recon_loss(hs, pos.cuda(), neg.cuda())
+        prb = torch.nn.L1Loss()(model.pred_prob(hf), G.prob)
+        _, _, _, fnc = ops.vae_func_loss(hf=hf, tt_pair_index=G.tt_pair_index, tt_sim=G.tt_sim)
+        (weights[0] * rec + weights[1] * prb + weights[2] * fnc).backward()
+    finally:
+        ops.set_precision("fp32")
+    total, parts, grads = oracle_train_grads("xmg", sd, oracle_inputs(G, pos, neg), weights, 2)
+    e_hs, e_hf = rel(hs, parts["hs"]), rel(hf, parts["hf"])
+    assert e_hs < BF16_TOL and e_hf < BF16_TOL, (e_hs, e_hf)
+    assert e_hs > 1e-5, "bf16 mode did not engage (result is fp32-accurate)"
+    for got, key in ((rec, "recon"), (prb, "prob"), (fnc, "func")):
+        assert abs(float(got) - float(parts[key])) < BF16_TOL * max(1.0, abs(float(parts[key]))), key
+    worst = 0.0
+    for k, p in model.named_parameters():
+        ref = grads.get(k)
+        if ref is None or any(t in k for t in ZERO_TAGS) or k.endswith("attn_lin.weight") or k.endswith("msg_k.weight"):
+            continue
+        worst = max(worst, rel(p.grad, ref))
+    assert worst < 5e-2, worst
