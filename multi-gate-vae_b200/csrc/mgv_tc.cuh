@@ -164,6 +164,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Registers -> the calling warp's 32 TMEM lanes, 16 / 8 / 4 consecutive columns (asynchronous: tmem_st_wait before
+// the data is read back or handed to another thread).
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------ descriptors
 constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128 = 2;
@@ -203,6 +226,24 @@ __device__ __forceinline__ void mma(uint32_t d_tmem, uint64_t adesc, uint64_t bd
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows = lanes, 16 fp16 of K = 8 packed 32-bit columns per
+// K step) lives in tensor memory, written there by tcgen05.st.
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <bool LOWP>
+__device__ __forceinline__ void mma3p_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                         uint32_t idesc, uint32_t accumulate) {
+    mma_ts(d_tmem, a_hi, b_hi, idesc, accumulate);
+    if (!LOWP) {
+        mma_ts(d_tmem, a_lo, b_hi, idesc, 1u);
+        mma_ts(d_tmem, a_hi, b_lo, idesc, 1u);
+    }
 }
 // hi.hi + lo.hi + hi.lo for one K step; `step` = descriptor start-address increment (bytes >> 4 applied here).
 __device__ __forceinline__ void mma3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,

@@ -1,0 +1,891 @@
+// Struct encoder BACKWARD on the 5th-generation tensor cores (the forward is struct_tc.cu): MultiGCNEncoder.forward
+// (digae_layer.py:257-277) with AggConv (arch/gcn_conv.py:30-42) differentiated step by step in reverse.  Per half-round
+// step k = 2R .. 1 two kernels, 128-node tiles, fp16 hi/lo planes with fp32 accumulation in tensor memory:
+//
+//   struct_bwd_pw_kernel   (persistent, weights resident, warp-specialised like the forward)
+//     gather   [agg | h | x deg 1] operand tile of state_{k-1}  and  d state_k = part + sum of the neighbours' d agg_{k+1}
+//     MMA      recompute the GRU pre-activations (identical products to the forward)            -> TMEM columns 0..255
+//     epilogue thread = node: gates, LayerNorm backward, GRU backward; d gates (d r, d z, d gi_n, d gh_n) go back into
+//              the SAME tensor-memory columns, first as fp32, then -- scaled by the tile's power of two -- as fp16 hi/lo
+//              planes (16 gates = 8 + 8 packed columns), which is the A operand of
+//     MMA      d agg = d gi Wc,  d part = d gh Whh   (A from tensor memory, B = the forward's weight image read MN-major)
+//     epilogue d agg / d part -> HBM for step k-1; d ln_w / d ln_b partial sums live in tensor memory per thread
+//     The operand tile (bulk copy) and the d-gate planes also go to HBM for
+//   struct_bwd_wgrad_kernel (persistent, streaming): d W^T-free weight gradient  d Wcx | d Whh | d b  +=  d gates^T [agg | h | x deg 1]
+//     both operands MN-major straight from the bulk-copied planes, K = nodes, accumulators persistent in tensor memory
+//     (2 x 144 columns at a 160-column stride) over all tiles of the CTA, flushed once into the CTA's private partial block.
+//
+// Shared memory cannot hold weights (112 KB) + operand tile (72 KB) + d-gate planes (128 KB) and tensor memory cannot hold
+// recompute (256) + data-gradient (128) + weight-gradient (288) columns, hence the split; the hand-off buffers are
+// processed in chunks of tiles so they stay L2-sized.
+#include <stdlib.h>
+#include <string.h>
+#include "struct_layout.cuh"
+
+long long* mgv_debug_trace();
+size_t mgv_struct_image_bytes(int num_enc);
+int mgv_struct_build_image(const float* weights, int num_enc, uint8_t* image, int precision, cudaStream_t st);
+int mgv_struct_bwd_legacy_grid(void);
+size_t mgv_struct_bwd_legacy_workspace_bytes(int64_t N, int32_t num_enc);
+int mgv_struct_encoder_bwd_legacy(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
+                                  int32_t feat, const float* x, const float* weights, const float* states,
+                                  const float* gout, float* grads, void* ws, size_t ws_bytes, int32_t precision,
+                                  mgv_stream_t stream);
+
+namespace {
+using namespace struct_layout;
+
+constexpr int SGRAD = MGV_STRUCT_GRAD_FLOATS;
+constexpr int EPI_WARPS = 4, GATHER_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + GATHER_WARPS + 1) * 32;
+constexpr int LDGS = 68;                                   // d state staging row stride (floats)
+constexpr uint32_t DG_TILE_BYTES = 131072;                 // [hi: 4 gate blocks x 16 KB | lo: 4 x 16 KB], SW128 rows = nodes
+constexpr int CHUNK_TILES = 1024;                          // tiles per encoder per kernel pair
+
+// ---- shared memory of the pointwise kernel (after the weight image and the operand tile, struct_layout.cuh)
+constexpr uint32_t S_G = A_X_LO + 4096;                    // d state_k staging, fp32 [128][LDGS]
+constexpr uint32_t S_LN = S_G + TM * LDGS * 4;             // ln_w, ln_b
+constexpr uint32_t S_AMAX = S_LN + 512;                    // 3 rotating tile-amax words
+constexpr uint32_t S_BAR = S_AMAX + 16;                    // 9 mbarriers
+constexpr uint32_t S_TMEM = S_BAR + 128;
+constexpr uint32_t P_SMEM = S_TMEM + 64 + 1024;            // + alignment slack
+static_assert(P_SMEM <= 227 * 1024, "struct backward: shared memory");
+static_assert(A_TILE_BYTES + TM * LDGS * 4 >= TM * 132 * 4, "LayerNorm gradient scratch aliases the tile + staging");
+// tensor memory columns
+constexpr uint32_t T_ACC = 0, T_OUT = 256, T_LNP = 384;
+
+struct BwdTC {
+    int N, feat, layernorm, first, last, dir;
+    int tile_beg, tile_end;    // this launch's chunk of tiles
+    const int* ptr;            // neighbour CSR of this step's direction
+    const int* idx;
+    const int* order;
+    const int* gdesc;
+    const unsigned* tile_cost;
+    const float* x;
+    const uint8_t* image;      // weight image of (enc 0, this dir); encoder stride 2 * IMG_BYTES
+    const float* prev;         // state_{k-1}, enc 0
+    size_t enc_stride;
+    const float* gout;         // [enc][N][64]
+    const float* in_part; const float* in_agg;
+    float* out_part; float* out_agg;
+    uint8_t* abuf;             // [enc][chunk tiles][A_TILE_BYTES]
+    uint8_t* dgbuf;            // [enc][chunk tiles][DG_TILE_BYTES]
+    float* scales;             // [enc][chunk tiles]
+    unsigned* smin;            // [enc] min of the chunk's tile scales (float bits)
+    float* partial;            // [enc][gxp][2][SGRAD]
+    int gxp;
+    int chunk_cap;             // tiles per encoder the hand-off buffers are sized for
+    long long* trace;
+};
+#define PTRACE(slot) do { if (p.trace && it < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + it) * 16 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void tmem_ld4x4(uint32_t taddr, float (&v)[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[4 * k]), "=r"(r[4 * k + 1]), "=r"(r[4 * k + 2]), "=r"(r[4 * k + 3]) : "r"(taddr + 64u * k) : "memory");
+}
+__device__ __forceinline__ void split_store_sw128(uint32_t hi_base, uint32_t lo_base, int row, int c, const float (&v)[8]) {
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    const uint32_t off = tc::sw128_off(row, c);
+    tc::st_shared_v4(hi_base + off, hi);
+    tc::st_shared_v4(lo_base + off, lo);
+}
+// Power of two s with amax * s in [2^8, 2^9) (amax > 0), else 1.
+__device__ __forceinline__ float pow2_scale(float amax) {
+    if (!(amax > 0.f) || !isfinite(amax)) return 1.0f;
+    const int e = (int)((__float_as_uint(amax) >> 23) & 0xff) - 127;
+    int k = 8 - e;
+    k = k < -100 ? -100 : (k > 100 ? 100 : k);
+    return __uint_as_float((uint32_t)(k + 127) << 23);
+}
+__device__ __forceinline__ float pow2_scale_keep(float amax, float cur) {
+    const float v = amax * cur;
+    if (v >= 4.0f && v <= 8192.0f) return cur;
+    return (amax > 0.f) ? pow2_scale(amax) : cur;
+}
+
+// One neighbour of each of the lane's 4 rows per trip (8 x 16-byte loads in flight), next trip's ids prefetched.
+__device__ __forceinline__ void neighbour_sum(const float* __restrict__ src, const int* __restrict__ idx, const int (&beg)[4],
+                                              const int (&cnt)[4], const int (&j0)[4], int maxc, int c, float (&acc)[4][8]) {
+    int jn[4];
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) jn[ps] = j0[ps];
+    for (int sl = 0; sl < maxc; ++sl) {
+        int j[4];
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            j[ps] = jn[ps];
+            if (sl + 1 < cnt[ps]) jn[ps] = idx[beg[ps] + sl + 1] & NODE_MASK;
+        }
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            va[ps] = make_float4(0.f, 0.f, 0.f, 0.f); vb[ps] = va[ps];
+            if (sl < cnt[ps]) {
+                va[ps] = mgv_ld4(src + (size_t)j[ps] * D + c * 8);
+                vb[ps] = mgv_ld4(src + (size_t)j[ps] * D + c * 8 + 4);
+            }
+        }
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            acc[ps][0] += va[ps].x; acc[ps][1] += va[ps].y; acc[ps][2] += va[ps].z; acc[ps][3] += va[ps].w;
+            acc[ps][4] += vb[ps].x; acc[ps][5] += vb[ps].y; acc[ps][6] += vb[ps].z; acc[ps][7] += vb[ps].w;
+        }
+    }
+}
+
+// ======================================================================================= recompute + pointwise + data gradient
+__global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int enc = blockIdx.y;
+    const float* prev = p.prev + (size_t)enc * p.enc_stride;
+    const size_t eoff = (size_t)enc * p.N * D;
+    const uint8_t* image = p.image + (size_t)enc * 2 * IMG_BYTES;
+
+    const uint32_t bar_w = sbase + S_BAR, bar_a_full = bar_w + 8, bar_a_empty = bar_w + 16, bar_g_empty = bar_w + 24;
+    const uint32_t bar_acc_full = bar_w + 32, bar_dg_full = bar_w + 40, bar_out_full = bar_w + 48, bar_acc_empty = bar_w + 56;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + S_TMEM);
+    float* s_ln = reinterpret_cast<float*>(sgen + S_LN);
+    unsigned* s_amax = reinterpret_cast<unsigned*>(sgen + S_AMAX);
+    float* s_g = reinterpret_cast<float*>(sgen + S_G);
+
+    if (tid == 0) {
+        tc::mbar_init(bar_w, 1);
+        tc::mbar_init(bar_a_full, GATHER_WARPS * 32);
+        tc::mbar_init(bar_a_empty, 2);                 // recompute MMAs complete + operand-tile bulk store has read the tile
+        tc::mbar_init(bar_g_empty, EPI_WARPS * 32);
+        tc::mbar_init(bar_acc_full, 1);
+        tc::mbar_init(bar_dg_full, EPI_WARPS * 32);
+        tc::mbar_init(bar_out_full, 1);
+        tc::mbar_init(bar_acc_empty, EPI_WARPS * 32);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(bar_w, IMG_W);
+#pragma unroll 1
+        for (uint32_t o = 0; o < IMG_W; o += 16384u) tc::bulk_g2s(sbase + o, image + o, 16384u, bar_w);
+    }
+    if (tid < 2 * D) s_ln[tid] = __ldg(reinterpret_cast<const float*>(image + IMG_W) + tid);
+    if (tid < 4) s_amax[tid] = 0u;
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+    const int ntiles_all = (p.N + TM - 1) / TM;
+    int tile_beg, tile_end;
+    {
+        const unsigned long long c0 = p.tile_cost[p.tile_beg], c1 = p.tile_cost[p.tile_end];
+        const unsigned lo = (unsigned)(c0 + (c1 - c0) * blockIdx.x / gridDim.x), hi = (unsigned)(c0 + (c1 - c0) * (blockIdx.x + 1) / gridDim.x);
+        tile_beg = tc::warp_lower_bound(p.tile_cost, ntiles_all, lo, lane);
+        tile_end = tc::warp_lower_bound(p.tile_cost, ntiles_all, hi, lane);
+        tile_beg = max(tile_beg, p.tile_beg);
+        tile_end = min(tile_end, p.tile_end);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp >= EPI_WARPS && warp < EPI_WARPS + GATHER_WARPS) {
+        // ===================================================================== gather
+        const int gw = warp - EPI_WARPS, rg = lane >> 3, c = lane & 7;
+        const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
+        const float* gsrc = p.last ? p.gout + eoff : p.in_part + eoff;
+        const float* asrc = p.in_agg + eoff;
+        int it = 0;
+        for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+            int node[4], beg[4], cnt[4], j0[4];
+            int maxc = 0;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const int r = tile * TM + gw * 16 + ps * 4 + rg;
+                const int4 d = (r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
+                node[ps] = d.x; beg[ps] = d.y; cnt[ps] = d.z; j0[ps] = d.w;
+                maxc = max(maxc, cnt[ps]);
+            }
+            float acc[4][8];
+            float xe[4];
+            // own state rows and the lane's feature element
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                xe[ps] = 0.f;
+                if (node[ps] >= 0) {
+                    a = mgv_ld4(prev + (size_t)node[ps] * D + c * 8);
+                    b = mgv_ld4(prev + (size_t)node[ps] * D + c * 8 + 4);
+                    if (c < p.feat) xe[ps] = p.x[(size_t)node[ps] * p.feat + c];
+                }
+                acc[ps][0] = a.x; acc[ps][1] = a.y; acc[ps][2] = a.z; acc[ps][3] = a.w;
+                acc[ps][4] = b.x; acc[ps][5] = b.y; acc[ps][6] = b.z; acc[ps][7] = b.w;
+            }
+            tc::mbar_wait(bar_a_empty, (uint32_t)((it & 1) ^ 1));            // previous tile's MMAs and bulk store have read the tile
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const int row = gw * 16 + ps * 4 + rg;
+                split_store_sw128(sbase + A_H_HI, sbase + A_H_LO, row, c, acc[ps]);
+                float xv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) xv[e] = __shfl_sync(0xffffffffu, xe[ps], (lane & 24) + e);
+                if (c == 1) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) xv[e] = 0.f;
+                    if (node[ps] >= 0) { xv[0] = (float)cnt[ps]; xv[1] = 1.0f; }
+                }
+                if (c < 2) {
+                    uint4 hi, lo;
+                    tc::split8(xv, hi, lo);
+                    const uint32_t off = tc::plain16_off(row, c);
+                    tc::st_shared_v4(sbase + A_X_HI + off, hi);
+                    tc::st_shared_v4(sbase + A_X_LO + off, lo);
+                }
+            }
+            // neighbour sum of state_{k-1}
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[ps][e] = 0.f;
+            neighbour_sum(prev, p.idx, beg, cnt, j0, maxc, c, acc);
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) split_store_sw128(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps]);
+            // d state_k = d part (or the incoming gradient at the last step) + neighbour sum of d agg_{k+1}
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (node[ps] >= 0) {
+                    a = mgv_ld4(gsrc + (size_t)node[ps] * D + c * 8);
+                    b = mgv_ld4(gsrc + (size_t)node[ps] * D + c * 8 + 4);
+                }
+                acc[ps][0] = a.x; acc[ps][1] = a.y; acc[ps][2] = a.z; acc[ps][3] = a.w;
+                acc[ps][4] = b.x; acc[ps][5] = b.y; acc[ps][6] = b.z; acc[ps][7] = b.w;
+            }
+            if (!p.last) neighbour_sum(asrc, p.idx, beg, cnt, j0, maxc, c, acc);
+            tc::mbar_wait(bar_g_empty, (uint32_t)((it & 1) ^ 1));            // previous tile's epilogue has read the staging rows
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                float* dst = s_g + (gw * 16 + ps * 4 + rg) * LDGS + c * 8;
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[ps][0], acc[ps][1], acc[ps][2], acc[ps][3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[ps][4], acc[ps][5], acc[ps][6], acc[ps][7]);
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(bar_a_full);
+        }
+    } else if (warp == EPI_WARPS + GATHER_WARPS) {
+        // ===================================================================== MMA issue + bulk stores (one thread)
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+                const uint32_t ph = (uint32_t)(it & 1);
+                if (it == 0) tc::mbar_wait(bar_w, 0u);
+                tc::mbar_wait(bar_acc_empty, ph ^ 1u);                       // previous tile's epilogue is done with tensor memory
+                tc::mbar_wait(bar_a_full, ph);
+                tc::fence_after_sync();
+                PTRACE(0);
+                const uint32_t d = tmem + T_ACC;
+                tc::mma3(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
+                         tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false), 0u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma3(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                             tc::desc_k_sw128(sbase + WHH_HI + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 32 * j),
+                             tc::make_idesc(128, 128, false, false), 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma3(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                             tc::desc_k_sw128(sbase + WHH_HI + 16384 + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 16384 + 32 * j),
+                             tc::make_idesc(128, 64, false, false), 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
+                             tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
+                             tc::make_idesc(128, 192, false, false), 1u);
+                tc::mma_commit(bar_a_empty);
+                tc::mma_commit(bar_acc_full);
+                // operand tile -> HBM for the weight-gradient kernel
+                {
+                    uint8_t* dst = p.abuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * A_TILE_BYTES;
+#pragma unroll 1
+                    for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_s2g(dst + o, sbase + A_AGG_HI + o, 8192u);
+                    tc::bulk_commit();
+                    tc::bulk_wait_read0();
+                    tc::mbar_arrive(bar_a_empty);
+                }
+                PTRACE(1);
+                tc::mbar_wait(bar_dg_full, ph);
+                tc::fence_after_sync();
+                PTRACE(2);
+                if (!p.first) {
+                    const uint32_t o = tmem + T_OUT;
+                    const uint32_t i128 = tc::make_idesc(128, 128, false, true), i64 = tc::make_idesc(128, 64, false, true);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {        // d r, d z: [d agg | d part] += d g . [Wc | Whh] rows 16 s ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, WHH_HI - WC_HI),
+                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, WHH_LO - WC_LO), i128, s > 0 ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int s = 8; s < 12; ++s) {       // d gi_n: d agg += . Wc rows 128 ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, 0),
+                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, 0), i64, 1u);
+                    }
+#pragma unroll
+                    for (int s = 12; s < 16; ++s) {      // d gh_n: d part += . Whh rows 128 ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o + 64u, a, a + 8u, tc::desc_mn_sw128(sbase + WHH_HI + 2048u * (s - 4), 0),
+                                            tc::desc_mn_sw128(sbase + WHH_LO + 2048u * (s - 4), 0), i64, 1u);
+                    }
+                    tc::mma_commit(bar_out_full);
+                }
+                PTRACE(3);
+            }
+            tc::bulk_wait0();
+        }
+    } else if (warp < EPI_WARPS) {
+        // ===================================================================== epilogue: thread = tile row = TMEM lane
+        const int row = warp * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t t_acc = tl + T_ACC, t_out = tl + T_OUT, t_lnp = tl + T_LNP;
+        const float* gs = s_g + row * LDGS;
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 4) tc::tmem_st4(t_lnp + cc, 0.f, 0.f, 0.f, 0.f);
+        tc::tmem_st_wait();
+        float run_scale = 1.0f;
+        int it = 0;
+        for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+            const uint32_t ph = (uint32_t)(it & 1);
+            const bool valid = tile * TM + row < p.N;
+            const int node = valid ? p.order[tile * TM + row] : 0;
+            const float* hrow = prev + (size_t)node * D;
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            tc::mbar_wait(bar_acc_full, ph);
+            tc::mbar_wait(bar_a_full, ph);
+            tc::fence_after_sync();
+            if (tid == 0) PTRACE(4);
+            // ---- pass 1: gates (kept in tensor memory: r, z, n overwrite their pre-activations), pre-LayerNorm output
+            float xh[D];
+            {
+                float g0[16], g1[16];
+                float4 h0 = valid ? mgv_ld4(hrow) : zero4, h1;
+                tmem_ld4x4(t_acc, g0);
+#pragma unroll
+                for (int ch = 0; ch < 16; ch += 2) {
+                    tc::tmem_ld_wait();
+                    tmem_ld4x4(t_acc + 4 * (ch + 1), g1);
+                    h1 = valid ? mgv_ld4(hrow + 4 * (ch + 1)) : zero4;
+                    {
+                        const float hv[4] = {h0.x, h0.y, h0.z, h0.w};
+                        float r[4], z[4], n[4], hn;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            gru_gates(g0[e], g0[4 + e], g0[8 + e], g0[12 + e], r[e], z[e], n[e], hn);
+                            xh[4 * ch + e] = fmaf(z[e], hv[e] - n[e], n[e]);
+                        }
+                        tc::tmem_st4(t_acc + 4 * ch, r[0], r[1], r[2], r[3]);
+                        tc::tmem_st4(t_acc + 64 + 4 * ch, z[0], z[1], z[2], z[3]);
+                        tc::tmem_st4(t_acc + 128 + 4 * ch, n[0], n[1], n[2], n[3]);
+                    }
+                    tc::tmem_ld_wait();
+                    if (ch + 2 < 16) {
+                        tmem_ld4x4(t_acc + 4 * (ch + 2), g0);
+                        h0 = valid ? mgv_ld4(hrow + 4 * (ch + 2)) : zero4;
+                    }
+                    {
+                        const float hv[4] = {h1.x, h1.y, h1.z, h1.w};
+                        float r[4], z[4], n[4], hn;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            gru_gates(g1[e], g1[4 + e], g1[8 + e], g1[12 + e], r[e], z[e], n[e], hn);
+                            xh[4 * (ch + 1) + e] = fmaf(z[e], hv[e] - n[e], n[e]);
+                        }
+                        tc::tmem_st4(t_acc + 4 * (ch + 1), r[0], r[1], r[2], r[3]);
+                        tc::tmem_st4(t_acc + 64 + 4 * (ch + 1), z[0], z[1], z[2], z[3]);
+                        tc::tmem_st4(t_acc + 128 + 4 * (ch + 1), n[0], n[1], n[2], n[3]);
+                    }
+                }
+            }
+            // ---- LayerNorm statistics (same two-pass form as the forward), x^ stays in xh; LayerNorm parameter
+            //      gradients accumulate per thread in tensor memory
+            float rstd = 1.0f, c1 = 0.f, c2 = 0.f;
+            if (p.layernorm) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int e = 0; e < D; e += 4) { s0 += xh[e]; s1 += xh[e + 1]; s2 += xh[e + 2]; s3 += xh[e + 3]; }
+                const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / D);
+                s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+                for (int e = 0; e < D; e += 4) {
+                    xh[e] -= mean; xh[e + 1] -= mean; xh[e + 2] -= mean; xh[e + 3] -= mean;
+                    s0 = fmaf(xh[e], xh[e], s0); s1 = fmaf(xh[e + 1], xh[e + 1], s1);
+                    s2 = fmaf(xh[e + 2], xh[e + 2], s2); s3 = fmaf(xh[e + 3], xh[e + 3], s3);
+                }
+                rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / D) + LN_EPS);
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    float lw[8], lb[8];
+                    tc::tmem_ld8(t_lnp + 8 * c8, lw);
+                    tc::tmem_ld8(t_lnp + 64 + 8 * c8, lb);
+                    const float4 ga = lds4(gs + 8 * c8), gb = lds4(gs + 8 * c8 + 4);
+                    const float4 wa = lds4(s_ln + 8 * c8), wb = lds4(s_ln + 8 * c8 + 4);
+                    const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float xv = xh[8 * c8 + e] * rstd;
+                        xh[8 * c8 + e] = xv;
+                        const float gwv = gv[e] * wv[e];
+                        c1 += gwv;
+                        c2 = fmaf(gwv, xv, c2);
+                        lw[e] = fmaf(gv[e], xv, lw[e]);
+                        lb[e] += gv[e];
+                    }
+                    tc::tmem_st8(t_lnp + 8 * c8, *reinterpret_cast<const uint32_t(*)[8]>(&lw));
+                    tc::tmem_st8(t_lnp + 64 + 8 * c8, *reinterpret_cast<const uint32_t(*)[8]>(&lb));
+                }
+                c1 *= (1.0f / D);
+                c2 *= (1.0f / D);
+            }
+            tc::tmem_st_wait();
+            if (tid == 0) PTRACE(5);
+            // ---- pass 2: LayerNorm backward + GRU backward, fp32 d gates back into tensor memory, g z kept in xh
+            float amax = 0.f;
+            {
+                float g0[16], g1[16];
+                tmem_ld4x4(t_acc, g0);
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch) {
+                    float (&gc)[16] = (ch & 1) ? g1 : g0;
+                    float (&gn)[16] = (ch & 1) ? g0 : g1;
+                    const float4 g4 = lds4(gs + 4 * ch);
+                    const float4 w4 = lds4(s_ln + 4 * ch);
+                    const float4 h4 = valid ? mgv_ld4(hrow + 4 * ch) : zero4;
+                    tc::tmem_ld_wait();
+                    if (ch + 1 < 16) tmem_ld4x4(t_acc + 4 * (ch + 1), gn);
+                    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, hv[4] = {h4.x, h4.y, h4.z, h4.w};
+                    float dr[4], dz[4], dni[4], dnh[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float r = gc[e], z = gc[4 + e], n = gc[8 + e], hn = gc[12 + e];
+                        const float xv = xh[4 * ch + e];
+                        const float dxh = p.layernorm ? rstd * (fmaf(gv[e], wv[e], -c1) - xv * c2) : gv[e];
+                        const float dn = dxh * (1.0f - z);
+                        const float dzz = dxh * (hv[e] - n);
+                        dni[e] = dn * (1.0f - n * n);
+                        dr[e] = dni[e] * hn * r * (1.0f - r);
+                        dz[e] = dzz * z * (1.0f - z);
+                        dnh[e] = dni[e] * r;
+                        xh[4 * ch + e] = dxh * z;
+                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dr[e]), fabsf(dz[e])), fabsf(dni[e])));
+                    }
+                    tc::tmem_st4(t_acc + 4 * ch, dr[0], dr[1], dr[2], dr[3]);
+                    tc::tmem_st4(t_acc + 64 + 4 * ch, dz[0], dz[1], dz[2], dz[3]);
+                    tc::tmem_st4(t_acc + 128 + 4 * ch, dni[0], dni[1], dni[2], dni[3]);
+                    tc::tmem_st4(t_acc + 192 + 4 * ch, dnh[0], dnh[1], dnh[2], dnh[3]);
+                }
+            }
+            tc::mbar_arrive(bar_g_empty);
+            // ---- tile-wide power-of-two scale (fp16 range), shared with the weight-gradient kernel through HBM
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            if (lane == 0) atomicMax(s_amax + (it % 3), __float_as_uint(amax));
+            tc::named_bar_sync(1, EPI_WARPS * 32);
+            const float scale = pow2_scale_keep(__uint_as_float(s_amax[it % 3]), run_scale);
+            run_scale = scale;
+            if (tid == 0) {
+                s_amax[(it + 2) % 3] = 0u;
+                p.scales[(size_t)enc * p.chunk_cap + (tile - p.tile_beg)] = scale;
+                atomicMin(p.smin + enc, __float_as_uint(scale));
+            }
+            tc::tmem_st_wait();
+            if (tid == 0) PTRACE(6);
+            // ---- pass 3: fp32 d gates -> scaled fp16 hi/lo planes, in place (A operand of the data-gradient MMAs) and to HBM
+            {
+                uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * DG_TILE_BYTES;
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    float v[16];
+                    tc::tmem_ld16(t_acc + 16 * s, v);
+                    tc::tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) tc::split2(v[2 * e] * scale, v[2 * e + 1] * scale, pk[e], pk[8 + e]);
+                    tc::tmem_st16(t_acc + 16 * s, pk);
+                    uint8_t* hb = dg + (s >> 2) * 16384;
+                    const uint32_t o0 = tc::sw128_off(row, 2 * (s & 3)), o1 = tc::sw128_off(row, 2 * (s & 3) + 1);
+                    *reinterpret_cast<uint4*>(hb + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(hb + o1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    *reinterpret_cast<uint4*>(hb + 65536 + o0) = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+                    *reinterpret_cast<uint4*>(hb + 65536 + o1) = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                }
+            }
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            tc::mbar_arrive(bar_dg_full);
+            if (tid == 0) PTRACE(7);
+            // ---- data gradients of step k-1
+            if (!p.first) {
+                tc::mbar_wait(bar_out_full, ph);
+                tc::fence_after_sync();
+                if (tid == 0) PTRACE(8);
+                const float inv = 1.0f / scale;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    float a[8], q[8];
+                    tc::tmem_ld8(t_out + 8 * c8, a);
+                    tc::tmem_ld8(t_out + 64 + 8 * c8, q);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { a[e] *= inv; q[e] = fmaf(q[e], inv, xh[8 * c8 + e]); }
+                    if (valid) {
+                        stg8(p.out_agg + eoff + (size_t)node * D + 8 * c8, a);
+                        stg8(p.out_part + eoff + (size_t)node * D + 8 * c8, q);
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(bar_acc_empty);
+            if (tid == 0) PTRACE(9);
+        }
+    }
+    // ---- LayerNorm parameter gradients: per-thread partial sums (tensor memory) -> column sums -> this CTA's partial block
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    float* scratch = reinterpret_cast<float*>(sgen + A_AGG_HI);      // [128][132], the tile and staging buffers are idle now
+    if (warp < EPI_WARPS) {
+        const int row = warp * 32 + lane;
+        const uint32_t t_lnp = tmem + ((uint32_t)(warp * 32) << 16) + T_LNP;
+#pragma unroll 1
+        for (int c8 = 0; c8 < 16; ++c8) {
+            float v[8];
+            tc::tmem_ld8(t_lnp + 8 * c8, v);
+            tc::tmem_ld_wait();
+            *reinterpret_cast<float4*>(scratch + row * 132 + 8 * c8) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(scratch + row * 132 + 8 * c8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid < 2 * D && p.layernorm && tile_beg < tile_end) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < TM; ++r) s += scratch[r * 132 + tid];
+        float* part = p.partial + (((size_t)enc * p.gxp + blockIdx.x) * 2 + p.dir) * SGRAD;
+        part[O_LNW + tid] += s;
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ======================================================================================= weight gradients (streaming)
+constexpr int W_THREADS = 6 * 32;          // warp 0 bulk-copy producer, warp 1 MMA issue, warps 2-5 rescale + flush
+// stage = 64 nodes (half a tile): d-gate planes, operand planes
+constexpr uint32_t ST_DG_HI = 0, ST_DG_LO = 32768, ST_AGG_HI = 65536, ST_H_HI = 73728, ST_AGG_LO = 81920, ST_H_LO = 90112;
+constexpr uint32_t ST_X_HI = 98304, ST_X_LO = 100352, ST_BYTES = 102400;
+constexpr uint32_t W_BAR = 2 * ST_BYTES;   // full[2], ready[2], empty[2], done
+constexpr uint32_t W_TMEM = W_BAR + 64;
+constexpr uint32_t W_SMEM = W_TMEM + 64 + 1024;
+static_assert(W_SMEM <= 227 * 1024, "struct weight gradient: shared memory");
+
+struct WgTC {
+    int ntiles;                // tiles of this chunk
+    int chunk_cap;
+    int dir, gxp;
+    const uint8_t* abuf;
+    const uint8_t* dgbuf;
+    const float* scales;
+    const unsigned* smin;
+    float* partial;
+};
+
+__global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const WgTC p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int enc = blockIdx.y;
+    const uint32_t bar_full = sbase + W_BAR, bar_ready = bar_full + 16, bar_empty = bar_full + 32, bar_done = bar_full + 48;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + W_TMEM);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(bar_full + 8 * s, 1);
+            tc::mbar_init(bar_ready + 8 * s, 4 * 32);
+            tc::mbar_init(bar_empty + 8 * s, 1);
+        }
+        tc::mbar_init(bar_done, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const int tile_beg = (int)((long long)p.ntiles * blockIdx.x / gridDim.x);
+    const int tile_end = (int)((long long)p.ntiles * (blockIdx.x + 1) / gridDim.x);
+    const int nhalf = 2 * (tile_end - tile_beg);
+    const float smin = __uint_as_float(p.smin[enc]);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nhalf; ++i) {
+                const int s = i & 1, tile = tile_beg + (i >> 1), h = i & 1;
+                tc::mbar_wait(bar_empty + 8 * s, (uint32_t)(((i >> 1) & 1) ^ 1));
+                tc::mbar_expect_tx(bar_full + 8 * s, ST_BYTES);
+                const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 8192;
+                const uint8_t* at = p.abuf + ((size_t)enc * p.chunk_cap + tile) * A_TILE_BYTES;
+                const uint32_t st = sbase + (uint32_t)s * ST_BYTES, bar = bar_full + 8 * s;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    tc::bulk_g2s(st + ST_DG_HI + 8192u * b, dg + 16384 * b, 8192u, bar);
+                    tc::bulk_g2s(st + ST_DG_LO + 8192u * b, dg + 65536 + 16384 * b, 8192u, bar);
+                }
+                tc::bulk_g2s(st + ST_AGG_HI, at + 0 + h * 8192, 8192u, bar);
+                tc::bulk_g2s(st + ST_AGG_LO, at + 16384 + h * 8192, 8192u, bar);
+                tc::bulk_g2s(st + ST_H_HI, at + 32768 + h * 8192, 8192u, bar);
+                tc::bulk_g2s(st + ST_H_LO, at + 49152 + h * 8192, 8192u, bar);
+                tc::bulk_g2s(st + ST_X_HI, at + 65536 + h * 2048, 2048u, bar);
+                tc::bulk_g2s(st + ST_X_LO, at + 69632 + h * 2048, 2048u, bar);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t i128 = tc::make_idesc(128, 128, true, true), i16 = tc::make_idesc(128, 16, true, true);
+            for (int i = 0; i < nhalf; ++i) {
+                const int s = i & 1;
+                tc::mbar_wait(bar_ready + 8 * s, (uint32_t)((i >> 1) & 1));
+                tc::fence_after_sync();
+                const uint32_t st = sbase + (uint32_t)s * ST_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t acc = (i > 0 || j > 0) ? 1u : 0u;
+                    const uint64_t b_hi = tc::desc_mn_sw128(st + ST_AGG_HI + 2048u * j, 8192), b_lo = tc::desc_mn_sw128(st + ST_AGG_LO + 2048u * j, 8192);
+                    const uint64_t x_hi = tc::desc_mn_plain16(st + ST_X_HI + 512u * j), x_lo = tc::desc_mn_plain16(st + ST_X_LO + 512u * j);
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const uint64_t a_hi = tc::desc_mn_sw128(st + ST_DG_HI + 16384u * g + 2048u * j, 8192);
+                        const uint64_t a_lo = tc::desc_mn_sw128(st + ST_DG_LO + 16384u * g + 2048u * j, 8192);
+                        tc::mma3(tmem + 160u * g, a_hi, a_lo, b_hi, b_lo, i128, acc);
+                        tc::mma3(tmem + 160u * g + 128u, a_hi, a_lo, x_hi, x_lo, i16, acc);
+                    }
+                }
+                tc::mma_commit(bar_empty + 8 * s);
+            }
+            tc::mma_commit(bar_done);
+        }
+    } else {
+        // rescale the tile's planes from its own power-of-two scale to the chunk-wide one, then hand the stage to the MMA thread
+        const int t128 = tid - 64;
+        for (int i = 0; i < nhalf; ++i) {
+            const int s = i & 1, tile = tile_beg + (i >> 1);
+            tc::mbar_wait(bar_full + 8 * s, (uint32_t)((i >> 1) & 1));
+            const float m = smin / p.scales[(size_t)enc * p.chunk_cap + tile];
+            if (m != 1.0f) {
+                const __half2 m2 = __float2half2_rn(m);
+                uint4* st = reinterpret_cast<uint4*>(sgen + (size_t)s * ST_BYTES);
+#pragma unroll 4
+                for (int q = t128; q < 65536 / 16; q += 128) {
+                    uint4 v = st[q];
+                    __half2* h = reinterpret_cast<__half2*>(&v);
+                    h[0] = __hmul2(h[0], m2); h[1] = __hmul2(h[1], m2); h[2] = __hmul2(h[2], m2); h[3] = __hmul2(h[3], m2);
+                    st[q] = v;
+                }
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(bar_ready + 8 * s);
+        }
+        // flush: thread = accumulator row = d-gate column
+        if (nhalf > 0) {
+            tc::mbar_wait(bar_done, 0u);
+            tc::fence_after_sync();
+            const int L = (warp & 3) * 32 + lane;
+            const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            float* part = p.partial + (((size_t)enc * p.gxp + blockIdx.x) * 2 + p.dir) * SGRAD;
+            const float un = 1.0f / smin;
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                const int o = (g == 0) ? L : (L < 64 ? 128 + L : 64 + L);        // gate row of Wcx (g 0, or d gi_n) / Whh (g 0, or d gh_n)
+                const bool wc = (g == 0) || L < 64, wh = (g == 0) || L >= 64;
+#pragma unroll 1
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    float a[8], b[8];
+                    tc::tmem_ld8(tl + 160u * g + 8 * c8, a);
+                    tc::tmem_ld8(tl + 160u * g + 64 + 8 * c8, b);
+                    tc::tmem_ld_wait();
+                    if (wc) {
+                        float* d = part + O_WCX + o * LDC + 8 * c8;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) d[e] += a[e] * un;
+                    }
+                    if (wh) {
+                        float* d = part + O_WHH + o * LDM + 8 * c8;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) d[e] += b[e] * un;
+                    }
+                }
+                float v[16];
+                tc::tmem_ld16(tl + 160u * g + 128, v);
+                tc::tmem_ld_wait();
+                if (wc) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) part[O_WCX + o * LDC + D + e] += v[e] * un;
+                    part[O_BC + o] += v[8] * un;
+                    part[O_BIH + o] += v[9] * un;
+                    if (g == 0) part[O_BHH + o] += v[9] * un;
+                } else {
+                    part[O_BHH + o] += v[9] * un;
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+__global__ void struct_reduce_tc_kernel(const float* __restrict__ partial, int gxp, float* __restrict__ grads, int num_enc) {
+    const size_t total = (size_t)num_enc * 2 * SGRAD;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int enc = (int)(idx / (2 * SGRAD));
+    const size_t rem = idx % (2 * (size_t)SGRAD);
+    float s = 0.f;
+    for (int b = 0; b < gxp; ++b) s += partial[((size_t)enc * gxp + b) * 2 * SGRAD + rem];
+    grads[idx] = s;
+}
+
+__global__ void fill_u32_kernel(unsigned* p, unsigned v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+int sm_count(int* sms) {
+    int dev = 0;
+    MGV_CUDA(cudaGetDevice(&dev));
+    MGV_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+    return MGV_OK;
+}
+
+bool use_legacy(int precision) {
+    if (precision != 0) return true;
+    const char* e = getenv("MGV_STRUCT_BWD");
+    return e && !strcmp(e, "mma");
+}
+
+size_t tc_workspace_bytes(int64_t N, int num_enc) {
+    int sms = 148;
+    sm_count(&sms);
+    const int64_t ntiles = (N + TM - 1) / TM;
+    const int64_t cap = ntiles < CHUNK_TILES ? ntiles : CHUNK_TILES;
+    size_t b = mgv_struct_image_bytes(num_enc) + 256;
+    b += 4 * mgv_align_up((size_t)num_enc * N * D * 4 + 256, 256);
+    b += mgv_align_up((size_t)sms * 2 * SGRAD * 4 + 256, 256);
+    b += mgv_align_up((size_t)num_enc * cap * A_TILE_BYTES + 1024, 1024);
+    b += mgv_align_up((size_t)num_enc * cap * DG_TILE_BYTES + 1024, 1024);
+    b += mgv_align_up((size_t)num_enc * cap * 4 + 256, 256);
+    const int64_t chunks = (ntiles + CHUNK_TILES - 1) / CHUNK_TILES;
+    b += mgv_align_up((size_t)(chunks > 0 ? chunks : 1) * 2 * 4 + 256, 256) + 4096;   // smin words of one step (re-filled per step)
+    return b;
+}
+
+}  // namespace
+
+extern "C" int mgv_struct_bwd_grid(void) { return mgv_struct_bwd_legacy_grid(); }
+
+extern "C" size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc) {
+    const size_t a = mgv_struct_bwd_legacy_workspace_bytes(N, num_enc), b = tc_workspace_bytes(N, num_enc);
+    return a > b ? a : b;
+}
+
+extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
+                                      int32_t feat, const float* x, const float* weights, const float* states,
+                                      const float* gout, float* grads, void* ws, size_t ws_bytes, int32_t precision,
+                                      mgv_stream_t stream) {
+    if (use_legacy(precision))
+        return mgv_struct_encoder_bwd_legacy(sch, num_enc, rounds, layernorm, feat, x, weights, states, gout, grads, ws, ws_bytes,
+                                             precision, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    MGV_REQUIRE(sch != nullptr, "struct encoder: null schedule");
+    MGV_REQUIRE(num_enc >= 1 && num_enc <= 2, "struct encoder: num_enc must be 1 or 2");
+    MGV_REQUIRE(rounds >= 1, "struct encoder: rounds must be >= 1");
+    MGV_REQUIRE(feat >= 0 && feat <= MGV_MAX_FEAT, "struct encoder: dim_feature %d > %d", feat, MGV_MAX_FEAT);
+    const int N = sch->N;
+    MGV_CUDA(cudaMemsetAsync(grads, 0, (size_t)num_enc * 2 * SGRAD * sizeof(float), st));
+    if (N == 0) return MGV_OK;
+    MGV_REQUIRE(sch->deg_order_in && sch->deg_order_out && sch->tile_cost_in && sch->tile_cost_out && sch->gdesc_in && sch->gdesc_out,
+                "struct encoder: the schedule carries no degree order (mgv_build_degree_order)");
+    if (ws_bytes < mgv_struct_bwd_workspace_bytes(N, num_enc)) {
+        mgv_set_error("mgv_struct_encoder_bwd: workspace %zu < %zu bytes", ws_bytes, mgv_struct_bwd_workspace_bytes(N, num_enc));
+        return MGV_ERR_WORKSPACE;
+    }
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc != MGV_OK) return rc;
+    const int ntiles = (N + TM - 1) / TM;
+    const int cap = ntiles < CHUNK_TILES ? ntiles : CHUNK_TILES;
+    const int chunks = (ntiles + CHUNK_TILES - 1) / CHUNK_TILES;
+    const int gxp = sms / num_enc > 0 ? sms / num_enc : 1;
+    const int steps = 2 * rounds;
+    const size_t slot = (size_t)N * D;
+    const size_t enc_stride = (size_t)(steps + 1) * slot;
+
+    MgvArena a(ws, ws_bytes);
+    uint8_t* image = a.take<uint8_t>((size_t)num_enc * 2 * IMG_BYTES);
+    float* part[2];
+    float* agg[2];
+    part[0] = a.take<float>((size_t)num_enc * slot); part[1] = a.take<float>((size_t)num_enc * slot);
+    agg[0] = a.take<float>((size_t)num_enc * slot); agg[1] = a.take<float>((size_t)num_enc * slot);
+    float* partial = a.take<float>((size_t)num_enc * gxp * 2 * SGRAD);
+    a.off = mgv_align_up(a.off, 1024);
+    uint8_t* abuf = a.take<uint8_t>((size_t)num_enc * cap * A_TILE_BYTES);
+    a.off = mgv_align_up(a.off, 1024);
+    uint8_t* dgbuf = a.take<uint8_t>((size_t)num_enc * cap * DG_TILE_BYTES);
+    float* scales = a.take<float>((size_t)num_enc * cap);
+    unsigned* smin = a.take<unsigned>((size_t)chunks * 2);
+    MGV_REQUIRE(a.ok(), "mgv_struct_encoder_bwd: workspace layout overflow");
+    rc = mgv_struct_build_image(weights, num_enc, image, 0, st);
+    if (rc != MGV_OK) return rc;
+    MGV_CUDA(cudaMemsetAsync(partial, 0, (size_t)num_enc * gxp * 2 * SGRAD * sizeof(float), st));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM));
+
+    for (int k = steps; k >= 1; --k) {
+        const int dir = (k & 1) ? 0 : 1;
+        fill_u32_kernel<<<(chunks * 2 + 63) / 64, 64, 0, st>>>(smin, 0x7f000000u, chunks * 2);
+        mgv_count_launches(1);
+        for (int ch = 0; ch < chunks; ++ch) {
+            const int tb = ch * CHUNK_TILES, te = (tb + CHUNK_TILES < ntiles) ? tb + CHUNK_TILES : ntiles;
+            int gx = gxp;
+            if (gx > te - tb) gx = te - tb;
+            BwdTC p{};
+            p.N = N; p.feat = feat; p.layernorm = layernorm; p.first = (k == 1); p.last = (k == steps); p.dir = dir;
+            p.tile_beg = tb; p.tile_end = te;
+            p.ptr = dir == 0 ? sch->in_ptr : sch->out_ptr;
+            p.idx = dir == 0 ? sch->in_src : sch->out_pack;
+            p.order = dir == 0 ? sch->deg_order_in : sch->deg_order_out;
+            p.gdesc = dir == 0 ? sch->gdesc_in : sch->gdesc_out;
+            p.tile_cost = dir == 0 ? sch->tile_cost_in : sch->tile_cost_out;
+            p.x = x;
+            p.image = image + (size_t)dir * IMG_BYTES;
+            p.prev = states + (size_t)(k - 1) * slot;
+            p.enc_stride = enc_stride;
+            p.gout = gout;
+            p.in_part = part[k & 1]; p.in_agg = agg[k & 1];
+            p.out_part = part[(k - 1) & 1]; p.out_agg = agg[(k - 1) & 1];
+            p.abuf = abuf; p.dgbuf = dgbuf; p.scales = scales; p.smin = smin + 2 * ch;
+            p.partial = partial; p.gxp = gxp; p.chunk_cap = cap;
+            p.trace = (k == 2 && ch == 0) ? mgv_debug_trace() : nullptr;
+            struct_bwd_pw_kernel<<<dim3(gx, num_enc), THREADS, P_SMEM, st>>>(p);
+            WgTC w{};
+            w.ntiles = te - tb; w.chunk_cap = cap; w.dir = dir; w.gxp = gxp;
+            w.abuf = abuf; w.dgbuf = dgbuf; w.scales = scales; w.smin = smin + 2 * ch; w.partial = partial;
+            struct_bwd_wgrad_kernel<<<dim3(gx, num_enc), W_THREADS, W_SMEM, st>>>(w);
+            mgv_count_launches(2);
+        }
+    }
+    const size_t total = (size_t)num_enc * 2 * SGRAD;
+    struct_reduce_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, gxp, grads, num_enc);
+    mgv_count_launches(1);
+    return mgv_check_cuda(cudaGetLastError(), "mgv_struct_encoder_bwd");
+}

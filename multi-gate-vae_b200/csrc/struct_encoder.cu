@@ -423,14 +423,14 @@ void fill_step(StepDev& p, const mgv_schedule* sch, int k, int steps, int layern
 
 }  // namespace
 
-extern "C" int mgv_struct_bwd_grid(void) {
+int mgv_struct_bwd_legacy_grid(void) {
     int gx = 0;
     if (persistent_gx(1, 1 << 30, &gx) != MGV_OK) return -1;
     return gx;
 }
 
-extern "C" size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc) {
-    int gx = mgv_struct_bwd_grid();
+size_t mgv_struct_bwd_legacy_workspace_bytes(int64_t N, int32_t num_enc) {
+    int gx = mgv_struct_bwd_legacy_grid();
     if (gx < 1) gx = 256;
     size_t b = 0;
     b += 4 * mgv_align_up((size_t)num_enc * N * D * 4 + 256, 256);              // part/agg ping-pong
@@ -438,7 +438,9 @@ extern "C" size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc) {
     return b + 1024;
 }
 
-extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
+// mma.sync path: precision = 1 (bf16 planes), and precision = 0 when MGV_STRUCT_BWD=mma is set (A/B checks against the
+// tcgen05 path in struct_bwd_tc.cu, which owns the public entry point).
+int mgv_struct_encoder_bwd_legacy(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
                                       int32_t feat, const float* x, const float* weights, const float* states,
                                       const float* gout, float* grads, void* ws, size_t ws_bytes,
                                       int32_t precision, mgv_stream_t stream) {
@@ -448,9 +450,9 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     const int N = sch->N;
     MGV_CUDA(cudaMemsetAsync(grads, 0, (size_t)num_enc * 2 * SGRAD * sizeof(float), st));
     if (N == 0) return MGV_OK;
-    if (ws_bytes < mgv_struct_bwd_workspace_bytes(N, num_enc)) {
+    if (ws_bytes < mgv_struct_bwd_legacy_workspace_bytes(N, num_enc)) {
         mgv_set_error("mgv_struct_encoder_bwd: workspace %zu < %zu bytes", ws_bytes,
-                      mgv_struct_bwd_workspace_bytes(N, num_enc));
+                      mgv_struct_bwd_legacy_workspace_bytes(N, num_enc));
         return MGV_ERR_WORKSPACE;
     }
     int gx = 0;

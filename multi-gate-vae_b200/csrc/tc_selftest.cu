@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(int mode, const flo
     if (mode == 2) { a_bytes = TM * 32; b_bytes = (uint32_t)N * 32; }
     if (mode == 3) { a_bytes = 2u * TM * 128; b_bytes = TM * 32; }
     if (mode == 4) { a_bytes = 3u * TM * 128; b_bytes = 192u * 128; }
+    if (mode == 5) { a_bytes = 0; b_bytes = 2u * 64 * 128; }
     a_bytes = (a_bytes + 1023u) & ~1023u;
     b_bytes = (b_bytes + 1023u) & ~1023u;
     const uint32_t a_hi = base, a_lo = base + a_bytes, b_hi = base + 2 * a_bytes, b_lo = b_hi + b_bytes;
@@ -65,11 +66,29 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(int mode, const flo
     if (mode == 2) { store_plain16(a_hi, a_lo, A, 16, TM, tid, 128); store_plain16(b_hi, b_lo, B, 16, N, tid, 128); }
     if (mode == 3) { store_sw128(a_hi, a_lo, A, 128, TM, 128, tid, 128); store_plain16(b_hi, b_lo, B, 16, TM, tid, 128); }
     if (mode == 4) { store_sw128(a_hi, a_lo, A, 192, TM, 192, tid, 128); store_sw128(b_hi, b_lo, B, 64, 192, 64, tid, 128); }
+    // mode 5: A [128 x 64] lives in TENSOR MEMORY (fp16 hi/lo, 2 values per 32-bit column: K step j = columns
+    // 16 j .. 16 j + 7 hi, 16 j + 8 .. 16 j + 15 lo, starting at column 128); B = W [64 x 128] as two SW128 blocks
+    // (columns 0..63, 64..127) read MN-major with N = 128.
+    if (mode == 5) { store_sw128(b_hi, b_lo, B, 128, 64, 64, tid, 128); store_sw128(b_hi + 8192, b_lo + 8192, B + 64, 128, 64, 64, tid, 128); }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
+    if (mode == 5) {
+        const int row = warp * 32 + lane;
+        const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + 128u;
+        for (int j = 0; j < 4; ++j) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) tc::split2(A[row * 64 + 16 * j + 2 * e], A[row * 64 + 16 * j + 2 * e + 1], pk[e], pk[8 + e]);
+            tc::tmem_st16(ta + 16u * j, pk);
+        }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
 
     if (tid == 0) {
         uint32_t acc = 0;
@@ -110,11 +129,20 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(int mode, const flo
                 acc = 1;
             }
         }
+        else if (mode == 5) {
+            const uint32_t idesc = tc::make_idesc(128, 128, false, true);
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t bo = 2048u * j;
+                tc::mma3p_ts<false>(tmem, tmem + 128u + 16u * j, tmem + 128u + 16u * j + 8u,
+                                    tc::desc_mn_sw128(b_hi + bo, 8192), tc::desc_mn_sw128(b_lo + bo, 8192), idesc, acc);
+                acc = 1;
+            }
+        }
         tc::mma_commit(tc::smem_u32(&bar));
     }
     tc::mbar_wait(tc::smem_u32(&bar), 0);
     tc::fence_after_sync();
-    const int nout = (mode == 3) ? 16 : (mode == 4 ? 64 : N);
+    const int nout = (mode == 3) ? 16 : (mode == 4 ? 64 : (mode == 5 ? 128 : N));
     const int row = warp * 32 + lane;
     for (int c0 = 0; c0 < nout; c0 += 16) {
         float v[16];
@@ -132,7 +160,7 @@ __global__ void __launch_bounds__(128, 1) tc_selftest_kernel(int mode, const flo
 }  // namespace
 
 extern "C" int mgv_tc_selftest(int32_t mode, const float* A, const float* B, float* D, int32_t K, int32_t N, mgv_stream_t stream) {
-    MGV_REQUIRE(mode >= 0 && mode <= 4, "tc selftest: mode 0..4");
+    MGV_REQUIRE(mode >= 0 && mode <= 5, "tc selftest: mode 0..5");
     MGV_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "tc selftest: N must be a multiple of 16 in [16, 256]");
     MGV_REQUIRE(mode != 0 || (K >= 64 && K <= 128 && K % 64 == 0), "tc selftest: mode 0 needs K in {64, 128}");
     MGV_REQUIRE(mode != 1 || N % 64 == 0, "tc selftest: mode 1 needs N % 64 == 0");

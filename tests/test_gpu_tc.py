@@ -66,3 +66,12 @@ def test_small_magnitudes_and_saturation():
     A2 = A.clone()
     A2[0, 0] = 1e6
     assert torch.isfinite(_run(0, A2, B, 64, 64, 64)).all()
+
+
+def test_a_operand_from_tensor_memory():
+    """dG (fp16 hi/lo written to tensor memory by tcgen05.st) x MN-major weights, N = 128 from two 64-column blocks:
+    the data-gradient product of the struct-encoder backward."""
+    g = torch.Generator().manual_seed(9)
+    A = torch.randn(128, 64, generator=g).cuda()
+    W = (torch.randn(64, 128, generator=g) * 0.125).cuda()
+    assert _rel(_run(5, A, W, 64, 128, 128), A.double() @ W.double()) < 2e-6
