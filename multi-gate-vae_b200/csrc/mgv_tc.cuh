@@ -97,6 +97,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     __trap();
 }
 
+// Whole-warp wait that keeps the issue slots of the SM sub-partition free for the warps doing work: lane 0 polls
+// with a sleep between attempts, the other lanes park at the warp barrier.  (A 32-lane try_wait spin loop in the
+// waiting roles starves the epilogue warp sharing their scheduler: measured ~8 cycles per instruction.)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane, unsigned sleep_ns = 64) {
+    if (lane == 0) {
+        for (int it = 0; it < (1 << 22); ++it) {
+            uint32_t done;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.b32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            if (done) break;
+            __nanosleep(sleep_ns);
+            if (it == (1 << 22) - 1) __trap();
+        }
+    }
+    __syncwarp();
+}
+// Single-thread variant (the MMA-issue thread).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned sleep_ns = 64) {
+    for (int it = 0; it < (1 << 22); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        __nanosleep(sleep_ns);
+    }
+    __trap();
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -176,6 +210,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"

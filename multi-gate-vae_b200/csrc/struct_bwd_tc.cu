@@ -39,8 +39,8 @@ constexpr int SGRAD = MGV_STRUCT_GRAD_FLOATS;
 constexpr int EPI_WARPS = 4, GATHER_WARPS = 8;
 constexpr int THREADS = (EPI_WARPS + GATHER_WARPS + 1) * 32;
 constexpr int LDGS = 68;                                   // d state staging row stride (floats)
-constexpr uint32_t DG_TILE_BYTES = 131072;                 // [hi: 4 gate blocks x 16 KB | lo: 4 x 16 KB], SW128 rows = nodes
-constexpr int CHUNK_TILES = 1024;                          // tiles per encoder per kernel pair
+constexpr uint32_t DG_TILE_BYTES = 131072;                 // [hi | lo][8-gate chunk (32)][node row (128)][16 B]: no-swizzle core matrices
+constexpr int CHUNK_TILES_DEFAULT = 1024;                  // tiles per encoder per kernel pair (MGV_STRUCT_CHUNK overrides: tuning)
 
 // ---- shared memory of the pointwise kernel (after the weight image and the operand tile, struct_layout.cuh)
 constexpr uint32_t S_G = A_X_LO + 4096;                    // d state_k staging, fp32 [128][LDGS]
@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
             int node[4], beg[4], cnt[4], j0[4];
             int maxc = 0;
+            if (warp == EPI_WARPS && lane == 0) PTRACE(13);
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
                 const int r = tile * TM + gw * 16 + ps * 4 + rg;
@@ -221,7 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 acc[ps][0] = a.x; acc[ps][1] = a.y; acc[ps][2] = a.z; acc[ps][3] = a.w;
                 acc[ps][4] = b.x; acc[ps][5] = b.y; acc[ps][6] = b.z; acc[ps][7] = b.w;
             }
-            tc::mbar_wait(bar_a_empty, (uint32_t)((it & 1) ^ 1));            // previous tile's MMAs and bulk store have read the tile
+            tc::mbar_wait_warp(bar_a_empty, (uint32_t)((it & 1) ^ 1), lane, 128);            // previous tile's MMAs and bulk store have read the tile
+            if (warp == EPI_WARPS && lane == 0) PTRACE(11);
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
                 const int row = gw * 16 + ps * 4 + rg;
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             neighbour_sum(prev, p.idx, beg, cnt, j0, maxc, c, acc);
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) split_store_sw128(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps]);
+            if (warp == EPI_WARPS && lane == 0) PTRACE(14);
             // d state_k = d part (or the incoming gradient at the last step) + neighbour sum of d agg_{k+1}
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 acc[ps][4] = b.x; acc[ps][5] = b.y; acc[ps][6] = b.z; acc[ps][7] = b.w;
             }
             if (!p.last) neighbour_sum(asrc, p.idx, beg, cnt, j0, maxc, c, acc);
-            tc::mbar_wait(bar_g_empty, (uint32_t)((it & 1) ^ 1));            // previous tile's epilogue has read the staging rows
+            tc::mbar_wait_warp(bar_g_empty, (uint32_t)((it & 1) ^ 1), lane, 128);            // previous tile's epilogue has read the staging rows
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
                 float* dst = s_g + (gw * 16 + ps * 4 + rg) * LDGS + c * 8;
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             }
             tc::fence_async_smem();
             tc::mbar_arrive(bar_a_full);
+            if (warp == EPI_WARPS && lane == 0) PTRACE(15);
         }
     } else if (warp == EPI_WARPS + GATHER_WARPS) {
         // ===================================================================== MMA issue + bulk stores (one thread)
@@ -278,9 +282,9 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             int it = 0;
             for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
                 const uint32_t ph = (uint32_t)(it & 1);
-                if (it == 0) tc::mbar_wait(bar_w, 0u);
-                tc::mbar_wait(bar_acc_empty, ph ^ 1u);                       // previous tile's epilogue is done with tensor memory
-                tc::mbar_wait(bar_a_full, ph);
+                if (it == 0) tc::mbar_wait_sleep(bar_w, 0u);
+                tc::mbar_wait_sleep(bar_acc_empty, ph ^ 1u, 128);                      // previous tile's epilogue is done with tensor memory
+                tc::mbar_wait_sleep(bar_a_full, ph, 128);
                 tc::fence_after_sync();
                 PTRACE(0);
                 const uint32_t d = tmem + T_ACC;
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     tc::mbar_arrive(bar_a_empty);
                 }
                 PTRACE(1);
-                tc::mbar_wait(bar_dg_full, ph);
+                tc::mbar_wait_sleep(bar_dg_full, ph, 128);
                 tc::fence_after_sync();
                 PTRACE(2);
                 if (!p.first) {
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     for (int s = 0; s < 8; ++s) {        // d r, d z: [d agg | d part] += d g . [Wc | Whh] rows 16 s ..
                         const uint32_t a = tmem + T_ACC + 16u * s;
                         tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, WHH_HI - WC_HI),
-                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, WHH_LO - WC_LO), i128, s > 0 ? 1u : 0u);
+                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, WHH_LO - WC_LO), i128, 1u);
                     }
 #pragma unroll
                     for (int s = 8; s < 12; ++s) {       // d gi_n: d agg += . Wc rows 128 ..
@@ -345,6 +349,13 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         }
     } else if (warp < EPI_WARPS) {
         // ===================================================================== epilogue: thread = tile row = TMEM lane
+        // All per-row arrays live in the thread's tensor-memory lane, so every loop below is ROLLED (8 units per trip):
+        // a fully unrolled body is > 100 KB of straight-line code that one warp executes once per tile, i.e. pure
+        // instruction-cache misses (measured: 8 cycles per instruction).
+        //   T_ACC   r | z | gi_n | gh_n pre-activations -> r | z | n | gh_n -> fp32 d gates -> fp16 hi/lo planes
+        //   T_OUT   [0, 64) own state row h (later zero = d agg accumulator init), [64, 128) pre-LayerNorm output ->
+        //           g z (the direct part of d part), scaled: the data-gradient MMAs accumulate on top of both
+        //   T_LNP   d ln_w | d ln_b partial sums of this thread's rows
         const int row = warp * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
         const uint32_t t_acc = tl + T_ACC, t_out = tl + T_OUT, t_lnp = tl + T_LNP;
@@ -358,135 +369,119 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             const uint32_t ph = (uint32_t)(it & 1);
             const bool valid = tile * TM + row < p.N;
             const int node = valid ? p.order[tile * TM + row] : 0;
-            const float* hrow = prev + (size_t)node * D;
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            tc::mbar_wait(bar_acc_full, ph);
-            tc::mbar_wait(bar_a_full, ph);
-            tc::fence_after_sync();
-            if (tid == 0) PTRACE(4);
-            // ---- pass 1: gates (kept in tensor memory: r, z, n overwrite their pre-activations), pre-LayerNorm output
-            float xh[D];
-            {
-                float g0[16], g1[16];
-                float4 h0 = valid ? mgv_ld4(hrow) : zero4, h1;
-                tmem_ld4x4(t_acc, g0);
+            // own state row -> tensor memory (before the accumulator wait: overlaps the recompute MMAs)
+#pragma unroll 4
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float h[8];
+                if (valid) ldg8(prev + (size_t)node * D + 8 * c8, h);
+                else {
 #pragma unroll
-                for (int ch = 0; ch < 16; ch += 2) {
-                    tc::tmem_ld_wait();
-                    tmem_ld4x4(t_acc + 4 * (ch + 1), g1);
-                    h1 = valid ? mgv_ld4(hrow + 4 * (ch + 1)) : zero4;
-                    {
-                        const float hv[4] = {h0.x, h0.y, h0.z, h0.w};
-                        float r[4], z[4], n[4], hn;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            gru_gates(g0[e], g0[4 + e], g0[8 + e], g0[12 + e], r[e], z[e], n[e], hn);
-                            xh[4 * ch + e] = fmaf(z[e], hv[e] - n[e], n[e]);
-                        }
-                        tc::tmem_st4(t_acc + 4 * ch, r[0], r[1], r[2], r[3]);
-                        tc::tmem_st4(t_acc + 64 + 4 * ch, z[0], z[1], z[2], z[3]);
-                        tc::tmem_st4(t_acc + 128 + 4 * ch, n[0], n[1], n[2], n[3]);
-                    }
-                    tc::tmem_ld_wait();
-                    if (ch + 2 < 16) {
-                        tmem_ld4x4(t_acc + 4 * (ch + 2), g0);
-                        h0 = valid ? mgv_ld4(hrow + 4 * (ch + 2)) : zero4;
-                    }
-                    {
-                        const float hv[4] = {h1.x, h1.y, h1.z, h1.w};
-                        float r[4], z[4], n[4], hn;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            gru_gates(g1[e], g1[4 + e], g1[8 + e], g1[12 + e], r[e], z[e], n[e], hn);
-                            xh[4 * (ch + 1) + e] = fmaf(z[e], hv[e] - n[e], n[e]);
-                        }
-                        tc::tmem_st4(t_acc + 4 * (ch + 1), r[0], r[1], r[2], r[3]);
-                        tc::tmem_st4(t_acc + 64 + 4 * (ch + 1), z[0], z[1], z[2], z[3]);
-                        tc::tmem_st4(t_acc + 128 + 4 * (ch + 1), n[0], n[1], n[2], n[3]);
-                    }
+                    for (int e = 0; e < 8; ++e) h[e] = 0.f;
                 }
+                tc::tmem_st8f(t_out + 8 * c8, h);
             }
-            // ---- LayerNorm statistics (same two-pass form as the forward), x^ stays in xh; LayerNorm parameter
-            //      gradients accumulate per thread in tensor memory
-            float rstd = 1.0f, c1 = 0.f, c2 = 0.f;
-            if (p.layernorm) {
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            tc::mbar_wait_warp(bar_acc_full, ph, lane, 32);
+            tc::mbar_wait_warp(bar_a_full, ph, lane, 32);
+            tc::fence_after_sync();
+            tc::tmem_st_wait();
+            if (tid == 0) PTRACE(4);
+            // ---- pass 1: gates, pre-LayerNorm output
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float gr[8], gz[8], gi[8], gh[8], h[8];
+                tc::tmem_ld8(t_acc + 8 * c8, gr);
+                tc::tmem_ld8(t_acc + 64 + 8 * c8, gz);
+                tc::tmem_ld8(t_acc + 128 + 8 * c8, gi);
+                tc::tmem_ld8(t_acc + 192 + 8 * c8, gh);
+                tc::tmem_ld8(t_out + 8 * c8, h);
+                tc::tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < D; e += 4) { s0 += xh[e]; s1 += xh[e + 1]; s2 += xh[e + 2]; s3 += xh[e + 3]; }
-                const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / D);
-                s0 = s1 = s2 = s3 = 0.f;
-#pragma unroll
-                for (int e = 0; e < D; e += 4) {
-                    xh[e] -= mean; xh[e + 1] -= mean; xh[e + 2] -= mean; xh[e + 3] -= mean;
-                    s0 = fmaf(xh[e], xh[e], s0); s1 = fmaf(xh[e + 1], xh[e + 1], s1);
-                    s2 = fmaf(xh[e + 2], xh[e + 2], s2); s3 = fmaf(xh[e + 3], xh[e + 3], s3);
+                for (int e = 0; e < 8; ++e) {
+                    float r, z, n, hn;
+                    gru_gates(gr[e], gz[e], gi[e], gh[e], r, z, n, hn);
+                    gr[e] = r; gz[e] = z; gi[e] = n;
+                    h[e] = fmaf(z, h[e] - n, n);
+                    sum += h[e];
                 }
-                rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / D) + LN_EPS);
-#pragma unroll
+                tc::tmem_st8f(t_acc + 8 * c8, gr);
+                tc::tmem_st8f(t_acc + 64 + 8 * c8, gz);
+                tc::tmem_st8f(t_acc + 128 + 8 * c8, gi);
+                tc::tmem_st8f(t_out + 64 + 8 * c8, h);
+            }
+            tc::tmem_st_wait();
+            if (tid == 0) PTRACE(10);
+            // ---- LayerNorm statistics (two-pass, like the forward) and the two row sums of its backward
+            float mean = 0.f, rstd = 1.0f, c1 = 0.f, c2 = 0.f;
+            if (p.layernorm) {
+                mean = sum * (1.0f / D);
+                float var = 0.f;
+#pragma unroll 1
                 for (int c8 = 0; c8 < 8; ++c8) {
-                    float lw[8], lb[8];
-                    tc::tmem_ld8(t_lnp + 8 * c8, lw);
-                    tc::tmem_ld8(t_lnp + 64 + 8 * c8, lb);
+                    float xv[8];
+                    tc::tmem_ld8(t_out + 64 + 8 * c8, xv);
                     const float4 ga = lds4(gs + 8 * c8), gb = lds4(gs + 8 * c8 + 4);
                     const float4 wa = lds4(s_ln + 8 * c8), wb = lds4(s_ln + 8 * c8 + 4);
-                    const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    const float gw[8] = {ga.x * wa.x, ga.y * wa.y, ga.z * wa.z, ga.w * wa.w, gb.x * wb.x, gb.y * wb.y, gb.z * wb.z, gb.w * wb.w};
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float xv = xh[8 * c8 + e] * rstd;
-                        xh[8 * c8 + e] = xv;
-                        const float gwv = gv[e] * wv[e];
-                        c1 += gwv;
-                        c2 = fmaf(gwv, xv, c2);
-                        lw[e] = fmaf(gv[e], xv, lw[e]);
-                        lb[e] += gv[e];
+                        const float d = xv[e] - mean;
+                        var = fmaf(d, d, var);
+                        c1 += gw[e];
+                        c2 = fmaf(gw[e], d, c2);
                     }
-                    tc::tmem_st8(t_lnp + 8 * c8, *reinterpret_cast<const uint32_t(*)[8]>(&lw));
-                    tc::tmem_st8(t_lnp + 64 + 8 * c8, *reinterpret_cast<const uint32_t(*)[8]>(&lb));
                 }
+                rstd = rsqrtf(var * (1.0f / D) + LN_EPS);
                 c1 *= (1.0f / D);
-                c2 *= (1.0f / D);
+                c2 *= rstd * (1.0f / D);
             }
-            tc::tmem_st_wait();
             if (tid == 0) PTRACE(5);
-            // ---- pass 2: LayerNorm backward + GRU backward, fp32 d gates back into tensor memory, g z kept in xh
+            // ---- pass 2: LayerNorm backward + GRU backward -> fp32 d gates in place, g z, LayerNorm parameter gradients
             float amax = 0.f;
-            {
-                float g0[16], g1[16];
-                tmem_ld4x4(t_acc, g0);
+#pragma unroll 1
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float r[8], z[8], n[8], hn[8], h[8], xv[8], lw[8], lb[8];
+                tc::tmem_ld8(t_acc + 8 * c8, r);
+                tc::tmem_ld8(t_acc + 64 + 8 * c8, z);
+                tc::tmem_ld8(t_acc + 128 + 8 * c8, n);
+                tc::tmem_ld8(t_acc + 192 + 8 * c8, hn);
+                tc::tmem_ld8(t_out + 8 * c8, h);
+                tc::tmem_ld8(t_out + 64 + 8 * c8, xv);
+                if (p.layernorm) { tc::tmem_ld8(t_lnp + 8 * c8, lw); tc::tmem_ld8(t_lnp + 64 + 8 * c8, lb); }
+                const float4 ga = lds4(gs + 8 * c8), gb = lds4(gs + 8 * c8 + 4);
+                const float4 wa = lds4(s_ln + 8 * c8), wb = lds4(s_ln + 8 * c8 + 4);
+                const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                tc::tmem_ld_wait();
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch) {
-                    float (&gc)[16] = (ch & 1) ? g1 : g0;
-                    float (&gn)[16] = (ch & 1) ? g0 : g1;
-                    const float4 g4 = lds4(gs + 4 * ch);
-                    const float4 w4 = lds4(s_ln + 4 * ch);
-                    const float4 h4 = valid ? mgv_ld4(hrow + 4 * ch) : zero4;
-                    tc::tmem_ld_wait();
-                    if (ch + 1 < 16) tmem_ld4x4(t_acc + 4 * (ch + 1), gn);
-                    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, hv[4] = {h4.x, h4.y, h4.z, h4.w};
-                    float dr[4], dz[4], dni[4], dnh[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float r = gc[e], z = gc[4 + e], n = gc[8 + e], hn = gc[12 + e];
-                        const float xv = xh[4 * ch + e];
-                        const float dxh = p.layernorm ? rstd * (fmaf(gv[e], wv[e], -c1) - xv * c2) : gv[e];
-                        const float dn = dxh * (1.0f - z);
-                        const float dzz = dxh * (hv[e] - n);
-                        dni[e] = dn * (1.0f - n * n);
-                        dr[e] = dni[e] * hn * r * (1.0f - r);
-                        dz[e] = dzz * z * (1.0f - z);
-                        dnh[e] = dni[e] * r;
-                        xh[4 * ch + e] = dxh * z;
-                        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dr[e]), fabsf(dz[e])), fabsf(dni[e])));
+                for (int e = 0; e < 8; ++e) {
+                    float dxh = gv[e];
+                    if (p.layernorm) {
+                        const float xn = (xv[e] - mean) * rstd;
+                        lw[e] = fmaf(gv[e], xn, lw[e]);
+                        lb[e] += gv[e];
+                        dxh = rstd * (fmaf(gv[e], wv[e], -c1) - xn * c2);
                     }
-                    tc::tmem_st4(t_acc + 4 * ch, dr[0], dr[1], dr[2], dr[3]);
-                    tc::tmem_st4(t_acc + 64 + 4 * ch, dz[0], dz[1], dz[2], dz[3]);
-                    tc::tmem_st4(t_acc + 128 + 4 * ch, dni[0], dni[1], dni[2], dni[3]);
-                    tc::tmem_st4(t_acc + 192 + 4 * ch, dnh[0], dnh[1], dnh[2], dnh[3]);
+                    const float dn = dxh * (1.0f - z[e]);
+                    const float dzz = dxh * (h[e] - n[e]);
+                    const float dni = dn * (1.0f - n[e] * n[e]);
+                    const float dr = dni * hn[e] * r[e] * (1.0f - r[e]);
+                    const float dz = dzz * z[e] * (1.0f - z[e]);
+                    hn[e] = dni * r[e];
+                    xv[e] = dxh * z[e];
+                    r[e] = dr; z[e] = dz; n[e] = dni;
+                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dr), fabsf(dz)), fabsf(dni)));
                 }
+                tc::tmem_st8f(t_acc + 8 * c8, r);
+                tc::tmem_st8f(t_acc + 64 + 8 * c8, z);
+                tc::tmem_st8f(t_acc + 128 + 8 * c8, n);
+                tc::tmem_st8f(t_acc + 192 + 8 * c8, hn);
+                tc::tmem_st8f(t_out + 64 + 8 * c8, xv);
+                if (p.layernorm) { tc::tmem_st8f(t_lnp + 8 * c8, lw); tc::tmem_st8f(t_lnp + 64 + 8 * c8, lb); }
             }
             tc::mbar_arrive(bar_g_empty);
+            if (tid == 0) PTRACE(12);
             // ---- tile-wide power-of-two scale (fp16 range), shared with the weight-gradient kernel through HBM
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -501,10 +496,11 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             }
             tc::tmem_st_wait();
             if (tid == 0) PTRACE(6);
-            // ---- pass 3: fp32 d gates -> scaled fp16 hi/lo planes, in place (A operand of the data-gradient MMAs) and to HBM
+            // ---- pass 3: fp32 d gates -> scaled fp16 hi/lo planes, in place (A operand of the data-gradient MMAs) and to
+            //      HBM [plane][8-gate chunk (32)][node row (128)][16 B]: a warp's 32 rows write 512 contiguous bytes
             {
-                uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * DG_TILE_BYTES;
-#pragma unroll
+                uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * DG_TILE_BYTES + row * 16;
+#pragma unroll 2
                 for (int s = 0; s < 16; ++s) {
                     float v[16];
                     tc::tmem_ld16(t_acc + 16 * s, v);
@@ -513,12 +509,26 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
 #pragma unroll
                     for (int e = 0; e < 8; ++e) tc::split2(v[2 * e] * scale, v[2 * e + 1] * scale, pk[e], pk[8 + e]);
                     tc::tmem_st16(t_acc + 16 * s, pk);
-                    uint8_t* hb = dg + (s >> 2) * 16384;
-                    const uint32_t o0 = tc::sw128_off(row, 2 * (s & 3)), o1 = tc::sw128_off(row, 2 * (s & 3) + 1);
-                    *reinterpret_cast<uint4*>(hb + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(hb + o1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    *reinterpret_cast<uint4*>(hb + 65536 + o0) = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-                    *reinterpret_cast<uint4*>(hb + 65536 + o1) = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                    uint8_t* hb = dg + (size_t)(2 * s) * 2048;
+                    *reinterpret_cast<uint4*>(hb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(hb + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    *reinterpret_cast<uint4*>(hb + 65536) = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+                    *reinterpret_cast<uint4*>(hb + 65536 + 2048) = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                }
+                // accumulator init of the data-gradient MMAs: d agg = 0, d part = scale * g z
+                if (!p.first) {
+#pragma unroll 2
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        float q[8];
+                        tc::tmem_ld8(t_out + 64 + 8 * c8, q);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) q[e] *= scale;
+                        tc::tmem_st8f(t_out + 64 + 8 * c8, q);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) q[e] = 0.f;
+                        tc::tmem_st8f(t_out + 8 * c8, q);
+                    }
                 }
             }
             tc::tmem_st_wait();
@@ -527,18 +537,18 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             if (tid == 0) PTRACE(7);
             // ---- data gradients of step k-1
             if (!p.first) {
-                tc::mbar_wait(bar_out_full, ph);
+                tc::mbar_wait_warp(bar_out_full, ph, lane, 32);
                 tc::fence_after_sync();
                 if (tid == 0) PTRACE(8);
                 const float inv = 1.0f / scale;
-#pragma unroll
+#pragma unroll 2
                 for (int c8 = 0; c8 < 8; ++c8) {
                     float a[8], q[8];
                     tc::tmem_ld8(t_out + 8 * c8, a);
                     tc::tmem_ld8(t_out + 64 + 8 * c8, q);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { a[e] *= inv; q[e] = fmaf(q[e], inv, xh[8 * c8 + e]); }
+                    for (int e = 0; e < 8; ++e) { a[e] *= inv; q[e] *= inv; }
                     if (valid) {
                         stg8(p.out_agg + eoff + (size_t)node * D + 8 * c8, a);
                         stg8(p.out_part + eoff + (size_t)node * D + 8 * c8, q);
@@ -631,15 +641,15 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
         if (lane == 0) {
             for (int i = 0; i < nhalf; ++i) {
                 const int s = i & 1, tile = tile_beg + (i >> 1), h = i & 1;
-                tc::mbar_wait(bar_empty + 8 * s, (uint32_t)(((i >> 1) & 1) ^ 1));
+                tc::mbar_wait_sleep(bar_empty + 8 * s, (uint32_t)(((i >> 1) & 1) ^ 1));
                 tc::mbar_expect_tx(bar_full + 8 * s, ST_BYTES);
-                const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 8192;
+                const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 1024;
                 const uint8_t* at = p.abuf + ((size_t)enc * p.chunk_cap + tile) * A_TILE_BYTES;
                 const uint32_t st = sbase + (uint32_t)s * ST_BYTES, bar = bar_full + 8 * s;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    tc::bulk_g2s(st + ST_DG_HI + 8192u * b, dg + 16384 * b, 8192u, bar);
-                    tc::bulk_g2s(st + ST_DG_LO + 8192u * b, dg + 65536 + 16384 * b, 8192u, bar);
+#pragma unroll 1
+                for (int ck = 0; ck < 32; ++ck) {      // 64 rows of each 8-gate chunk: 1 KB
+                    tc::bulk_g2s(st + ST_DG_HI + 1024u * ck, dg + 2048 * ck, 1024u, bar);
+                    tc::bulk_g2s(st + ST_DG_LO + 1024u * ck, dg + 65536 + 2048 * ck, 1024u, bar);
                 }
                 tc::bulk_g2s(st + ST_AGG_HI, at + 0 + h * 8192, 8192u, bar);
                 tc::bulk_g2s(st + ST_AGG_LO, at + 16384 + h * 8192, 8192u, bar);
@@ -654,7 +664,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
             const uint32_t i128 = tc::make_idesc(128, 128, true, true), i16 = tc::make_idesc(128, 16, true, true);
             for (int i = 0; i < nhalf; ++i) {
                 const int s = i & 1;
-                tc::mbar_wait(bar_ready + 8 * s, (uint32_t)((i >> 1) & 1));
+                tc::mbar_wait_sleep(bar_ready + 8 * s, (uint32_t)((i >> 1) & 1), 32);
                 tc::fence_after_sync();
                 const uint32_t st = sbase + (uint32_t)s * ST_BYTES;
 #pragma unroll
@@ -664,8 +674,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
                     const uint64_t x_hi = tc::desc_mn_plain16(st + ST_X_HI + 512u * j), x_lo = tc::desc_mn_plain16(st + ST_X_LO + 512u * j);
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
-                        const uint64_t a_hi = tc::desc_mn_sw128(st + ST_DG_HI + 16384u * g + 2048u * j, 8192);
-                        const uint64_t a_lo = tc::desc_mn_sw128(st + ST_DG_LO + 16384u * g + 2048u * j, 8192);
+                        // d gates^T: 16 chunks of 8 gates 1 KB apart (SBO), 8-node K groups 128 B apart (LBO), no swizzle
+                        const uint64_t a_hi = tc::make_desc(st + ST_DG_HI + 16384u * g + 256u * j, 128, 1024, tc::LAYOUT_NONE);
+                        const uint64_t a_lo = tc::make_desc(st + ST_DG_LO + 16384u * g + 256u * j, 128, 1024, tc::LAYOUT_NONE);
                         tc::mma3(tmem + 160u * g, a_hi, a_lo, b_hi, b_lo, i128, acc);
                         tc::mma3(tmem + 160u * g + 128u, a_hi, a_lo, x_hi, x_lo, i16, acc);
                     }
@@ -679,7 +690,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
         const int t128 = tid - 64;
         for (int i = 0; i < nhalf; ++i) {
             const int s = i & 1, tile = tile_beg + (i >> 1);
-            tc::mbar_wait(bar_full + 8 * s, (uint32_t)((i >> 1) & 1));
+            tc::mbar_wait_warp(bar_full + 8 * s, (uint32_t)((i >> 1) & 1), lane, 32);
             const float m = smin / p.scales[(size_t)enc * p.chunk_cap + tile];
             if (m != 1.0f) {
                 const __half2 m2 = __float2half2_rn(m);
@@ -697,7 +708,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
         }
         // flush: thread = accumulator row = d-gate column
         if (nhalf > 0) {
-            tc::mbar_wait(bar_done, 0u);
+            tc::mbar_wait_warp(bar_done, 0u, lane, 64);
             tc::fence_after_sync();
             const int L = (warp & 3) * 32 + lane;
             const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -767,6 +778,12 @@ int sm_count(int* sms) {
     return MGV_OK;
 }
 
+int chunk_tiles() {
+    const char* e = getenv("MGV_STRUCT_CHUNK");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : CHUNK_TILES_DEFAULT;
+}
+
 bool use_legacy(int precision) {
     if (precision != 0) return true;
     const char* e = getenv("MGV_STRUCT_BWD");
@@ -777,6 +794,7 @@ size_t tc_workspace_bytes(int64_t N, int num_enc) {
     int sms = 148;
     sm_count(&sms);
     const int64_t ntiles = (N + TM - 1) / TM;
+    const int CHUNK_TILES = chunk_tiles();
     const int64_t cap = ntiles < CHUNK_TILES ? ntiles : CHUNK_TILES;
     size_t b = mgv_struct_image_bytes(num_enc) + 256;
     b += 4 * mgv_align_up((size_t)num_enc * N * D * 4 + 256, 256);
@@ -823,6 +841,7 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     int rc = sm_count(&sms);
     if (rc != MGV_OK) return rc;
     const int ntiles = (N + TM - 1) / TM;
+    const int CHUNK_TILES = chunk_tiles();
     const int cap = ntiles < CHUNK_TILES ? ntiles : CHUNK_TILES;
     const int chunks = (ntiles + CHUNK_TILES - 1) / CHUNK_TILES;
     const int gxp = sms / num_enc > 0 ? sms / num_enc : 1;
