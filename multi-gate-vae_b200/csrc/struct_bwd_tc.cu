@@ -36,10 +36,10 @@ namespace {
 using namespace struct_layout;
 
 constexpr int SGRAD = MGV_STRUCT_GRAD_FLOATS;
-constexpr int EPI_WARPS = 4, GATHER_WARPS = 8;
+constexpr int EPI_WARPS = 4, GATHER_WARPS = 16;             // 16 gather warps x 2 rows per lane: twice the loads in flight
 constexpr int THREADS = (EPI_WARPS + GATHER_WARPS + 1) * 32;
 constexpr int LDGS = 68;                                   // d state staging row stride (floats)
-constexpr uint32_t DG_TILE_BYTES = 131072;                 // [hi | lo][8-gate chunk (32)][node row (128)][16 B]: no-swizzle core matrices
+constexpr uint32_t DG_TILE_BYTES = 131072;                 // [hi | lo][64-node half][8-gate chunk (32)][node row (64)][16 B]: no-swizzle core matrices
 constexpr int CHUNK_TILES_DEFAULT = 1024;                  // tiles per encoder per kernel pair (MGV_STRUCT_CHUNK overrides: tuning)
 
 // ---- shared memory of the pointwise kernel (after the weight image and the operand tile, struct_layout.cuh)
@@ -191,86 +191,132 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + GATHER_WARPS) {
         // ===================================================================== gather
+        // lane = (row group rg, 16-byte chunk c): 8 lanes cover one 256-byte row; a lane owns 2 rows of the tile.
+        // ONE wave of independent loads (own state row, own gradient row, first neighbour of both
+        // sums, second neighbour ids), then one wave per further neighbour: the dependent-load chain of a tile is
+        // max(1, degree) latencies; the next tile's row descriptors are loaded one tile ahead.
         const int gw = warp - EPI_WARPS, rg = lane >> 3, c = lane & 7;
         const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
         const float* gsrc = p.last ? p.gout + eoff : p.in_part + eoff;
         const float* asrc = p.in_agg + eoff;
+        const bool nbg = !p.last;
+        int4 dn[2];
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {
+            const int r = tile_beg * TM + gw * 8 + ps * 4 + rg;
+            dn[ps] = (tile_beg < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
+        }
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
-            int node[4], beg[4], cnt[4], j0[4];
-            int maxc = 0;
             if (warp == EPI_WARPS && lane == 0) PTRACE(13);
+            int4 dc[2];
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int r = tile * TM + gw * 16 + ps * 4 + rg;
-                const int4 d = (r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
-                node[ps] = d.x; beg[ps] = d.y; cnt[ps] = d.z; j0[ps] = d.w;
-                maxc = max(maxc, cnt[ps]);
+            for (int ps = 0; ps < 2; ++ps) dc[ps] = dn[ps];
+#pragma unroll
+            for (int ps = 0; ps < 2; ++ps) {
+                const int r = (tile + 1) * TM + gw * 8 + ps * 4 + rg;
+                dn[ps] = (tile + 1 < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
             }
-            float acc[4][8];
-            float xe[4];
-            // own state rows and the lane's feature element
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                xe[ps] = 0.f;
-                if (node[ps] >= 0) {
-                    a = mgv_ld4(prev + (size_t)node[ps] * D + c * 8);
-                    b = mgv_ld4(prev + (size_t)node[ps] * D + c * 8 + 4);
-                    if (c < p.feat) xe[ps] = p.x[(size_t)node[ps] * p.feat + c];
+            for (int hf = 0; hf < 1; ++hf) {
+                int node[2], beg[2], cnt[2], jn[2];
+                float4 h[2][2], g[2][2], vp[2][2], va[2][2];
+                float xe[2];
+                int maxc = 0;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int4 d = dc[2 * hf + q];
+                    node[q] = d.x; beg[q] = d.y; cnt[q] = d.z; jn[q] = d.w;
+                    maxc = max(maxc, cnt[q]);
+                    h[q][0] = z4; h[q][1] = z4; g[q][0] = z4; g[q][1] = z4; vp[q][0] = z4; vp[q][1] = z4; va[q][0] = z4; va[q][1] = z4;
+                    xe[q] = 0.f;
+                    if (node[q] >= 0) {
+                        h[q][0] = mgv_ld4(prev + (size_t)node[q] * D + c * 8);
+                        h[q][1] = mgv_ld4(prev + (size_t)node[q] * D + c * 8 + 4);
+                        g[q][0] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8);
+                        g[q][1] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8 + 4);
+                        if (c < p.feat) xe[q] = p.x[(size_t)node[q] * p.feat + c];
+                    }
+                    if (cnt[q] > 0) {
+                        vp[q][0] = mgv_ld4(prev + (size_t)jn[q] * D + c * 8);
+                        vp[q][1] = mgv_ld4(prev + (size_t)jn[q] * D + c * 8 + 4);
+                        if (nbg) {
+                            va[q][0] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8);
+                            va[q][1] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8 + 4);
+                        }
+                    }
+                    if (cnt[q] > 1) jn[q] = p.idx[beg[q] + 1] & NODE_MASK;
                 }
-                acc[ps][0] = a.x; acc[ps][1] = a.y; acc[ps][2] = a.z; acc[ps][3] = a.w;
-                acc[ps][4] = b.x; acc[ps][5] = b.y; acc[ps][6] = b.z; acc[ps][7] = b.w;
-            }
-            tc::mbar_wait_warp(bar_a_empty, (uint32_t)((it & 1) ^ 1), lane, 128);            // previous tile's MMAs and bulk store have read the tile
-            if (warp == EPI_WARPS && lane == 0) PTRACE(11);
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int row = gw * 16 + ps * 4 + rg;
-                split_store_sw128(sbase + A_H_HI, sbase + A_H_LO, row, c, acc[ps]);
-                float xv[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) xv[e] = __shfl_sync(0xffffffffu, xe[ps], (lane & 24) + e);
-                if (c == 1) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) xv[e] = 0.f;
-                    if (node[ps] >= 0) { xv[0] = (float)cnt[ps]; xv[1] = 1.0f; }
+                if (hf == 0) {
+                    tc::mbar_wait_warp(bar_a_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's MMAs and bulk store have read the tile
+                    if (warp == EPI_WARPS && lane == 0) PTRACE(11);
                 }
-                if (c < 2) {
-                    uint4 hi, lo;
-                    tc::split8(xv, hi, lo);
-                    const uint32_t off = tc::plain16_off(row, c);
-                    tc::st_shared_v4(sbase + A_X_HI + off, hi);
-                    tc::st_shared_v4(sbase + A_X_LO + off, lo);
+                float ap[2][8], ag[2][8];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int row = gw * 8 + q * 4 + rg;
+                    const float h8[8] = {h[q][0].x, h[q][0].y, h[q][0].z, h[q][0].w, h[q][1].x, h[q][1].y, h[q][1].z, h[q][1].w};
+                    split_store_sw128(sbase + A_H_HI, sbase + A_H_LO, row, c, h8);
+                    float xv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) xv[e] = __shfl_sync(0xffffffffu, xe[q], (lane & 24) + e);
+                    if (c == 1) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) xv[e] = 0.f;
+                        if (node[q] >= 0) { xv[0] = (float)cnt[q]; xv[1] = 1.0f; }
+                    }
+                    if (c < 2) {
+                        uint4 hi, lo;
+                        tc::split8(xv, hi, lo);
+                        const uint32_t off = tc::plain16_off(row, c);
+                        tc::st_shared_v4(sbase + A_X_HI + off, hi);
+                        tc::st_shared_v4(sbase + A_X_LO + off, lo);
+                    }
+                    ap[q][0] = vp[q][0].x; ap[q][1] = vp[q][0].y; ap[q][2] = vp[q][0].z; ap[q][3] = vp[q][0].w;
+                    ap[q][4] = vp[q][1].x; ap[q][5] = vp[q][1].y; ap[q][6] = vp[q][1].z; ap[q][7] = vp[q][1].w;
+                    ag[q][0] = g[q][0].x + va[q][0].x; ag[q][1] = g[q][0].y + va[q][0].y; ag[q][2] = g[q][0].z + va[q][0].z; ag[q][3] = g[q][0].w + va[q][0].w;
+                    ag[q][4] = g[q][1].x + va[q][1].x; ag[q][5] = g[q][1].y + va[q][1].y; ag[q][6] = g[q][1].z + va[q][1].z; ag[q][7] = g[q][1].w + va[q][1].w;
                 }
-            }
-            // neighbour sum of state_{k-1}
+                for (int sl = 1; sl < maxc; ++sl) {
+                    int j[2];
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps)
+                    for (int q = 0; q < 2; ++q) {
+                        j[q] = jn[q];
+                        if (sl + 1 < cnt[q]) jn[q] = p.idx[beg[q] + sl + 1] & NODE_MASK;
+                    }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[ps][e] = 0.f;
-            neighbour_sum(prev, p.idx, beg, cnt, j0, maxc, c, acc);
+                    for (int q = 0; q < 2; ++q) {
+                        vp[q][0] = z4; vp[q][1] = z4; va[q][0] = z4; va[q][1] = z4;
+                        if (sl < cnt[q]) {
+                            vp[q][0] = mgv_ld4(prev + (size_t)j[q] * D + c * 8);
+                            vp[q][1] = mgv_ld4(prev + (size_t)j[q] * D + c * 8 + 4);
+                            if (nbg) {
+                                va[q][0] = mgv_ld4(asrc + (size_t)j[q] * D + c * 8);
+                                va[q][1] = mgv_ld4(asrc + (size_t)j[q] * D + c * 8 + 4);
+                            }
+                        }
+                    }
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) split_store_sw128(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps]);
-            if (warp == EPI_WARPS && lane == 0) PTRACE(14);
-            // d state_k = d part (or the incoming gradient at the last step) + neighbour sum of d agg_{k+1}
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                if (node[ps] >= 0) {
-                    a = mgv_ld4(gsrc + (size_t)node[ps] * D + c * 8);
-                    b = mgv_ld4(gsrc + (size_t)node[ps] * D + c * 8 + 4);
+                    for (int q = 0; q < 2; ++q) {
+                        ap[q][0] += vp[q][0].x; ap[q][1] += vp[q][0].y; ap[q][2] += vp[q][0].z; ap[q][3] += vp[q][0].w;
+                        ap[q][4] += vp[q][1].x; ap[q][5] += vp[q][1].y; ap[q][6] += vp[q][1].z; ap[q][7] += vp[q][1].w;
+                        ag[q][0] += va[q][0].x; ag[q][1] += va[q][0].y; ag[q][2] += va[q][0].z; ag[q][3] += va[q][0].w;
+                        ag[q][4] += va[q][1].x; ag[q][5] += va[q][1].y; ag[q][6] += va[q][1].z; ag[q][7] += va[q][1].w;
+                    }
                 }
-                acc[ps][0] = a.x; acc[ps][1] = a.y; acc[ps][2] = a.z; acc[ps][3] = a.w;
-                acc[ps][4] = b.x; acc[ps][5] = b.y; acc[ps][6] = b.z; acc[ps][7] = b.w;
-            }
-            if (!p.last) neighbour_sum(asrc, p.idx, beg, cnt, j0, maxc, c, acc);
-            tc::mbar_wait_warp(bar_g_empty, (uint32_t)((it & 1) ^ 1), lane, 128);            // previous tile's epilogue has read the staging rows
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                float* dst = s_g + (gw * 16 + ps * 4 + rg) * LDGS + c * 8;
-                *reinterpret_cast<float4*>(dst) = make_float4(acc[ps][0], acc[ps][1], acc[ps][2], acc[ps][3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[ps][4], acc[ps][5], acc[ps][6], acc[ps][7]);
+                for (int q = 0; q < 2; ++q) split_store_sw128(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 8 + q * 4 + rg, c, ap[q]);
+                if (hf == 0) {
+                    if (warp == EPI_WARPS && lane == 0) PTRACE(14);
+                    tc::mbar_wait_warp(bar_g_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's epilogue has read the staging rows
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float* dst = s_g + (gw * 8 + q * 4 + rg) * LDGS + c * 8;
+                    *reinterpret_cast<float4*>(dst) = make_float4(ag[q][0], ag[q][1], ag[q][2], ag[q][3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(ag[q][4], ag[q][5], ag[q][6], ag[q][7]);
+                }
             }
             tc::fence_async_smem();
             tc::mbar_arrive(bar_a_full);
@@ -440,22 +486,21 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             // ---- pass 2: LayerNorm backward + GRU backward -> fp32 d gates in place, g z, LayerNorm parameter gradients
             float amax = 0.f;
 #pragma unroll 1
-            for (int c8 = 0; c8 < 8; ++c8) {
-                float r[8], z[8], n[8], hn[8], h[8], xv[8], lw[8], lb[8];
-                tc::tmem_ld8(t_acc + 8 * c8, r);
-                tc::tmem_ld8(t_acc + 64 + 8 * c8, z);
-                tc::tmem_ld8(t_acc + 128 + 8 * c8, n);
-                tc::tmem_ld8(t_acc + 192 + 8 * c8, hn);
-                tc::tmem_ld8(t_out + 8 * c8, h);
-                tc::tmem_ld8(t_out + 64 + 8 * c8, xv);
-                if (p.layernorm) { tc::tmem_ld8(t_lnp + 8 * c8, lw); tc::tmem_ld8(t_lnp + 64 + 8 * c8, lb); }
-                const float4 ga = lds4(gs + 8 * c8), gb = lds4(gs + 8 * c8 + 4);
-                const float4 wa = lds4(s_ln + 8 * c8), wb = lds4(s_ln + 8 * c8 + 4);
-                const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            for (int c4 = 0; c4 < 16; ++c4) {          // 4 units per trip: the 21-warp CTA leaves 80 registers per thread
+                float r[4], z[4], n[4], hn[4], h[4], xv[4], lw[4], lb[4];
+                tc::tmem_ld4(t_acc + 4 * c4, r);
+                tc::tmem_ld4(t_acc + 64 + 4 * c4, z);
+                tc::tmem_ld4(t_acc + 128 + 4 * c4, n);
+                tc::tmem_ld4(t_acc + 192 + 4 * c4, hn);
+                tc::tmem_ld4(t_out + 4 * c4, h);
+                tc::tmem_ld4(t_out + 64 + 4 * c4, xv);
+                if (p.layernorm) { tc::tmem_ld4(t_lnp + 4 * c4, lw); tc::tmem_ld4(t_lnp + 64 + 4 * c4, lb); }
+                const float4 ga = lds4(gs + 4 * c4), wa = lds4(s_ln + 4 * c4);
+                const float gv[4] = {ga.x, ga.y, ga.z, ga.w};
+                const float wv[4] = {wa.x, wa.y, wa.z, wa.w};
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
+                for (int e = 0; e < 4; ++e) {
                     float dxh = gv[e];
                     if (p.layernorm) {
                         const float xn = (xv[e] - mean) * rstd;
@@ -473,12 +518,15 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     r[e] = dr; z[e] = dz; n[e] = dni;
                     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dr), fabsf(dz)), fabsf(dni)));
                 }
-                tc::tmem_st8f(t_acc + 8 * c8, r);
-                tc::tmem_st8f(t_acc + 64 + 8 * c8, z);
-                tc::tmem_st8f(t_acc + 128 + 8 * c8, n);
-                tc::tmem_st8f(t_acc + 192 + 8 * c8, hn);
-                tc::tmem_st8f(t_out + 64 + 8 * c8, xv);
-                if (p.layernorm) { tc::tmem_st8f(t_lnp + 8 * c8, lw); tc::tmem_st8f(t_lnp + 64 + 8 * c8, lb); }
+                tc::tmem_st4(t_acc + 4 * c4, r[0], r[1], r[2], r[3]);
+                tc::tmem_st4(t_acc + 64 + 4 * c4, z[0], z[1], z[2], z[3]);
+                tc::tmem_st4(t_acc + 128 + 4 * c4, n[0], n[1], n[2], n[3]);
+                tc::tmem_st4(t_acc + 192 + 4 * c4, hn[0], hn[1], hn[2], hn[3]);
+                tc::tmem_st4(t_out + 64 + 4 * c4, xv[0], xv[1], xv[2], xv[3]);
+                if (p.layernorm) {
+                    tc::tmem_st4(t_lnp + 4 * c4, lw[0], lw[1], lw[2], lw[3]);
+                    tc::tmem_st4(t_lnp + 64 + 4 * c4, lb[0], lb[1], lb[2], lb[3]);
+                }
             }
             tc::mbar_arrive(bar_g_empty);
             if (tid == 0) PTRACE(12);
@@ -497,9 +545,9 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             tc::tmem_st_wait();
             if (tid == 0) PTRACE(6);
             // ---- pass 3: fp32 d gates -> scaled fp16 hi/lo planes, in place (A operand of the data-gradient MMAs) and to
-            //      HBM [plane][8-gate chunk (32)][node row (128)][16 B]: a warp's 32 rows write 512 contiguous bytes
+            //      HBM [plane][64-node half][8-gate chunk (32)][node row (64)][16 B]: a warp's 32 rows write 512 contiguous bytes
             {
-                uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * DG_TILE_BYTES + row * 16;
+                uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * DG_TILE_BYTES + (row >> 6) * 32768 + (row & 63) * 16;
 #pragma unroll 2
                 for (int s = 0; s < 16; ++s) {
                     float v[16];
@@ -509,11 +557,11 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
 #pragma unroll
                     for (int e = 0; e < 8; ++e) tc::split2(v[2 * e] * scale, v[2 * e + 1] * scale, pk[e], pk[8 + e]);
                     tc::tmem_st16(t_acc + 16 * s, pk);
-                    uint8_t* hb = dg + (size_t)(2 * s) * 2048;
+                    uint8_t* hb = dg + (size_t)(2 * s) * 1024;
                     *reinterpret_cast<uint4*>(hb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(hb + 2048) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    *reinterpret_cast<uint4*>(hb + 1024) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     *reinterpret_cast<uint4*>(hb + 65536) = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-                    *reinterpret_cast<uint4*>(hb + 65536 + 2048) = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                    *reinterpret_cast<uint4*>(hb + 65536 + 1024) = make_uint4(pk[12], pk[13], pk[14], pk[15]);
                 }
                 // accumulator init of the data-gradient MMAs: d agg = 0, d part = scale * g z
                 if (!p.first) {
@@ -643,14 +691,13 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
                 const int s = i & 1, tile = tile_beg + (i >> 1), h = i & 1;
                 tc::mbar_wait_sleep(bar_empty + 8 * s, (uint32_t)(((i >> 1) & 1) ^ 1));
                 tc::mbar_expect_tx(bar_full + 8 * s, ST_BYTES);
-                const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 1024;
+                const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 32768;
                 const uint8_t* at = p.abuf + ((size_t)enc * p.chunk_cap + tile) * A_TILE_BYTES;
                 const uint32_t st = sbase + (uint32_t)s * ST_BYTES, bar = bar_full + 8 * s;
-#pragma unroll 1
-                for (int ck = 0; ck < 32; ++ck) {      // 64 rows of each 8-gate chunk: 1 KB
-                    tc::bulk_g2s(st + ST_DG_HI + 1024u * ck, dg + 2048 * ck, 1024u, bar);
-                    tc::bulk_g2s(st + ST_DG_LO + 1024u * ck, dg + 65536 + 2048 * ck, 1024u, bar);
-                }
+                tc::bulk_g2s(st + ST_DG_HI, dg, 16384u, bar);
+                tc::bulk_g2s(st + ST_DG_HI + 16384u, dg + 16384, 16384u, bar);
+                tc::bulk_g2s(st + ST_DG_LO, dg + 65536, 16384u, bar);
+                tc::bulk_g2s(st + ST_DG_LO + 16384u, dg + 65536 + 16384, 16384u, bar);
                 tc::bulk_g2s(st + ST_AGG_HI, at + 0 + h * 8192, 8192u, bar);
                 tc::bulk_g2s(st + ST_AGG_LO, at + 16384 + h * 8192, 8192u, bar);
                 tc::bulk_g2s(st + ST_H_HI, at + 32768 + h * 8192, 8192u, bar);
