@@ -258,7 +258,19 @@ int mgv_recon_loss_bwd(const float* st, int32_t N, const int64_t* pos, int64_t E
  *   mode 2: D[128][N]  = A[128][16] . B[N][16]^T                                (plain 16-column tiles)
  *   mode 3: D[128][16] = A[128 rows][128]^T . B[128 rows][16]                   (MN-major SW128 x MN-major plain)
  *   mode 4: D[128][64] = A[128][192] . B[192][64]                               (K-major x MN-major: data-gradient form)
+ *   mode 5: D[128][128] = A[128][64] . B[64][128]      A written to TENSOR MEMORY (tcgen05.st), B MN-major from two
+ *           64-column blocks: the data-gradient product of the struct-encoder backward (struct_bwd_tc.cu)
  */
+/* ------------------------------------------------------------------ small Linear layers around the path
+ * Weight / bias gradient of y = x W^T + b for the nn.Linear layers whose input is one row per node: hs_linear,
+ * hs_decompose (dg_ae_model_mig.py:46-47) and the readout MLP (arch/mlp.py:14-56):
+ *     dW[O][I] = sum_n gy[n][O] x[n][I],  db[O] = sum_n gy[n][O]   (db may be NULL),  1 <= I, O <= 128, fp32, deterministic.
+ * Replaces torch.autograd's AddmmBackward weight GEMM, which a library runs as one output tile on one SM with K = N.
+ */
+size_t mgv_linear_wgrad_workspace_bytes(int64_t N, int32_t I, int32_t O);
+int mgv_linear_wgrad(const float* x, const float* gy, int64_t N, int32_t I, int32_t O, float* dW, float* db,
+                     void* ws, size_t ws_bytes, mgv_stream_t stream);
+
 int mgv_tc_selftest(int32_t mode, const float* A, const float* B, float* D, int32_t K, int32_t N, mgv_stream_t stream);
 
 #define MGV_OK 0

@@ -68,6 +68,7 @@ __global__ void struct_unpack_kernel(const StructParams sp, const float* __restr
         if (j < D * D) {                                             // d w[k][c] = sum_o wih[o][k] gWc[o][c]
             const int k = j / D, c = j % D;
             float acc = 0.f;
+#pragma unroll 8
             for (int o = 0; o < G3; ++o) acc = fmaf(__ldg(wih + o * ldw + k), __ldg(G + O_WCX + o * NLDC + c), acc);
             v = acc;
         } else if ((j -= D * D) < D) {                               // d b[k] = sum_o wih[o][k] gbc[o]
@@ -173,7 +174,7 @@ extern "C" int mgv_struct_unpack_grads(const void* const* params, int32_t num_en
     const int ldw = D + feat;
     const int per_dir = D * D + D + G3 * ldw + G3 * D + 2 * G3;
     const int per_enc = 2 * per_dir + (layernorm ? 2 * D : 0);
-    struct_unpack_kernel<<<dim3(32, num_enc * 2), 256, 0, (cudaStream_t)stream>>>(sp, grads, out, per_enc);
+    struct_unpack_kernel<<<dim3(128, num_enc * 2), 256, 0, (cudaStream_t)stream>>>(sp, grads, out, per_enc);
     mgv_count_launches(1);
     return mgv_check_cuda(cudaGetLastError(), "mgv_struct_unpack_grads");
 }

@@ -637,6 +637,12 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// Fire-and-forget vector add to global memory (the block is private to this CTA; a read-modify-write loop would pay one
+// memory round trip per element: measured 55 000 cycles for the 113 KB block).
+__device__ __forceinline__ void red_add4(float4* dst, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ======================================================================================= weight gradients (streaming)
 constexpr int W_THREADS = 6 * 32;          // warp 0 bulk-copy producer, warp 1 MMA issue, warps 2-5 rescale + flush
 // stage = 64 nodes (half a tile): d-gate planes, operand planes
@@ -656,7 +662,9 @@ struct WgTC {
     const float* scales;
     const unsigned* smin;
     float* partial;
+    long long* trace;          // optional [CTA][16 stages][16] clock64 samples (dev tool)
 };
+#define WTRACE(slot) do { if (p.trace && i < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + i) * 16 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const WgTC p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -689,7 +697,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
         if (lane == 0) {
             for (int i = 0; i < nhalf; ++i) {
                 const int s = i & 1, tile = tile_beg + (i >> 1), h = i & 1;
+                WTRACE(0);
                 tc::mbar_wait_sleep(bar_empty + 8 * s, (uint32_t)(((i >> 1) & 1) ^ 1));
+                WTRACE(1);
                 tc::mbar_expect_tx(bar_full + 8 * s, ST_BYTES);
                 const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 32768;
                 const uint8_t* at = p.abuf + ((size_t)enc * p.chunk_cap + tile) * A_TILE_BYTES;
@@ -711,8 +721,10 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
             const uint32_t i128 = tc::make_idesc(128, 128, true, true), i16 = tc::make_idesc(128, 16, true, true);
             for (int i = 0; i < nhalf; ++i) {
                 const int s = i & 1;
+                WTRACE(4);
                 tc::mbar_wait_sleep(bar_ready + 8 * s, (uint32_t)((i >> 1) & 1), 32);
                 tc::fence_after_sync();
+                WTRACE(5);
                 const uint32_t st = sbase + (uint32_t)s * ST_BYTES;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -729,6 +741,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
                     }
                 }
                 tc::mma_commit(bar_empty + 8 * s);
+                WTRACE(6);
             }
             tc::mma_commit(bar_done);
         }
@@ -738,6 +751,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
         for (int i = 0; i < nhalf; ++i) {
             const int s = i & 1, tile = tile_beg + (i >> 1);
             tc::mbar_wait_warp(bar_full + 8 * s, (uint32_t)((i >> 1) & 1), lane, 32);
+            if (tid == 64) WTRACE(2);
             const float m = smin / p.scales[(size_t)enc * p.chunk_cap + tile];
             if (m != 1.0f) {
                 const __half2 m2 = __float2half2_rn(m);
@@ -752,49 +766,58 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
             }
             tc::fence_async_smem();
             tc::mbar_arrive(bar_ready + 8 * s);
+            if (tid == 64) WTRACE(3);
         }
         // flush: thread = accumulator row = d-gate column
         if (nhalf > 0) {
+            const int i = 0;
+            if (tid == 64) WTRACE(8);
             tc::mbar_wait_warp(bar_done, 0u, lane, 64);
             tc::fence_after_sync();
+            if (tid == 64) WTRACE(9);
+            // tensor memory -> shared memory (the stages are idle) -> coalesced vector reductions into the partial block
             const int L = (warp & 3) * 32 + lane;
             const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             float* part = p.partial + (((size_t)enc * p.gxp + blockIdx.x) * 2 + p.dir) * SGRAD;
+            float* stg = reinterpret_cast<float*>(sgen);                  // [2 groups][128 rows][FLD]
+            constexpr int FLD = 148;
             const float un = 1.0f / smin;
 #pragma unroll 1
-            for (int g = 0; g < 2; ++g) {
-                const int o = (g == 0) ? L : (L < 64 ? 128 + L : 64 + L);        // gate row of Wcx (g 0, or d gi_n) / Whh (g 0, or d gh_n)
-                const bool wc = (g == 0) || L < 64, wh = (g == 0) || L >= 64;
-#pragma unroll 1
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    float a[8], b[8];
-                    tc::tmem_ld8(tl + 160u * g + 8 * c8, a);
-                    tc::tmem_ld8(tl + 160u * g + 64 + 8 * c8, b);
+            for (int g = 0; g < 2; ++g)
+#pragma unroll 2
+                for (int c8 = 0; c8 < 18; ++c8) {
+                    float v[8];
+                    tc::tmem_ld8(tl + 160u * g + 8 * c8, v);
                     tc::tmem_ld_wait();
-                    if (wc) {
-                        float* d = part + O_WCX + o * LDC + 8 * c8;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) d[e] += a[e] * un;
-                    }
-                    if (wh) {
-                        float* d = part + O_WHH + o * LDM + 8 * c8;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) d[e] += b[e] * un;
-                    }
+                    float* d = stg + (g * 128 + L) * FLD + 8 * c8;
+                    *reinterpret_cast<float4*>(d) = make_float4(v[0] * un, v[1] * un, v[2] * un, v[3] * un);
+                    *reinterpret_cast<float4*>(d + 4) = make_float4(v[4] * un, v[5] * un, v[6] * un, v[7] * un);
                 }
-                float v[16];
-                tc::tmem_ld16(tl + 160u * g + 128, v);
-                tc::tmem_ld_wait();
-                if (wc) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) part[O_WCX + o * LDC + D + e] += v[e] * un;
-                    part[O_BC + o] += v[8] * un;
-                    part[O_BIH + o] += v[9] * un;
-                    if (g == 0) part[O_BHH + o] += v[9] * un;
-                } else {
-                    part[O_BHH + o] += v[9] * un;
+            tc::named_bar_sync(1, 4 * 32);
+            float4* part4 = reinterpret_cast<float4*>(part);
+            for (int q = t128; q < G3 * 19; q += 128) {                   // d Wcx rows: 64 agg columns, 8 feature columns, 4 pad
+                const int o = q / 19, c4 = q % 19;
+                if (c4 < 18) {
+                    const int g = o >= 128 ? 1 : 0, col = c4 < 16 ? 4 * c4 : 128 + 4 * (c4 - 16);
+                    const float4 v = *reinterpret_cast<const float4*>(stg + (g * 128 + o - 128 * g) * FLD + col);
+                    red_add4(part4 + (O_WCX + o * LDC) / 4 + c4, v);
                 }
             }
+            for (int q = t128; q < G3 * 17; q += 128) {                   // d Whh rows (d gh_n rows live in group 1, rows 64..127)
+                const int o = q / 17, c4 = q % 17;
+                if (c4 < 16) {
+                    const int row = o >= 128 ? 128 + o - 64 : o;
+                    const float4 v = *reinterpret_cast<const float4*>(stg + row * FLD + 64 + 4 * c4);
+                    red_add4(part4 + (O_WHH + o * LDM) / 4 + c4, v);
+                }
+            }
+            for (int o = t128; o < G3; o += 128) {                        // biases: deg column -> d bc, ones column -> d b_ih, d b_hh
+                const int rc = o >= 128 ? 128 + o - 128 : o, rh = o >= 128 ? 128 + o - 64 : o;
+                atomicAdd(part + O_BC + o, stg[rc * FLD + 136]);
+                atomicAdd(part + O_BIH + o, stg[rc * FLD + 137]);
+                atomicAdd(part + O_BHH + o, stg[rh * FLD + 137]);
+            }
+            if (tid == 64) WTRACE(10);
         }
     }
     tc::fence_before_sync();
@@ -941,11 +964,12 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
             p.out_part = part[(k - 1) & 1]; p.out_agg = agg[(k - 1) & 1];
             p.abuf = abuf; p.dgbuf = dgbuf; p.scales = scales; p.smin = smin + 2 * ch;
             p.partial = partial; p.gxp = gxp; p.chunk_cap = cap;
-            p.trace = (k == 2 && ch == 0) ? mgv_debug_trace() : nullptr;
+            p.trace = (k == 2 && ch == 0 && !getenv("MGV_TRACE_WGRAD")) ? mgv_debug_trace() : nullptr;
             struct_bwd_pw_kernel<<<dim3(gx, num_enc), THREADS, P_SMEM, st>>>(p);
             WgTC w{};
             w.ntiles = te - tb; w.chunk_cap = cap; w.dir = dir; w.gxp = gxp;
             w.abuf = abuf; w.dgbuf = dgbuf; w.scales = scales; w.smin = smin + 2 * ch; w.partial = partial;
+            w.trace = (k == 2 && ch == 0 && getenv("MGV_TRACE_WGRAD")) ? mgv_debug_trace() : nullptr;
             struct_bwd_wgrad_kernel<<<dim3(gx, num_enc), W_THREADS, W_SMEM, st>>>(w);
             mgv_count_launches(2);
         }

@@ -31,8 +31,8 @@ class LevelModel(nn.Module):
         super().__init__()
         setattr(self, self.ENCODER_ATTR, struct_encoder)
         self.decoder = DirectedInnerProductDecoder()
-        self.hs_linear = nn.Linear(dim_hidden * 2, dim_hidden)
-        self.hs_decompose = nn.Linear(dim_hidden, dim_hidden * 2)
+        self.hs_linear = ops.Linear(dim_hidden * 2, dim_hidden)
+        self.hs_decompose = ops.Linear(dim_hidden, dim_hidden * 2)
         self.num_rounds = num_rounds
         self.enable_encode = enable_encode
         self.enable_reverse = enable_reverse

@@ -171,6 +171,52 @@ def level_sweep(hs, sched, rounds, codes, modules):
     return LevelSweepFunction.apply(hs, sched, int(rounds), tuple(int(c) for c in codes), *params)
 
 
+# =========================================================================== small Linear layers (one row per node)
+class LinearFunction(torch.autograd.Function):
+    """y = x W^T + b.  Forward and d x are library GEMMs (N x O x I, parallel over the nodes); d W / d b sum over the
+    NODES into at most 128 x 128 outputs -- one tile on one SM for a library GEMM -- and run in csrc/linear.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        nat.require_cuda(x, "x")
+        x_c = _f32(x, "x")
+        ctx.save_for_backward(x_c, weight)
+        ctx.has_bias = bias is not None
+        return torch.addmm(bias, x_c, weight.t()) if bias is not None else x_c @ weight.t()
+
+    @staticmethod
+    def backward(ctx, gy):
+        x_c, weight = ctx.saved_tensors
+        dev = x_c.device
+        gy_c = _f32(gy, "gy")
+        O, I = weight.shape
+        N = x_c.shape[0]
+        gx = gy_c @ weight if ctx.needs_input_grad[0] else None
+        dW = torch.empty_like(weight, dtype=torch.float32)
+        db = torch.empty(O, dtype=torch.float32, device=dev) if ctx.has_bias else None
+        lib = nat.lib()
+        with torch.cuda.device(dev):
+            nb = lib.mgv_linear_wgrad_workspace_bytes(N, I, O)
+            ws = nat.workspace(nb, dev)
+            with _timed("linear_wgrad", dev):
+                nat.check(lib.mgv_linear_wgrad(nat.ptr(x_c), nat.ptr(gy_c), N, I, O, nat.ptr(dW), nat.ptr(db) if db is not None else None,
+                                               nat.ptr(ws), nb, nat.stream_of(dev)), "mgv_linear_wgrad")
+        return gx, dW, db
+
+
+def linear(x, weight, bias=None):
+    if x.dim() != 2 or weight.shape[0] > 128 or weight.shape[1] > 128 or not x.is_cuda:
+        return torch.nn.functional.linear(x, weight, bias)      # shapes outside the kernel's range: plain library path
+    return LinearFunction.apply(x, weight, bias)
+
+
+class Linear(torch.nn.Linear):
+    """nn.Linear (same parameters / checkpoint keys) whose weight gradient runs in csrc/linear.cu."""
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)
+
+
 # =========================================================================== struct encoder
 _S_WCX, _S_WHH, _S_BC, _S_BIH, _S_BHH, _S_LNW, _S_LNB = 0, 14592, 27648, 27840, 28032, 28224, 28288
 _LDC, _LDM = 76, 68

@@ -28,6 +28,17 @@ if os.environ.get("MGV_STRUCT_BWD") == "mma":
         print("%-28s mean %7.0f  med %7.0f  max %7.0f cycles" % (n, d.mean(), d.median(), d.max()))
     d = (t[:, :, 7] - t[:, :, 0])[valid]
     print("tile total mean %.0f cycles" % d.mean())
+elif os.environ.get("MGV_TRACE_WGRAD"):
+    spans = [("producer: wait stage empty", 0, 1), ("stage: copies issued -> landed", 1, 2), ("rescale + hand-over", 2, 3),
+             ("MMA: wait ready", 4, 5), ("MMA: issue", 5, 6)]
+    valid = (t[:, :, 0] > 0) & (t[:, :, 6] > 0)
+    for n, a, b in spans:
+        d = (t[:, :, b] - t[:, :, a])[valid]
+        print("%-46s mean %7.0f  med %7.0f  max %7.0f cycles" % (n, d.mean(), d.median(), d.max()))
+    per = (t[:, 1:, 5] - t[:, :-1, 5])[valid[:, 1:] & valid[:, :-1]]
+    print("stage period mean %.0f cycles" % per.mean())
+    v0 = t[:, 0, 10] > 0
+    print("first copy -> flush start %.0f, wait done %.0f, flush %.0f cycles" % ((t[:, 0, 8] - t[:, 0, 0])[v0].mean(), (t[:, 0, 9] - t[:, 0, 8])[v0].mean(), (t[:, 0, 10] - t[:, 0, 9])[v0].mean()))
 else:
     # tcgen05 pointwise kernel (struct_bwd_tc.cu): slots 0-3 MMA thread, 4-9 epilogue thread 0
     spans = [("MMA: recompute issue + tile bulk store", 0, 1), ("MMA: wait for d-gate planes", 1, 2), ("MMA: data-gradient issue", 2, 3),
