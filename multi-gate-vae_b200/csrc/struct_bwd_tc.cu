@@ -36,8 +36,8 @@ namespace {
 using namespace struct_layout;
 
 constexpr int SGRAD = MGV_STRUCT_GRAD_FLOATS;
-constexpr int EPI_WARPS = 4, GATHER_WARPS = 16;             // 16 gather warps x 2 rows per lane: twice the loads in flight
-constexpr int THREADS = (EPI_WARPS + GATHER_WARPS + 1) * 32;
+constexpr int EPI_WARPS = 8, GATHER_WARPS = 16;             // epilogue: 2 warps per 32 TMEM lanes (32 units each); gather: 2 rows per lane
+constexpr int THREADS = (EPI_WARPS + GATHER_WARPS) * 32;    // 24 warps = 6 per scheduler -> 80 registers; MMAs are issued by epilogue thread 0
 constexpr int LDGS = 68;                                   // d state staging row stride (floats)
 constexpr uint32_t DG_TILE_BYTES = 131072;                 // [hi | lo][64-node half][8-gate chunk (32)][node row (64)][16 B]: no-swizzle core matrices
 constexpr int CHUNK_TILES_DEFAULT = 1024;                  // tiles per encoder per kernel pair (MGV_STRUCT_CHUNK overrides: tuning)
@@ -46,7 +46,8 @@ constexpr int CHUNK_TILES_DEFAULT = 1024;                  // tiles per encoder 
 constexpr uint32_t S_G = A_X_LO + 4096;                    // d state_k staging, fp32 [128][LDGS]
 constexpr uint32_t S_LN = S_G + TM * LDGS * 4;             // ln_w, ln_b
 constexpr uint32_t S_AMAX = S_LN + 512;                    // 3 rotating tile-amax words
-constexpr uint32_t S_BAR = S_AMAX + 16;                    // 9 mbarriers
+constexpr uint32_t S_EX = S_AMAX + 16;                     // row sums exchanged between the two epilogue warps of a row: [4][2][128]
+constexpr uint32_t S_BAR = S_EX + 4 * 2 * TM * 4;          // 6 mbarriers
 constexpr uint32_t S_TMEM = S_BAR + 128;
 constexpr uint32_t P_SMEM = S_TMEM + 64 + 1024;            // + alignment slack
 static_assert(P_SMEM <= 227 * 1024, "struct backward: shared memory");
@@ -78,6 +79,7 @@ struct BwdTC {
     int chunk_cap;             // tiles per encoder the hand-off buffers are sized for
     long long* trace;
 };
+#define PTRACE_MAX(slot) do { if (p.trace && it < 16) atomicMax(reinterpret_cast<unsigned long long*>(p.trace) + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + it) * 16 + (slot), (unsigned long long)clock64()); } while (0)
 #define PTRACE(slot) do { if (p.trace && it < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + it) * 16 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     const uint8_t* image = p.image + (size_t)enc * 2 * IMG_BYTES;
 
     const uint32_t bar_w = sbase + S_BAR, bar_a_full = bar_w + 8, bar_a_empty = bar_w + 16, bar_g_empty = bar_w + 24;
-    const uint32_t bar_acc_full = bar_w + 32, bar_dg_full = bar_w + 40, bar_out_full = bar_w + 48, bar_acc_empty = bar_w + 56;
+    const uint32_t bar_acc_full = bar_w + 32, bar_out_full = bar_w + 40;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + S_TMEM);
     float* s_ln = reinterpret_cast<float*>(sgen + S_LN);
     unsigned* s_amax = reinterpret_cast<unsigned*>(sgen + S_AMAX);
@@ -163,9 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         tc::mbar_init(bar_a_empty, 2);                 // recompute MMAs complete + operand-tile bulk store has read the tile
         tc::mbar_init(bar_g_empty, EPI_WARPS * 32);
         tc::mbar_init(bar_acc_full, 1);
-        tc::mbar_init(bar_dg_full, EPI_WARPS * 32);
         tc::mbar_init(bar_out_full, 1);
-        tc::mbar_init(bar_acc_empty, EPI_WARPS * 32);
         tc::fence_barrier_init();
         tc::mbar_expect_tx(bar_w, IMG_W);
 #pragma unroll 1
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= EPI_WARPS && warp < EPI_WARPS + GATHER_WARPS) {
+    if (warp >= EPI_WARPS) {
         // ===================================================================== gather
         // lane = (row group rg, 16-byte chunk c): 8 lanes cover one 256-byte row; a lane owns 2 rows of the tile.
         // ONE wave of independent loads (own state row, own gradient row, first neighbour of both
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 }
                 if (hf == 0) {
                     tc::mbar_wait_warp(bar_a_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's MMAs and bulk store have read the tile
-                    if (warp == EPI_WARPS && lane == 0) PTRACE(11);
+                    if (lane == 0) PTRACE_MAX(11);
                 }
                 float ap[2][8], ag[2][8];
 #pragma unroll
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
 #pragma unroll
                 for (int q = 0; q < 2; ++q) split_store_sw128(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 8 + q * 4 + rg, c, ap[q]);
                 if (hf == 0) {
-                    if (warp == EPI_WARPS && lane == 0) PTRACE(14);
+                    if (lane == 0) PTRACE_MAX(14);
                     tc::mbar_wait_warp(bar_g_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's epilogue has read the staging rows
                 }
 #pragma unroll
@@ -320,17 +320,52 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             }
             tc::fence_async_smem();
             tc::mbar_arrive(bar_a_full);
-            if (warp == EPI_WARPS && lane == 0) PTRACE(15);
+            if (lane == 0) PTRACE_MAX(15);
         }
-    } else if (warp == EPI_WARPS + GATHER_WARPS) {
-        // ===================================================================== MMA issue + bulk stores (one thread)
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
-                const uint32_t ph = (uint32_t)(it & 1);
+    } else {
+        // ===================================================================== epilogue: 2 threads per tile row = TMEM lane
+        // Warps q and 4 + q own lanes 32 q .. 32 q + 31; warp group wg = warp / 4 handles units 32 wg .. 32 wg + 31 of its
+        // row (row sums are exchanged through shared memory).  Thread 0 also issues the MMAs and the tile's bulk store.
+        // All per-row arrays live in the thread's tensor-memory lane, so every loop below is ROLLED: a fully unrolled
+        // body is > 100 KB of straight-line code that one warp executes once per tile, i.e. pure instruction-cache
+        // misses (measured: 8 cycles per instruction).
+        //   T_ACC   r | z | gi_n | gh_n pre-activations -> r | z | n | gh_n -> fp32 d gates -> fp16 hi/lo planes
+        //   T_OUT   [0, 64) own state row h (later zero = d agg accumulator init), [64, 128) pre-LayerNorm output ->
+        //           g z (the direct part of d part), scaled: the data-gradient MMAs accumulate on top of both
+        //   T_LNP   d ln_w | d ln_b partial sums of this thread's rows
+        const int wg = warp >> 2, row = (warp & 3) * 32 + lane, u0 = 32 * wg;
+        const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t t_acc = tl + T_ACC, t_out = tl + T_OUT, t_lnp = tl + T_LNP;
+        const float* gs = s_g + row * LDGS;
+        float* s_ex = reinterpret_cast<float*>(sgen + S_EX);
+        constexpr int EPI_T = EPI_WARPS * 32;
+#pragma unroll 1
+        for (int cc = 0; cc < 32; cc += 4) {
+            tc::tmem_st4(t_lnp + u0 + cc, 0.f, 0.f, 0.f, 0.f);
+            tc::tmem_st4(t_lnp + 64 + u0 + cc, 0.f, 0.f, 0.f, 0.f);
+        }
+        tc::tmem_st_wait();
+        float run_scale = 1.0f;
+        int it = 0;
+        for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+            const uint32_t ph = (uint32_t)(it & 1);
+            const bool valid = tile * TM + row < p.N;
+            const int node = valid ? p.order[tile * TM + row] : 0;
+            // own state row (this thread's 32 units) -> tensor memory, overlapping the recompute MMAs
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float h[8];
+                if (valid) ldg8(prev + (size_t)node * D + u0 + 8 * c8, h);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h[e] = 0.f;
+                }
+                tc::tmem_st8f(t_out + u0 + 8 * c8, h);
+            }
+            if (tid == 0) {
+                // ---- recompute MMAs of this tile (the previous tile's epilogue released tensor memory at its last barrier)
                 if (it == 0) tc::mbar_wait_sleep(bar_w, 0u);
-                tc::mbar_wait_sleep(bar_acc_empty, ph ^ 1u, 128);                      // previous tile's epilogue is done with tensor memory
-                tc::mbar_wait_sleep(bar_a_full, ph, 128);
+                tc::mbar_wait_sleep(bar_a_full, ph, 32);
                 tc::fence_after_sync();
                 PTRACE(0);
                 const uint32_t d = tmem + T_ACC;
@@ -354,77 +389,13 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 tc::mma_commit(bar_a_empty);
                 tc::mma_commit(bar_acc_full);
                 // operand tile -> HBM for the weight-gradient kernel
-                {
-                    uint8_t* dst = p.abuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * A_TILE_BYTES;
+                uint8_t* dst = p.abuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * A_TILE_BYTES;
 #pragma unroll 1
-                    for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_s2g(dst + o, sbase + A_AGG_HI + o, 8192u);
-                    tc::bulk_commit();
-                    tc::bulk_wait_read0();
-                    tc::mbar_arrive(bar_a_empty);
-                }
+                for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_s2g(dst + o, sbase + A_AGG_HI + o, 8192u);
+                tc::bulk_commit();
+                tc::bulk_wait_read0();
+                tc::mbar_arrive(bar_a_empty);
                 PTRACE(1);
-                tc::mbar_wait_sleep(bar_dg_full, ph, 128);
-                tc::fence_after_sync();
-                PTRACE(2);
-                if (!p.first) {
-                    const uint32_t o = tmem + T_OUT;
-                    const uint32_t i128 = tc::make_idesc(128, 128, false, true), i64 = tc::make_idesc(128, 64, false, true);
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) {        // d r, d z: [d agg | d part] += d g . [Wc | Whh] rows 16 s ..
-                        const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, WHH_HI - WC_HI),
-                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, WHH_LO - WC_LO), i128, 1u);
-                    }
-#pragma unroll
-                    for (int s = 8; s < 12; ++s) {       // d gi_n: d agg += . Wc rows 128 ..
-                        const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, 0),
-                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, 0), i64, 1u);
-                    }
-#pragma unroll
-                    for (int s = 12; s < 16; ++s) {      // d gh_n: d part += . Whh rows 128 ..
-                        const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o + 64u, a, a + 8u, tc::desc_mn_sw128(sbase + WHH_HI + 2048u * (s - 4), 0),
-                                            tc::desc_mn_sw128(sbase + WHH_LO + 2048u * (s - 4), 0), i64, 1u);
-                    }
-                    tc::mma_commit(bar_out_full);
-                }
-                PTRACE(3);
-            }
-            tc::bulk_wait0();
-        }
-    } else if (warp < EPI_WARPS) {
-        // ===================================================================== epilogue: thread = tile row = TMEM lane
-        // All per-row arrays live in the thread's tensor-memory lane, so every loop below is ROLLED (8 units per trip):
-        // a fully unrolled body is > 100 KB of straight-line code that one warp executes once per tile, i.e. pure
-        // instruction-cache misses (measured: 8 cycles per instruction).
-        //   T_ACC   r | z | gi_n | gh_n pre-activations -> r | z | n | gh_n -> fp32 d gates -> fp16 hi/lo planes
-        //   T_OUT   [0, 64) own state row h (later zero = d agg accumulator init), [64, 128) pre-LayerNorm output ->
-        //           g z (the direct part of d part), scaled: the data-gradient MMAs accumulate on top of both
-        //   T_LNP   d ln_w | d ln_b partial sums of this thread's rows
-        const int row = warp * 32 + lane;
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        const uint32_t t_acc = tl + T_ACC, t_out = tl + T_OUT, t_lnp = tl + T_LNP;
-        const float* gs = s_g + row * LDGS;
-#pragma unroll 1
-        for (int cc = 0; cc < 128; cc += 4) tc::tmem_st4(t_lnp + cc, 0.f, 0.f, 0.f, 0.f);
-        tc::tmem_st_wait();
-        float run_scale = 1.0f;
-        int it = 0;
-        for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
-            const uint32_t ph = (uint32_t)(it & 1);
-            const bool valid = tile * TM + row < p.N;
-            const int node = valid ? p.order[tile * TM + row] : 0;
-            // own state row -> tensor memory (before the accumulator wait: overlaps the recompute MMAs)
-#pragma unroll 4
-            for (int c8 = 0; c8 < 8; ++c8) {
-                float h[8];
-                if (valid) ldg8(prev + (size_t)node * D + 8 * c8, h);
-                else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) h[e] = 0.f;
-                }
-                tc::tmem_st8f(t_out + 8 * c8, h);
             }
             tc::mbar_wait_warp(bar_acc_full, ph, lane, 32);
             tc::mbar_wait_warp(bar_a_full, ph, lane, 32);
@@ -434,13 +405,14 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             // ---- pass 1: gates, pre-LayerNorm output
             float sum = 0.f;
 #pragma unroll 1
-            for (int c8 = 0; c8 < 8; ++c8) {
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const int u = u0 + 8 * c8;
                 float gr[8], gz[8], gi[8], gh[8], h[8];
-                tc::tmem_ld8(t_acc + 8 * c8, gr);
-                tc::tmem_ld8(t_acc + 64 + 8 * c8, gz);
-                tc::tmem_ld8(t_acc + 128 + 8 * c8, gi);
-                tc::tmem_ld8(t_acc + 192 + 8 * c8, gh);
-                tc::tmem_ld8(t_out + 8 * c8, h);
+                tc::tmem_ld8(t_acc + u, gr);
+                tc::tmem_ld8(t_acc + 64 + u, gz);
+                tc::tmem_ld8(t_acc + 128 + u, gi);
+                tc::tmem_ld8(t_acc + 192 + u, gh);
+                tc::tmem_ld8(t_out + u, h);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -450,24 +422,26 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     h[e] = fmaf(z, h[e] - n, n);
                     sum += h[e];
                 }
-                tc::tmem_st8f(t_acc + 8 * c8, gr);
-                tc::tmem_st8f(t_acc + 64 + 8 * c8, gz);
-                tc::tmem_st8f(t_acc + 128 + 8 * c8, gi);
-                tc::tmem_st8f(t_out + 64 + 8 * c8, h);
+                tc::tmem_st8f(t_acc + u, gr);
+                tc::tmem_st8f(t_acc + 64 + u, gz);
+                tc::tmem_st8f(t_acc + 128 + u, gi);
+                tc::tmem_st8f(t_out + 64 + u, h);
             }
             tc::tmem_st_wait();
-            if (tid == 0) PTRACE(10);
             // ---- LayerNorm statistics (two-pass, like the forward) and the two row sums of its backward
             float mean = 0.f, rstd = 1.0f, c1 = 0.f, c2 = 0.f;
             if (p.layernorm) {
-                mean = sum * (1.0f / D);
+                s_ex[wg * TM + row] = sum;
+                tc::named_bar_sync(1, EPI_T);
+                mean = (s_ex[row] + s_ex[TM + row]) * (1.0f / D);
                 float var = 0.f;
 #pragma unroll 1
-                for (int c8 = 0; c8 < 8; ++c8) {
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const int u = u0 + 8 * c8;
                     float xv[8];
-                    tc::tmem_ld8(t_out + 64 + 8 * c8, xv);
-                    const float4 ga = lds4(gs + 8 * c8), gb = lds4(gs + 8 * c8 + 4);
-                    const float4 wa = lds4(s_ln + 8 * c8), wb = lds4(s_ln + 8 * c8 + 4);
+                    tc::tmem_ld8(t_out + 64 + u, xv);
+                    const float4 ga = lds4(gs + u), gb = lds4(gs + u + 4);
+                    const float4 wa = lds4(s_ln + u), wb = lds4(s_ln + u + 4);
                     const float gw[8] = {ga.x * wa.x, ga.y * wa.y, ga.z * wa.z, ga.w * wa.w, gb.x * wb.x, gb.y * wb.y, gb.z * wb.z, gb.w * wb.w};
                     tc::tmem_ld_wait();
 #pragma unroll
@@ -478,6 +452,13 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                         c2 = fmaf(gw[e], d, c2);
                     }
                 }
+                s_ex[(2 + wg) * TM + row] = var;
+                s_ex[(4 + wg) * TM + row] = c1;
+                s_ex[(6 + wg) * TM + row] = c2;
+                tc::named_bar_sync(1, EPI_T);
+                var = s_ex[2 * TM + row] + s_ex[3 * TM + row];
+                c1 = s_ex[4 * TM + row] + s_ex[5 * TM + row];
+                c2 = s_ex[6 * TM + row] + s_ex[7 * TM + row];
                 rstd = rsqrtf(var * (1.0f / D) + LN_EPS);
                 c1 *= (1.0f / D);
                 c2 *= rstd * (1.0f / D);
@@ -486,16 +467,17 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             // ---- pass 2: LayerNorm backward + GRU backward -> fp32 d gates in place, g z, LayerNorm parameter gradients
             float amax = 0.f;
 #pragma unroll 1
-            for (int c4 = 0; c4 < 16; ++c4) {          // 4 units per trip: the 21-warp CTA leaves 80 registers per thread
+            for (int c4 = 0; c4 < 8; ++c4) {           // 4 units per trip (80 registers per thread)
+                const int u = u0 + 4 * c4;
                 float r[4], z[4], n[4], hn[4], h[4], xv[4], lw[4], lb[4];
-                tc::tmem_ld4(t_acc + 4 * c4, r);
-                tc::tmem_ld4(t_acc + 64 + 4 * c4, z);
-                tc::tmem_ld4(t_acc + 128 + 4 * c4, n);
-                tc::tmem_ld4(t_acc + 192 + 4 * c4, hn);
-                tc::tmem_ld4(t_out + 4 * c4, h);
-                tc::tmem_ld4(t_out + 64 + 4 * c4, xv);
-                if (p.layernorm) { tc::tmem_ld4(t_lnp + 4 * c4, lw); tc::tmem_ld4(t_lnp + 64 + 4 * c4, lb); }
-                const float4 ga = lds4(gs + 4 * c4), wa = lds4(s_ln + 4 * c4);
+                tc::tmem_ld4(t_acc + u, r);
+                tc::tmem_ld4(t_acc + 64 + u, z);
+                tc::tmem_ld4(t_acc + 128 + u, n);
+                tc::tmem_ld4(t_acc + 192 + u, hn);
+                tc::tmem_ld4(t_out + u, h);
+                tc::tmem_ld4(t_out + 64 + u, xv);
+                if (p.layernorm) { tc::tmem_ld4(t_lnp + u, lw); tc::tmem_ld4(t_lnp + 64 + u, lb); }
+                const float4 ga = lds4(gs + u), wa = lds4(s_ln + u);
                 const float gv[4] = {ga.x, ga.y, ga.z, ga.w};
                 const float wv[4] = {wa.x, wa.y, wa.z, wa.w};
                 tc::tmem_ld_wait();
@@ -518,14 +500,14 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     r[e] = dr; z[e] = dz; n[e] = dni;
                     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(dr), fabsf(dz)), fabsf(dni)));
                 }
-                tc::tmem_st4(t_acc + 4 * c4, r[0], r[1], r[2], r[3]);
-                tc::tmem_st4(t_acc + 64 + 4 * c4, z[0], z[1], z[2], z[3]);
-                tc::tmem_st4(t_acc + 128 + 4 * c4, n[0], n[1], n[2], n[3]);
-                tc::tmem_st4(t_acc + 192 + 4 * c4, hn[0], hn[1], hn[2], hn[3]);
-                tc::tmem_st4(t_out + 64 + 4 * c4, xv[0], xv[1], xv[2], xv[3]);
+                tc::tmem_st4(t_acc + u, r[0], r[1], r[2], r[3]);
+                tc::tmem_st4(t_acc + 64 + u, z[0], z[1], z[2], z[3]);
+                tc::tmem_st4(t_acc + 128 + u, n[0], n[1], n[2], n[3]);
+                tc::tmem_st4(t_acc + 192 + u, hn[0], hn[1], hn[2], hn[3]);
+                tc::tmem_st4(t_out + 64 + u, xv[0], xv[1], xv[2], xv[3]);
                 if (p.layernorm) {
-                    tc::tmem_st4(t_lnp + 4 * c4, lw[0], lw[1], lw[2], lw[3]);
-                    tc::tmem_st4(t_lnp + 64 + 4 * c4, lb[0], lb[1], lb[2], lb[3]);
+                    tc::tmem_st4(t_lnp + u, lw[0], lw[1], lw[2], lw[3]);
+                    tc::tmem_st4(t_lnp + 64 + u, lb[0], lb[1], lb[2], lb[3]);
                 }
             }
             tc::mbar_arrive(bar_g_empty);
@@ -534,7 +516,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
             if (lane == 0) atomicMax(s_amax + (it % 3), __float_as_uint(amax));
-            tc::named_bar_sync(1, EPI_WARPS * 32);
+            tc::named_bar_sync(1, EPI_T);
             const float scale = pow2_scale_keep(__uint_as_float(s_amax[it % 3]), run_scale);
             run_scale = scale;
             if (tid == 0) {
@@ -545,11 +527,13 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             tc::tmem_st_wait();
             if (tid == 0) PTRACE(6);
             // ---- pass 3: fp32 d gates -> scaled fp16 hi/lo planes, in place (A operand of the data-gradient MMAs) and to
-            //      HBM [plane][64-node half][8-gate chunk (32)][node row (64)][16 B]: a warp's 32 rows write 512 contiguous bytes
+            //      HBM [plane][64-node half][8-gate chunk (32)][node row (64)][16 B]: a warp's 32 rows write 512 contiguous bytes.
+            //      K step s = gates 16 s .. 16 s + 15; this warp group's units are the K steps with (s & 3) / 2 == wg.
             {
                 uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * DG_TILE_BYTES + (row >> 6) * 32768 + (row & 63) * 16;
 #pragma unroll 2
-                for (int s = 0; s < 16; ++s) {
+                for (int k = 0; k < 8; ++k) {
+                    const int s = 4 * (k >> 1) + 2 * wg + (k & 1);
                     float v[16];
                     tc::tmem_ld16(t_acc + 16 * s, v);
                     tc::tmem_ld_wait();
@@ -566,47 +550,75 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 // accumulator init of the data-gradient MMAs: d agg = 0, d part = scale * g z
                 if (!p.first) {
 #pragma unroll 2
-                    for (int c8 = 0; c8 < 8; ++c8) {
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const int u = u0 + 8 * c8;
                         float q[8];
-                        tc::tmem_ld8(t_out + 64 + 8 * c8, q);
+                        tc::tmem_ld8(t_out + 64 + u, q);
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int e = 0; e < 8; ++e) q[e] *= scale;
-                        tc::tmem_st8f(t_out + 64 + 8 * c8, q);
+                        tc::tmem_st8f(t_out + 64 + u, q);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) q[e] = 0.f;
-                        tc::tmem_st8f(t_out + 8 * c8, q);
+                        tc::tmem_st8f(t_out + u, q);
                     }
                 }
             }
             tc::tmem_st_wait();
             tc::fence_before_sync();
-            tc::mbar_arrive(bar_dg_full);
+            tc::named_bar_sync(1, EPI_T);
             if (tid == 0) PTRACE(7);
             // ---- data gradients of step k-1
             if (!p.first) {
+                if (tid == 0) {
+                    tc::fence_after_sync();
+                    const uint32_t o = tmem + T_OUT;
+                    const uint32_t i128 = tc::make_idesc(128, 128, false, true), i64 = tc::make_idesc(128, 64, false, true);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {        // d r, d z: [d agg | d part] += d g . [Wc | Whh] rows 16 s ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, WHH_HI - WC_HI),
+                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, WHH_LO - WC_LO), i128, 1u);
+                    }
+#pragma unroll
+                    for (int s = 8; s < 12; ++s) {       // d gi_n: d agg += . Wc rows 128 ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, 0),
+                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, 0), i64, 1u);
+                    }
+#pragma unroll
+                    for (int s = 12; s < 16; ++s) {      // d gh_n: d part += . Whh rows 128 ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o + 64u, a, a + 8u, tc::desc_mn_sw128(sbase + WHH_HI + 2048u * (s - 4), 0),
+                                            tc::desc_mn_sw128(sbase + WHH_LO + 2048u * (s - 4), 0), i64, 1u);
+                    }
+                    tc::mma_commit(bar_out_full);
+                    PTRACE(3);
+                }
                 tc::mbar_wait_warp(bar_out_full, ph, lane, 32);
                 tc::fence_after_sync();
                 if (tid == 0) PTRACE(8);
                 const float inv = 1.0f / scale;
 #pragma unroll 2
-                for (int c8 = 0; c8 < 8; ++c8) {
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const int u = u0 + 8 * c8;
                     float a[8], q[8];
-                    tc::tmem_ld8(t_out + 8 * c8, a);
-                    tc::tmem_ld8(t_out + 64 + 8 * c8, q);
+                    tc::tmem_ld8(t_out + u, a);
+                    tc::tmem_ld8(t_out + 64 + u, q);
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { a[e] *= inv; q[e] *= inv; }
                     if (valid) {
-                        stg8(p.out_agg + eoff + (size_t)node * D + 8 * c8, a);
-                        stg8(p.out_part + eoff + (size_t)node * D + 8 * c8, q);
+                        stg8(p.out_agg + eoff + (size_t)node * D + u, a);
+                        stg8(p.out_part + eoff + (size_t)node * D + u, q);
                     }
                 }
             }
             tc::fence_before_sync();
-            tc::mbar_arrive(bar_acc_empty);
+            tc::named_bar_sync(1, EPI_T);                // tensor memory is free for the next tile's recompute
             if (tid == 0) PTRACE(9);
         }
+        if (tid == 0) tc::bulk_wait0();
     }
     // ---- LayerNorm parameter gradients: per-thread partial sums (tensor memory) -> column sums -> this CTA's partial block
     tc::fence_before_sync();
@@ -614,15 +626,16 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     tc::fence_after_sync();
     float* scratch = reinterpret_cast<float*>(sgen + A_AGG_HI);      // [128][132], the tile and staging buffers are idle now
     if (warp < EPI_WARPS) {
-        const int row = warp * 32 + lane;
-        const uint32_t t_lnp = tmem + ((uint32_t)(warp * 32) << 16) + T_LNP;
+        const int row = (warp & 3) * 32 + lane, u0 = 32 * (warp >> 2);
+        const uint32_t t_lnp = tmem + ((uint32_t)((warp & 3) * 32) << 16) + T_LNP;
 #pragma unroll 1
-        for (int c8 = 0; c8 < 16; ++c8) {
+        for (int c8 = 0; c8 < 8; ++c8) {
+            const int col = (c8 < 4) ? u0 + 8 * c8 : 64 + u0 + 8 * (c8 - 4);
             float v[8];
-            tc::tmem_ld8(t_lnp + 8 * c8, v);
+            tc::tmem_ld8(t_lnp + col, v);
             tc::tmem_ld_wait();
-            *reinterpret_cast<float4*>(scratch + row * 132 + 8 * c8) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(scratch + row * 132 + 8 * c8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<float4*>(scratch + row * 132 + col) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(scratch + row * 132 + col + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
     tc::fence_before_sync();
