@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         }
         tc::tmem_st_wait();
         float run_scale = 1.0f;
+        const uint64_t pol_stream = tc::l2_policy_evict_first();      // hand-off buffers: written once, read once by the next kernel
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
             const uint32_t ph = (uint32_t)(it & 1);
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 // operand tile -> HBM for the weight-gradient kernel
                 uint8_t* dst = p.abuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * A_TILE_BYTES;
 #pragma unroll 1
-                for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_s2g(dst + o, sbase + A_AGG_HI + o, 8192u);
+                for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_s2g_hint(dst + o, sbase + A_AGG_HI + o, 8192u, pol_stream);
                 tc::bulk_commit();
                 tc::bulk_wait_read0();
                 tc::mbar_arrive(bar_a_empty);
@@ -542,10 +543,10 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     for (int e = 0; e < 8; ++e) tc::split2(v[2 * e] * scale, v[2 * e + 1] * scale, pk[e], pk[8 + e]);
                     tc::tmem_st16(t_acc + 16 * s, pk);
                     uint8_t* hb = dg + (size_t)(2 * s) * 1024;
-                    *reinterpret_cast<uint4*>(hb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(hb + 1024) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    *reinterpret_cast<uint4*>(hb + 65536) = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-                    *reinterpret_cast<uint4*>(hb + 65536 + 1024) = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+                    tc::stg_v4_hint(hb, make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
+                    tc::stg_v4_hint(hb + 1024, make_uint4(pk[4], pk[5], pk[6], pk[7]), pol_stream);
+                    tc::stg_v4_hint(hb + 65536, make_uint4(pk[8], pk[9], pk[10], pk[11]), pol_stream);
+                    tc::stg_v4_hint(hb + 65536 + 1024, make_uint4(pk[12], pk[13], pk[14], pk[15]), pol_stream);
                 }
                 // accumulator init of the data-gradient MMAs: d agg = 0, d part = scale * g z
                 if (!p.first) {
@@ -708,6 +709,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
 
     if (warp == 0) {
         if (lane == 0) {
+            const uint64_t pol = tc::l2_policy_evict_first();
             for (int i = 0; i < nhalf; ++i) {
                 const int s = i & 1, tile = tile_beg + (i >> 1), h = i & 1;
                 WTRACE(0);
@@ -717,16 +719,16 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
                 const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 32768;
                 const uint8_t* at = p.abuf + ((size_t)enc * p.chunk_cap + tile) * A_TILE_BYTES;
                 const uint32_t st = sbase + (uint32_t)s * ST_BYTES, bar = bar_full + 8 * s;
-                tc::bulk_g2s(st + ST_DG_HI, dg, 16384u, bar);
-                tc::bulk_g2s(st + ST_DG_HI + 16384u, dg + 16384, 16384u, bar);
-                tc::bulk_g2s(st + ST_DG_LO, dg + 65536, 16384u, bar);
-                tc::bulk_g2s(st + ST_DG_LO + 16384u, dg + 65536 + 16384, 16384u, bar);
-                tc::bulk_g2s(st + ST_AGG_HI, at + 0 + h * 8192, 8192u, bar);
-                tc::bulk_g2s(st + ST_AGG_LO, at + 16384 + h * 8192, 8192u, bar);
-                tc::bulk_g2s(st + ST_H_HI, at + 32768 + h * 8192, 8192u, bar);
-                tc::bulk_g2s(st + ST_H_LO, at + 49152 + h * 8192, 8192u, bar);
-                tc::bulk_g2s(st + ST_X_HI, at + 65536 + h * 2048, 2048u, bar);
-                tc::bulk_g2s(st + ST_X_LO, at + 69632 + h * 2048, 2048u, bar);
+                tc::bulk_g2s_hint(st + ST_DG_HI, dg, 16384u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_DG_HI + 16384u, dg + 16384, 16384u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_DG_LO, dg + 65536, 16384u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_DG_LO + 16384u, dg + 65536 + 16384, 16384u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_AGG_HI, at + 0 + h * 8192, 8192u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_AGG_LO, at + 16384 + h * 8192, 8192u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_H_HI, at + 32768 + h * 8192, 8192u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_H_LO, at + 49152 + h * 8192, 8192u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_X_HI, at + 65536 + h * 2048, 2048u, bar, pol);
+                tc::bulk_g2s_hint(st + ST_X_LO, at + 69632 + h * 2048, 2048u, bar, pol);
             }
         }
     } else if (warp == 1) {
