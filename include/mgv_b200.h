@@ -38,7 +38,7 @@ extern "C" {
 #define MGV_CODE_SHIFT 28        /* out_pack = dst | (code(dst) << 28)                          */
 #define MGV_MAX_FEAT 8           /* struct encoder: dim_feature <= 8 (config.py:14 default 6)   */
 #define MGV_TILE_ROWS 128        /* nodes per tensor-core tile (UMMA M)                          */
-#define MGV_TILE_FIXED_COST 512  /* per-tile fixed cost, in node-row reads, of the tile cost model */
+#define MGV_TILE_FIXED_COST 2048 /* per-tile fixed cost, in node-row reads, of the tile cost model */
 
 /* Floats per gate-code weight block of the level sweep (see mgv_sweep_pack layout below). */
 #define MGV_SWEEP_PACK_FLOATS 66112

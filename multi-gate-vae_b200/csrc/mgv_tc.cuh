@@ -320,20 +320,21 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// First index t in [0, n] with a[t] >= target, a non-decreasing with a[n] >= target.  Whole warp, ~log32(n)
-// dependent loads instead of log2(n).
-__device__ __forceinline__ int warp_lower_bound(const unsigned* __restrict__ a, int n, unsigned target, int lane) {
+// First index t in [0, n] with a[t] - adj * t >= target, the adjusted sequence non-decreasing with its last element
+// >= target.  Whole warp, ~log32(n) dependent loads instead of log2(n).  `adj` lowers the per-tile fixed cost of the
+// tile cost model for kernels whose per-neighbour work is larger (the backward gathers two rows per neighbour).
+__device__ __forceinline__ int warp_lower_bound(const unsigned* __restrict__ a, int n, unsigned target, int lane, unsigned adj = 0u) {
     int lo = 0, hi = n;
     while (lo < hi) {
         const int span = hi - lo;
         if (span <= 32) {
             const int m = lo + lane;
-            const bool ge = (m < hi) ? (a[m] >= target) : true;
+            const bool ge = (m < hi) ? (a[m] - adj * (unsigned)m >= target) : true;
             const unsigned bal = __ballot_sync(0xffffffffu, ge);
             return lo + __ffs(bal) - 1;
         }
         const int m = lo + (int)(((long long)span * (lane + 1)) / 33);
-        const bool ge = a[m] >= target;
+        const bool ge = a[m] - adj * (unsigned)m >= target;
         const unsigned bal = __ballot_sync(0xffffffffu, ge);
         if (bal == 0u) {
             lo = lo + (int)(((long long)span * 32) / 33) + 1;
