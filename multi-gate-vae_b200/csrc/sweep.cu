@@ -381,71 +381,121 @@ struct BwdSmem {
 };
 
 // Pull  sum over out-edges e=(v->k) of  alpha_e * dxbar_k + dscore_e * u_code(k)  (128-wide, lane chunk of 4).
+// Fan-out is heavy-tailed (primary inputs and shared sub-expressions feed tens of gates), and the per-edge chain
+// out_pack -> out_slot -> alpha / dscore -> dxbar row is three dependent loads, so the edges are taken a WARP AT A TIME:
+// every lane fetches the metadata of one edge (the chains of 32 edges run in parallel), the rows are then gathered
+// 8 at a time with the ids broadcast by shuffles, and  sum_e dscore_e u_code(e)  is accumulated per code and applied
+// once at the end (no u loads in the loop).
 __device__ __forceinline__ float4 pull_out_edges(const SweepDev& p, int v, int lane) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const int beg = p.out_ptr[v], end = p.out_ptr[v + 1];
-    for (int q0 = beg; q0 < end; q0 += 4) {
-        float4 dx[4], uu[4];
-        float a[4], ds[4];
-        const int cnt = min(4, end - q0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            a[i] = 0.f; ds[i] = 0.f;
-            dx[i] = make_float4(0.f, 0.f, 0.f, 0.f); uu[i] = dx[i];
-            if (i < cnt) {
-                const int pk = p.out_pack[q0 + i];
-                const int c = (pk >> MGV_CODE_SHIFT) & 7;
-                if ((p.handled >> c) & 1u) {
-                    const int k = pk & NODE_MASK;
-                    const int slot = p.out_slot[q0 + i];
-                    a[i] = p.alpha[slot];
-                    ds[i] = p.dscore[slot];
-                    dx[i] = mgv_ld4(p.dxb + (size_t)k * D2 + 4 * lane);
-                    uu[i] = mgv_ldg4(p.weights + (size_t)c * PACK + O_U + 4 * lane);
-                }
+    float sds[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned present = 0u;
+    for (int q0 = beg; q0 < end; q0 += 32) {
+        const int q = q0 + lane;
+        int kk = -1, c = 0;
+        float a = 0.f, ds = 0.f;
+        if (q < end) {
+            const int pk = p.out_pack[q];
+            c = (pk >> MGV_CODE_SHIFT) & 7;
+            if ((p.handled >> c) & 1u) {
+                kk = pk & NODE_MASK;
+                const int slot = p.out_slot[q];
+                a = p.alpha[slot];
+                ds = p.dscore[slot];
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            mgv_fma4(acc, a[i], dx[i]);
-            mgv_fma4(acc, ds[i], uu[i]);
+        for (int cc = 0; cc < 6; ++cc) sds[cc] += (kk >= 0 && c == cc + 1) ? ds : 0.f;
+        present |= (kk >= 0) ? (1u << c) : 0u;
+        const int ne = min(32, end - q0);
+        for (int i = 0; i < ne; i += 8) {
+            float4 dx[8];
+            float aa[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kj = __shfl_sync(0xffffffffu, kk, (i + j) & 31);
+                aa[j] = __shfl_sync(0xffffffffu, a, (i + j) & 31);
+                dx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i + j < ne && kj >= 0) dx[j] = mgv_ld4(p.dxb + (size_t)kj * D2 + 4 * lane);
+                else aa[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mgv_fma4(acc, aa[j], dx[j]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) present |= __shfl_xor_sync(0xffffffffu, present, o);
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) {
+        if ((present >> (cc + 1)) & 1u) {
+            float t = sds[cc];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            mgv_fma4(acc, t, mgv_ldg4(p.weights + (size_t)(cc + 1) * PACK + O_U + 4 * lane));
         }
     }
     return acc;
 }
-// The same for a half-warp: lane l16 owns columns 8 l16 .. 8 l16 + 7.
-__device__ __forceinline__ void pull_out_edges16(const SweepDev& p, int v, int l16, float (&acc)[8]) {
+// The same for a half-warp: lane l16 owns columns 8 l16 .. 8 l16 + 7 (16 edges per metadata wave, rows 4 at a time).
+__device__ __forceinline__ void pull_out_edges16(const SweepDev& p, int v, int l16, unsigned hmask, int lane, float (&acc)[8]) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     const int beg = p.out_ptr[v], end = p.out_ptr[v + 1];
-    for (int q0 = beg; q0 < end; q0 += 2) {
-        float4 dx[2][2], uu[2][2];
-        float a[2], ds[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            a[i] = 0.f; ds[i] = 0.f;
-            dx[i][0] = make_float4(0.f, 0.f, 0.f, 0.f); dx[i][1] = dx[i][0]; uu[i][0] = dx[i][0]; uu[i][1] = dx[i][0];
-            if (q0 + i < end) {
-                const int pk = p.out_pack[q0 + i];
-                const int c = (pk >> MGV_CODE_SHIFT) & 7;
-                if ((p.handled >> c) & 1u) {
-                    const int k = pk & NODE_MASK;
-                    const int slot = p.out_slot[q0 + i];
-                    a[i] = p.alpha[slot];
-                    ds[i] = p.dscore[slot];
-                    dx[i][0] = mgv_ld4(p.dxb + (size_t)k * D2 + 8 * l16);
-                    dx[i][1] = mgv_ld4(p.dxb + (size_t)k * D2 + 8 * l16 + 4);
-                    uu[i][0] = mgv_ldg4(p.weights + (size_t)c * PACK + O_U + 8 * l16);
-                    uu[i][1] = mgv_ldg4(p.weights + (size_t)c * PACK + O_U + 8 * l16 + 4);
-                }
+    const int hb = lane & 16;
+    float sds[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned present = 0u;
+    for (int q0 = beg; q0 < end; q0 += 16) {
+        const int q = q0 + l16;
+        int kk = -1, c = 0;
+        float a = 0.f, ds = 0.f;
+        if (q < end) {
+            const int pk = p.out_pack[q];
+            c = (pk >> MGV_CODE_SHIFT) & 7;
+            if ((p.handled >> c) & 1u) {
+                kk = pk & NODE_MASK;
+                const int slot = p.out_slot[q];
+                a = p.alpha[slot];
+                ds = p.dscore[slot];
             }
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            acc[0] = fmaf(a[i], dx[i][0].x, fmaf(ds[i], uu[i][0].x, acc[0])); acc[1] = fmaf(a[i], dx[i][0].y, fmaf(ds[i], uu[i][0].y, acc[1]));
-            acc[2] = fmaf(a[i], dx[i][0].z, fmaf(ds[i], uu[i][0].z, acc[2])); acc[3] = fmaf(a[i], dx[i][0].w, fmaf(ds[i], uu[i][0].w, acc[3]));
-            acc[4] = fmaf(a[i], dx[i][1].x, fmaf(ds[i], uu[i][1].x, acc[4])); acc[5] = fmaf(a[i], dx[i][1].y, fmaf(ds[i], uu[i][1].y, acc[5]));
-            acc[6] = fmaf(a[i], dx[i][1].z, fmaf(ds[i], uu[i][1].z, acc[6])); acc[7] = fmaf(a[i], dx[i][1].w, fmaf(ds[i], uu[i][1].w, acc[7]));
+        for (int cc = 0; cc < 6; ++cc) sds[cc] += (kk >= 0 && c == cc + 1) ? ds : 0.f;
+        present |= (kk >= 0) ? (1u << c) : 0u;
+        const int ne = min(16, end - q0);
+        for (int i = 0; i < ne; i += 4) {
+            float4 dx[4][2];
+            float aa[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kj = __shfl_sync(hmask, kk, hb + ((i + j) & 15));
+                aa[j] = __shfl_sync(hmask, a, hb + ((i + j) & 15));
+                dx[j][0] = make_float4(0.f, 0.f, 0.f, 0.f); dx[j][1] = dx[j][0];
+                if (i + j < ne && kj >= 0) {
+                    dx[j][0] = mgv_ld4(p.dxb + (size_t)kj * D2 + 8 * l16);
+                    dx[j][1] = mgv_ld4(p.dxb + (size_t)kj * D2 + 8 * l16 + 4);
+                } else aa[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[0] = fmaf(aa[j], dx[j][0].x, acc[0]); acc[1] = fmaf(aa[j], dx[j][0].y, acc[1]);
+                acc[2] = fmaf(aa[j], dx[j][0].z, acc[2]); acc[3] = fmaf(aa[j], dx[j][0].w, acc[3]);
+                acc[4] = fmaf(aa[j], dx[j][1].x, acc[4]); acc[5] = fmaf(aa[j], dx[j][1].y, acc[5]);
+                acc[6] = fmaf(aa[j], dx[j][1].z, acc[6]); acc[7] = fmaf(aa[j], dx[j][1].w, acc[7]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) present |= __shfl_xor_sync(hmask, present, o);
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) {
+        if ((present >> (cc + 1)) & 1u) {
+            float t = sds[cc];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(hmask, t, o);
+            const float4 u0 = mgv_ldg4(p.weights + (size_t)(cc + 1) * PACK + O_U + 8 * l16), u1 = mgv_ldg4(p.weights + (size_t)(cc + 1) * PACK + O_U + 8 * l16 + 4);
+            acc[0] = fmaf(t, u0.x, acc[0]); acc[1] = fmaf(t, u0.y, acc[1]); acc[2] = fmaf(t, u0.z, acc[2]); acc[3] = fmaf(t, u0.w, acc[3]);
+            acc[4] = fmaf(t, u1.x, acc[4]); acc[5] = fmaf(t, u1.y, acc[5]); acc[6] = fmaf(t, u1.z, acc[6]); acc[7] = fmaf(t, u1.w, acc[7]);
         }
     }
 }
@@ -526,7 +576,7 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         if (row < rows) {
                             node = p.order[t0 + row];
                             float pl[8];
-                            pull_out_edges16(p, node, l16, pl);
+                            pull_out_edges16(p, node, l16, hmask, lane, pl);
                             if (l16 < 8) {
                                 float* gp = p.ghs + (size_t)node * D + 8 * l16;
                                 float4 c0 = mgv_ld4(gp), c1 = mgv_ld4(gp + 4);
