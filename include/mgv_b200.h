@@ -179,10 +179,14 @@ int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint32_t handle
  *  27648 bc[192]   27840 bih[192]   28032 bhh[192]   28224 ln_w[64]   28288 ln_b[64]   (pad to 28416)
  * x: float [N][feat] (feat <= MGV_MAX_FEAT).  states: float [num_enc][2*rounds+1][N][64] out
  * (slot 0 = ones, written by the call; slot 2*rounds = encoder output).
+ * tiles: NULL (inference) or mgv_struct_tiles_bytes(N, num_enc, rounds) bytes out: the [agg | h | x deg 1] tensor-core operand
+ * tile of every step ([num_enc][2*rounds][ceil(N/128)][73728 bytes], fp16 hi/lo planes), which mgv_struct_encoder_bwd
+ * recomputes from instead of gathering the neighbour sums a second time (precision MGV_PRECISION_FP32 only).
  */
 size_t mgv_struct_fwd_workspace_bytes(int64_t N, int32_t num_enc);
+size_t mgv_struct_tiles_bytes(int64_t N, int32_t num_enc, int32_t rounds);
 int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
-                           int32_t feat, const float* x, const float* weights, float* states,
+                           int32_t feat, const float* x, const float* weights, float* states, void* tiles,
                            void* ws, size_t ws_bytes, int32_t precision, mgv_stream_t stream);
 /* gout: float [num_enc][N][64] = d loss / d (encoder output).  grads: float
  * [num_enc][2][MGV_STRUCT_GRAD_FLOATS] out, SAME layout as the weight block (d Wcx, d Whh, d bc, d bih, d bhh,
@@ -191,8 +195,8 @@ int mgv_struct_bwd_grid(void);
 size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc);
 int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
                            int32_t feat, const float* x, const float* weights, const float* states,
-                           const float* gout, float* grads, void* ws, size_t ws_bytes, int32_t precision,
-                           mgv_stream_t stream);
+                           const void* tiles, const float* gout, float* grads, void* ws, size_t ws_bytes,
+                           int32_t precision, mgv_stream_t stream);
 
 /* ------------------------------------------------------------------ fused reparam + KL + func loss
  * Replaces DirectedGVAE.sample's elementwise part (digvae_model.py:138-141), the KL of

@@ -3,16 +3,18 @@
 // step k = 2R .. 1 two kernels, 128-node tiles, fp16 hi/lo planes with fp32 accumulation in tensor memory:
 //
 //   struct_bwd_pw_kernel   (persistent, weights resident, warp-specialised like the forward)
-//     gather   [agg | h | x deg 1] operand tile of state_{k-1}  and  d state_k = part + sum of the neighbours' d agg_{k+1}
+//     tile     [agg | h | x deg 1] operand tile of state_{k-1}: bulk copy of the tile the FORWARD saved (no second gather)
+//     gather   d state_k = part + sum of the neighbours' d agg_{k+1}
 //     MMA      recompute the GRU pre-activations (identical products to the forward)            -> TMEM columns 0..255
 //     epilogue thread = node: gates, LayerNorm backward, GRU backward; d gates (d r, d z, d gi_n, d gh_n) go back into
 //              the SAME tensor-memory columns, first as fp32, then -- scaled by the tile's power of two -- as fp16 hi/lo
 //              planes (16 gates = 8 + 8 packed columns), which is the A operand of
 //     MMA      d agg = d gi Wc,  d part = d gh Whh   (A from tensor memory, B = the forward's weight image read MN-major)
 //     epilogue d agg / d part -> HBM for step k-1; d ln_w / d ln_b partial sums live in tensor memory per thread
-//     The operand tile (bulk copy) and the d-gate planes also go to HBM for
+//     The d-gate planes also go to HBM for
 //   struct_bwd_wgrad_kernel (persistent, streaming): d W^T-free weight gradient  d Wcx | d Whh | d b  +=  d gates^T [agg | h | x deg 1]
-//     both operands MN-major straight from the bulk-copied planes, K = nodes, accumulators persistent in tensor memory
+//     both operands MN-major straight from bulk-copied planes (d gates from the kernel above, operand tiles from the
+//     forward), K = nodes, accumulators persistent in tensor memory
 //     (2 x 144 columns at a 160-column stride) over all tiles of the CTA, flushed once into the CTA's private partial block.
 //
 // Shared memory cannot hold weights (112 KB) + operand tile (72 KB) + d-gate planes (128 KB) and tensor memory cannot hold
@@ -70,7 +72,8 @@ struct BwdTC {
     const float* gout;         // [enc][N][64]
     const float* in_part; const float* in_agg;
     float* out_part; float* out_agg;
-    uint8_t* abuf;             // [enc][chunk tiles][A_TILE_BYTES]
+    const uint8_t* tiles;      // operand tiles saved by the forward for this step, enc 0: [tile][A_TILE_BYTES]
+    size_t tiles_enc_stride;   // bytes between encoders
     uint8_t* dgbuf;            // [enc][chunk tiles][DG_TILE_BYTES]
     float* scales;             // [enc][chunk tiles]
     unsigned* smin;            // [enc] min of the chunk's tile scales (float bits)
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     const size_t eoff = (size_t)enc * p.N * D;
     const uint8_t* image = p.image + (size_t)enc * 2 * IMG_BYTES;
 
-    const uint32_t bar_w = sbase + S_BAR, bar_a_full = bar_w + 8, bar_a_empty = bar_w + 16, bar_g_empty = bar_w + 24;
+    const uint32_t bar_w = sbase + S_BAR, bar_a_full = bar_w + 8, bar_t_full = bar_w + 16, bar_g_empty = bar_w + 24;
     const uint32_t bar_acc_full = bar_w + 32, bar_out_full = bar_w + 40;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + S_TMEM);
     float* s_ln = reinterpret_cast<float*>(sgen + S_LN);
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     if (tid == 0) {
         tc::mbar_init(bar_w, 1);
         tc::mbar_init(bar_a_full, GATHER_WARPS * 32);
-        tc::mbar_init(bar_a_empty, 2);                 // recompute MMAs complete + operand-tile bulk store has read the tile
+        tc::mbar_init(bar_t_full, 1);                  // operand tile (bulk copy of the forward's saved tile) has landed
         tc::mbar_init(bar_g_empty, EPI_WARPS * 32);
         tc::mbar_init(bar_acc_full, 1);
         tc::mbar_init(bar_out_full, 1);
@@ -192,11 +195,12 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     const uint32_t tmem = *tmem_slot;
 
     if (warp >= EPI_WARPS) {
-        // ===================================================================== gather
-        // lane = (row group rg, 16-byte chunk c): 8 lanes cover one 256-byte row; a lane owns 2 rows of the tile.
-        // ONE wave of independent loads (own state row, own gradient row, first neighbour of both
-        // sums, second neighbour ids), then one wave per further neighbour: the dependent-load chain of a tile is
-        // max(1, degree) latencies; the next tile's row descriptors are loaded one tile ahead.
+        // ===================================================================== gather of d state_k
+        // d state_k = d part (or the incoming gradient at the last step) + neighbour sum of d agg_{k+1}, fp32, into the
+        // staging rows.  (The [agg | h | x deg 1] operand tile is NOT re-gathered: the forward saved it, thread 0 bulk-copies it.)
+        // lane = (row group rg, 16-byte chunk c): 8 lanes cover one 256-byte row; a lane owns 2 rows of the tile.  ONE wave of
+        // independent loads (own row, first neighbour, second-neighbour id), then one wave per further neighbour; the next
+        // tile's row descriptors are loaded one tile ahead.
         const int gw = warp - EPI_WARPS, rg = lane >> 3, c = lane & 7;
         const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
         const float* gsrc = p.last ? p.gout + eoff : p.in_part + eoff;
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         }
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
-            if (warp == EPI_WARPS && lane == 0) PTRACE(13);
+            if (lane == 0) PTRACE_MAX(13);
             int4 dc[2];
 #pragma unroll
             for (int ps = 0; ps < 2; ++ps) dc[ps] = dn[ps];
@@ -219,108 +223,68 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 const int r = (tile + 1) * TM + gw * 8 + ps * 4 + rg;
                 dn[ps] = (tile + 1 < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
             }
+            int node[2], beg[2], cnt[2], jn[2];
+            float4 g[2][2], va[2][2];
+            int maxc = 0;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int hf = 0; hf < 1; ++hf) {
-                int node[2], beg[2], cnt[2], jn[2];
-                float4 h[2][2], g[2][2], vp[2][2], va[2][2];
-                float xe[2];
-                int maxc = 0;
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int4 d = dc[2 * hf + q];
-                    node[q] = d.x; beg[q] = d.y; cnt[q] = d.z; jn[q] = d.w;
-                    maxc = max(maxc, cnt[q]);
-                    h[q][0] = z4; h[q][1] = z4; g[q][0] = z4; g[q][1] = z4; vp[q][0] = z4; vp[q][1] = z4; va[q][0] = z4; va[q][1] = z4;
-                    xe[q] = 0.f;
-                    if (node[q] >= 0) {
-                        h[q][0] = mgv_ld4(prev + (size_t)node[q] * D + c * 8);
-                        h[q][1] = mgv_ld4(prev + (size_t)node[q] * D + c * 8 + 4);
-                        g[q][0] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8);
-                        g[q][1] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8 + 4);
-                        if (c < p.feat) xe[q] = p.x[(size_t)node[q] * p.feat + c];
-                    }
-                    if (cnt[q] > 0) {
-                        vp[q][0] = mgv_ld4(prev + (size_t)jn[q] * D + c * 8);
-                        vp[q][1] = mgv_ld4(prev + (size_t)jn[q] * D + c * 8 + 4);
-                        if (nbg) {
-                            va[q][0] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8);
-                            va[q][1] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8 + 4);
-                        }
-                    }
-                    if (cnt[q] > 1) jn[q] = p.idx[beg[q] + 1] & NODE_MASK;
+            for (int q = 0; q < 2; ++q) {
+                const int4 d = dc[q];
+                node[q] = d.x; beg[q] = d.y; cnt[q] = nbg ? d.z : 0; jn[q] = d.w;
+                maxc = max(maxc, cnt[q]);
+                g[q][0] = z4; g[q][1] = z4; va[q][0] = z4; va[q][1] = z4;
+                if (node[q] >= 0) {
+                    g[q][0] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8);
+                    g[q][1] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8 + 4);
                 }
-                if (hf == 0) {
-                    tc::mbar_wait_warp(bar_a_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's MMAs and bulk store have read the tile
-                    if (lane == 0) PTRACE_MAX(11);
+                if (cnt[q] > 0) {
+                    va[q][0] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8);
+                    va[q][1] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8 + 4);
                 }
-                float ap[2][8], ag[2][8];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int row = gw * 8 + q * 4 + rg;
-                    const float h8[8] = {h[q][0].x, h[q][0].y, h[q][0].z, h[q][0].w, h[q][1].x, h[q][1].y, h[q][1].z, h[q][1].w};
-                    split_store_sw128(sbase + A_H_HI, sbase + A_H_LO, row, c, h8);
-                    float xv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) xv[e] = __shfl_sync(0xffffffffu, xe[q], (lane & 24) + e);
-                    if (c == 1) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) xv[e] = 0.f;
-                        if (node[q] >= 0) { xv[0] = (float)cnt[q]; xv[1] = 1.0f; }
-                    }
-                    if (c < 2) {
-                        uint4 hi, lo;
-                        tc::split8(xv, hi, lo);
-                        const uint32_t off = tc::plain16_off(row, c);
-                        tc::st_shared_v4(sbase + A_X_HI + off, hi);
-                        tc::st_shared_v4(sbase + A_X_LO + off, lo);
-                    }
-                    ap[q][0] = vp[q][0].x; ap[q][1] = vp[q][0].y; ap[q][2] = vp[q][0].z; ap[q][3] = vp[q][0].w;
-                    ap[q][4] = vp[q][1].x; ap[q][5] = vp[q][1].y; ap[q][6] = vp[q][1].z; ap[q][7] = vp[q][1].w;
-                    ag[q][0] = g[q][0].x + va[q][0].x; ag[q][1] = g[q][0].y + va[q][0].y; ag[q][2] = g[q][0].z + va[q][0].z; ag[q][3] = g[q][0].w + va[q][0].w;
-                    ag[q][4] = g[q][1].x + va[q][1].x; ag[q][5] = g[q][1].y + va[q][1].y; ag[q][6] = g[q][1].z + va[q][1].z; ag[q][7] = g[q][1].w + va[q][1].w;
-                }
-                for (int sl = 1; sl < maxc; ++sl) {
-                    int j[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        j[q] = jn[q];
-                        if (sl + 1 < cnt[q]) jn[q] = p.idx[beg[q] + sl + 1] & NODE_MASK;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        vp[q][0] = z4; vp[q][1] = z4; va[q][0] = z4; va[q][1] = z4;
-                        if (sl < cnt[q]) {
-                            vp[q][0] = mgv_ld4(prev + (size_t)j[q] * D + c * 8);
-                            vp[q][1] = mgv_ld4(prev + (size_t)j[q] * D + c * 8 + 4);
-                            if (nbg) {
-                                va[q][0] = mgv_ld4(asrc + (size_t)j[q] * D + c * 8);
-                                va[q][1] = mgv_ld4(asrc + (size_t)j[q] * D + c * 8 + 4);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        ap[q][0] += vp[q][0].x; ap[q][1] += vp[q][0].y; ap[q][2] += vp[q][0].z; ap[q][3] += vp[q][0].w;
-                        ap[q][4] += vp[q][1].x; ap[q][5] += vp[q][1].y; ap[q][6] += vp[q][1].z; ap[q][7] += vp[q][1].w;
-                        ag[q][0] += va[q][0].x; ag[q][1] += va[q][0].y; ag[q][2] += va[q][0].z; ag[q][3] += va[q][0].w;
-                        ag[q][4] += va[q][1].x; ag[q][5] += va[q][1].y; ag[q][6] += va[q][1].z; ag[q][7] += va[q][1].w;
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) split_store_sw128(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 8 + q * 4 + rg, c, ap[q]);
-                if (hf == 0) {
-                    if (lane == 0) PTRACE_MAX(14);
-                    tc::mbar_wait_warp(bar_g_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's epilogue has read the staging rows
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    float* dst = s_g + (gw * 8 + q * 4 + rg) * LDGS + c * 8;
-                    *reinterpret_cast<float4*>(dst) = make_float4(ag[q][0], ag[q][1], ag[q][2], ag[q][3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(ag[q][4], ag[q][5], ag[q][6], ag[q][7]);
-                }
+                if (cnt[q] > 1) jn[q] = p.idx[beg[q] + 1] & NODE_MASK;
             }
-            tc::fence_async_smem();
+            float ag[2][8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                ag[q][0] = g[q][0].x + va[q][0].x; ag[q][1] = g[q][0].y + va[q][0].y; ag[q][2] = g[q][0].z + va[q][0].z; ag[q][3] = g[q][0].w + va[q][0].w;
+                ag[q][4] = g[q][1].x + va[q][1].x; ag[q][5] = g[q][1].y + va[q][1].y; ag[q][6] = g[q][1].z + va[q][1].z; ag[q][7] = g[q][1].w + va[q][1].w;
+            }
+            // further neighbours, two per row per trip
+            for (int sl = 1; sl < maxc; sl += 2) {
+                int j[2][2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    j[q][0] = jn[q];
+                    j[q][1] = (sl + 1 < cnt[q]) ? (p.idx[beg[q] + sl + 1] & NODE_MASK) : 0;
+                    if (sl + 2 < cnt[q]) jn[q] = p.idx[beg[q] + sl + 2] & NODE_MASK;
+                }
+                float4 wa[2][2][2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        wa[q][t][0] = z4; wa[q][t][1] = z4;
+                        if (sl + t < cnt[q]) {
+                            wa[q][t][0] = mgv_ld4(asrc + (size_t)j[q][t] * D + c * 8);
+                            wa[q][t][1] = mgv_ld4(asrc + (size_t)j[q][t] * D + c * 8 + 4);
+                        }
+                    }
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        ag[q][0] += wa[q][t][0].x; ag[q][1] += wa[q][t][0].y; ag[q][2] += wa[q][t][0].z; ag[q][3] += wa[q][t][0].w;
+                        ag[q][4] += wa[q][t][1].x; ag[q][5] += wa[q][t][1].y; ag[q][6] += wa[q][t][1].z; ag[q][7] += wa[q][t][1].w;
+                    }
+            }
+            if (lane == 0) PTRACE_MAX(14);
+            tc::mbar_wait_warp(bar_g_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's epilogue has read the staging rows
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float* dst = s_g + (gw * 8 + q * 4 + rg) * LDGS + c * 8;
+                *reinterpret_cast<float4*>(dst) = make_float4(ag[q][0], ag[q][1], ag[q][2], ag[q][3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(ag[q][4], ag[q][5], ag[q][6], ag[q][7]);
+            }
             tc::mbar_arrive(bar_a_full);
             if (lane == 0) PTRACE_MAX(15);
         }
@@ -347,60 +311,69 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             tc::tmem_st4(t_lnp + 64 + u0 + cc, 0.f, 0.f, 0.f, 0.f);
         }
         tc::tmem_st_wait();
+        // thread 0: the 39 recompute MMAs of a tile (bit-identical products to the forward), once its operand tile has landed
+        auto issue_recompute = [&](uint32_t tph) {
+            tc::mbar_wait_sleep(bar_t_full, tph, 32);
+            tc::fence_after_sync();
+            const uint32_t d = tmem + T_ACC;
+            tc::mma3(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
+                     tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false), 0u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                tc::mma3(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                         tc::desc_k_sw128(sbase + WHH_HI + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 32 * j),
+                         tc::make_idesc(128, 128, false, false), 1u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                tc::mma3(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                         tc::desc_k_sw128(sbase + WHH_HI + 16384 + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 16384 + 32 * j),
+                         tc::make_idesc(128, 64, false, false), 1u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
+                         tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
+                         tc::make_idesc(128, 192, false, false), 1u);
+            tc::mma_commit(bar_acc_full);
+        };
         float run_scale = 1.0f;
         const uint64_t pol_stream = tc::l2_policy_evict_first();      // hand-off buffers: written once, read once by the next kernel
+        // thread 0: bulk copy of the forward's saved operand tile into the (idle) tile buffer
+        auto load_tile = [&](int t) {
+            const uint8_t* src = p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)t * A_TILE_BYTES;
+            tc::mbar_expect_tx(bar_t_full, A_TILE_BYTES);
+#pragma unroll 1
+            for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_g2s(sbase + A_AGG_HI + o, src + o, 8192u, bar_t_full);
+        };
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
             const uint32_t ph = (uint32_t)(it & 1);
             const bool valid = tile * TM + row < p.N;
             const int node = valid ? p.order[tile * TM + row] : 0;
-            // own state row (this thread's 32 units) -> tensor memory, overlapping the recompute MMAs
+            if (tid == 0 && it == 0) {
+                tc::mbar_wait_sleep(bar_w, 0u);
+                load_tile(tile);
+                issue_recompute(0u);
+            }
+            // own state row (this thread's 32 units) -> tensor memory, from the operand tile's h planes (hi + lo is h to
+            // 2^-22: no second global read of the row); the tile is overwritten by the next bulk copy after the barrier
+            tc::mbar_wait_warp(bar_t_full, ph, lane, 32);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
+                const uint32_t off = tc::sw128_off(row, 4 * wg + c8);
+                const uint4 hi = *reinterpret_cast<const uint4*>(sgen + A_H_HI + off), lo = *reinterpret_cast<const uint4*>(sgen + A_H_LO + off);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
+                const __half2* l2 = reinterpret_cast<const __half2*>(&lo);
                 float h[8];
-                if (valid) ldg8(prev + (size_t)node * D + u0 + 8 * c8, h);
-                else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) h[e] = 0.f;
+                for (int e = 0; e < 4; ++e) {
+                    const float2 a = __half22float2(h2[e]), bq = __half22float2(l2[e]);
+                    h[2 * e] = a.x + bq.x; h[2 * e + 1] = a.y + bq.y;
                 }
                 tc::tmem_st8f(t_out + u0 + 8 * c8, h);
             }
-            if (tid == 0) {
-                // ---- recompute MMAs of this tile (the previous tile's epilogue released tensor memory at its last barrier)
-                if (it == 0) tc::mbar_wait_sleep(bar_w, 0u);
-                tc::mbar_wait_sleep(bar_a_full, ph, 32);
-                tc::fence_after_sync();
-                PTRACE(0);
-                const uint32_t d = tmem + T_ACC;
-                tc::mma3(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
-                         tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false), 0u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    tc::mma3(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
-                             tc::desc_k_sw128(sbase + WHH_HI + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 32 * j),
-                             tc::make_idesc(128, 128, false, false), 1u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    tc::mma3(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
-                             tc::desc_k_sw128(sbase + WHH_HI + 16384 + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 16384 + 32 * j),
-                             tc::make_idesc(128, 64, false, false), 1u);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
-                             tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
-                             tc::make_idesc(128, 192, false, false), 1u);
-                tc::mma_commit(bar_a_empty);
-                tc::mma_commit(bar_acc_full);
-                // operand tile -> HBM for the weight-gradient kernel
-                uint8_t* dst = p.abuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * A_TILE_BYTES;
-#pragma unroll 1
-                for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_s2g_hint(dst + o, sbase + A_AGG_HI + o, 8192u, pol_stream);
-                tc::bulk_commit();
-                tc::bulk_wait_read0();
-                tc::mbar_arrive(bar_a_empty);
-                PTRACE(1);
-            }
+            tc::named_bar_sync(1, EPI_T);
             tc::mbar_wait_warp(bar_acc_full, ph, lane, 32);
+            if (tid == 0 && tile + 1 < tile_end) load_tile(tile + 1);       // the MMAs have read the tile: fetch the next one
             tc::mbar_wait_warp(bar_a_full, ph, lane, 32);
             tc::fence_after_sync();
             tc::tmem_st_wait();
@@ -597,6 +570,9 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     }
                     tc::mma_commit(bar_out_full);
                     PTRACE(3);
+                    // the next tile's recompute runs behind the data-gradient MMAs (in issue order) while the epilogue
+                    // stores this tile's outputs: it only writes T_ACC, which the epilogue is done with
+                    if (tile + 1 < tile_end) issue_recompute(ph ^ 1u);
                 }
                 tc::mbar_wait_warp(bar_out_full, ph, lane, 32);
                 tc::fence_after_sync();
@@ -617,11 +593,12 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     }
                 }
             }
-            tc::fence_before_sync();
-            tc::named_bar_sync(1, EPI_T);                // tensor memory is free for the next tile's recompute
+            if (p.first && tid == 0 && tile + 1 < tile_end) {
+                tc::fence_after_sync();
+                issue_recompute(ph ^ 1u);
+            }
             if (tid == 0) PTRACE(9);
         }
-        if (tid == 0) tc::bulk_wait0();
     }
     // ---- LayerNorm parameter gradients: per-thread partial sums (tensor memory) -> column sums -> this CTA's partial block
     tc::fence_before_sync();
@@ -673,7 +650,9 @@ struct WgTC {
     int ntiles;                // tiles of this chunk
     int chunk_cap;
     int dir, gxp;
-    const uint8_t* abuf;
+    const uint8_t* tiles;      // the forward's saved operand tiles of this step, enc 0
+    size_t tiles_enc_stride;
+    int tile_base;             // first tile of this chunk
     const uint8_t* dgbuf;
     const float* scales;
     const unsigned* smin;
@@ -719,7 +698,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
                 WTRACE(1);
                 tc::mbar_expect_tx(bar_full + 8 * s, ST_BYTES);
                 const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 32768;
-                const uint8_t* at = p.abuf + ((size_t)enc * p.chunk_cap + tile) * A_TILE_BYTES;
+                const uint8_t* at = p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)(p.tile_base + tile) * A_TILE_BYTES;
                 const uint32_t st = sbase + (uint32_t)s * ST_BYTES, bar = bar_full + 8 * s;
                 tc::bulk_g2s_hint(st + ST_DG_HI, dg, 16384u, bar, pol);
                 tc::bulk_g2s_hint(st + ST_DG_HI + 16384u, dg + 16384, 16384u, bar, pol);
@@ -886,7 +865,6 @@ size_t tc_workspace_bytes(int64_t N, int num_enc) {
     size_t b = mgv_struct_image_bytes(num_enc) + 256;
     b += 4 * mgv_align_up((size_t)num_enc * N * D * 4 + 256, 256);
     b += mgv_align_up((size_t)sms * 2 * SGRAD * 4 + 256, 256);
-    b += mgv_align_up((size_t)num_enc * cap * A_TILE_BYTES + 1024, 1024);
     b += mgv_align_up((size_t)num_enc * cap * DG_TILE_BYTES + 1024, 1024);
     b += mgv_align_up((size_t)num_enc * cap * 4 + 256, 256);
     const int64_t chunks = (ntiles + CHUNK_TILES - 1) / CHUNK_TILES;
@@ -905,8 +883,8 @@ extern "C" size_t mgv_struct_bwd_workspace_bytes(int64_t N, int32_t num_enc) {
 
 extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
                                       int32_t feat, const float* x, const float* weights, const float* states,
-                                      const float* gout, float* grads, void* ws, size_t ws_bytes, int32_t precision,
-                                      mgv_stream_t stream) {
+                                      const void* tiles, const float* gout, float* grads, void* ws, size_t ws_bytes,
+                                      int32_t precision, mgv_stream_t stream) {
     if (use_legacy(precision))
         return mgv_struct_encoder_bwd_legacy(sch, num_enc, rounds, layernorm, feat, x, weights, states, gout, grads, ws, ws_bytes,
                                              precision, stream);
@@ -920,6 +898,7 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     if (N == 0) return MGV_OK;
     MGV_REQUIRE(sch->deg_order_in && sch->deg_order_out && sch->tile_cost_in && sch->tile_cost_out && sch->gdesc_in && sch->gdesc_out,
                 "struct encoder: the schedule carries no degree order (mgv_build_degree_order)");
+    MGV_REQUIRE(tiles != nullptr, "mgv_struct_encoder_bwd: the operand tiles saved by mgv_struct_encoder_fwd are required (tiles == NULL)");
     if (ws_bytes < mgv_struct_bwd_workspace_bytes(N, num_enc)) {
         mgv_set_error("mgv_struct_encoder_bwd: workspace %zu < %zu bytes", ws_bytes, mgv_struct_bwd_workspace_bytes(N, num_enc));
         return MGV_ERR_WORKSPACE;
@@ -943,8 +922,6 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     part[0] = a.take<float>((size_t)num_enc * slot); part[1] = a.take<float>((size_t)num_enc * slot);
     agg[0] = a.take<float>((size_t)num_enc * slot); agg[1] = a.take<float>((size_t)num_enc * slot);
     float* partial = a.take<float>((size_t)num_enc * gxp * 2 * SGRAD);
-    a.off = mgv_align_up(a.off, 1024);
-    uint8_t* abuf = a.take<uint8_t>((size_t)num_enc * cap * A_TILE_BYTES);
     a.off = mgv_align_up(a.off, 1024);
     uint8_t* dgbuf = a.take<uint8_t>((size_t)num_enc * cap * DG_TILE_BYTES);
     float* scales = a.take<float>((size_t)num_enc * cap);
@@ -979,13 +956,16 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
             p.gout = gout;
             p.in_part = part[k & 1]; p.in_agg = agg[k & 1];
             p.out_part = part[(k - 1) & 1]; p.out_agg = agg[(k - 1) & 1];
-            p.abuf = abuf; p.dgbuf = dgbuf; p.scales = scales; p.smin = smin + 2 * ch;
+            p.tiles = (const uint8_t*)tiles + (size_t)(k - 1) * ntiles * A_TILE_BYTES;
+            p.tiles_enc_stride = (size_t)steps * ntiles * A_TILE_BYTES;
+            p.dgbuf = dgbuf; p.scales = scales; p.smin = smin + 2 * ch;
             p.partial = partial; p.gxp = gxp; p.chunk_cap = cap;
             p.trace = (k == 2 && ch == 0 && !getenv("MGV_TRACE_WGRAD")) ? mgv_debug_trace() : nullptr;
             struct_bwd_pw_kernel<<<dim3(gx, num_enc), THREADS, P_SMEM, st>>>(p);
             WgTC w{};
             w.ntiles = te - tb; w.chunk_cap = cap; w.dir = dir; w.gxp = gxp;
-            w.abuf = abuf; w.dgbuf = dgbuf; w.scales = scales; w.smin = smin + 2 * ch; w.partial = partial;
+            w.tiles = p.tiles; w.tiles_enc_stride = p.tiles_enc_stride; w.tile_base = tb;
+            w.dgbuf = dgbuf; w.scales = scales; w.smin = smin + 2 * ch; w.partial = partial;
             w.trace = (k == 2 && ch == 0 && getenv("MGV_TRACE_WGRAD")) ? mgv_debug_trace() : nullptr;
             struct_bwd_wgrad_kernel<<<dim3(gx, num_enc), W_THREADS, W_SMEM, st>>>(w);
             mgv_count_launches(2);

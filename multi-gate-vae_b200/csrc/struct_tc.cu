@@ -43,6 +43,8 @@ struct StepTC {
     const float* prev;         // state_{k-1}, enc 0
     float* next;               // state_k, enc 0
     size_t enc_stride;         // floats between encoders in the states buffer
+    uint8_t* tiles;            // optional: operand tiles of this step, enc 0 ([tile][A_TILE_BYTES]); saved for the backward
+    size_t tiles_enc_stride;   // bytes between encoders in the tile buffer
     long long* trace;          // optional [CTA][16 tiles][16] clock64 samples (dev tool), may be null
 };
 #define TRACE(slot) do { if (p.trace && it < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + it) * 16 + (slot)] = clock64(); } while (0)
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
     // ---- one-time setup: barriers, weights -> shared memory (bulk async copy, overlaps the first gather), tensor memory
     if (tid == 0) {
         tc::mbar_init(bar_a_full, GATHER_WARPS * 32);
-        tc::mbar_init(bar_a_empty, 1);
+        tc::mbar_init(bar_a_empty, p.tiles ? 2 : 1);       // MMAs complete (+ the tile's bulk store has read it)
         tc::mbar_init(bar_acc_full, 1);
         tc::mbar_init(bar_acc_full + 8, 1);
         tc::mbar_init(bar_acc_empty, EPI_WARPS * 32);
@@ -308,8 +310,17 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                              tc::make_idesc(128, 192, false, false, LOWP), 1u);
                 tc::mma_commit(bar_a_empty);
                 tc::mma_commit(bar_acc_full + 8 * b);
+                if (p.tiles) {      // operand tile -> HBM: the backward recomputes from it instead of re-gathering
+                    uint8_t* dst = p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)tile * A_TILE_BYTES;
+#pragma unroll 1
+                    for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_s2g(dst + o, sbase + A_AGG_HI + o, 8192u);
+                    tc::bulk_commit();
+                    tc::bulk_wait_read0();
+                    tc::mbar_arrive(bar_a_empty);
+                }
                 TRACE(7);
             }
+            if (p.tiles) tc::bulk_wait0();
         }
     } else if (warp < EPI_WARPS) {
         // ===================================================================== epilogue: thread = tile row = TMEM lane
@@ -416,8 +427,13 @@ extern "C" size_t mgv_struct_fwd_workspace_bytes(int64_t N, int32_t num_enc) {
     return mgv_struct_image_bytes(num_enc) + 1024;
 }
 
+extern "C" size_t mgv_struct_tiles_bytes(int64_t N, int32_t num_enc, int32_t rounds) {
+    const size_t ntiles = (size_t)((N + TM - 1) / TM);
+    return (size_t)num_enc * 2 * rounds * ntiles * A_TILE_BYTES;
+}
+
 extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, int32_t rounds, int32_t layernorm,
-                                      int32_t feat, const float* x, const float* weights, float* states,
+                                      int32_t feat, const float* x, const float* weights, float* states, void* tiles,
                                       void* ws, size_t ws_bytes, int32_t precision, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MGV_REQUIRE(sch != nullptr, "struct encoder: null schedule");
@@ -467,6 +483,9 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         p.prev = states + (size_t)(k - 1) * slot;
         p.next = states + (size_t)k * slot;
         p.enc_stride = enc_stride;
+        // tile buffer [enc][step][tile][A_TILE_BYTES] (fp16 hi/lo planes: not written in bf16 mode, whose backward re-gathers)
+        p.tiles = (tiles && precision == 0) ? (uint8_t*)tiles + (size_t)(k - 1) * ntiles * A_TILE_BYTES : nullptr;
+        p.tiles_enc_stride = (size_t)steps * ntiles * A_TILE_BYTES;
         p.trace = (k == steps) ? g_trace : nullptr;
         if (precision == 1) struct_fwd_tc_kernel<true><<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
         else struct_fwd_tc_kernel<false><<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);

@@ -257,14 +257,20 @@ class StructEncoderFunction(torch.autograd.Function):
         prec = _prec()
         pack = _struct_pack(enc_params, layernorm, dev)
         states = torch.empty(num_enc, 2 * rounds + 1, max(N, 1), nat.D, dtype=torch.float32, device=dev)
+        # training: the forward also saves every step's tensor-core operand tile; the backward recomputes from those
+        # instead of gathering the neighbour sums a second time (fp32-accurate mode; the bf16 backward re-gathers)
+        need_tiles = prec == 0 and N > 0 and any(ctx.needs_input_grad[5:])
+        tiles = (torch.empty(lib.mgv_struct_tiles_bytes(N, num_enc, rounds), dtype=torch.uint8, device=dev)
+                 if need_tiles else None)
         with torch.cuda.device(dev):
             nb = lib.mgv_struct_fwd_workspace_bytes(N, num_enc)
             ws = nat.workspace(nb, dev)
             with _timed("struct_encoder_fwd", dev):
               nat.check(lib.mgv_struct_encoder_fwd(csr.c_struct(), num_enc, rounds, int(layernorm), feat,
-                                                 nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(ws), nb,
+                                                 nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(tiles), nat.ptr(ws), nb,
                                                  prec, nat.stream_of(dev)),
                       "mgv_struct_encoder_fwd")
+        ctx.tiles = tiles
         ctx.csr, ctx.rounds, ctx.layernorm, ctx.num_enc, ctx.feat, ctx.per = csr, rounds, layernorm, num_enc, feat, per
         ctx.prec = prec
         ctx.save_for_backward(x_c, pack, states)
@@ -286,7 +292,7 @@ class StructEncoderFunction(torch.autograd.Function):
             ws = nat.workspace(nb, dev)
             with _timed("struct_encoder_bwd", dev):
               nat.check(lib.mgv_struct_encoder_bwd(csr.c_struct(), num_enc, rounds, int(ctx.layernorm), feat,
-                                                 nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(g),
+                                                 nat.ptr(x_c), nat.ptr(pack), nat.ptr(states), nat.ptr(ctx.tiles), nat.ptr(g),
                                                  nat.ptr(grads), nat.ptr(ws), nb, ctx.prec, nat.stream_of(dev)),
                       "mgv_struct_encoder_bwd")
         params = ctx.saved_params

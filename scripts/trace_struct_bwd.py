@@ -40,22 +40,16 @@ elif os.environ.get("MGV_TRACE_WGRAD"):
     v0 = t[:, 0, 10] > 0
     print("first copy -> flush start %.0f, wait done %.0f, flush %.0f cycles" % ((t[:, 0, 8] - t[:, 0, 0])[v0].mean(), (t[:, 0, 9] - t[:, 0, 8])[v0].mean(), (t[:, 0, 10] - t[:, 0, 9])[v0].mean()))
 else:
-    # tcgen05 pointwise kernel (struct_bwd_tc.cu): slots 0-3 MMA thread, 4-9 epilogue thread 0
-    spans = [("MMA: recompute issue + tile bulk store", 0, 1), ("data-gradient issue (thread 0)", 7, 3),
-             ("recompute MMAs (issue -> accumulators ready)", 0, 4), ("epilogue pass 1 + LayerNorm stats", 4, 5),
-             
-             ("   pass 2 loop", 5, 12), ("   amax + named barrier + st wait", 12, 6),
-             ("epilogue pass 2 + tile scale", 5, 6), ("epilogue pass 3 (planes -> TMEM + HBM)", 6, 7),
-             ("data-gradient MMAs (planes ready -> done)", 7, 8), ("epilogue output stores", 8, 9)]
-    spans += [("gather: descriptors + own rows + wait a_empty", 13, 11), ("gather: tile stores + neighbour sum of states", 11, 14),
-              ("gather: d state rows + neighbour sum + wait g_empty + store", 14, 15), ("gather: tile total", 13, 15),
-              ("gather done -> MMA start (same tile)", 15, 0), ("epilogue done -> next MMA start", 9, 16)]
-    t = torch.cat([t, torch.cat([t[:, 1:, 0:1], torch.zeros(t.shape[0], 1, 1, dtype=t.dtype)], 1), torch.cat([t[:, 1:, 10:11], torch.zeros(t.shape[0], 1, 1, dtype=t.dtype)], 1)], 2)
-    valid = (t[:, :, 0] > 0) & (t[:, :, 9] > 0) & (t[:, :, 16] > 0) & (t[:, :, 3] > 0)
+    # tcgen05 pointwise kernel (struct_bwd_tc.cu): slots 3-12 epilogue thread 0, 13-15 slowest gather warp
+    t = torch.cat([t, torch.cat([t[:, 1:, 4:5], torch.zeros(t.shape[0], 1, 1, dtype=t.dtype)], 1)], 2)      # slot 16 = next tile's slot 4
+    spans = [("pass 1 + LayerNorm statistics", 4, 5), ("pass 2 (LN + GRU backward)", 5, 12), ("tile scale (amax, barrier)", 12, 6),
+             ("pass 3 (planes -> TMEM + HBM) + barrier", 6, 7), ("MMA issue: data gradient + next recompute (thread 0)", 7, 3),
+             ("data-gradient MMAs (planes ready -> done)", 7, 8), ("output stores", 8, 9),
+             ("tile end -> next tile's accumulators ready", 9, 16),
+             ("gather: d state rows + neighbour sums (slowest warp)", 13, 14), ("gather: wait g_empty + store", 14, 15)]
+    valid = (t[:, :, 4] > 0) & (t[:, :, 9] > 0) & (t[:, :, 16] > 0) & (t[:, :, 3] > 0)
     for n, a, b in spans:
         d = (t[:, :, b] - t[:, :, a])[valid]
-        print("%-46s mean %7.0f  med %7.0f  max %7.0f cycles" % (n, d.mean(), d.median(), d.max()))
-    d = (t[:, :, 9] - t[:, :, 0])[valid]
-    print("tile (MMA start -> epilogue done) mean %.0f cycles" % d.mean())
-    nxt = (t[:, 1:, 0] - t[:, :-1, 0])[valid[:, 1:] & valid[:, :-1]]
-    print("tile period mean %.0f cycles (n=%d)" % (nxt.mean(), nxt.numel()))
+        print("%-56s mean %7.0f  med %7.0f  max %7.0f cycles" % (n, d.mean(), d.median(), d.max()))
+    d = (t[:, :, 16] - t[:, :, 4])[valid]
+    print("tile period mean %.0f cycles (n=%d)" % (d.mean(), d.numel()))
