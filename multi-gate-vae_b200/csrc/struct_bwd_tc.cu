@@ -38,8 +38,8 @@ namespace {
 using namespace struct_layout;
 
 constexpr int SGRAD = MGV_STRUCT_GRAD_FLOATS;
-constexpr int EPI_WARPS = 8, GATHER_WARPS = 16;             // epilogue: 2 warps per 32 TMEM lanes (32 units each); gather: 2 rows per lane
-constexpr int THREADS = (EPI_WARPS + GATHER_WARPS) * 32;    // 24 warps = 6 per scheduler -> 80 registers; MMAs are issued by epilogue thread 0
+constexpr int EPI_WARPS = 8, GATHER_WARPS = 8;              // epilogue: 2 warps per 32 TMEM lanes (32 units each); gather: 4 rows per lane
+constexpr int THREADS = (EPI_WARPS + GATHER_WARPS + 1) * 32; // + the MMA / bulk-copy warp: 17 warps, 5 on one scheduler -> 96 registers
 constexpr int LDGS = 68;                                   // d state staging row stride (floats)
 constexpr uint32_t DG_TILE_BYTES = 131072;                 // [hi | lo][64-node half][8-gate chunk (32)][node row (64)][16 B]: no-swizzle core matrices
 constexpr int CHUNK_TILES_DEFAULT = 1024;                  // tiles per encoder per kernel pair (MGV_STRUCT_CHUNK overrides: tuning)
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     const uint8_t* image = p.image + (size_t)enc * 2 * IMG_BYTES;
 
     const uint32_t bar_w = sbase + S_BAR, bar_a_full = bar_w + 8, bar_t_full = bar_w + 16, bar_g_empty = bar_w + 24;
-    const uint32_t bar_acc_full = bar_w + 32, bar_out_full = bar_w + 40;
+    const uint32_t bar_acc_full = bar_w + 32, bar_out_full = bar_w + 40, bar_h_read = bar_w + 48, bar_dg_full = bar_w + 56;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + S_TMEM);
     float* s_ln = reinterpret_cast<float*>(sgen + S_LN);
     unsigned* s_amax = reinterpret_cast<unsigned*>(sgen + S_AMAX);
@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         tc::mbar_init(bar_g_empty, EPI_WARPS * 32);
         tc::mbar_init(bar_acc_full, 1);
         tc::mbar_init(bar_out_full, 1);
+        tc::mbar_init(bar_h_read, EPI_WARPS * 32);      // the epilogue has copied the tile's h rows: the tile may be overwritten
+        tc::mbar_init(bar_dg_full, EPI_WARPS * 32);     // d-gate planes are in tensor memory
         tc::fence_barrier_init();
         tc::mbar_expect_tx(bar_w, IMG_W);
 #pragma unroll 1
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp >= EPI_WARPS) {
+    if (warp >= EPI_WARPS && warp < EPI_WARPS + GATHER_WARPS) {
         // ===================================================================== gather of d state_k
         // d state_k = d part (or the incoming gradient at the last step) + neighbour sum of d agg_{k+1}, fp32, into the
         // staging rows.  (The [agg | h | x deg 1] operand tile is NOT re-gathered: the forward saved it, thread 0 bulk-copies it.)
@@ -206,92 +208,171 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         const float* gsrc = p.last ? p.gout + eoff : p.in_part + eoff;
         const float* asrc = p.in_agg + eoff;
         const bool nbg = !p.last;
-        int4 dn[2];
+        int4 dn[4];
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
-            const int r = tile_beg * TM + gw * 8 + ps * 4 + rg;
+        for (int ps = 0; ps < 4; ++ps) {
+            const int r = tile_beg * TM + gw * 16 + ps * 4 + rg;
             dn[ps] = (tile_beg < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
         }
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
             if (lane == 0) PTRACE_MAX(13);
-            int4 dc[2];
+            int4 dc[4];
 #pragma unroll
-            for (int ps = 0; ps < 2; ++ps) dc[ps] = dn[ps];
+            for (int ps = 0; ps < 4; ++ps) dc[ps] = dn[ps];
 #pragma unroll
-            for (int ps = 0; ps < 2; ++ps) {
-                const int r = (tile + 1) * TM + gw * 8 + ps * 4 + rg;
+            for (int ps = 0; ps < 4; ++ps) {
+                const int r = (tile + 1) * TM + gw * 16 + ps * 4 + rg;
                 dn[ps] = (tile + 1 < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
             }
-            int node[2], beg[2], cnt[2], jn[2];
-            float4 g[2][2], va[2][2];
-            int maxc = 0;
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int4 d = dc[q];
-                node[q] = d.x; beg[q] = d.y; cnt[q] = nbg ? d.z : 0; jn[q] = d.w;
-                maxc = max(maxc, cnt[q]);
-                g[q][0] = z4; g[q][1] = z4; va[q][0] = z4; va[q][1] = z4;
-                if (node[q] >= 0) {
-                    g[q][0] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8);
-                    g[q][1] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8 + 4);
-                }
-                if (cnt[q] > 0) {
-                    va[q][0] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8);
-                    va[q][1] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8 + 4);
-                }
-                if (cnt[q] > 1) jn[q] = p.idx[beg[q] + 1] & NODE_MASK;
-            }
-            float ag[2][8];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                ag[q][0] = g[q][0].x + va[q][0].x; ag[q][1] = g[q][0].y + va[q][0].y; ag[q][2] = g[q][0].z + va[q][0].z; ag[q][3] = g[q][0].w + va[q][0].w;
-                ag[q][4] = g[q][1].x + va[q][1].x; ag[q][5] = g[q][1].y + va[q][1].y; ag[q][6] = g[q][1].z + va[q][1].z; ag[q][7] = g[q][1].w + va[q][1].w;
-            }
-            // further neighbours, two per row per trip
-            for (int sl = 1; sl < maxc; sl += 2) {
-                int j[2][2];
+            for (int hf = 0; hf < 2; ++hf) {           // the lane's 4 rows, two at a time
+                int node[2], beg[2], cnt[2], jn[2];
+                float4 g[2][2], va[2][2];
+                int maxc = 0;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    j[q][0] = jn[q];
-                    j[q][1] = (sl + 1 < cnt[q]) ? (p.idx[beg[q] + sl + 1] & NODE_MASK) : 0;
-                    if (sl + 2 < cnt[q]) jn[q] = p.idx[beg[q] + sl + 2] & NODE_MASK;
+                    const int4 d = dc[2 * hf + q];
+                    node[q] = d.x; beg[q] = d.y; cnt[q] = nbg ? d.z : 0; jn[q] = d.w;
+                    maxc = max(maxc, cnt[q]);
+                    g[q][0] = z4; g[q][1] = z4; va[q][0] = z4; va[q][1] = z4;
+                    if (node[q] >= 0) {
+                        g[q][0] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8);
+                        g[q][1] = mgv_ld4(gsrc + (size_t)node[q] * D + c * 8 + 4);
+                    }
+                    if (cnt[q] > 0) {
+                        va[q][0] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8);
+                        va[q][1] = mgv_ld4(asrc + (size_t)jn[q] * D + c * 8 + 4);
+                    }
+                    if (cnt[q] > 1) jn[q] = p.idx[beg[q] + 1] & NODE_MASK;
                 }
-                float4 wa[2][2][2];
+                float ag[2][8];
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+                for (int q = 0; q < 2; ++q) {
+                    ag[q][0] = g[q][0].x + va[q][0].x; ag[q][1] = g[q][0].y + va[q][0].y; ag[q][2] = g[q][0].z + va[q][0].z; ag[q][3] = g[q][0].w + va[q][0].w;
+                    ag[q][4] = g[q][1].x + va[q][1].x; ag[q][5] = g[q][1].y + va[q][1].y; ag[q][6] = g[q][1].z + va[q][1].z; ag[q][7] = g[q][1].w + va[q][1].w;
+                }
+                // further neighbours, two per row per trip
+                for (int sl = 1; sl < maxc; sl += 2) {
+                    int j[2][2];
 #pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        wa[q][t][0] = z4; wa[q][t][1] = z4;
-                        if (sl + t < cnt[q]) {
-                            wa[q][t][0] = mgv_ld4(asrc + (size_t)j[q][t] * D + c * 8);
-                            wa[q][t][1] = mgv_ld4(asrc + (size_t)j[q][t] * D + c * 8 + 4);
+                    for (int q = 0; q < 2; ++q) {
+                        j[q][0] = jn[q];
+                        j[q][1] = (sl + 1 < cnt[q]) ? (p.idx[beg[q] + sl + 1] & NODE_MASK) : 0;
+                        if (sl + 2 < cnt[q]) jn[q] = p.idx[beg[q] + sl + 2] & NODE_MASK;
+                    }
+                    float4 wa[2][2][2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            wa[q][t][0] = z4; wa[q][t][1] = z4;
+                            if (sl + t < cnt[q]) {
+                                wa[q][t][0] = mgv_ld4(asrc + (size_t)j[q][t] * D + c * 8);
+                                wa[q][t][1] = mgv_ld4(asrc + (size_t)j[q][t] * D + c * 8 + 4);
+                            }
                         }
-                    }
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+                    for (int q = 0; q < 2; ++q)
 #pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        ag[q][0] += wa[q][t][0].x; ag[q][1] += wa[q][t][0].y; ag[q][2] += wa[q][t][0].z; ag[q][3] += wa[q][t][0].w;
-                        ag[q][4] += wa[q][t][1].x; ag[q][5] += wa[q][t][1].y; ag[q][6] += wa[q][t][1].z; ag[q][7] += wa[q][t][1].w;
-                    }
-            }
-            if (lane == 0) PTRACE_MAX(14);
-            tc::mbar_wait_warp(bar_g_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's epilogue has read the staging rows
+                        for (int t = 0; t < 2; ++t) {
+                            ag[q][0] += wa[q][t][0].x; ag[q][1] += wa[q][t][0].y; ag[q][2] += wa[q][t][0].z; ag[q][3] += wa[q][t][0].w;
+                            ag[q][4] += wa[q][t][1].x; ag[q][5] += wa[q][t][1].y; ag[q][6] += wa[q][t][1].z; ag[q][7] += wa[q][t][1].w;
+                        }
+                }
+                if (hf == 0) {
+                    if (lane == 0) PTRACE_MAX(14);
+                    tc::mbar_wait_warp(bar_g_empty, (uint32_t)((it & 1) ^ 1), lane, 64);   // previous tile's epilogue has read the staging rows
+                }
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                float* dst = s_g + (gw * 8 + q * 4 + rg) * LDGS + c * 8;
-                *reinterpret_cast<float4*>(dst) = make_float4(ag[q][0], ag[q][1], ag[q][2], ag[q][3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(ag[q][4], ag[q][5], ag[q][6], ag[q][7]);
+                for (int q = 0; q < 2; ++q) {
+                    float* dst = s_g + (gw * 16 + (2 * hf + q) * 4 + rg) * LDGS + c * 8;
+                    *reinterpret_cast<float4*>(dst) = make_float4(ag[q][0], ag[q][1], ag[q][2], ag[q][3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(ag[q][4], ag[q][5], ag[q][6], ag[q][7]);
+                }
             }
             tc::mbar_arrive(bar_a_full);
             if (lane == 0) PTRACE_MAX(15);
         }
-    } else {
+    } else if (warp == EPI_WARPS + GATHER_WARPS) {
+        // ===================================================================== MMA issue + operand-tile bulk copies (one thread)
+        if (lane == 0 && tile_beg < tile_end) {
+            auto load_tile = [&](int t) {       // the forward's saved operand tile -> the (idle) tile buffer
+                const uint8_t* src = p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)t * A_TILE_BYTES;
+                tc::mbar_expect_tx(bar_t_full, A_TILE_BYTES);
+#pragma unroll 1
+                for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_g2s(sbase + A_AGG_HI + o, src + o, 8192u, bar_t_full);
+            };
+            auto issue_recompute = [&](uint32_t tph) {     // the 39 recompute MMAs of a tile (bit-identical products to the forward)
+                tc::mbar_wait_sleep(bar_t_full, tph, 32);
+                tc::fence_after_sync();
+                const uint32_t d = tmem + T_ACC;
+                tc::mma3(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
+                         tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false), 0u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma3(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                             tc::desc_k_sw128(sbase + WHH_HI + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 32 * j),
+                             tc::make_idesc(128, 128, false, false), 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma3(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                             tc::desc_k_sw128(sbase + WHH_HI + 16384 + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 16384 + 32 * j),
+                             tc::make_idesc(128, 64, false, false), 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
+                             tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
+                             tc::make_idesc(128, 192, false, false), 1u);
+                tc::mma_commit(bar_acc_full);
+            };
+            tc::mbar_wait_sleep(bar_w, 0u);
+            load_tile(tile_beg);
+            issue_recompute(0u);
+            int it = 0;
+            for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+                const uint32_t ph = (uint32_t)(it & 1);
+                // the tile buffer is free once the recompute MMAs have read it and the epilogue has copied its h rows
+                tc::mbar_wait_sleep(bar_acc_full, ph, 32);
+                tc::mbar_wait_sleep(bar_h_read, ph, 32);
+                if (tile + 1 < tile_end) load_tile(tile + 1);
+                tc::mbar_wait_sleep(bar_dg_full, ph, 32);
+                tc::fence_after_sync();
+                PTRACE(7);
+                if (!p.first) {
+                    const uint32_t o = tmem + T_OUT;
+                    const uint32_t i128 = tc::make_idesc(128, 128, false, true), i64 = tc::make_idesc(128, 64, false, true);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {        // d r, d z: [d agg | d part] += d g . [Wc | Whh] rows 16 s ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, WHH_HI - WC_HI),
+                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, WHH_LO - WC_LO), i128, 1u);
+                    }
+#pragma unroll
+                    for (int s = 8; s < 12; ++s) {       // d gi_n: d agg += . Wc rows 128 ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, 0),
+                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, 0), i64, 1u);
+                    }
+#pragma unroll
+                    for (int s = 12; s < 16; ++s) {      // d gh_n: d part += . Whh rows 128 ..
+                        const uint32_t a = tmem + T_ACC + 16u * s;
+                        tc::mma3p_ts<false>(o + 64u, a, a + 8u, tc::desc_mn_sw128(sbase + WHH_HI + 2048u * (s - 4), 0),
+                                            tc::desc_mn_sw128(sbase + WHH_LO + 2048u * (s - 4), 0), i64, 1u);
+                    }
+                    tc::mma_commit(bar_out_full);
+                }
+                // the next tile's recompute runs behind the data-gradient MMAs (in issue order) while the epilogue stores
+                // this tile's outputs: it only writes T_ACC, which the epilogue is done with
+                if (tile + 1 < tile_end) issue_recompute(ph ^ 1u);
+                PTRACE(3);
+            }
+        }
+    } else if (warp < EPI_WARPS) {
         // ===================================================================== epilogue: 2 threads per tile row = TMEM lane
         // Warps q and 4 + q own lanes 32 q .. 32 q + 31; warp group wg = warp / 4 handles units 32 wg .. 32 wg + 31 of its
-        // row (row sums are exchanged through shared memory).  Thread 0 also issues the MMAs and the tile's bulk store.
+        // row (row sums are exchanged through shared memory).  
         // All per-row arrays live in the thread's tensor-memory lane, so every loop below is ROLLED: a fully unrolled
         // body is > 100 KB of straight-line code that one warp executes once per tile, i.e. pure instruction-cache
         // misses (measured: 8 cycles per instruction).
@@ -311,49 +392,13 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             tc::tmem_st4(t_lnp + 64 + u0 + cc, 0.f, 0.f, 0.f, 0.f);
         }
         tc::tmem_st_wait();
-        // thread 0: the 39 recompute MMAs of a tile (bit-identical products to the forward), once its operand tile has landed
-        auto issue_recompute = [&](uint32_t tph) {
-            tc::mbar_wait_sleep(bar_t_full, tph, 32);
-            tc::fence_after_sync();
-            const uint32_t d = tmem + T_ACC;
-            tc::mma3(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
-                     tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false), 0u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                tc::mma3(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
-                         tc::desc_k_sw128(sbase + WHH_HI + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 32 * j),
-                         tc::make_idesc(128, 128, false, false), 1u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                tc::mma3(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
-                         tc::desc_k_sw128(sbase + WHH_HI + 16384 + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 16384 + 32 * j),
-                         tc::make_idesc(128, 64, false, false), 1u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
-                         tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
-                         tc::make_idesc(128, 192, false, false), 1u);
-            tc::mma_commit(bar_acc_full);
-        };
         float run_scale = 1.0f;
         const uint64_t pol_stream = tc::l2_policy_evict_first();      // hand-off buffers: written once, read once by the next kernel
-        // thread 0: bulk copy of the forward's saved operand tile into the (idle) tile buffer
-        auto load_tile = [&](int t) {
-            const uint8_t* src = p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)t * A_TILE_BYTES;
-            tc::mbar_expect_tx(bar_t_full, A_TILE_BYTES);
-#pragma unroll 1
-            for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_g2s(sbase + A_AGG_HI + o, src + o, 8192u, bar_t_full);
-        };
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
             const uint32_t ph = (uint32_t)(it & 1);
             const bool valid = tile * TM + row < p.N;
             const int node = valid ? p.order[tile * TM + row] : 0;
-            if (tid == 0 && it == 0) {
-                tc::mbar_wait_sleep(bar_w, 0u);
-                load_tile(tile);
-                issue_recompute(0u);
-            }
             // own state row (this thread's 32 units) -> tensor memory, from the operand tile's h planes (hi + lo is h to
             // 2^-22: no second global read of the row); the tile is overwritten by the next bulk copy after the barrier
             tc::mbar_wait_warp(bar_t_full, ph, lane, 32);
@@ -371,9 +416,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 }
                 tc::tmem_st8f(t_out + u0 + 8 * c8, h);
             }
-            tc::named_bar_sync(1, EPI_T);
+            tc::mbar_arrive(bar_h_read);
             tc::mbar_wait_warp(bar_acc_full, ph, lane, 32);
-            if (tid == 0 && tile + 1 < tile_end) load_tile(tile + 1);       // the MMAs have read the tile: fetch the next one
             tc::mbar_wait_warp(bar_a_full, ph, lane, 32);
             tc::fence_after_sync();
             tc::tmem_st_wait();
@@ -542,38 +586,9 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             }
             tc::tmem_st_wait();
             tc::fence_before_sync();
-            tc::named_bar_sync(1, EPI_T);
-            if (tid == 0) PTRACE(7);
+            tc::mbar_arrive(bar_dg_full);
             // ---- data gradients of step k-1
             if (!p.first) {
-                if (tid == 0) {
-                    tc::fence_after_sync();
-                    const uint32_t o = tmem + T_OUT;
-                    const uint32_t i128 = tc::make_idesc(128, 128, false, true), i64 = tc::make_idesc(128, 64, false, true);
-#pragma unroll
-                    for (int s = 0; s < 8; ++s) {        // d r, d z: [d agg | d part] += d g . [Wc | Whh] rows 16 s ..
-                        const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, WHH_HI - WC_HI),
-                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, WHH_LO - WC_LO), i128, 1u);
-                    }
-#pragma unroll
-                    for (int s = 8; s < 12; ++s) {       // d gi_n: d agg += . Wc rows 128 ..
-                        const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, 0),
-                                            tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, 0), i64, 1u);
-                    }
-#pragma unroll
-                    for (int s = 12; s < 16; ++s) {      // d gh_n: d part += . Whh rows 128 ..
-                        const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o + 64u, a, a + 8u, tc::desc_mn_sw128(sbase + WHH_HI + 2048u * (s - 4), 0),
-                                            tc::desc_mn_sw128(sbase + WHH_LO + 2048u * (s - 4), 0), i64, 1u);
-                    }
-                    tc::mma_commit(bar_out_full);
-                    PTRACE(3);
-                    // the next tile's recompute runs behind the data-gradient MMAs (in issue order) while the epilogue
-                    // stores this tile's outputs: it only writes T_ACC, which the epilogue is done with
-                    if (tile + 1 < tile_end) issue_recompute(ph ^ 1u);
-                }
                 tc::mbar_wait_warp(bar_out_full, ph, lane, 32);
                 tc::fence_after_sync();
                 if (tid == 0) PTRACE(8);
@@ -592,10 +607,6 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                         stg8(p.out_part + eoff + (size_t)node * D + u, q);
                     }
                 }
-            }
-            if (p.first && tid == 0 && tile + 1 < tile_end) {
-                tc::fence_after_sync();
-                issue_recompute(ph ^ 1u);
             }
             if (tid == 0) PTRACE(9);
         }
