@@ -64,13 +64,20 @@ __device__ __forceinline__ void tmem_ld4x4(uint32_t taddr, float (&v)[16]) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(r[4 * k]), "=r"(r[4 * k + 1]), "=r"(r[4 * k + 2]), "=r"(r[4 * k + 3]) : "r"(taddr + 64u * k) : "memory");
 }
+// `gt` (optional): the same 16-byte chunks also go to the tile image in HBM that the backward recomputes from
+// (a row's 8 chunks are one 128-byte line, so a warp's 4 rows write 4 full lines per plane).
 template <bool LOWP>
-__device__ __forceinline__ void split_store_sw128(uint32_t hi_base, uint32_t lo_base, int row, int c, const float (&v)[8]) {
+__device__ __forceinline__ void split_store_sw128(uint32_t hi_base, uint32_t lo_base, int row, int c, const float (&v)[8],
+                                                  uint8_t* gt = nullptr, uint32_t g_hi = 0, uint32_t g_lo = 0) {
     uint4 hi, lo;
     tc::split8p<LOWP>(v, hi, lo);
     const uint32_t off = tc::sw128_off(row, c);
     tc::st_shared_v4(hi_base + off, hi);
     if (!LOWP) tc::st_shared_v4(lo_base + off, lo);
+    if (gt) {
+        *reinterpret_cast<uint4*>(gt + g_hi + off) = hi;
+        *reinterpret_cast<uint4*>(gt + g_lo + off) = lo;
+    }
 }
 
 // ======================================================================================= weight image
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
     // ---- one-time setup: barriers, weights -> shared memory (bulk async copy, overlaps the first gather), tensor memory
     if (tid == 0) {
         tc::mbar_init(bar_a_full, GATHER_WARPS * 32);
-        tc::mbar_init(bar_a_empty, p.tiles ? 2 : 1);       // MMAs complete (+ the tile's bulk store has read it)
+        tc::mbar_init(bar_a_empty, 1);
         tc::mbar_init(bar_acc_full, 1);
         tc::mbar_init(bar_acc_full + 8, 1);
         tc::mbar_init(bar_acc_empty, EPI_WARPS * 32);
@@ -186,6 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
             if (warp == EPI_WARPS && lane == 0) TRACE(0);
+            uint8_t* gt = p.tiles ? p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)tile * A_TILE_BYTES : nullptr;
             // ---- loads into registers (overlap the previous tile's MMAs): own-state rows, the lane's feature element,
             //      first neighbour rows, second neighbour ids, next tile's descriptors
             int node[4], beg[4], cnt[4], jn[4];
@@ -223,7 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             for (int ps = 0; ps < 4; ++ps) {
                 const int row = gw * 16 + ps * 4 + rg;
                 const float h8[8] = {ha[ps].x, ha[ps].y, ha[ps].z, ha[ps].w, hb[ps].x, hb[ps].y, hb[ps].z, hb[ps].w};
-                split_store_sw128<LOWP>(sbase + A_H_HI, sbase + A_H_LO, row, c, h8);
+                split_store_sw128<LOWP>(sbase + A_H_HI, sbase + A_H_LO, row, c, h8, gt, A_H_HI - A_AGG_HI, A_H_LO - A_AGG_HI);
                 float xv[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) xv[e] = __shfl_sync(0xffffffffu, xe[ps], (lane & 24) + e);   // features of this row
@@ -238,6 +246,10 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                     const uint32_t off = tc::plain16_off(row, c);
                     tc::st_shared_v4(sbase + A_X_HI + off, hi);
                     if (!LOWP) tc::st_shared_v4(sbase + A_X_LO + off, lo);
+                    if (gt) {
+                        *reinterpret_cast<uint4*>(gt + (A_X_HI - A_AGG_HI) + off) = hi;
+                        *reinterpret_cast<uint4*>(gt + (A_X_LO - A_AGG_HI) + off) = lo;
+                    }
                 }
             }
             if (warp == EPI_WARPS && lane == 0) TRACE(3);
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             }
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps)
-                split_store_sw128<LOWP>(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps]);
+                split_store_sw128<LOWP>(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps], gt, 0u, A_AGG_LO - A_AGG_HI);
             if (warp == EPI_WARPS && lane == 0) TRACE(4);
             tc::fence_async_smem();
             tc::mbar_arrive(bar_a_full);
@@ -310,17 +322,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                              tc::make_idesc(128, 192, false, false, LOWP), 1u);
                 tc::mma_commit(bar_a_empty);
                 tc::mma_commit(bar_acc_full + 8 * b);
-                if (p.tiles) {      // operand tile -> HBM: the backward recomputes from it instead of re-gathering
-                    uint8_t* dst = p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)tile * A_TILE_BYTES;
-#pragma unroll 1
-                    for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_s2g(dst + o, sbase + A_AGG_HI + o, 8192u);
-                    tc::bulk_commit();
-                    tc::bulk_wait_read0();
-                    tc::mbar_arrive(bar_a_empty);
-                }
                 TRACE(7);
             }
-            if (p.tiles) tc::bulk_wait0();
         }
     } else if (warp < EPI_WARPS) {
         // ===================================================================== epilogue: thread = tile row = TMEM lane
