@@ -8,12 +8,11 @@
 
 namespace {
 
-constexpr int LR = 32;             // node rows staged per trip
 constexpr int RG = 8;              // partial groups summed in parallel by the reduce kernel
 
 // Thread (ty, tx) owns the contiguous TO x TI output block (TO ty .., TI tx ..): 128-bit shared-memory reads,
 // TO + TI loaded floats per TO * TI FMAs.
-template <int TO, int TI>
+template <int TO, int TI, int LR>
 __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, long long N,
                                                            int I, int O, int IP, int OP, float* __restrict__ partial) {
     extern __shared__ __align__(16) float sm[];
@@ -112,19 +111,21 @@ int grid_blocks(long long N) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long trips = (N + LR - 1) / LR;
+    long long trips = (N + 127) / 128;
     long long g = 2LL * sms;
     if (g > trips) g = trips;
     return g < 1 ? 1 : (int)g;
 }
 
-template <int TO, int TI>
-void launch(int nblk, cudaStream_t st, const float* x, const float* gy, long long N, int I, int O, float* partial) {
+template <int TO, int TI, int LR>
+int launch(int nblk, cudaStream_t st, const float* x, const float* gy, long long N, int I, int O, float* partial) {
     const int IP = (I + TI - 1) / TI * TI, OP = (O + TO - 1) / TO * TO;
     int nt = (IP / TI) * (OP / TO);
-    nt = (nt + 31) / 32 * 32;
+    nt = nt < 256 ? 256 : (nt + 31) / 32 * 32;          // idle compute threads still help stage the rows
     const size_t smem = (size_t)LR * (IP + OP) * sizeof(float);
-    linear_wgrad_kernel<TO, TI><<<nblk, nt, smem, st>>>(x, gy, N, I, O, IP, OP, partial);
+    MGV_CUDA(cudaFuncSetAttribute((const void*)linear_wgrad_kernel<TO, TI, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    linear_wgrad_kernel<TO, TI, LR><<<nblk, nt, smem, st>>>(x, gy, N, I, O, IP, OP, partial);
+    return MGV_OK;
 }
 
 }  // namespace
@@ -151,10 +152,12 @@ extern "C" int mgv_linear_wgrad(const float* x, const float* gy, int64_t N, int3
     float* partial = (float*)ws;
     // thread tile: 8 wide along a dimension of >= 64 features, else 4 (<= 16 x 16 threads)
     const bool o8 = O > 32, i8 = I > 32;
-    if (o8 && i8) launch<8, 8>(nblk, st, x, gy, N, I, O, partial);
-    else if (o8) launch<8, 4>(nblk, st, x, gy, N, I, O, partial);
-    else if (i8) launch<4, 8>(nblk, st, x, gy, N, I, O, partial);
-    else launch<4, 4>(nblk, st, x, gy, N, I, O, partial);
+    int rc;
+    if (o8 && i8) rc = launch<8, 8, 64>(nblk, st, x, gy, N, I, O, partial);
+    else if (o8) rc = launch<8, 4, 128>(nblk, st, x, gy, N, I, O, partial);
+    else if (i8) rc = launch<4, 8, 128>(nblk, st, x, gy, N, I, O, partial);
+    else rc = launch<4, 4, 128>(nblk, st, x, gy, N, I, O, partial);
+    if (rc != MGV_OK) return rc;
     const int total = O * I + O;
     linear_wgrad_reduce_kernel<<<(total + 31) / 32, 256, 0, st>>>(partial, nblk, I, O, dW, db);
     mgv_count_launches(2);

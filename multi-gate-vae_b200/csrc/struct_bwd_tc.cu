@@ -182,12 +182,11 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     const int ntiles_all = (p.N + TM - 1) / TM;
     int tile_beg, tile_end;
     {
-        // the backward moves two rows per neighbour: weigh neighbours twice as much as the forward's cost model does
-        constexpr unsigned ADJ = MGV_TILE_FIXED_COST - MGV_TILE_FIXED_COST / 4;
-        const unsigned long long c0 = p.tile_cost[p.tile_beg] - ADJ * (unsigned)p.tile_beg, c1 = p.tile_cost[p.tile_end] - ADJ * (unsigned)p.tile_end;
-        const unsigned lo = (unsigned)(c0 + (c1 - c0) * blockIdx.x / gridDim.x), hi = (unsigned)(c0 + (c1 - c0) * (blockIdx.x + 1) / gridDim.x);
-        tile_beg = tc::warp_lower_bound(p.tile_cost, ntiles_all, lo, lane, ADJ);
-        tile_end = tc::warp_lower_bound(p.tile_cost, ntiles_all, hi, lane, ADJ);
+        // equal tile counts per CTA: with the operand tile bulk-copied, a tile's time is set by the epilogue (constant per
+        // 128 nodes), not by its neighbour count as in the forward's cost model
+        const long long nt = p.tile_end - p.tile_beg;
+        tile_beg = p.tile_beg + (int)(nt * blockIdx.x / gridDim.x);
+        tile_end = p.tile_beg + (int)(nt * (blockIdx.x + 1) / gridDim.x);
         tile_beg = max(tile_beg, p.tile_beg);
         tile_end = min(tile_end, p.tile_end);
     }
