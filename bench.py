@@ -80,6 +80,8 @@ class ClockSampler(object):
         self.index = index
 
     def start(self):
+        if os.environ.get("MGV_BENCH_NO_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -232,11 +234,29 @@ def run_ours(args, w):
         st = trainer.train_step(fresh(resident[i % nb]))
         return st["loss"]
 
+    e2e_trace = [] if os.environ.get("MGV_BENCH_VERBOSE") else None
+
     def step_e2e(i):
-        st = trainer.train_step(host[i % nb].copy_to(dev, non_blocking=True))
-        return float(st["loss"].item())          # device -> host read of the step's result
+        t0 = time.perf_counter()
+        b = host[i % nb].copy_to(dev, non_blocking=True)
+        t1 = time.perf_counter()
+        st = trainer.train_step(b)
+        t2 = time.perf_counter()
+        v = float(st["loss"].item())             # device -> host read of the step's result
+        if e2e_trace is not None:
+            e2e_trace.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2)))
+        return v
 
     def timed(fn, k):
+        import gc
+        gc.collect()                    # no cyclic-GC pause (tens of ms) inside a timed region of a few steps
+        gc.disable()
+        try:
+            return timed_(fn, k)
+        finally:
+            gc.enable()
+
+    def timed_(fn, k):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -249,6 +269,12 @@ def run_ours(args, w):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item())
 
+    # setup (not a warm-up step): one pass over every DISTINCT batch so that the caching allocator owns blocks for
+    # each batch's sizes -- a first-seen batch inside the timed region costs cudaMalloc calls of several hundred MB
+    # (measured: 7.8 instead of 4.6 ms / step with --warmup 3 and 4 distinct batches)
+    for i in range(nb):
+        step_resident(i)
+        step_e2e(i)
     for i in range(args.warmup):
         step_resident(i)
         step_e2e(i)
@@ -261,8 +287,12 @@ def run_ours(args, w):
     prof = ops.profile_summary()
     ops.PROFILE = None
     launches = _native.lib().mgv_kernel_launches() - launches0
+    step_e2e(0)                               # untimed: back from the resident loop to the host-fed path
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop()
+    if e2e_trace:
+        for t in e2e_trace[-args.steps:]:
+            print("e2e step: h2d issue %.2f  train_step host %.2f  loss.item() wait %.2f ms" % t, file=sys.stderr)
     from deepgate.schedule import check_deferred_errors
     check_deferred_errors()                   # asynchronous input validation of every schedule built above
 
@@ -343,6 +373,7 @@ def run_ours(args, w):
                        "gates_per_step_per_gpu": mean_stats["gates"] * w["rounds"], "sweep_rounds": w["rounds"],
                        "s_rounds": 4, "t_rounds": 4, "layernorm": True, "dim_hidden": 64, "parallelism": "dp%d" % world,
                        "step": "schedule build + forward + recon/prob/func losses + backward + allreduce + Adam",
+                       "setup": "one untimed pass over each distinct batch before the warm-up steps (allocator pools)",
                        "l2": "%d distinct batches rotated; per-batch working set (struct states %d MB) exceeds the 126 MB L2"
                              % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},
             "e2e": {"value": e2e, "unit": "gates/s", "ms_per_step": ms_e2e / args.steps,
