@@ -331,3 +331,51 @@ def test_bf16_mode_within_stated_tolerance():
             continue
         worst = max(worst, rel(p.grad, ref))
     assert worst < 5e-2, worst
+
+
+def test_struct_backward_paths_agree_on_a_large_heavy_tailed_graph(monkeypatch):
+    """The tcgen05 backward (csrc/struct_bwd_tc.cu: one chunk and many chunks of tiles) against the mma.sync backward
+    (csrc/struct_encoder.cu, selected by MGV_STRUCT_BWD=mma) on ~20 000 nodes with fan-outs up to the hundreds:
+    three independent code paths for the same gradients (tile hand-off buffers, per-tile power-of-two scales, chunk-wide
+    rescale, tile order = degree order)."""
+    import deepgate
+    from deepgate import synth
+    import numpy as np
+    circuits = synth.make_circuits("mig", 3, 12, 6500, cfg=77)
+    for ci, c in enumerate(circuits):             # hubs: re-route one fan-in of ~300 gates per circuit to 3 primary inputs
+        ei = c["edge_index"]
+        rng = np.random.default_rng(900 + ci)
+        for hub, cnt in ((0, 200), (1, 90), (2, 40)):
+            gates = rng.choice(np.arange(200, c["x"].shape[0]), size=cnt, replace=False)
+            for gte in gates:
+                rows = np.nonzero(ei[:, 1] == gte)[0]
+                if rows.size and not (ei[rows, 0] == hub).any():
+                    ei[rows[0], 0] = hub
+    G = deepgate.circuits_to_batch(circuits, "cuda")
+    sd = O.synth_state_dict("mig", 41, layernorm=True)
+    code = G.gate.reshape(-1).long()
+    feat = torch.nn.functional.one_hot((code == 1).long(), 6).float()
+    gsrc = torch.Generator().manual_seed(5)
+    ws = torch.randn(G.x.size(0), 64, generator=gsrc).cuda()
+    wt = torch.randn(G.x.size(0), 64, generator=gsrc).cuda()
+    outdeg = torch.bincount(G.edge_index[0], minlength=code.numel())
+    assert int(outdeg.max()) >= 64, "the generator should produce heavy fan-out nodes"
+
+    def run(env):
+        for k in ("MGV_STRUCT_BWD", "MGV_STRUCT_CHUNK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, s_rounds=2, t_rounds=2, layernorm=True).cuda()
+        enc.load_state_dict({k[len("mig_struct_encoder."):]: v for k, v in sd.items() if k.startswith("mig_struct_encoder.")})
+        s, t = enc(feat, feat, G.edge_index)
+        ((s * ws).sum() + (t * wt).sum()).backward()
+        torch.cuda.synchronize()
+        return s.detach(), t.detach(), {k: p.grad.clone() for k, p in enc.named_parameters()}
+
+    s0, t0, g0 = run({"MGV_STRUCT_BWD": "mma"})
+    for env in ({}, {"MGV_STRUCT_CHUNK": "16"}):
+        s1, t1, g1 = run(env)
+        assert torch.equal(s0, s1) and torch.equal(t0, t1)            # same forward kernel
+        for k in g0:
+            assert rel(g1[k], g0[k]) < 1e-4, (env, k, rel(g1[k], g0[k]))
