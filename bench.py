@@ -287,9 +287,10 @@ def run_ours(args, w):
     prof = ops.profile_summary()
     ops.PROFILE = None
     launches = _native.lib().mgv_kernel_launches() - launches0
+    clocks = sampler.stop()                   # clocks are sampled over the device-resident timed region only: nvidia-smi polling
+    #                                           takes driver locks that the per-step synchronising end-to-end loop is sensitive to
     step_e2e(0)                               # untimed: back from the resident loop to the host-fed path
     ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop()
     if e2e_trace:
         for t in e2e_trace[-args.steps:]:
             print("e2e step: h2d issue %.2f  train_step host %.2f  loss.item() wait %.2f ms" % t, file=sys.stderr)
