@@ -45,8 +45,9 @@ LOSS_W = (1.0, 4.0, 4.0)      # stage-3 weights of the reference schedule (train
 def make_host_batch(w, rank, idx):
     import deepgate
     from deepgate import synth
+    # ranks draw different circuits of the SAME sizes (size-bucketed sampler): weak scaling without size skew between ranks
     circuits = synth.make_circuits(w["mix"], w["batch"], w["n_pi"], w["n_gates"],
-                                   cfg=w["cfg"] + 100 * rank + 10 * idx, window=w["window"])
+                                   cfg=w["cfg"] + 100 * rank + 10 * idx, window=w["window"], size_cfg=w["cfg"] + 10 * idx)
     return deepgate.circuits_to_batch(circuits)
 
 
@@ -374,6 +375,7 @@ def run_ours(args, w):
                        "gates_per_step_per_gpu": mean_stats["gates"] * w["rounds"], "sweep_rounds": w["rounds"],
                        "s_rounds": 4, "t_rounds": 4, "layernorm": True, "dim_hidden": 64, "parallelism": "dp%d" % world,
                        "step": "schedule build + forward + recon/prob/func losses + backward + allreduce + Adam",
+                       "ranks": "every rank draws its own circuits, with the same circuit sizes on all ranks (size-bucketed sampler)",
                        "setup": "one untimed pass over each distinct batch before the warm-up steps (allocator pools)",
                        "l2": "%d distinct batches rotated; per-batch working set (struct states %d MB) exceeds the 126 MB L2"
                              % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},

@@ -65,13 +65,16 @@ def make_circuit(kind, n_pi, n_gates, seed, window=None, n_pairs=64):
             "tt_pair_index": tt_pair_index, "tt_sim": tt_sim, "kind": kind}
 
 
-def make_circuits(kind, batch, n_pi, n_gates, cfg=0, window=None, n_pairs=64):
+def make_circuits(kind, batch, n_pi, n_gates, cfg=0, window=None, n_pairs=64, size_cfg=None):
     """``batch`` circuits; ``n_pi``/``n_gates`` may be ints or (lo, hi) ranges.
-    Seed of circuit i is 1000*cfg + i."""
+    Seed of circuit i is 1000*cfg + i.  ``size_cfg`` (default ``cfg``) seeds the SIZE draw
+    separately: data-parallel ranks pass the same ``size_cfg`` and different ``cfg`` to get size-balanced batches
+    (same circuit sizes, different circuits), the usual bucketed sampler of a DDP loader."""
     out = []
+    size_cfg = cfg if size_cfg is None else size_cfg
     for i in range(batch):
         seed = 1000 * cfg + i
-        r = np.random.default_rng(10_000_019 * (cfg + 1) + i)
+        r = np.random.default_rng(10_000_019 * (size_cfg + 1) + i)
         pi = n_pi if np.isscalar(n_pi) else int(r.integers(n_pi[0], n_pi[1] + 1))
         ng = n_gates if np.isscalar(n_gates) else int(r.integers(n_gates[0], n_gates[1] + 1))
         out.append(make_circuit(kind, pi, ng, seed, window=window, n_pairs=n_pairs))

@@ -47,8 +47,11 @@ class FlatGradAllReduce(object):
                 p.grad = torch.zeros_like(p)
         grads = [p.grad for p in self.params]
         self.flat = torch.cat([g.reshape(-1) for g in grads])
-        torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM)
-        self.flat.div_(world)
+        if torch.distributed.get_backend() == "nccl":
+            torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.AVG)      # the mean inside the collective
+        else:
+            torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM)
+            self.flat.div_(world)
         views, off = [], 0
         for g in grads:
             n = g.numel()
