@@ -71,7 +71,9 @@ def batch_stats(b, kind):
 
 
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 25 ms from before the warm-up until after the timed region (its start-up alone can take
+    longer than a short timed region); only the samples whose timestamps fall inside [mark_begin, mark_end] are used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -79,6 +81,7 @@ class ClockSampler(object):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         if os.environ.get("MGV_BENCH_NO_SAMPLER"):
@@ -90,9 +93,16 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        import datetime
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -102,13 +112,16 @@ class ClockSampler(object):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.t0 is not None and self.t1 is not None and not (self.t0 - 0.03 <= ts <= self.t1 + 0.03):
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
-            for nme, val in zip(names, f[3:7]):
+            for nme, val in zip(names, f[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         os.unlink(self.path)
@@ -266,10 +279,14 @@ def run_ours(args, w):
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if os.environ.get("MGV_BENCH_VERBOSE"):
+            print("rank %d: %s: %d steps, %.2f ms on the device clock" % (rank, fn.__name__, k, float(ms.item())), file=sys.stderr)
         if world > 1:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local)
+    sampler.start()
     # setup (not a warm-up step): one pass over every DISTINCT batch so that the caching allocator owns blocks for
     # each batch's sizes -- a first-seen batch inside the timed region costs cudaMalloc calls of several hundred MB
     # (measured: 7.8 instead of 4.6 ms / step with --warmup 3 and 4 distinct batches)
@@ -279,11 +296,11 @@ def run_ours(args, w):
     for i in range(args.warmup):
         step_resident(i)
         step_e2e(i)
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = _native.lib().mgv_kernel_launches()
     ops.PROFILE = {}
+    sampler.mark_begin()
     ms = timed(step_resident, args.steps)
+    sampler.mark_end()
     torch.cuda.synchronize(dev)
     prof = ops.profile_summary()
     ops.PROFILE = None
