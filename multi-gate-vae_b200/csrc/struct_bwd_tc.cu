@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
 
     const uint32_t bar_w = sbase + S_BAR, bar_a_full = bar_w + 8, bar_t_full = bar_w + 16, bar_g_empty = bar_w + 24;
     const uint32_t bar_acc_full = bar_w + 32, bar_out_full = bar_w + 40, bar_h_read = bar_w + 48, bar_dg_full = bar_w + 56;
+    const uint32_t bar_dg_stored = bar_w + 64;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + S_TMEM);
     float* s_ln = reinterpret_cast<float*>(sgen + S_LN);
     unsigned* s_amax = reinterpret_cast<unsigned*>(sgen + S_AMAX);
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         tc::mbar_init(bar_out_full, 1);
         tc::mbar_init(bar_h_read, EPI_WARPS * 32);      // the epilogue has copied the tile's h rows: the tile may be overwritten
         tc::mbar_init(bar_dg_full, EPI_WARPS * 32);     // d-gate planes are in tensor memory
+        tc::mbar_init(bar_dg_stored, EPI_WARPS * 32);   // ... and have been copied to HBM: T_ACC may be overwritten
         tc::fence_barrier_init();
         tc::mbar_expect_tx(bar_w, IMG_W);
 #pragma unroll 1
@@ -364,7 +366,10 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 }
                 // the next tile's recompute runs behind the data-gradient MMAs (in issue order) while the epilogue stores
                 // this tile's outputs: it only writes T_ACC, which the epilogue is done with
-                if (tile + 1 < tile_end) issue_recompute(ph ^ 1u);
+                if (tile + 1 < tile_end) {
+                    tc::mbar_wait_sleep(bar_dg_stored, ph, 32);      // the epilogue re-reads the planes for their HBM copy
+                    issue_recompute(ph ^ 1u);
+                }
                 PTRACE(3);
             }
         }
@@ -560,11 +565,6 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
 #pragma unroll
                     for (int e = 0; e < 8; ++e) tc::split2(v[2 * e] * scale, v[2 * e + 1] * scale, pk[e], pk[8 + e]);
                     tc::tmem_st16(t_acc + 16 * s, pk);
-                    uint8_t* hb = dg + (size_t)(2 * s) * 1024;
-                    tc::stg_v4_hint(hb, make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
-                    tc::stg_v4_hint(hb + 1024, make_uint4(pk[4], pk[5], pk[6], pk[7]), pol_stream);
-                    tc::stg_v4_hint(hb + 65536, make_uint4(pk[8], pk[9], pk[10], pk[11]), pol_stream);
-                    tc::stg_v4_hint(hb + 65536 + 1024, make_uint4(pk[12], pk[13], pk[14], pk[15]), pol_stream);
                 }
                 // accumulator init of the data-gradient MMAs: d agg = 0, d part = scale * g z
                 if (!p.first) {
@@ -586,6 +586,32 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             tc::tmem_st_wait();
             tc::fence_before_sync();
             tc::mbar_arrive(bar_dg_full);
+            // ---- pass 3b, while the data-gradient MMAs run: the planes (re-read from tensor memory, which the MMAs only
+            //      read) -> HBM [plane][64-node half][8-gate chunk (32)][node row (64)][16 B] for the weight-gradient kernel
+            {
+                uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * DG_TILE_BYTES + (row >> 6) * 32768 + (row & 63) * 16;
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b) {          // gate block b (r, z, gi_n, gh_n): this warp group's two K steps, one wait
+                    const int s0 = 4 * b + 2 * wg;
+                    float v0[16], v1[16];
+                    tc::tmem_ld16(t_acc + 16 * s0, v0);
+                    tc::tmem_ld16(t_acc + 16 * (s0 + 1), v1);
+                    tc::tmem_ld_wait();
+                    const uint32_t* pk = reinterpret_cast<const uint32_t*>(v0);
+                    const uint32_t* qk = reinterpret_cast<const uint32_t*>(v1);
+                    uint8_t* hb = dg + (size_t)(2 * s0) * 1024;
+                    tc::stg_v4_hint(hb, make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
+                    tc::stg_v4_hint(hb + 1024, make_uint4(pk[4], pk[5], pk[6], pk[7]), pol_stream);
+                    tc::stg_v4_hint(hb + 2048, make_uint4(qk[0], qk[1], qk[2], qk[3]), pol_stream);
+                    tc::stg_v4_hint(hb + 3072, make_uint4(qk[4], qk[5], qk[6], qk[7]), pol_stream);
+                    tc::stg_v4_hint(hb + 65536, make_uint4(pk[8], pk[9], pk[10], pk[11]), pol_stream);
+                    tc::stg_v4_hint(hb + 65536 + 1024, make_uint4(pk[12], pk[13], pk[14], pk[15]), pol_stream);
+                    tc::stg_v4_hint(hb + 65536 + 2048, make_uint4(qk[8], qk[9], qk[10], qk[11]), pol_stream);
+                    tc::stg_v4_hint(hb + 65536 + 3072, make_uint4(qk[12], qk[13], qk[14], qk[15]), pol_stream);
+                }
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(bar_dg_stored);
             // ---- data gradients of step k-1
             if (!p.first) {
                 tc::mbar_wait_warp(bar_out_full, ph, lane, 32);
