@@ -42,7 +42,7 @@ constexpr int EPI_WARPS = 8, GATHER_WARPS = 8;              // epilogue: 2 warps
 constexpr int THREADS = (EPI_WARPS + GATHER_WARPS + 1) * 32; // + the MMA / bulk-copy warp: 17 warps, 5 on one scheduler -> 96 registers
 constexpr int LDGS = 68;                                   // d state staging row stride (floats)
 constexpr uint32_t DG_TILE_BYTES = 131072;                 // [hi | lo][64-node half][8-gate chunk (32)][node row (64)][16 B]: no-swizzle core matrices
-constexpr int CHUNK_TILES_DEFAULT = 1024;                  // tiles per encoder per kernel pair (MGV_STRUCT_CHUNK overrides: tuning)
+constexpr int CHUNK_TILES_DEFAULT = 2048;                  // tiles per encoder per kernel pair (MGV_STRUCT_CHUNK overrides: tuning)
 
 // ---- shared memory of the pointwise kernel (after the weight image and the operand tile, struct_layout.cuh)
 constexpr uint32_t S_G = A_X_LO + 4096;                    // d state_k staging, fp32 [128][LDGS]
