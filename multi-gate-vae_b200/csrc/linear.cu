@@ -16,8 +16,7 @@ template <int TO, int TI, int LR>
 __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, long long N,
                                                            int I, int O, int IP, int OP, float* __restrict__ partial) {
     extern __shared__ __align__(16) float sm[];
-    float* Xs = sm;                      // [LR][IP]
-    float* Gs = sm + LR * IP;            // [LR][OP]
+    const int stage_floats = LR * (IP + OP);           // two stages: [LR][IP] rows of x, then [LR][OP] rows of gy
     const int tid = threadIdx.x, nt = blockDim.x;
     const int ntx = IP / TI, tx = tid % ntx, ty = tid / ntx;
     const bool active = ty < OP / TO;
@@ -32,14 +31,25 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restri
     const long long trips = (N + LR - 1) / LR;
     const long long t0 = trips * blockIdx.x / gridDim.x, t1 = trips * (blockIdx.x + 1) / gridDim.x;
     const bool vec = (I == IP) && (O == OP) && (I % 4 == 0) && (O % 4 == 0);
-    for (long long t = t0; t < t1; ++t) {
+    // stage the rows of trip t (asynchronous 16-byte copies when the rows are dense and aligned; rows past N read 0 bytes)
+    auto stage = [&](long long t, int buf) {
+        float* Xs = sm + buf * stage_floats;
+        float* Gs = Xs + LR * IP;
         const long long r0 = t * LR;
         const int rows = (int)((N - r0 < LR) ? (N - r0) : LR);
-        if (vec) {      // the staged rows are one contiguous block of x / gy
-            const float4* xs = reinterpret_cast<const float4*>(x + r0 * I);
-            const float4* gs = reinterpret_cast<const float4*>(gy + r0 * O);
-            for (int q = tid; q < LR * I / 4; q += nt) reinterpret_cast<float4*>(Xs)[q] = (q < rows * I / 4) ? xs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = tid; q < LR * O / 4; q += nt) reinterpret_cast<float4*>(Gs)[q] = (q < rows * O / 4) ? gs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec) {
+            const float* xs = x + r0 * I;
+            const float* gs = gy + r0 * O;
+            for (int q = tid; q < LR * I / 4; q += nt) {
+                const unsigned src = (q < rows * I / 4) ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(Xs + 4 * q)),
+                             "l"(src ? xs + 4 * q : x), "r"(src) : "memory");
+            }
+            for (int q = tid; q < LR * O / 4; q += nt) {
+                const unsigned src = (q < rows * O / 4) ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(Gs + 4 * q)),
+                             "l"(src ? gs + 4 * q : gy), "r"(src) : "memory");
+            }
         } else {
             for (int q = tid; q < LR * IP; q += nt) {
                 const int r = q / IP, c = q % IP;
@@ -50,15 +60,29 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restri
                 Gs[q] = (r < rows && c < O) ? gy[(r0 + r) * O + c] : 0.f;
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (t0 < t1) stage(t0, 0);
+    for (long long t = t0; t < t1; ++t) {
+        const int buf = (int)((t - t0) & 1);
+        if (t + 1 < t1) {
+            stage(t + 1, buf ^ 1);                     // the other stage was released by the barrier at the end of the last trip
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncthreads();
+        const float* Xs = sm + buf * stage_floats;
+        const float* Gs = Xs + LR * IP;
         if (active) {
 #pragma unroll 4
             for (int r = 0; r < LR; ++r) {
                 float g[TO], xv[TI];
 #pragma unroll
                 for (int a = 0; a < TO; a += 4) *reinterpret_cast<float4*>(&g[a]) = *reinterpret_cast<const float4*>(Gs + r * OP + TO * ty + a);
+                // x columns of this thread: 4 tx .. 4 tx + 3 and (8-wide tiles) IP / 2 + 4 tx ..: a 16-byte lane stride
 #pragma unroll
-                for (int b = 0; b < TI; b += 4) *reinterpret_cast<float4*>(&xv[b]) = *reinterpret_cast<const float4*>(Xs + r * IP + TI * tx + b);
+                for (int b = 0; b < TI; b += 4) *reinterpret_cast<float4*>(&xv[b]) = *reinterpret_cast<const float4*>(Xs + r * IP + (b / 4) * (IP / 2) + 4 * tx);
 #pragma unroll
                 for (int a = 0; a < TO; ++a) {
                     bsum[a] += g[a];
@@ -77,7 +101,7 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restri
         if (o < O) {
 #pragma unroll
             for (int b = 0; b < TI; ++b) {
-                const int i = TI * tx + b;
+                const int i = (b / 4) * (IP / 2) + 4 * tx + (b & 3);
                 if (i < I) P[(size_t)o * I + i] = acc[a][b];
             }
             if (tx == 0) P[(size_t)O * I + o] = bsum[a];
@@ -122,7 +146,7 @@ int launch(int nblk, cudaStream_t st, const float* x, const float* gy, long long
     const int IP = (I + TI - 1) / TI * TI, OP = (O + TO - 1) / TO * TO;
     int nt = (IP / TI) * (OP / TO);
     nt = nt < 256 ? 256 : (nt + 31) / 32 * 32;          // idle compute threads still help stage the rows
-    const size_t smem = (size_t)LR * (IP + OP) * sizeof(float);
+    const size_t smem = 2 * (size_t)LR * (IP + OP) * sizeof(float);
     MGV_CUDA(cudaFuncSetAttribute((const void*)linear_wgrad_kernel<TO, TI, LR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     linear_wgrad_kernel<TO, TI, LR><<<nblk, nt, smem, st>>>(x, gy, N, I, O, IP, OP, partial);
     return MGV_OK;
