@@ -777,15 +777,30 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
                         const int off = (lane < 16) ? 4 * lane : 4 * (lane - 16);
                         float A = 0.f;
                         float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int q = beg; q < end; ++q) {
-                            const int j = p.in_src[q];
-                            const float* rowp = (lane < 16) ? (p.hs + (size_t)j * D) : (hf_cur + (size_t)j * D);
-                            const float4 xj = mgv_ld4(rowp + off);
-                            const float dal = mgv_warp_sum(mgv_dot4(dxb4, xj)) + dS;
-                            const float a = p.alpha[q];
-                            A = fmaf(a, dal, A);
-                            mgv_fma4(v4, a * dal, xj);
-                            if (lane == 0) p.dscore[q] = dal;
+                        for (int q0 = beg; q0 < end; q0 += 4) {           // 4 in-edges per trip: ids, then rows, in flight together
+                            const int cnt = min(4, end - q0);
+                            float a[4];
+                            float4 xj[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                a[i] = 0.f;
+                                xj[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (i < cnt) {
+                                    const int j = p.in_src[q0 + i];
+                                    a[i] = p.alpha[q0 + i];
+                                    const float* rowp = (lane < 16) ? (p.hs + (size_t)j * D) : (hf_cur + (size_t)j * D);
+                                    xj[i] = mgv_ld4(rowp + off);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                if (i < cnt) {
+                                    const float dal = mgv_warp_sum(mgv_dot4(dxb4, xj[i])) + dS;
+                                    A = fmaf(a[i], dal, A);
+                                    mgv_fma4(v4, a[i] * dal, xj[i]);
+                                    if (lane == 0) p.dscore[q0 + i] = dal;
+                                }
+                            }
                         }
                         __syncwarp();
                         for (int q = beg + lane; q < end; q += 32) p.dscore[q] = p.alpha[q] * (p.dscore[q] - A);
