@@ -17,6 +17,7 @@
 //   warp  12    one thread issues the MMAs of a tile once the tile is full; completion frees the tile (tcgen05.commit)
 //   warps 0-3   epilogue, thread = node = TMEM lane: tensor memory -> GRU gates -> LayerNorm -> state_k
 //               (two accumulator buffers: the epilogue of tile t overlaps the gather and MMAs of tile t+1)
+#include <stdlib.h>
 #include "struct_layout.cuh"
 
 namespace {
@@ -472,6 +473,8 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         fill_ones_kernel<<<(unsigned)((slot + 255) / 256), 256, 0, st>>>(states + e * enc_stride, slot);
         mgv_count_launches(1);
     }
+    const char* ts_env = getenv("MGV_TRACE_STEP");          // dev tool: which step's kernel records the phase trace
+    const int trace_step = (ts_env && atoi(ts_env) > 0) ? atoi(ts_env) : steps;
     for (int k = 1; k <= steps; ++k) {
         const int dir = (k & 1) ? 0 : 1;
         StepTC p{};
@@ -489,7 +492,7 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         // tile buffer [enc][step][tile][A_TILE_BYTES] (fp16 hi/lo planes: not written in bf16 mode, whose backward re-gathers)
         p.tiles = (tiles && precision == 0) ? (uint8_t*)tiles + (size_t)(k - 1) * ntiles * A_TILE_BYTES : nullptr;
         p.tiles_enc_stride = (size_t)steps * ntiles * A_TILE_BYTES;
-        p.trace = (k == steps) ? g_trace : nullptr;
+        p.trace = (k == trace_step) ? g_trace : nullptr;
         if (precision == 1) struct_fwd_tc_kernel<true><<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
         else struct_fwd_tc_kernel<false><<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
         mgv_count_launches(1);
