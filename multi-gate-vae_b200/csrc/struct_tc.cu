@@ -18,6 +18,7 @@
 //   warps 0-3   epilogue, thread = node = TMEM lane: tensor memory -> GRU gates -> LayerNorm -> state_k
 //               (two accumulator buffers: the epilogue of tile t overlaps the gather and MMAs of tile t+1)
 #include <stdlib.h>
+#include <string.h>
 #include "struct_layout.cuh"
 
 namespace {
@@ -29,8 +30,6 @@ constexpr uint32_t S_BAR = S_EX + 2048;             // 7 mbarriers
 constexpr uint32_t S_TMEM = S_BAR + 64;
 constexpr uint32_t F_SMEM = S_TMEM + 64 + 1024;     // + alignment slack
 
-constexpr int EPI_WARPS = 4, GATHER_WARPS = 8;
-constexpr int THREADS = (EPI_WARPS + GATHER_WARPS + 1) * 32;   // + the MMA warp  (13 warps: register pools are per 4 warps -> 128 regs/thread)
 
 struct StepTC {
     int N, feat, layernorm;
@@ -133,8 +132,11 @@ __global__ void struct_image_kernel(const float* __restrict__ pack, uint8_t* __r
 }
 
 // ======================================================================================= forward step
-template <bool LOWP>
-__global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC p) {
+// RPL = rows per gather lane (4 -> 8 gather warps, 2 -> 16: twice the loads in flight), EW = epilogue warps (4: one thread
+// per node; 8: two threads per node, 32 units each, LayerNorm row sums exchanged through shared memory).
+template <bool LOWP, int RPL, int EW>
+__global__ void __launch_bounds__((EW + 128 / (4 * RPL) + 1) * 32, 1) struct_fwd_tc_kernel(const StepTC p) {
+    constexpr int EPI_WARPS = EW, GATHER_WARPS = 128 / (4 * RPL), UPT = 64 / (EW / 4);     // units per epilogue thread
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
@@ -182,13 +184,13 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + GATHER_WARPS) {
         // ===================================================================== gather
-        // lane = (row group rg, 16-byte chunk c): 8 lanes cover one 256-byte state row; a lane owns 4 rows of the tile.
+        // lane = (row group rg, 16-byte chunk c): 8 lanes cover one 256-byte state row; a lane owns RPL rows of the tile.
         const int gw = warp - EPI_WARPS, rg = lane >> 3, c = lane & 7;
         const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
-        int4 dn[4];                                   // row descriptors of the NEXT tile, loaded one tile ahead
+        int4 dn[RPL];                                   // row descriptors of the NEXT tile, loaded one tile ahead
 #pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-            const int r = tile_beg * TM + gw * 16 + ps * 4 + rg;
+        for (int ps = 0; ps < RPL; ++ps) {
+            const int r = tile_beg * TM + gw * (4 * RPL) + ps * 4 + rg;
             dn[ps] = (tile_beg < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
         }
         int it = 0;
@@ -197,14 +199,14 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             uint8_t* gt = p.tiles ? p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)tile * A_TILE_BYTES : nullptr;
             // ---- loads into registers (overlap the previous tile's MMAs): own-state rows, the lane's feature element,
             //      first neighbour rows, second neighbour ids, next tile's descriptors
-            int node[4], beg[4], cnt[4], jn[4];
+            int node[RPL], beg[RPL], cnt[RPL], jn[RPL];
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) { node[ps] = dn[ps].x; beg[ps] = dn[ps].y; cnt[ps] = dn[ps].z; jn[ps] = dn[ps].w; }
-            float4 ha[4], hb[4], va[4], vb[4];
-            float xe[4];
+            for (int ps = 0; ps < RPL; ++ps) { node[ps] = dn[ps].x; beg[ps] = dn[ps].y; cnt[ps] = dn[ps].z; jn[ps] = dn[ps].w; }
+            float4 ha[RPL], hb[RPL], va[RPL], vb[RPL];
+            float xe[RPL];
             int maxc = 0;
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
+            for (int ps = 0; ps < RPL; ++ps) {
                 ha[ps] = make_float4(0.f, 0.f, 0.f, 0.f); hb[ps] = ha[ps]; va[ps] = ha[ps]; vb[ps] = ha[ps];
                 xe[ps] = 0.f;
                 maxc = max(maxc, cnt[ps]);
@@ -220,8 +222,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                 if (cnt[ps] > 1) jn[ps] = p.idx[beg[ps] + 1] & NODE_MASK;
             }
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int r = (tile + 1) * TM + gw * 16 + ps * 4 + rg;
+            for (int ps = 0; ps < RPL; ++ps) {
+                const int r = (tile + 1) * TM + gw * (4 * RPL) + ps * 4 + rg;
                 dn[ps] = (tile + 1 < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
             }
             if (warp == EPI_WARPS && lane == 0) TRACE(1);
@@ -229,8 +231,8 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             if (warp == EPI_WARPS && lane == 0) TRACE(2);
             // ---- own state rows and the [x deg 1] block
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int row = gw * 16 + ps * 4 + rg;
+            for (int ps = 0; ps < RPL; ++ps) {
+                const int row = gw * (4 * RPL) + ps * 4 + rg;
                 const float h8[8] = {ha[ps].x, ha[ps].y, ha[ps].z, ha[ps].w, hb[ps].x, hb[ps].y, hb[ps].z, hb[ps].w};
                 split_store_sw128<LOWP>(sbase + A_H_HI, sbase + A_H_LO, row, c, h8, gt, A_H_HI - A_AGG_HI, A_H_LO - A_AGG_HI);
                 float xv[8];
@@ -256,21 +258,21 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             if (warp == EPI_WARPS && lane == 0) TRACE(3);
             // ---- neighbour sums: one neighbour of each of the lane's 4 rows per trip (8 x 16-byte loads in flight),
             //      next trip's neighbour ids prefetched
-            float acc[4][8];
+            float acc[RPL][8];
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
+            for (int ps = 0; ps < RPL; ++ps) {
                 acc[ps][0] = va[ps].x; acc[ps][1] = va[ps].y; acc[ps][2] = va[ps].z; acc[ps][3] = va[ps].w;
                 acc[ps][4] = vb[ps].x; acc[ps][5] = vb[ps].y; acc[ps][6] = vb[ps].z; acc[ps][7] = vb[ps].w;
             }
             for (int sl = 1; sl < maxc; ++sl) {
-                int j[4];
+                int j[RPL];
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps) {
+                for (int ps = 0; ps < RPL; ++ps) {
                     j[ps] = jn[ps];
                     if (sl + 1 < cnt[ps]) jn[ps] = p.idx[beg[ps] + sl + 1] & NODE_MASK;
                 }
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps) {
+                for (int ps = 0; ps < RPL; ++ps) {
                     va[ps] = make_float4(0.f, 0.f, 0.f, 0.f); vb[ps] = va[ps];
                     if (sl < cnt[ps]) {
                         va[ps] = mgv_ld4(prev + (size_t)j[ps] * D + c * 8);
@@ -278,14 +280,14 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                     }
                 }
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps) {
+                for (int ps = 0; ps < RPL; ++ps) {
                     acc[ps][0] += va[ps].x; acc[ps][1] += va[ps].y; acc[ps][2] += va[ps].z; acc[ps][3] += va[ps].w;
                     acc[ps][4] += vb[ps].x; acc[ps][5] += vb[ps].y; acc[ps][6] += vb[ps].z; acc[ps][7] += vb[ps].w;
                 }
             }
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps)
-                split_store_sw128<LOWP>(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * 16 + ps * 4 + rg, c, acc[ps], gt, 0u, A_AGG_LO - A_AGG_HI);
+            for (int ps = 0; ps < RPL; ++ps)
+                split_store_sw128<LOWP>(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * (4 * RPL) + ps * 4 + rg, c, acc[ps], gt, 0u, A_AGG_LO - A_AGG_HI);
             if (warp == EPI_WARPS && lane == 0) TRACE(4);
             tc::fence_async_smem();
             tc::mbar_arrive(bar_a_full);
@@ -327,32 +329,34 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             }
         }
     } else if (warp < EPI_WARPS) {
-        // ===================================================================== epilogue: thread = tile row = TMEM lane
+        // ===================================================================== epilogue: EW / 4 threads per tile row = TMEM lane
+        // Warps q, 4 + q, .. own lanes 32 q .. 32 q + 31; warp group wg = warp / 4 handles units UPT wg .. of its row.
         // Gates are read 4 units at a time (r, z, gi_n, gh_n -> 16 registers) with the next chunk's tensor-memory loads
         // in flight while the current chunk is computed.
-        const int row = warp * 32 + lane;
+        const int wg = warp >> 2, row = (warp & 3) * 32 + lane, u0 = UPT * wg;
+        float* s_ex = reinterpret_cast<float*>(sgen + S_EX);          // [2 quantities][2 warp groups][128 rows]
         int it = 0;
         for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
             const int b = it & 1;
             const bool valid = tile * TM + row < p.N;
             const int node = valid ? p.order[tile * TM + row] : 0;
-            float h[D];
+            float h[UPT];
             if (valid) {
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) ldg8(prev + (size_t)node * D + 8 * ch, *reinterpret_cast<float(*)[8]>(&h[8 * ch]));
+                for (int ch = 0; ch < UPT / 8; ++ch) ldg8(prev + (size_t)node * D + u0 + 8 * ch, *reinterpret_cast<float(*)[8]>(&h[8 * ch]));
             } else {
 #pragma unroll
-                for (int e = 0; e < D; ++e) h[e] = 0.f;
+                for (int e = 0; e < UPT; ++e) h[e] = 0.f;
             }
             if (tid == 0) TRACE(8);
             tc::mbar_wait(bar_acc_full + 8 * b, (uint32_t)((it >> 1) & 1));
             tc::fence_after_sync();
             if (tid == 0) TRACE(9);
-            const uint32_t ta = tmem + (uint32_t)b * 256u + ((uint32_t)(warp * 32) << 16);
+            const uint32_t ta = tmem + (uint32_t)b * 256u + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)u0;
             float g0[16], g1[16];
             tmem_ld4x4(ta, g0);
 #pragma unroll
-            for (int ch = 0; ch < 16; ch += 2) {
+            for (int ch = 0; ch < UPT / 4; ch += 2) {
                 tc::tmem_ld_wait();
                 tmem_ld4x4(ta + 4 * (ch + 1), g1);
 #pragma unroll
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
                     h[4 * ch + e] = fmaf(z, h[4 * ch + e] - n, n);          // (1 - z) n + z h
                 }
                 tc::tmem_ld_wait();
-                if (ch + 2 < 16) tmem_ld4x4(ta + 4 * (ch + 2), g0);
+                if (ch + 2 < UPT / 4) tmem_ld4x4(ta + 4 * (ch + 2), g0);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     float r, z, n, hnb;
@@ -376,26 +380,38 @@ __global__ void __launch_bounds__(THREADS, 1) struct_fwd_tc_kernel(const StepTC 
             if (p.layernorm) {
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                for (int e = 0; e < D; e += 4) { s0 += h[e]; s1 += h[e + 1]; s2 += h[e + 2]; s3 += h[e + 3]; }
-                const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / D);
+                for (int e = 0; e < UPT; e += 4) { s0 += h[e]; s1 += h[e + 1]; s2 += h[e + 2]; s3 += h[e + 3]; }
+                float tot = (s0 + s1) + (s2 + s3);
+                if (EW == 8) {
+                    s_ex[wg * TM + row] = tot;
+                    tc::named_bar_sync(1, EW * 32);
+                    tot = s_ex[row] + s_ex[TM + row];
+                }
+                const float mean = tot * (1.0f / D);
                 s0 = s1 = s2 = s3 = 0.f;
 #pragma unroll
-                for (int e = 0; e < D; e += 4) {
+                for (int e = 0; e < UPT; e += 4) {
                     h[e] -= mean; h[e + 1] -= mean; h[e + 2] -= mean; h[e + 3] -= mean;
                     s0 = fmaf(h[e], h[e], s0); s1 = fmaf(h[e + 1], h[e + 1], s1);
                     s2 = fmaf(h[e + 2], h[e + 2], s2); s3 = fmaf(h[e + 3], h[e + 3], s3);
                 }
-                const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / D) + LN_EPS);
+                tot = (s0 + s1) + (s2 + s3);
+                if (EW == 8) {
+                    s_ex[(2 + wg) * TM + row] = tot;
+                    tc::named_bar_sync(1, EW * 32);
+                    tot = s_ex[2 * TM + row] + s_ex[3 * TM + row];
+                }
+                const float rstd = rsqrtf(tot * (1.0f / D) + LN_EPS);
 #pragma unroll
-                for (int e = 0; e < D; e += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(s_ln + e), b4 = *reinterpret_cast<const float4*>(s_ln + D + e);
+                for (int e = 0; e < UPT; e += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(s_ln + u0 + e), b4 = *reinterpret_cast<const float4*>(s_ln + D + u0 + e);
                     h[e] = fmaf(h[e] * rstd, w4.x, b4.x); h[e + 1] = fmaf(h[e + 1] * rstd, w4.y, b4.y);
                     h[e + 2] = fmaf(h[e + 2] * rstd, w4.z, b4.z); h[e + 3] = fmaf(h[e + 3] * rstd, w4.w, b4.w);
                 }
             }
             if (valid) {
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) stg8(next + (size_t)node * D + 8 * ch, *reinterpret_cast<float(*)[8]>(&h[8 * ch]));
+                for (int ch = 0; ch < UPT / 8; ++ch) stg8(next + (size_t)node * D + u0 + 8 * ch, *reinterpret_cast<float(*)[8]>(&h[8 * ch]));
             }
             if (tid == 0) TRACE(11);
         }
@@ -460,8 +476,13 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
     const int steps = 2 * rounds;
     const size_t slot = (size_t)N * D;
     const size_t enc_stride = (size_t)(steps + 1) * slot;
-    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+    // launch shape: 16 gather warps x 2 rows per lane + 8 epilogue warps (25 warps, 72 registers), or the 13-warp shape
+    // (8 gather warps x 4 rows, 4 epilogue warps, 128 registers) with MGV_STRUCT_FWD=v1 (A/B) and in bf16 mode
+    const char* fwd_env = getenv("MGV_STRUCT_FWD");
+    const bool wide = precision == 0 && !(fwd_env && !strcmp(fwd_env, "v1"));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<false, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<false, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
     int dev = 0, sms = 0;
     MGV_CUDA(cudaGetDevice(&dev));
     MGV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -493,8 +514,9 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         p.tiles = (tiles && precision == 0) ? (uint8_t*)tiles + (size_t)(k - 1) * ntiles * A_TILE_BYTES : nullptr;
         p.tiles_enc_stride = (size_t)steps * ntiles * A_TILE_BYTES;
         p.trace = (k == trace_step) ? g_trace : nullptr;
-        if (precision == 1) struct_fwd_tc_kernel<true><<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
-        else struct_fwd_tc_kernel<false><<<dim3(gx, num_enc), THREADS, F_SMEM, st>>>(p);
+        if (precision == 1) struct_fwd_tc_kernel<true, 4, 4><<<dim3(gx, num_enc), 13 * 32, F_SMEM, st>>>(p);
+        else if (wide) struct_fwd_tc_kernel<false, 2, 8><<<dim3(gx, num_enc), 25 * 32, F_SMEM, st>>>(p);
+        else struct_fwd_tc_kernel<false, 4, 4><<<dim3(gx, num_enc), 13 * 32, F_SMEM, st>>>(p);
         mgv_count_launches(1);
     }
     return mgv_check_cuda(cudaGetLastError(), "mgv_struct_encoder_fwd");
