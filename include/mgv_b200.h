@@ -38,6 +38,7 @@ extern "C" {
 #define MGV_CODE_SHIFT 28        /* out_pack = dst | (code(dst) << 28)                          */
 #define MGV_MAX_FEAT 8           /* struct encoder: dim_feature <= 8 (config.py:14 default 6)   */
 #define MGV_TILE_ROWS 128        /* nodes per tensor-core tile (UMMA M)                          */
+#define MGV_TILE_WAVE_COST 128   /* per dependent neighbour wave (= largest degree of the tile) of the tile cost model    */
 #define MGV_TILE_FIXED_COST 2048 /* per-tile fixed cost, in node-row reads, of the tile cost model */
 
 /* Floats per gate-code weight block of the level sweep (see mgv_sweep_pack layout below). */
@@ -100,7 +101,7 @@ int mgv_build_level_lists(const int32_t* level, const int32_t* code, int32_t N, 
 /* Degree order of one CSR direction, for the tensor-core tiles of the struct encoder: order[N] = node ids sorted
  * by DESCENDING degree (degrees >= 255 tie), ascending id inside a degree, so the 128 rows of a tile have
  * near-equal fan-in/out and the gather lanes of a warp run the same trip count.  tile_cost[ntiles + 1], ntiles =
- * ceil(N / MGV_TILE_ROWS): exclusive prefix of (MGV_TILE_FIXED_COST + rows + neighbours) per tile; persistent CTAs
+ * ceil(N / MGV_TILE_ROWS): exclusive prefix of (MGV_TILE_FIXED_COST + rows + neighbours + MGV_TILE_WAVE_COST * largest degree) per tile; persistent CTAs
  * take contiguous tile ranges of equal cost.
  * gdesc[N][4] (16-byte aligned): {node, first CSR slot, degree, first neighbour id} per row of the order.
  */

@@ -346,20 +346,29 @@ __global__ void gather_desc_kernel(const int32_t* __restrict__ ptr, const int32_
     const int b = ptr[v], c = ptr[v + 1] - b;
     gdesc[r] = make_int4(v, b, c, c > 0 ? (idx[b] & ((1 << MGV_CODE_SHIFT) - 1)) : 0);
 }
-// cost[t] = MGV_TILE_FIXED_COST + rows + neighbours of the 128-row tile t of the degree order (one warp per tile)
+// cost[t] = MGV_TILE_FIXED_COST + rows + neighbours + MGV_TILE_WAVE_COST * (largest degree) of the 128-row tile t of the degree
+// order (one warp per tile): a gather lane walks its rows' neighbours in dependent load waves, so a tile's time grows with
+// its LARGEST degree, not only with its neighbour count (measured: 450 cycles per wave, 9 500 for a degree <= 2 tile)
 __global__ void tile_cost_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ order, int n, int ntiles,
                                  uint32_t* __restrict__ cost) {
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (t > ntiles) return;
     uint32_t c = 0;
     if (t < ntiles) {
+        uint32_t dmax = 0;
         for (int r = t * MGV_TILE_ROWS + lane; r < n && r < (t + 1) * MGV_TILE_ROWS; r += 32) {
             const int v = order[r];
-            c += 1u + (uint32_t)(ptr[v + 1] - ptr[v]);
+            const uint32_t d = (uint32_t)(ptr[v + 1] - ptr[v]);
+            c += 1u + d;
+            dmax = d > dmax ? d : dmax;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        c += MGV_TILE_FIXED_COST;
+        for (int o = 16; o > 0; o >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            const uint32_t m = __shfl_xor_sync(0xffffffffu, dmax, o);
+            dmax = m > dmax ? m : dmax;
+        }
+        c += MGV_TILE_FIXED_COST + MGV_TILE_WAVE_COST * (dmax < 4096u ? dmax : 4096u);
     }
     if (lane == 0) cost[t] = c;                      // cost[ntiles] = 0: the scan turns it into the total
 }
