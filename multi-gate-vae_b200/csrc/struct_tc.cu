@@ -68,15 +68,15 @@ __device__ __forceinline__ void tmem_ld4x4(uint32_t taddr, float (&v)[16]) {
 // (a row's 8 chunks are one 128-byte line, so a warp's 4 rows write 4 full lines per plane).
 template <bool LOWP>
 __device__ __forceinline__ void split_store_sw128(uint32_t hi_base, uint32_t lo_base, int row, int c, const float (&v)[8],
-                                                  uint8_t* gt = nullptr, uint32_t g_hi = 0, uint32_t g_lo = 0) {
+                                                  uint8_t* gt = nullptr, uint32_t g_hi = 0, uint32_t g_lo = 0, uint64_t pol = 0) {
     uint4 hi, lo;
     tc::split8p<LOWP>(v, hi, lo);
     const uint32_t off = tc::sw128_off(row, c);
     tc::st_shared_v4(hi_base + off, hi);
     if (!LOWP) tc::st_shared_v4(lo_base + off, lo);
-    if (gt) {
-        *reinterpret_cast<uint4*>(gt + g_hi + off) = hi;
-        *reinterpret_cast<uint4*>(gt + g_lo + off) = lo;
+    if (gt) {       // read once, much later, by the backward: do not let it displace the state rows in L2
+        tc::stg_v4_hint(gt + g_hi + off, hi, pol);
+        tc::stg_v4_hint(gt + g_lo + off, lo, pol);
     }
 }
 
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__((EW + 128 / (4 * RPL) + 1) * 32, 1) struct_fwd
         // lane = (row group rg, 16-byte chunk c): 8 lanes cover one 256-byte state row; a lane owns RPL rows of the tile.
         const int gw = warp - EPI_WARPS, rg = lane >> 3, c = lane & 7;
         const int4* gdesc = reinterpret_cast<const int4*>(p.gdesc);
+        const uint64_t pol_stream = tc::l2_policy_evict_first();
         int4 dn[RPL];                                   // row descriptors of the NEXT tile, loaded one tile ahead
 #pragma unroll
         for (int ps = 0; ps < RPL; ++ps) {
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__((EW + 128 / (4 * RPL) + 1) * 32, 1) struct_fwd
             for (int ps = 0; ps < RPL; ++ps) {
                 const int row = gw * (4 * RPL) + ps * 4 + rg;
                 const float h8[8] = {ha[ps].x, ha[ps].y, ha[ps].z, ha[ps].w, hb[ps].x, hb[ps].y, hb[ps].z, hb[ps].w};
-                split_store_sw128<LOWP>(sbase + A_H_HI, sbase + A_H_LO, row, c, h8, gt, A_H_HI - A_AGG_HI, A_H_LO - A_AGG_HI);
+                split_store_sw128<LOWP>(sbase + A_H_HI, sbase + A_H_LO, row, c, h8, gt, A_H_HI - A_AGG_HI, A_H_LO - A_AGG_HI, pol_stream);
                 float xv[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) xv[e] = __shfl_sync(0xffffffffu, xe[ps], (lane & 24) + e);   // features of this row
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__((EW + 128 / (4 * RPL) + 1) * 32, 1) struct_fwd
                     tc::st_shared_v4(sbase + A_X_HI + off, hi);
                     if (!LOWP) tc::st_shared_v4(sbase + A_X_LO + off, lo);
                     if (gt) {
-                        *reinterpret_cast<uint4*>(gt + (A_X_HI - A_AGG_HI) + off) = hi;
-                        *reinterpret_cast<uint4*>(gt + (A_X_LO - A_AGG_HI) + off) = lo;
+                        tc::stg_v4_hint(gt + (A_X_HI - A_AGG_HI) + off, hi, pol_stream);
+                        tc::stg_v4_hint(gt + (A_X_LO - A_AGG_HI) + off, lo, pol_stream);
                     }
                 }
             }
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__((EW + 128 / (4 * RPL) + 1) * 32, 1) struct_fwd
             }
 #pragma unroll
             for (int ps = 0; ps < RPL; ++ps)
-                split_store_sw128<LOWP>(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * (4 * RPL) + ps * 4 + rg, c, acc[ps], gt, 0u, A_AGG_LO - A_AGG_HI);
+                split_store_sw128<LOWP>(sbase + A_AGG_HI, sbase + A_AGG_LO, gw * (4 * RPL) + ps * 4 + rg, c, acc[ps], gt, 0u, A_AGG_LO - A_AGG_HI, pol_stream);
             if (warp == EPI_WARPS && lane == 0) TRACE(4);
             tc::fence_async_smem();
             tc::mbar_arrive(bar_a_full);
