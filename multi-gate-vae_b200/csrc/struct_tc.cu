@@ -11,11 +11,13 @@
 // issued as tcgen05.mma kind::f16 on fp16 hi/lo planes (csrc/mgv_tc.cuh) with the accumulator in tensor
 // memory; biases and the degree term ride along as two extra K columns, so the epilogue is gates + LayerNorm.
 //
-// Persistent CTAs (one per SM, weights resident in shared memory for the whole launch), warp-specialised:
-//   warps 4-11  gather: neighbour sums, own state and [x deg 1] -> fp16 hi/lo -> operand tile (UMMA layout);
-//               rows come in descending-degree order (mgv_build_degree_order) so a warp's lanes run equal trip counts
-//   warp  12    one thread issues the MMAs of a tile once the tile is full; completion frees the tile (tcgen05.commit)
-//   warps 0-3   epilogue, thread = node = TMEM lane: tensor memory -> GRU gates -> LayerNorm -> state_k
+// Persistent CTAs (one per SM, weights resident in shared memory for the whole launch), warp-specialised
+// (default shape: 8 epilogue + 16 gather + 1 MMA warp; the kernel is templated on it):
+//   gather      neighbour sums, own state and [x deg 1] -> fp16 hi/lo -> operand tile (UMMA layout), 2 rows per lane;
+//               rows come in descending-degree order (mgv_build_degree_order) so a warp's lanes run equal trip counts;
+//               in a training step the same chunks also go to the tile image in HBM that the backward recomputes from
+//   MMA warp    one thread issues the MMAs of a tile once the tile is full; completion frees the tile (tcgen05.commit)
+//   epilogue    two threads per node = TMEM lane (32 units each): tensor memory -> GRU gates -> LayerNorm -> state_k
 //               (two accumulator buffers: the epilogue of tile t overlaps the gather and MMAs of tile t+1)
 #include <stdlib.h>
 #include <string.h>
