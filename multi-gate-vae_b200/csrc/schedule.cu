@@ -95,12 +95,14 @@ inline size_t scan_tmp_count(int64_t n) { return (size_t)((n + SCAN_TILE - 1) / 
 // ------------------------------------------------------------------------------------ radix sort
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_PER_WARP = 256;                       // items per warp (8 steps of 32)
-constexpr int RS_TILE = RS_WARPS * RS_PER_WARP;        // 2048 items per block
 constexpr int RS_BINS = 256;
+// items per warp: 256 (8 steps of 32) for large inputs; 64 up to a million keys, where 2048-item blocks would leave most
+// SMs idle (100 k edges = 49 blocks) and each pass is a latency chain of 8 match/scatter steps per warp
+inline int rs_per_warp(int64_t m) { return m <= (1 << 20) ? 64 : 256; }
+inline int rs_tile(int64_t m) { return RS_WARPS * rs_per_warp(m); }
 
 __global__ void radix_hist_kernel(const uint32_t* __restrict__ keys, int m, int shift,
-                                  uint32_t* __restrict__ hist, int nblk) {
+                                  uint32_t* __restrict__ hist, int nblk, int RS_TILE) {
     __shared__ uint32_t h[RS_BINS];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -115,7 +117,8 @@ __global__ void radix_hist_kernel(const uint32_t* __restrict__ keys, int m, int 
 
 __global__ void radix_scatter_kernel(const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
                                      uint32_t* __restrict__ kout, uint32_t* __restrict__ vout, int m, int shift,
-                                     const uint32_t* __restrict__ offs, int nblk) {
+                                     const uint32_t* __restrict__ offs, int nblk, int RS_PER_WARP) {
+    const int RS_TILE = RS_WARPS * RS_PER_WARP;
     __shared__ uint32_t wcnt[RS_WARPS][RS_BINS];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
@@ -163,19 +166,20 @@ __global__ void radix_scatter_kernel(const uint32_t* __restrict__ kin, const uin
 struct SortBufs {
     uint32_t *k0, *v0, *k1, *v1, *hist, *tmp;
 };
-inline size_t sort_hist_count(int64_t m) { return (size_t)RS_BINS * (size_t)((m + RS_TILE - 1) / RS_TILE) + 1; }
+inline size_t sort_hist_count(int64_t m) { return (size_t)RS_BINS * (size_t)((m + rs_tile(m) - 1) / rs_tile(m)) + 1; }
 
 // Stable sort of (k0, v0)[m] by the low `bits` bits of the key.  Result pointers returned.
 int radix_sort_pairs(SortBufs b, int m, int bits, uint32_t** kres, uint32_t** vres, cudaStream_t st) {
     uint32_t *ki = b.k0, *vi = b.v0, *ko = b.k1, *vo = b.v1;
     if (m > 0) {
+        const int RS_TILE = rs_tile(m);
         const int nblk = (m + RS_TILE - 1) / RS_TILE;
         for (int shift = 0; shift < bits; shift += 8) {
-            radix_hist_kernel<<<nblk, RS_THREADS, 0, st>>>(ki, m, shift, b.hist, nblk);
+            radix_hist_kernel<<<nblk, RS_THREADS, 0, st>>>(ki, m, shift, b.hist, nblk, RS_TILE);
             mgv_count_launches(1);
             int rc = exclusive_scan(b.hist, b.hist, RS_BINS * nblk, b.tmp, st);
             if (rc != MGV_OK) return rc;
-            radix_scatter_kernel<<<nblk, RS_THREADS, 0, st>>>(ki, vi, ko, vo, m, shift, b.hist, nblk);
+            radix_scatter_kernel<<<nblk, RS_THREADS, 0, st>>>(ki, vi, ko, vo, m, shift, b.hist, nblk, rs_per_warp(m));
             mgv_count_launches(1);
             uint32_t* t;
             t = ki; ki = ko; ko = t;

@@ -284,8 +284,10 @@ class StructEncoderFunction(torch.autograd.Function):
         csr, rounds, num_enc, feat, per = ctx.csr, ctx.rounds, ctx.num_enc, ctx.feat, ctx.per
         dev = x_c.device
         N, D = csr.N, nat.D
-        g = torch.zeros(num_enc, max(N, 1), D, dtype=torch.float32, device=dev)
-        g[:, :N] = gout
+        if N > 0:
+            g = _f32(gout, "gout")                       # [num_enc, N, 64], used in place (no staging copy)
+        else:
+            g = torch.zeros(num_enc, 1, D, dtype=torch.float32, device=dev)
         grads = torch.empty(num_enc, 2, nat.STRUCT_GRAD_FLOATS, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             nb = lib.mgv_struct_bwd_workspace_bytes(N, num_enc)
