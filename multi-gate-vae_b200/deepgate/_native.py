@@ -119,7 +119,15 @@ def ptr(t):
     return _vp(t.data_ptr()) if t is not None else _vp(0)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_of(device):
+    """cudaStream_t of torch's current stream on ``device`` (the raw handle: no Stream object per call)."""
+    if _raw_stream is not None:
+        idx = device.index if isinstance(device, torch.device) else None
+        if idx is not None:
+            return _vp(_raw_stream(idx))
     return _vp(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -64,6 +64,9 @@ def profile_summary():
 
 
 def _f32(t, name):
+    # fast path (called ~100 times per training step): a contiguous fp32 CUDA tensor outside the graph is used as is
+    if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad:
+        return t
     return nat.require_cuda(t.detach().contiguous(), name, torch.float32)
 
 
