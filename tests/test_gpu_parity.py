@@ -379,3 +379,37 @@ def test_struct_backward_paths_agree_on_a_large_heavy_tailed_graph(monkeypatch):
         assert torch.equal(s0, s1) and torch.equal(t0, t1)            # same forward kernel
         for k in g0:
             assert rel(g1[k], g0[k]) < 1e-4, (env, k, rel(g1[k], g0[k]))
+
+
+@pytest.mark.parametrize("n_nodes", [1, 2, 127, 128, 129, 256, 385])
+def test_struct_backward_paths_agree_at_tile_boundaries(n_nodes, monkeypatch):
+    """Node counts around the 128-row tile size (and degenerate graphs): tcgen05 backward vs mma.sync backward."""
+    import deepgate
+    g = torch.Generator().manual_seed(n_nodes)
+    # random DAG: every node i > 0 draws up to 3 distinct predecessors among 0 .. i-1
+    src, dst = [], []
+    for i in range(1, n_nodes):
+        k = min(i, int(torch.randint(1, 4, (1,), generator=g)))
+        for j in torch.randperm(i, generator=g)[:k].tolist():
+            src.append(j); dst.append(i)
+    ei = torch.tensor([src, dst], dtype=torch.int64).reshape(2, -1).cuda()
+    feat = torch.nn.functional.one_hot(torch.randint(0, 2, (n_nodes,), generator=g), 6).float().cuda()
+    sd = O.synth_state_dict("mig", 43, layernorm=True)
+    ws = torch.randn(n_nodes, 64, generator=g).cuda()
+
+    def run(env):
+        monkeypatch.delenv("MGV_STRUCT_BWD", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, s_rounds=2, t_rounds=2, layernorm=True).cuda()
+        enc.load_state_dict({k[len("mig_struct_encoder."):]: v for k, v in sd.items() if k.startswith("mig_struct_encoder.")})
+        s, t = enc(feat, feat, ei)
+        ((s * ws).sum() + (t * t).sum()).backward()
+        torch.cuda.synchronize()
+        return s.detach(), {k: p.grad.clone() for k, p in enc.named_parameters()}
+
+    s0, g0 = run({"MGV_STRUCT_BWD": "mma"})
+    s1, g1 = run({})
+    assert torch.equal(s0, s1) and torch.isfinite(s1).all()
+    for k in g0:
+        assert rel(g1[k], g0[k]) < 1e-4, (k, rel(g1[k], g0[k]))
