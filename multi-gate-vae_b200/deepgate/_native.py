@@ -131,6 +131,28 @@ def stream_of(device):
     return _vp(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _NoCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def on_device(device):
+    """``torch.cuda.device(device)`` -- skipped when ``device`` already is the current device (the common case: one
+    process per GPU), which saves two context switches per library call."""
+    try:
+        if device.index is not None and torch.cuda.current_device() == device.index:
+            return _NOCTX
+    except Exception:
+        pass
+    return torch.cuda.device(device)
+
+
 def workspace(nbytes, device, zero=False):
     n = max(int(nbytes), 256)
     return (torch.zeros if zero else torch.empty)(n, dtype=torch.uint8, device=device)

@@ -117,7 +117,7 @@ class LevelSweepFunction(torch.autograd.Function):
         pack = _sweep_pack(params, codes, dev)
         hf_all = torch.zeros(rounds, max(N, 1), nat.D, dtype=torch.float32, device=dev)
         sync = torch.zeros(64, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             with _timed("level_sweep_fwd", dev):
               nat.check(lib.mgv_level_sweep_fwd(sched.c_struct(), rounds, mask, nat.ptr(pack), nat.ptr(hs_c),
                                               nat.ptr(hf_all), nat.ptr(sync), prec, nat.stream_of(dev)),
@@ -140,7 +140,7 @@ class LevelSweepFunction(torch.autograd.Function):
         ghf[:N] = g_hf
         grads = torch.empty(nat.NCODE, nat.SWEEP_GRAD_FLOATS, dtype=torch.float32, device=dev)
         sync = torch.zeros(64, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             nb = lib.mgv_sweep_bwd_workspace_bytes(N, sched.E)
             ws = nat.workspace(nb, dev)
             with _timed("level_sweep_bwd", dev):
@@ -151,7 +151,7 @@ class LevelSweepFunction(torch.autograd.Function):
         sel = _sweep_tables(params, codes)
         extra = torch.empty(max(len(codes), 1), 128 + D * 2 * D, dtype=torch.float32, device=dev)
         zero = torch.zeros(D * 2 * D, dtype=torch.float32, device=dev)     # query / key-bias / attn-bias cancel in the softmax
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             nat.check(lib.mgv_sweep_unpack_grads(_ptr_table(sel), _code_table(list(codes)), len(codes), nat.ptr(grads),
                                                  nat.ptr(extra), nat.stream_of(dev)), "mgv_sweep_unpack_grads")
         out = []
@@ -198,7 +198,7 @@ class LinearFunction(torch.autograd.Function):
         dW = torch.empty_like(weight, dtype=torch.float32)
         db = torch.empty(O, dtype=torch.float32, device=dev) if ctx.has_bias else None
         lib = nat.lib()
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             nb = lib.mgv_linear_wgrad_workspace_bytes(N, I, O)
             ws = nat.workspace(nb, dev)
             with _timed("linear_wgrad", dev):
@@ -265,7 +265,7 @@ class StructEncoderFunction(torch.autograd.Function):
         need_tiles = prec == 0 and N > 0 and any(ctx.needs_input_grad[5:])
         tiles = (torch.empty(lib.mgv_struct_tiles_bytes(N, num_enc, rounds), dtype=torch.uint8, device=dev)
                  if need_tiles else None)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             nb = lib.mgv_struct_fwd_workspace_bytes(N, num_enc)
             ws = nat.workspace(nb, dev)
             with _timed("struct_encoder_fwd", dev):
@@ -292,7 +292,7 @@ class StructEncoderFunction(torch.autograd.Function):
         else:
             g = torch.zeros(num_enc, 1, D, dtype=torch.float32, device=dev)
         grads = torch.empty(num_enc, 2, nat.STRUCT_GRAD_FLOATS, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             nb = lib.mgv_struct_bwd_workspace_bytes(N, num_enc)
             ws = nat.workspace(nb, dev)
             with _timed("struct_encoder_bwd", dev):
@@ -306,7 +306,7 @@ class StructEncoderFunction(torch.autograd.Function):
         per_enc = 2 * per_dir + (2 * D if ctx.layernorm else 0)
         flat = [_f32(t, "struct encoder parameter") for t in params]
         buf = torch.empty(num_enc, per_enc, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             nat.check(lib.mgv_struct_unpack_grads(_ptr_table(flat), num_enc, int(bool(ctx.layernorm)), feat, nat.ptr(grads),
                                                   nat.ptr(buf), nat.stream_of(dev)), "mgv_struct_unpack_grads")
         out = []
@@ -353,7 +353,7 @@ def negative_sample(csr, count):
     neg = torch.empty(2, int(count), dtype=torch.int64, device=dev)
     _NEG_COUNTER[0] += 1
     seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _NEG_COUNTER[0]) & 0xFFFFFFFFFFFFFFFF
-    with torch.cuda.device(dev):
+    with nat.on_device(dev):
         nat.check(lib.mgv_negative_sample(nat.ptr(csr.out_ptr), nat.ptr(csr.out_pack), csr.N, int(count), seed,
                                           nat.ptr(neg), nat.stream_of(dev)), "mgv_negative_sample")
     return neg
@@ -376,7 +376,7 @@ class ReconLossFunction(torch.autograd.Function):
         pred = torch.empty(max(Ep + En, 1), dtype=torch.int32, device=dev)
         ws = nat.workspace(16, dev)
         from .schedule import error_word
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             with _timed("recon_loss_fwd", dev):
               nat.check(lib.mgv_recon_loss_fwd(nat.ptr(st_c), N, nat.ptr(pos_c), Ep, nat.ptr(neg_c), En, nat.ptr(out),
                                              nat.ptr(sig), nat.ptr(pred), nat.ptr(ws), 16, nat.ptr(error_word(dev)),
@@ -392,7 +392,7 @@ class ReconLossFunction(torch.autograd.Function):
         dev = st_c.device
         gst = torch.zeros_like(st_c)
         gl = g_loss.detach().to(torch.float32).reshape(1).contiguous()
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             with _timed("recon_loss_bwd", dev):
               nat.check(lib.mgv_recon_loss_bwd(nat.ptr(st_c), int(st_c.shape[0]), nat.ptr(pos_c), int(pos_c.shape[1]),
                                              nat.ptr(neg_c), int(neg_c.shape[1]), nat.ptr(sig), nat.ptr(gl), nat.ptr(gst),
@@ -424,7 +424,7 @@ class VaeFuncLossFunction(torch.autograd.Function):
         tt_c = _f32(tt_sim.to(torch.float32), "tt_sim") if has_func else None
         z = torch.empty(2, N, nat.D, dtype=torch.float32, device=dev)
         out = torch.zeros(8, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             nb = lib.mgv_vae_func_workspace_bytes(P)
             ws = nat.workspace(nb, dev, zero=True)
             with _timed("vae_func_loss_fwd", dev):
@@ -454,7 +454,7 @@ class VaeFuncLossFunction(torch.autograd.Function):
             gmu, gls = torch.empty_like(mu_c), torch.empty_like(mu_c)
         if ctx.has_func:
             ghf = torch.zeros(ctx.hf_shape, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             with _timed("vae_func_loss_bwd", dev):
               nat.check(lib.mgv_vae_func_loss_bwd(nat.ptr(g2), nat.ptr(gz_c), nat.ptr(mu_c), nat.ptr(ls_c),
                                                 nat.ptr(eps_c), nat.ptr(gmu), nat.ptr(gls), N, nat.ptr(hf_c),

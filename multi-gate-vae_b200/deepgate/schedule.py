@@ -65,7 +65,7 @@ class GraphCSR(object):
         self.out_pack = torch.empty(max(self.E, 1), **i32)
         self.out_slot = torch.empty(max(self.E, 1), **i32)
         lib = nat.lib()
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             nb = lib.mgv_csr_workspace_bytes(self.N, self.E)
             ws = nat.workspace(nb, dev)
             nat.check(lib.mgv_build_csr(nat.ptr(edge_index), self.E, self.N, nat.ptr(self.code),
