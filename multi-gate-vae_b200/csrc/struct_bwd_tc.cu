@@ -67,8 +67,6 @@ struct BwdTC {
     const unsigned* tile_cost;
     const float* x;
     const uint8_t* image;      // weight image of (enc 0, this dir); encoder stride 2 * IMG_BYTES
-    const float* prev;         // state_{k-1}, enc 0
-    size_t enc_stride;
     const float* gout;         // [enc][N][64]
     const float* in_part; const float* in_agg;
     float* out_part; float* out_agg;
@@ -86,20 +84,6 @@ struct BwdTC {
 #define PTRACE(slot) do { if (p.trace && it < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + it) * 16 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void tmem_ld4x4(uint32_t taddr, float (&v)[16]) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(r[4 * k]), "=r"(r[4 * k + 1]), "=r"(r[4 * k + 2]), "=r"(r[4 * k + 3]) : "r"(taddr + 64u * k) : "memory");
-}
-__device__ __forceinline__ void split_store_sw128(uint32_t hi_base, uint32_t lo_base, int row, int c, const float (&v)[8]) {
-    uint4 hi, lo;
-    tc::split8(v, hi, lo);
-    const uint32_t off = tc::sw128_off(row, c);
-    tc::st_shared_v4(hi_base + off, hi);
-    tc::st_shared_v4(lo_base + off, lo);
-}
 // Power of two s with amax * s in [2^8, 2^9) (amax > 0), else 1.
 __device__ __forceinline__ float pow2_scale(float amax) {
     if (!(amax > 0.f) || !isfinite(amax)) return 1.0f;
@@ -114,36 +98,6 @@ __device__ __forceinline__ float pow2_scale_keep(float amax, float cur) {
     return (amax > 0.f) ? pow2_scale(amax) : cur;
 }
 
-// One neighbour of each of the lane's 4 rows per trip (8 x 16-byte loads in flight), next trip's ids prefetched.
-__device__ __forceinline__ void neighbour_sum(const float* __restrict__ src, const int* __restrict__ idx, const int (&beg)[4],
-                                              const int (&cnt)[4], const int (&j0)[4], int maxc, int c, float (&acc)[4][8]) {
-    int jn[4];
-#pragma unroll
-    for (int ps = 0; ps < 4; ++ps) jn[ps] = j0[ps];
-    for (int sl = 0; sl < maxc; ++sl) {
-        int j[4];
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-            j[ps] = jn[ps];
-            if (sl + 1 < cnt[ps]) jn[ps] = idx[beg[ps] + sl + 1] & NODE_MASK;
-        }
-        float4 va[4], vb[4];
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-            va[ps] = make_float4(0.f, 0.f, 0.f, 0.f); vb[ps] = va[ps];
-            if (sl < cnt[ps]) {
-                va[ps] = mgv_ld4(src + (size_t)j[ps] * D + c * 8);
-                vb[ps] = mgv_ld4(src + (size_t)j[ps] * D + c * 8 + 4);
-            }
-        }
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-            acc[ps][0] += va[ps].x; acc[ps][1] += va[ps].y; acc[ps][2] += va[ps].z; acc[ps][3] += va[ps].w;
-            acc[ps][4] += vb[ps].x; acc[ps][5] += vb[ps].y; acc[ps][6] += vb[ps].z; acc[ps][7] += vb[ps].w;
-        }
-    }
-}
-
 // ======================================================================================= recompute + pointwise + data gradient
 __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -151,7 +105,6 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int enc = blockIdx.y;
-    const float* prev = p.prev + (size_t)enc * p.enc_stride;
     const size_t eoff = (size_t)enc * p.N * D;
     const uint8_t* image = p.image + (size_t)enc * 2 * IMG_BYTES;
 
@@ -181,7 +134,6 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     if (tid < 2 * D) s_ln[tid] = __ldg(reinterpret_cast<const float*>(image + IMG_W) + tid);
     if (tid < 4) s_amax[tid] = 0u;
     if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-    const int ntiles_all = (p.N + TM - 1) / TM;
     int tile_beg, tile_end;
     {
         // equal tile counts per CTA: with the operand tile bulk-copied, a tile's time is set by the epilogue (constant per
@@ -550,11 +502,9 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             }
             tc::tmem_st_wait();
             if (tid == 0) PTRACE(6);
-            // ---- pass 3: fp32 d gates -> scaled fp16 hi/lo planes, in place (A operand of the data-gradient MMAs) and to
-            //      HBM [plane][64-node half][8-gate chunk (32)][node row (64)][16 B]: a warp's 32 rows write 512 contiguous bytes.
+            // ---- pass 3: fp32 d gates -> scaled fp16 hi/lo planes, in place (A operand of the data-gradient MMAs).
             //      K step s = gates 16 s .. 16 s + 15; this warp group's units are the K steps with (s & 3) / 2 == wg.
             {
-                uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + (tile - p.tile_beg)) * DG_TILE_BYTES + (row >> 6) * 32768 + (row & 63) * 16;
 #pragma unroll 2
                 for (int k = 0; k < 8; ++k) {
                     const int s = 4 * (k >> 1) + 2 * wg + (k & 1);
@@ -949,7 +899,7 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     const int gxp = sms / num_enc > 0 ? sms / num_enc : 1;
     const int steps = 2 * rounds;
     const size_t slot = (size_t)N * D;
-    const size_t enc_stride = (size_t)(steps + 1) * slot;
+    (void)states;          // the tcgen05 path recomputes from the saved operand tiles; only the mma.sync path reads the states
 
     MgvArena a(ws, ws_bytes);
     uint8_t* image = a.take<uint8_t>((size_t)num_enc * 2 * IMG_BYTES);
@@ -987,8 +937,6 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
             p.tile_cost = dir == 0 ? sch->tile_cost_in : sch->tile_cost_out;
             p.x = x;
             p.image = image + (size_t)dir * IMG_BYTES;
-            p.prev = states + (size_t)(k - 1) * slot;
-            p.enc_stride = enc_stride;
             p.gout = gout;
             p.in_part = part[k & 1]; p.in_agg = agg[k & 1];
             p.out_part = part[(k - 1) & 1]; p.out_agg = agg[(k - 1) & 1];

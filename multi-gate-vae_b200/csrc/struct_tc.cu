@@ -52,12 +52,6 @@ struct StepTC {
 #define TRACE(slot) do { if (p.trace && it < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + it) * 16 + (slot)] = clock64(); } while (0)
 
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-}
 // r, z, gi_n, gh_n of 4 consecutive units: columns c, 64 + c, 128 + c, 192 + c (4 each) of the accumulator
 __device__ __forceinline__ void tmem_ld4x4(uint32_t taddr, float (&v)[16]) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
