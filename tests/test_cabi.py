@@ -86,3 +86,17 @@ def test_host_levelisation_and_collate_match_oracle():
         c["edge_index"].shape[0] for c in circuits)
     with pytest.raises(ValueError):
         top_sort_host(torch.tensor([[0, 1], [1, 0]]).numpy(), 2)
+
+
+def test_rank_batches_are_size_balanced_and_rank_zero_is_the_single_gpu_workload():
+    """bench.py draws, for every rank, different circuits of the SAME sizes (size_cfg); rank 0 of an N-GPU run is the
+    single-GPU workload."""
+    import numpy as np
+    from deepgate import synth
+    base = synth.make_circuits("aig", 6, (16, 64), (500, 1500), cfg=2)
+    r0 = synth.make_circuits("aig", 6, (16, 64), (500, 1500), cfg=2, size_cfg=2)
+    r3 = synth.make_circuits("aig", 6, (16, 64), (500, 1500), cfg=302, size_cfg=2)
+    for a, b, c in zip(base, r0, r3):
+        assert np.array_equal(a["edge_index"], b["edge_index"]) and np.array_equal(a["x"], b["x"])
+        assert a["x"].shape == c["x"].shape                       # same node count ...
+        assert not np.array_equal(a["edge_index"], c["edge_index"])   # ... different circuit
