@@ -223,9 +223,11 @@ def run_ours(args, w):
     model = mod.Model(struct_encoder=enc, num_rounds=w["rounds"], dim_hidden=64)
     model.load_state_dict(O.synth_state_dict(w["kind"], 2), strict=False)      # same random-init weights on every rank
     tmp = tempfile.mkdtemp(prefix="mgv_bench_")
-    trainer = deepgate.Trainer(None, model, training_id="bench", save_dir=tmp, lr=1e-4,
-                               rc_prob_func_weight=list(LOSS_W), device=str(dev), batch_size=w["batch"],
-                               distributed=False)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):          # the Trainer prints its device like the reference's: stdout carries ONE JSON line
+        trainer = deepgate.Trainer(None, model, training_id="bench", save_dir=tmp, lr=1e-4,
+                                   rc_prob_func_weight=list(LOSS_W), device=str(dev), batch_size=w["batch"],
+                                   distributed=False)
     model.train()
     nb = args.batches
     host = [make_host_batch(w, rank, i).pin_memory() for i in range(nb)]
