@@ -206,7 +206,29 @@ def run_reference(args, w):
 
 
 # ------------------------------------------------------------------------------------------- our arm (B200)
+_SAVED_STDOUT = None
+
+
+def _stdout_to_stderr():
+    """Everything libraries write to file descriptor 1 while the benchmark runs (NCCL's version banner, the Trainer's
+    device line) goes to stderr: stdout carries exactly ONE JSON line."""
+    global _SAVED_STDOUT
+    sys.stdout.flush()
+    _SAVED_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _restore_stdout():
+    global _SAVED_STDOUT
+    if _SAVED_STDOUT is not None:
+        sys.stdout.flush()
+        os.dup2(_SAVED_STDOUT, 1)
+        os.close(_SAVED_STDOUT)
+        _SAVED_STDOUT = None
+
+
 def run_ours(args, w):
+    _stdout_to_stderr()
     import deepgate
     from deepgate import _native, ops
     from oracle import dg_oracle as O   # only for cpu_baseline (rank 0, N == 1) and the seeded weights helper
@@ -385,6 +407,7 @@ def run_ours(args, w):
                          "per-node subgraph loop" % (ns, w["batch"], gates, dt)}
     if rank == 0:
         h2d = sum(b.nbytes() for b in host) / len(host)
+        _restore_stdout()
         print(json.dumps({
             "metric": "gates_per_s_fwd_bwd", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
