@@ -331,7 +331,8 @@ __device__ __forceinline__ int warp_lower_bound(const unsigned* __restrict__ a, 
             const int m = lo + lane;
             const bool ge = (m < hi) ? (a[m] - adj * (unsigned)m >= target) : true;
             const unsigned bal = __ballot_sync(0xffffffffu, ge);
-            return lo + __ffs(bal) - 1;
+            // span == 32 with no entry >= target: every lane probed a real element, the ballot is empty -> hi
+            return bal == 0u ? hi : lo + __ffs(bal) - 1;
         }
         const int m = lo + (int)(((long long)span * (lane + 1)) / 33);
         const bool ge = a[m] - adj * (unsigned)m >= target;

@@ -198,37 +198,41 @@ inline int bits_for(uint64_t max_value) {
 }
 
 // ------------------------------------------------------------------------------------ CSR kernels
+// An end point outside [0, n) sets the flag and is read as node 0 by EVERY kernel below (keys, degrees, in_src, out_pack,
+// code lookup), so the CSR stays self-consistent and every index the compute kernels later follow is in range; the caller
+// raises when it reads the flag (deferred mode) or right away (validating mode).
+__device__ __forceinline__ int64_t sane_node(int64_t v, int n) { return (v < 0 || v >= n) ? 0 : v; }
+
 __global__ void edge_keys_kernel(const int64_t* __restrict__ ei, int64_t E, int row, uint32_t* __restrict__ keys,
                                  uint32_t* __restrict__ vals, uint32_t* __restrict__ deg, int n, int* __restrict__ bad) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const int64_t v = ei[(int64_t)row * E + e];
+    int64_t v = ei[(int64_t)row * E + e];
     if (v < 0 || v >= n) {
         atomicOr(bad, 1);
-        keys[e] = 0; vals[e] = (uint32_t)e;
-        return;
+        v = 0;
     }
     keys[e] = (uint32_t)v;
     vals[e] = (uint32_t)e;
     atomicAdd(&deg[v], 1u);
 }
 
-__global__ void fill_in_kernel(const uint32_t* __restrict__ eid_sorted, const int64_t* __restrict__ ei, int64_t E,
+__global__ void fill_in_kernel(const uint32_t* __restrict__ eid_sorted, const int64_t* __restrict__ ei, int64_t E, int n,
                                int32_t* __restrict__ in_src, uint32_t* __restrict__ slot_of_eid) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= E) return;
     const uint32_t e = eid_sorted[s];
-    in_src[s] = (int32_t)ei[e];                 // row 0 = src
+    in_src[s] = (int32_t)sane_node(ei[e], n);   // row 0 = src
     slot_of_eid[e] = (uint32_t)s;
 }
 
-__global__ void fill_out_kernel(const uint32_t* __restrict__ eid_sorted, const int64_t* __restrict__ ei, int64_t E,
+__global__ void fill_out_kernel(const uint32_t* __restrict__ eid_sorted, const int64_t* __restrict__ ei, int64_t E, int n,
                                 const uint32_t* __restrict__ slot_of_eid, const int32_t* __restrict__ code,
                                 int32_t* __restrict__ out_pack, int32_t* __restrict__ out_slot) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= E) return;
     const uint32_t e = eid_sorted[p];
-    const int32_t d = (int32_t)ei[E + e];       // row 1 = dst
+    const int32_t d = (int32_t)sane_node(ei[E + e], n);   // row 1 = dst
     int32_t c = 0;
     if (code != nullptr) {
         c = code[d];
@@ -476,11 +480,11 @@ extern "C" int mgv_build_csr(const int64_t* edge_index, int64_t E, int32_t N, co
         if (rc != MGV_OK) return rc;
         if (E > 0) {
             if (dir == 0) {
-                fill_in_kernel<<<eb, 256, 0, st>>>(vs, edge_index, E, in_src, slot_of_eid);
+                fill_in_kernel<<<eb, 256, 0, st>>>(vs, edge_index, E, N, in_src, slot_of_eid);
                 mgv_count_launches(1);
             }
             else {
-                fill_out_kernel<<<eb, 256, 0, st>>>(vs, edge_index, E, slot_of_eid, code, out_pack, out_slot);
+                fill_out_kernel<<<eb, 256, 0, st>>>(vs, edge_index, E, N, slot_of_eid, code, out_pack, out_slot);
                 mgv_count_launches(1);
             }
         }

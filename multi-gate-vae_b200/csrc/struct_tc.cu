@@ -172,6 +172,11 @@ __global__ void __launch_bounds__((EW + 128 / (4 * RPL) + 1) * 32, 1) struct_fwd
         const unsigned lo = (unsigned)(total * blockIdx.x / gridDim.x), hi = (unsigned)(total * (blockIdx.x + 1) / gridDim.x);
         tile_beg = tc::warp_lower_bound(p.tile_cost, ntiles, lo, lane);
         tile_end = tc::warp_lower_bound(p.tile_cost, ntiles, hi, lane);
+        // the ranges must partition [0, ntiles) whatever the search returns: first CTA starts at 0, last ends at ntiles
+        if (blockIdx.x == 0) tile_beg = 0;
+        if (blockIdx.x == gridDim.x - 1) tile_end = ntiles;
+        tile_beg = min(max(tile_beg, 0), ntiles);
+        tile_end = min(max(tile_end, tile_beg), ntiles);
     }
     tc::fence_before_sync();
     __syncthreads();

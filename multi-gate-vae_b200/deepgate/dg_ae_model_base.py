@@ -27,7 +27,8 @@ class LevelModel(nn.Module):
     ENCODER_ATTR = "struct_encoder"
     GATE_MODULES = ()          # ((gate code, suffix), ...) in registration order
 
-    def __init__(self, struct_encoder, num_rounds=1, dim_hidden=128, enable_encode=True, enable_reverse=True):
+    def __init__(self, struct_encoder, num_rounds=1, dim_hidden=128, enable_encode=True, enable_reverse=True,
+                 variational=False):
         super().__init__()
         setattr(self, self.ENCODER_ATTR, struct_encoder)
         self.decoder = DirectedInnerProductDecoder()
@@ -44,6 +45,15 @@ class LevelModel(nn.Module):
             setattr(self, "update_%s_func" % suffix, nn.GRU(dim_hidden, dim_hidden))
         self.readout_prob = MLP(dim_hidden, self.dim_mlp, 1, num_layer=3, p_drop=0.2, norm_layer="batchnorm",
                                 act_layer="relu")
+        # Variational configuration (BASELINE config 4; reference digvae_model.py:105-142 + trainer.py:145-151): the struct
+        # encoder's (s, t) go through DirectedGVAE.sample's reparameterisation -- same four Linear layers and names -- before
+        # hs_linear, and the KL term of trainer.py:145-148 comes out of the same fused launch.  Registered last so the
+        # non-variational checkpoint keys are untouched.
+        self.variational = bool(variational)
+        self.kl = None
+        if self.variational:
+            for name in ("fc_s_mu", "fc_s_logstd", "fc_t_mu", "fc_t_logstd"):
+                setattr(self, name, ops.Linear(dim_hidden, dim_hidden))
 
     # ------------------------------------------------------------------ hot path
     def forward(self, G):
@@ -53,12 +63,36 @@ class LevelModel(nn.Module):
         # feature is one_hot(1{gate code == 1}, 6)  (dg_ae_model_mig.py:71)
         feat = torch.nn.functional.one_hot(G.x[:, 1].to(torch.int64), num_classes=6).to(torch.float32)
         s, t = encoder(feat, feat, G.edge_index)
+        if self.variational:
+            noise = getattr(self, "sample_noise", None)        # injected Gaussian noise (parity tests); None = randn
+            s, t = self.sample(s, t, *(noise if noise is not None else (None, None)))
         hs = self.hs_linear(torch.cat([s, t], dim=-1))
         codes = [c for c, _ in self.GATE_MODULES]
         modules = [(getattr(self, "aggr_%s_func" % sfx), getattr(self, "update_%s_func" % sfx))
                    for _, sfx in self.GATE_MODULES]
         hf = ops.level_sweep(hs, sched, self.num_rounds, codes, modules)
+        try:
+            hs._mgv_sched = sched          # recon_loss(hs, ...) draws its negatives against THIS batch's edge set
+        except Exception:
+            pass
         return hs, hf
+
+    def sample(self, s, t, eps_s=None, eps_t=None):
+        """DirectedGVAE.sample (digvae_model.py:134-142): z = mu + exp(logstd) * eps for s and t; mu / logstd are stashed on
+        the module as the reference does (the trainer's KL reads them); reparameterisation + KL run in one fused launch."""
+        self.s_mu, self.s_logstd = self.fc_s_mu(s), self.fc_s_logstd(s)
+        self.t_mu, self.t_logstd = self.fc_t_mu(t), self.fc_t_logstd(t)
+        eps_s = torch.randn_like(self.s_mu) if eps_s is None else eps_s
+        eps_t = torch.randn_like(self.t_mu) if eps_t is None else eps_t
+        z_s, z_t, self.kl, _ = ops.vae_func_loss(torch.stack([self.s_mu, self.t_mu]), torch.stack([self.s_logstd, self.t_logstd]),
+                                                 torch.stack([eps_s, eps_t]))
+        return z_s, z_t
+
+    def kl_loss(self):
+        """trainer.py:145-148 for the last forward: sum over {s, t} of -0.5/N mean_i sum_d (1 + 2 logstd - mu^2 - exp(logstd)^2)."""
+        if self.kl is None:
+            raise RuntimeError("kl_loss() needs a forward pass of a variational model first")
+        return self.kl
 
     # ------------------------------------------------------------------ heads (torch.nn, adjacent to the path)
     def pred_prob(self, hf):
@@ -70,10 +104,15 @@ class LevelModel(nn.Module):
         st = self.hs_decompose(hs)
         if neg_edge_index is None:
             from . import schedule
-            csr = schedule._last["csr"]
+            # the out-CSR the sampler rejects against: the schedule of the forward that produced ``hs`` (same edge set as
+            # its permutation ``pos_edge_index``), else one built from ``pos_edge_index`` itself (keyed on that tensor)
+            csr = getattr(hs, "_mgv_sched", None)
             if csr is None or csr.N != st.size(0) or csr.E != pos_edge_index.size(1) or csr.device != st.device:
                 csr = schedule.csr_for(pos_edge_index, st.size(0))
-            neg_edge_index = ops.negative_sample(csr, pos_edge_index.size(1))
+            # reference: negative_sampling(add_self_loops(remove_self_loops(pos)), N) draws as many negatives as that edge
+            # set has entries, E + N for a DAG (dg_ae_model_mig.py:176-180), none of them a self loop or an edge
+            n_self = 0 if csr is getattr(hs, "_mgv_sched", None) else int((pos_edge_index[0] == pos_edge_index[1]).sum())
+            neg_edge_index = ops.negative_sample(csr, pos_edge_index.size(1) - n_self + st.size(0))
         loss, pred_bin = ops.recon_loss(st, pos_edge_index, neg_edge_index)
         ep, en = pos_edge_index.size(1), neg_edge_index.size(1)
         gt_bin = torch.cat([torch.ones(ep, dtype=torch.int32, device=hs.device),

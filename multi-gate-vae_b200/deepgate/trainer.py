@@ -5,7 +5,12 @@ Differences, all deliberate:
   * gradients ARE synchronised across ranks: one flat-buffer NCCL all-reduce (sum / world) per step
     -- the reference shards the data per rank but never all-reduces;
   * the edge "split" is an O(E) permutation instead of the N x N mask of preprocessing.py:56-69;
-  * the func loss (and, for VAE models, reparam + KL) runs in the fused CUDA kernel.
+  * the func loss (and, for VAE models, reparam + KL) runs in the fused CUDA kernel;
+  * replicas start from rank 0's parameters and buffers (broadcast at construction and after ``load``), as DDP does --
+    the reference sets no seed (train.py) so its ranks would train different models;
+  * a batch that fails the asynchronous input validation (node id / level / edge end out of range) does not update the
+    parameters: the device-side flag is handed to the fused Adam kernel as its ``found_inf`` operand (no host sync), and
+    the training loop raises when it next reads results (the reference raises an IndexError before the step).
 """
 import os
 import time
@@ -108,9 +113,28 @@ class Trainer(object):
                 group["fused"] = True
                 group["foreach"] = False
         self.model_epoch = 0
+        self.kl_weight = 0.0                 # the reference computes KL for VAE models but leaves it out of the total (trainer.py:167,227-231)
         self.grad_sync = FlatGradAllReduce(self.model.parameters())
+        self.sync_replicas()
         if self.local_rank == 0:
             self.logger = Logger(self.log_path)
+
+    def sync_replicas(self):
+        """Rank 0's parameters AND buffers (BatchNorm running statistics) to every rank, in one flat broadcast."""
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return
+        if torch.distributed.get_world_size() == 1:
+            return
+        tensors = [t for t in list(self.model.parameters()) + list(self.model.buffers())]
+        with torch.no_grad():
+            for dt in sorted({t.dtype for t in tensors}, key=str):
+                group = [t for t in tensors if t.dtype == dt]
+                flat = torch.cat([t.detach().reshape(-1) for t in group])
+                torch.distributed.broadcast(flat, src=0)
+                off = 0
+                for t in group:
+                    t.copy_(flat[off:off + t.numel()].view_as(t))
+                    off += t.numel()
 
     def set_training_args(self, rc_prob_func_weight=[], lr=-1, lr_step=-1, device="null"):
         if len(rc_prob_func_weight) == 3 and list(rc_prob_func_weight) != self.rc_prob_func_weight:
@@ -143,6 +167,7 @@ class Trainer(object):
             self.lr = group["lr"]
         self.model_epoch = checkpoint["epoch"]
         self.model.load(path)
+        self.sync_replicas()
         print("[INFO] Continue training from epoch {:}".format(self.model_epoch))
         return path
 
@@ -163,12 +188,25 @@ class Trainer(object):
         prob_loss = self.reg_loss(prob, batch["prob"])
         # func loss: 1 - cos -> z-norm -> L1 against z-norm(tt_sim)   (trainer.py:157-163), fused kernel
         _, _, _, func_loss = ops.vae_func_loss(hf=hf, tt_pair_index=batch["tt_pair_index"], tt_sim=batch["tt_sim"])
-        return {"recon_loss": loss, "pred_bin": pred_bin, "gt_bin": gt_bin, "prob_loss": prob_loss,
-                "func_loss": func_loss, "hs": hs, "hf": hf}
+        status = {"recon_loss": loss, "pred_bin": pred_bin, "gt_bin": gt_bin, "prob_loss": prob_loss,
+                  "func_loss": func_loss, "hs": hs, "hf": hf}
+        # Variational branch (trainer.py:145-151): models that stash s_mu / s_logstd / t_mu / t_logstd (DirectedGVAE.sample,
+        # digvae_model.py:134-142; here the level models built with ``variational=True``) report the KL term, which the
+        # fused reparam + KL kernel produced during forward.
+        if self._is_vae():
+            status["kl_loss"] = self.model.kl_loss()
+        return status
+
+    def _is_vae(self):
+        name = getattr(self.args, "model", "") if self.args is not None else ""
+        return ("VAE" in (name or "") or getattr(self.model, "variational", False)) and hasattr(self.model, "kl_loss")
 
     def total_loss(self, status):
         w = self.rc_prob_func_weight
-        return w[0] * status["recon_loss"] + w[1] * status["prob_loss"] + w[2] * status["func_loss"]
+        total = w[0] * status["recon_loss"] + w[1] * status["prob_loss"] + w[2] * status["func_loss"]
+        if self.kl_weight and "kl_loss" in status:
+            total = total + self.kl_weight * status["kl_loss"]
+        return total
 
     def train_step(self, batch, neg_edge_index=None):
         """zero_grad -> run_batch -> backward -> gradient all-reduce -> Adam step.  Returns the status dict."""
@@ -177,9 +215,27 @@ class Trainer(object):
         loss = self.total_loss(status)
         loss.backward()
         self.grad_sync()
-        self.optimizer.step()
+        self._guarded_step()
         status["loss"] = loss.detach()
         return status
+
+    def _guarded_step(self):
+        """optimizer.step() that leaves the parameters untouched when this step's batch failed the deferred input validation:
+        the flag word goes to the fused Adam kernel as ``found_inf`` (the GradScaler hook), so nothing synchronises."""
+        from .schedule import error_word
+        fused = str(self.device).startswith("cuda") and all(g.get("fused") for g in self.optimizer.param_groups)
+        if fused:
+            if getattr(self, "_found_inf", None) is None:
+                self._found_inf = torch.zeros(1, dtype=torch.float32, device=self.device)
+            torch.ne(error_word(torch.device(self.device)), 0, out=self._found_inf)         # one tiny launch, no sync
+            self.optimizer.found_inf = self._found_inf
+            self.optimizer.grad_scale = None
+            try:
+                self.optimizer.step()
+            finally:
+                del self.optimizer.found_inf, self.optimizer.grad_scale
+        else:
+            self.optimizer.step()
 
     # ------------------------------------------------------------------ loop
     def train(self, num_epoch, train_dataset, val_dataset):
@@ -190,6 +246,7 @@ class Trainer(object):
                                   num_workers=self.num_workers, sampler=sampler)
             return DataLoader(ds, batch_size=self.batch_size, shuffle=True, drop_last=True, num_workers=self.num_workers)
 
+        from .schedule import check_deferred_errors
         loaders = {"train": loader(train_dataset), "val": loader(val_dataset)}
         meters = {k: AverageMeter() for k in ("time", "recon", "prob", "func", "acc")}
         print("[INFO] Start training, lr = {:.4f}".format(self.optimizer.param_groups[0]["lr"]))
@@ -205,6 +262,7 @@ class Trainer(object):
                         with torch.no_grad():
                             status = self.run_batch(batch)
                     pred, gt = status["pred_bin"].cpu().numpy(), status["gt_bin"].cpu().numpy()
+                    check_deferred_errors()          # the stream is idle after the read-back above: one 4-byte read
                     meters["time"].update(time.time() - t0)
                     meters["recon"].update(status["recon_loss"].item())
                     meters["prob"].update(status["prob_loss"].item())
@@ -217,8 +275,6 @@ class Trainer(object):
                     self.logger.write("{}| Epoch: {:}/{:} |Recon: {:.4f} |ACC: {:.2f} |Prob: {:.4f} |Func: {:.4f}|Net: {:.2f}s\n".format(
                         phase, epoch, num_epoch, meters["recon"].avg, meters["acc"].avg * 100, meters["prob"].avg,
                         meters["func"].avg, meters["time"].avg))
-            from .schedule import check_deferred_errors
-            check_deferred_errors()
             self.model_epoch += 1
             if self.lr_step > 0 and self.model_epoch % self.lr_step == 0:
                 self.lr *= 0.1

@@ -167,15 +167,22 @@ def struct_encoder(P, enc, code, ei, s_rounds, t_rounds, layernorm):
 
 # --------------------------------------------------------------------------- model
 def model_forward(P, kind, code, edge_index, forward_level, num_rounds=1, s_rounds=4,
-                  t_rounds=4, layernorm=True, literal_subgraph=True, hs_override=None):
+                  t_rounds=4, layernorm=True, literal_subgraph=True, hs_override=None, vae_eps=None, stash=None):
     """``Model.forward(G) -> (hs, hf)``.  dg_ae_model_mig.py:64-132 and the aig/xmg/xag
     twins (aig :52-100, xmg :69-150, xag :64-124).  ``code`` is the int gate code per
-    node (= G.gate.squeeze(1)); ``forward_level`` as produced by top_sort."""
+    node (= G.gate.squeeze(1)); ``forward_level`` as produced by top_sort.
+    ``vae_eps = (eps_s, eps_t)``: the variational configuration (BASELINE config 4) -- the struct encoder's (s, t) pass
+    through DirectedGVAE.sample (digvae_model.py:134-142, parameters fc_{s,t}_{mu,logstd} in ``P``) before hs_linear and
+    (s_mu, s_logstd, t_mu, t_logstd) are appended to ``stash`` for the KL of trainer.py:145-148."""
     enc = ENCODER_ATTR[kind]
     dt = P["hs_linear.weight"].dtype
     n = code.numel()
     if hs_override is None:
         s, t = struct_encoder(P, enc, code, edge_index, s_rounds, t_rounds, layernorm)
+        if vae_eps is not None:
+            s, t, moments = vae_sample(P, s, t, vae_eps[0].to(dt), vae_eps[1].to(dt))
+            if stash is not None:
+                stash.append(moments)
         hs = linear(P, "hs_linear", torch.cat([s, t], dim=-1))
     else:
         hs = hs_override
@@ -271,26 +278,35 @@ def kl_loss(s_mu, s_ls, t_mu, t_ls, num_nodes):
 
 # --------------------------------------------------------------------------- train step
 def train_step_losses(P, kind, G, weights=(1.0, 4.0, 4.0), num_rounds=1, s_rounds=4, t_rounds=4,
-                      layernorm=True, literal_subgraph=True):
+                      layernorm=True, literal_subgraph=True, vae_eps=None, kl_weight=0.0):
     """Trainer.run_batch (trainer.py:131-174) + the weighted total (trainer.py:229-231),
     with ``train_pos_edge_index`` / ``neg_edge_index`` taken from ``G`` (the N x N edge
     split of preprocessing.py:56-69 is bypassed on both sides).
     ``G`` is a dict: code, edge_index, forward_level, prob, tt_pair_index, tt_sim,
     train_pos_edge_index, neg_edge_index."""
+    stash = []
     hs, hf = model_forward(P, kind, G["code"], G["edge_index"], G["forward_level"], num_rounds,
-                           s_rounds, t_rounds, layernorm, literal_subgraph)
+                           s_rounds, t_rounds, layernorm, literal_subgraph, vae_eps=vae_eps, stash=stash)
     rec, _, _ = recon_loss(P, hs, G["train_pos_edge_index"], G["neg_edge_index"])
     prb = prob_loss(P, hf, G["prob"])
     fnc = func_loss(hf, G["tt_pair_index"], G["tt_sim"])
     total = weights[0] * rec + weights[1] * prb + weights[2] * fnc
-    return total, {"recon": rec, "prob": prb, "func": fnc, "hs": hs, "hf": hf}
+    parts = {"recon": rec, "prob": prb, "func": fnc, "hs": hs, "hf": hf}
+    if stash:
+        parts["kl"] = kl_loss(*stash[0], num_nodes=G["code"].numel())
+        total = total + kl_weight * parts["kl"]
+    return total, parts
 
 
 # --------------------------------------------------------------------------- parameters
-def param_shapes(kind, dim=64, dim_feature=6, layernorm=True):
-    """Names and shapes of the reference Model's state_dict."""
+def param_shapes(kind, dim=64, dim_feature=6, layernorm=True, variational=False):
+    """Names and shapes of the reference Model's state_dict; ``variational`` adds
+    DirectedGVAE's fc_{s,t}_{mu,logstd} (digvae_model.py:111-114)."""
     enc = ENCODER_ATTR[kind]
     sh = {}
+    if variational:
+        for nme in ("fc_s_mu", "fc_s_logstd", "fc_t_mu", "fc_t_logstd"):
+            sh[nme + ".weight"], sh[nme + ".bias"] = (dim, dim), (dim,)
     for conv in ("source_conv", "target_conv"):
         p = "%s.%s" % (enc, conv)
         for a in ("aggr", "aggr_r"):
@@ -332,14 +348,17 @@ def param_shapes(kind, dim=64, dim_feature=6, layernorm=True):
     return sh
 
 
-def synth_state_dict(kind, seed, dim=64, dim_feature=6, layernorm=True, dtype=torch.float32):
+def synth_state_dict(kind, seed, dim=64, dim_feature=6, layernorm=True, dtype=torch.float32, variational=False):
     """Reproducible weights (numpy PCG64, independent of torch's init order): every
     matrix/bias ~ U(-1/sqrt(dim), 1/sqrt(dim)) like torch's default GRU/Linear scale;
     norm gains 1 + U(-.1,.1); running_var in [0.5, 1.5].  Keys in sorted order."""
     rng = np.random.default_rng(seed)
     out = {}
     bound = 1.0 / math.sqrt(dim)
-    for name, shape in sorted(param_shapes(kind, dim, dim_feature, layernorm).items()):
+    shapes = param_shapes(kind, dim, dim_feature, layernorm)
+    extra = {k: v for k, v in param_shapes(kind, dim, dim_feature, layernorm, variational).items() if k not in shapes}
+    # the variational head's tensors are drawn AFTER the base set, so a seed gives the same base weights either way
+    for name, shape in sorted(shapes.items()) + sorted(extra.items()):
         if name.endswith("running_var"):
             v = 0.5 + rng.random(shape)
         elif name.endswith("running_mean"):

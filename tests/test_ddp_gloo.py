@@ -45,6 +45,21 @@ def _worker(rank, world, port, out):
             assert int(b.edge_index.max()) < b.x.size(0)            # index keys were shifted per circuit
             seen.append(int(b.x.size(0)))
         out[("n", rank)] = seen
+        # replicas: every rank builds a differently initialised model (the reference's train.py sets no seed); the Trainer
+        # broadcasts rank 0's parameters and buffers at construction, and after one synchronised step they still agree
+        import tempfile
+        from deepgate.trainer import Trainer
+        torch.manual_seed(1000 + rank)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 2))
+        net[1].running_mean.add_(float(rank + 1))
+        tr = Trainer(None, net, training_id="r%d" % rank, save_dir=tempfile.mkdtemp(), lr=1e-2, device="cpu", distributed=False)
+        out[("sd0", rank)] = {k: v.clone() for k, v in tr.model.state_dict().items()}
+        xg = torch.Generator().manual_seed(7 + rank)
+        tr.optimizer.zero_grad()
+        tr.model(torch.randn(16, 6, generator=xg)).square().mean().backward()
+        tr.grad_sync()
+        tr._guarded_step()
+        out[("sd1", rank)] = {k: v.clone() for k, v in tr.model.state_dict().items() if "running" not in k and "num_batches" not in k}
     finally:
         dist.destroy_process_group()
 
@@ -65,3 +80,9 @@ def test_flat_grad_allreduce_is_mean_of_rank_grads_and_shards_are_disjoint():
         assert torch.allclose(got[0], mean0, atol=1e-7) and torch.allclose(got[1], mean1, atol=1e-7)
         assert torch.equal(got[2], torch.zeros(3, 3))               # a parameter without grad gets the (zero) mean
     assert len(out[("n", 0)]) == 2 and len(out[("n", 1)]) == 2      # 8 circuits -> 4 per rank -> 2 batches of 2
+    for tag in ("sd0", "sd1"):
+        a, b = out[(tag, 0)], out[(tag, 1)]
+        assert a.keys() == b.keys() and len(a) >= 4
+        for k in a:
+            assert torch.equal(a[k], b[k]), (tag, k)
+    assert float(out[("sd0", 1)]["1.running_mean"][0]) == 1.0        # rank 0's buffer (0 + 1), not rank 1's

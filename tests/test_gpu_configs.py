@@ -1,0 +1,135 @@
+"""GPU parity at the BASELINE.json configuration sizes (the CUDA path through the C ABI vs the CPU oracle on the same seeded
+inputs): cfg2 = the benchmark workload itself, cfg3 = XMG / XAG with multi-round propagation, cfg4 = all five updatable gate
+codes with reparameterisation + KL + func loss in fp32 and bf16, cfg5 = one 100 k-gate / 600+-level MIG.
+
+Tolerances (north_star): embeddings, losses and gradients within 1e-4 relative (max-norm per tensor) in fp32; the bf16
+configuration within 2e-2 (embeddings / losses) and 5e-2 (gradients)."""
+import pytest
+import torch
+
+from oracle import dg_oracle as O
+from util import build_model, check_grads, oracle_inputs, oracle_train_grads, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+BF16_TOL, BF16_GRAD_TOL = 2e-2, 5e-2
+W = (1.0, 4.0, 4.0)
+
+
+def run_both(kind, mix, batch, n_pi, n_gates, window, rounds, cfg, variational=False, kl_weight=0.0, precision="fp32",
+             weight_seed=2, n_pairs=64):
+    import deepgate
+    from deepgate import ops, synth
+    circuits = synth.make_circuits(mix, batch, n_pi, n_gates, cfg=cfg, window=window, n_pairs=n_pairs)
+    G = deepgate.circuits_to_batch(circuits, "cuda")
+    sd = O.synth_state_dict(kind, weight_seed, variational=variational)
+    model = build_model(kind, sd, rounds, variational=variational)
+    gen = torch.Generator().manual_seed(3)
+    E, n = G.edge_index.size(1), G.x.size(0)
+    pos = G.edge_index.cpu()[:, torch.randperm(E, generator=gen)]
+    neg = torch.randint(0, n, (2, E), generator=gen)
+    eps = (torch.randn(n, 64, generator=gen), torch.randn(n, 64, generator=gen)) if variational else None
+    ops.set_precision(precision)
+    try:
+        if variational:
+            model.sample_noise = (eps[0].cuda(), eps[1].cuda())
+        hs, hf = model(G)
+        rec, _, _ = model.recon_loss(hs, pos.cuda(), neg.cuda())
+        prb = torch.nn.L1Loss()(model.pred_prob(hf), G.prob)
+        _, _, _, fnc = ops.vae_func_loss(hf=hf, tt_pair_index=G.tt_pair_index, tt_sim=G.tt_sim)
+        total = W[0] * rec + W[1] * prb + W[2] * fnc
+        got = {"hs": hs, "hf": hf, "recon": rec, "prob": prb, "func": fnc}
+        if variational:
+            got["kl"] = model.kl_loss()
+            total = total + kl_weight * got["kl"]
+        total.backward()
+    finally:
+        ops.set_precision("fp32")
+    ref_total, parts, grads = oracle_train_grads(kind, sd, oracle_inputs(G, pos, neg), W, rounds, vae_eps=eps, kl_weight=kl_weight)
+    named = {k: p.grad for k, p in model.named_parameters()}
+    return G, got, parts, named, grads
+
+
+def assert_fp32(got, parts, named, grads, what):
+    e_hs, e_hf = rel(got["hs"], parts["hs"]), rel(got["hf"], parts["hf"])
+    assert e_hs < TOL and e_hf < TOL, (what, e_hs, e_hf)
+    for key in ("recon", "prob", "func", "kl"):
+        if key in parts:
+            assert abs(float(got[key]) - float(parts[key])) < TOL * max(1.0, abs(float(parts[key]))), (what, key)
+    worst = check_grads(named, grads, TOL, what)
+    print("%s: hs %.2e hf %.2e worst grad %.2e" % (what, e_hs, e_hf, worst))
+
+
+def test_cfg2_full_size_matches_oracle():
+    """DG_AE AIG encoder, batch 64, layernorm -- the exact batch bench.py times (seed cfg = 2, rank 0, batch 0)."""
+    G, got, parts, named, grads = run_both("aig", "aig", 64, (16, 64), (500, 1500), None, 1, cfg=2)
+    assert G.x.size(0) > 60000
+    assert_fp32(got, parts, named, grads, "cfg2")
+
+
+@pytest.mark.parametrize("kind,rounds", [("xmg", 2), ("xag", 4)])
+def test_cfg3_multi_round_batch64_matches_oracle(kind, rounds):
+    """XMG and XAG encoders with MAJ / XOR aggregators, batch 64, multi-round propagation."""
+    G, got, parts, named, grads = run_both(kind, kind, 64, (16, 64), (500, 1500), None, rounds, cfg=3)
+    assert G.x.size(0) > 60000
+    assert_fp32(got, parts, named, grads, "cfg3-%s-r%d" % (kind, rounds))
+
+
+def test_cfg4_all_codes_with_kl_and_func_fp32():
+    """Mixed batch with every updatable gate code (XMG model = superset), reparameterisation + KL + func loss."""
+    G, got, parts, named, grads = run_both("xmg", "xmg", 64, (16, 64), (500, 1500), None, 1, cfg=4, variational=True, kl_weight=1.0)
+    code = G.gate.reshape(-1)
+    assert all(int(((code == c) & (G.forward_level >= 1)).sum()) > 0 for c in (1, 2, 3, 4, 5))
+    assert float(parts["kl"]) > 0.0
+    assert_fp32(got, parts, named, grads, "cfg4-fp32")
+
+
+def test_cfg4_all_codes_with_kl_and_func_bf16():
+    """The bf16 configuration against the fp32 oracle within the stated tolerance, attention gradients included
+    (scale-relative: they are sums of terms that cancel per softmax group)."""
+    G, got, parts, named, grads = run_both("xmg", "xmg", 64, (16, 64), (500, 1500), None, 1, cfg=4, variational=True, kl_weight=1.0,
+                                           precision="bf16")
+    e_hs, e_hf = rel(got["hs"], parts["hs"]), rel(got["hf"], parts["hf"])
+    assert e_hs < BF16_TOL and e_hf < BF16_TOL, (e_hs, e_hf)
+    assert e_hs > 1e-5, "bf16 mode did not engage (result is fp32-accurate)"
+    for key in ("recon", "prob", "func", "kl"):
+        assert abs(float(got[key]) - float(parts[key])) < BF16_TOL * max(1.0, abs(float(parts[key]))), key
+    worst = 0.0
+    for k, ref in grads.items():
+        if ref is None or float(ref.abs().max()) == 0.0:
+            continue
+        g = named[k]
+        mod = k.split(".")[0]
+        if ".msg_q." in k or k.endswith("msg_k.bias") or k.endswith("attn_lin.bias"):
+            assert float(g.abs().max()) <= BF16_GRAD_TOL * float(grads[mod + ".msg_k.weight"].abs().max()) + 1e-12, k
+            continue
+        if k.endswith("attn_lin.weight") or k.endswith("msg_k.weight"):
+            vscale = float(grads[mod + ".msg_v.weight"].abs().max())
+            floor = BF16_GRAD_TOL * max(float(ref.abs().max()), 1e-2 * vscale)
+            if k.endswith("attn_lin.weight"):
+                assert float(g[:, :64].abs().max()) <= floor + 1e-12, k
+                g, ref = g[:, 64:], ref[:, 64:]
+            assert float((g.detach().double().cpu() - ref.double()).abs().max()) <= floor, k
+            continue
+        worst = max(worst, rel(g, ref))
+    assert worst < BF16_GRAD_TOL, worst
+    print("cfg4-bf16: hs %.2e hf %.2e worst grad %.2e" % (e_hs, e_hf, worst))
+
+
+def test_cfg5_one_100k_gate_600_level_circuit():
+    """Large synthetic MIG (100 k gates, window 880 -> 600+ levels): embeddings and gradients vs the oracle, and the error per
+    depth bucket -- the recurrence is contractive, so the error must not grow with depth."""
+    G, got, parts, named, grads = run_both("mig", "mig", 1, 16, 100000, 880, 1, cfg=5)
+    L = int(G.forward_level.max()) + 1
+    assert G.x.size(0) == 100016 and L >= 600
+    assert_fp32(got, parts, named, grads, "cfg5")
+    lvl = G.forward_level.cpu()
+    err = (got["hf"].detach().cpu().double() - parts["hf"].double()).abs().max(dim=1).values
+    scale = float(parts["hf"].abs().max())
+    buckets = []
+    for b in range(10):
+        sel = (lvl >= 1 + b * (L - 1) // 10) & (lvl < 1 + (b + 1) * (L - 1) // 10)
+        buckets.append(float(err[sel].max()) / scale)
+    print("cfg5 hf error by depth decile (relative to max |hf|):", " ".join("%.1e" % v for v in buckets))
+    assert max(buckets) < TOL
+    assert max(buckets[5:]) < 4 * max(buckets[:5]) + 1e-6, buckets             # flat across depth, not accumulating

@@ -413,3 +413,29 @@ def test_struct_backward_paths_agree_at_tile_boundaries(n_nodes, monkeypatch):
     assert torch.equal(s0, s1) and torch.isfinite(s1).all()
     for k in g0:
         assert rel(g1[k], g0[k]) < 1e-4, (k, rel(g1[k], g0[k]))
+
+
+@pytest.mark.parametrize("n_nodes", [3969, 4000, 4096, 135400, 137000])
+def test_struct_forward_at_the_tile_search_boundaries(n_nodes):
+    """Tile counts at which the warp-cooperative range search of the struct forward (csrc/mgv_tc.cuh warp_lower_bound) ends
+    on a window of exactly 32 entries with no entry >= the target (32 tiles; 1057-1089 tiles): round 1 returned lo - 1 there
+    and the last CTA skipped its trailing tiles (states stayed uninitialised).  Every row of the output is compared."""
+    import deepgate
+    from deepgate import synth
+    c = synth.make_circuit("mig", 16, n_nodes - 16, seed=n_nodes, window=2000)
+    G = deepgate.circuits_to_batch([c], "cuda")
+    assert G.x.size(0) == n_nodes
+    sd = O.synth_state_dict("mig", 44, layernorm=True)
+    enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, s_rounds=1, t_rounds=1, layernorm=True).cuda()
+    enc.load_state_dict({k[len("mig_struct_encoder."):]: v for k, v in sd.items() if k.startswith("mig_struct_encoder.")})
+    code = G.gate.reshape(-1).long()
+    feat = torch.nn.functional.one_hot((code == 1).long(), 6).float()
+    with torch.no_grad():
+        s, t = enc(feat, feat, G.edge_index)
+    P = {k: v for k, v in sd.items() if k.startswith("mig_struct_encoder.")}
+    so = O.multi_gcn_encoder(P, "mig_struct_encoder.source_conv", feat.cpu(), G.edge_index.cpu(), 1, True)
+    to = O.multi_gcn_encoder(P, "mig_struct_encoder.target_conv", feat.cpu(), G.edge_index.cpu(), 1, True)
+    assert torch.isfinite(s).all() and torch.isfinite(t).all()
+    err_s = (s.cpu() - so).abs().max(dim=1).values
+    assert float(err_s.max()) < TOL * float(so.abs().max()), int(err_s.argmax())
+    assert rel(t, to) < TOL

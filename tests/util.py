@@ -19,12 +19,14 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def build_model(kind, state_dict, num_rounds=1, device="cuda", s_rounds=4, t_rounds=4, layernorm=True):
+def build_model(kind, state_dict, num_rounds=1, device="cuda", s_rounds=4, t_rounds=4, layernorm=True, variational=False):
     import deepgate
     enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, enable_reverse=True,
                                                      s_rounds=s_rounds, t_rounds=t_rounds, layernorm=layernorm)
-    model = getattr(deepgate, KIND_MODULE[kind]).Model(struct_encoder=enc, num_rounds=num_rounds, dim_hidden=64)
-    model.load_state_dict(state_dict, strict=False)
+    kw = {"variational": True} if variational else {}
+    model = getattr(deepgate, KIND_MODULE[kind]).Model(struct_encoder=enc, num_rounds=num_rounds, dim_hidden=64, **kw)
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing), (missing, unexpected)
     return model.to(device).eval()
 
 
@@ -63,9 +65,10 @@ def check_grads(named_grads, ref_grads, tol, what=""):
             continue
         if k.endswith("attn_lin.weight") or k.endswith("msg_k.weight"):
             # attention parameters: exactly zero for fan-in-1 gates (alpha == 1), and the query half of
-            # attn_lin.weight is mathematically zero -> absolute floor tied to the value path's scale
+            # attn_lin.weight is mathematically zero -> absolute floor tied to the value path's scale (only reached by
+            # the fan-in-1 codes; for the others the bound is tol * max |ref|, the plain max-norm relative bar)
             vscale = float(ref_grads[k.split(".")[0] + ".msg_v.weight"].abs().max())
-            floor = tol * max(float(ref.abs().max()), 1e-2 * vscale)
+            floor = tol * max(float(ref.abs().max()), 1e-3 * vscale)
             if k.endswith("attn_lin.weight"):
                 assert float(got[:, :64].abs().max()) <= floor + 1e-12, (what, k)
                 got, ref = got[:, 64:], ref[:, 64:]
