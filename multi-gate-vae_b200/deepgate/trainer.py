@@ -226,8 +226,8 @@ class Trainer(object):
         fused = str(self.device).startswith("cuda") and all(g.get("fused") for g in self.optimizer.param_groups)
         if fused:
             if getattr(self, "_found_inf", None) is None:
-                self._found_inf = torch.zeros(1, dtype=torch.float32, device=self.device)
-            torch.ne(error_word(torch.device(self.device)), 0, out=self._found_inf)         # one tiny launch, no sync
+                self._found_inf = torch.zeros((), dtype=torch.float32, device=self.device)
+            torch.ne(error_word(torch.device(self.device))[0], 0, out=self._found_inf)      # one tiny launch, no sync
             self.optimizer.found_inf = self._found_inf
             self.optimizer.grad_scale = None
             try:

@@ -178,8 +178,12 @@ def test_replay_of_train_py_call_sequence(tmp_path, monkeypatch, kind, mix, mode
             if trainer.local_rank == 0:
                 trainer.save(os.path.join(trainer.log_dir, "stage_%d.pth" % (stage + 1)))
         after = trainer.model.state_dict()
-        moved = [k for k in before if before[k].is_floating_point() and not torch.equal(before[k], after[k])]
-        assert len(moved) > 0.8 * sum(v.is_floating_point() for v in before.values())         # the steps trained the model
+        # the steps trained the model: every tensor moved, except those whose gradient is mathematically zero (the query
+        # path / key bias / attention bias cancel in the softmax; fan-in-1 gates have no attention gradient at all)
+        frozen = (".msg_q.", "msg_k.bias", "attn_lin.bias", "aggr_not_func.attn_lin", "aggr_not_func.msg_k")
+        still = [k for k in before if before[k].is_floating_point() and torch.equal(before[k], after[k])
+                 and not any(tag in k for tag in frozen)]
+        assert not still, still
         assert all(torch.isfinite(v).all() for v in after.values() if v.is_floating_point())
         log = open(trainer.log_path).read()
         assert log.count("train|") == 2 and log.count("val|") == 2
