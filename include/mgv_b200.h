@@ -114,8 +114,10 @@ int mgv_build_degree_order(const int32_t* ptr, const int32_t* idx, int32_t N, in
  * twins): per round, per level >= 1, per handled code: TFMlpAggr (arch/tfmlp.py:31-46) over the
  * predecessors' [hs || hf] rows, then the code's nn.GRU cell with h = hf[node], hf[node] <- h'.
  *
- * weights: float [MGV_NCODE][MGV_SWEEP_PACK_FLOATS]; handled_mask bit c set = code c has an
- * aggregator/GRU pair.  Block layout (floats), D = 64:
+ * weights: the buffer mgv_sweep_pack fills (mgv_sweep_pack_bytes() bytes: natural blocks float [MGV_NCODE][MGV_SWEEP_PACK_FLOATS],
+ * then the tensor-core weight images); handled_mask bit c set = code c has an aggregator/GRU pair.  rounds = 1 (the reference
+ * default) runs on the tcgen05 kernels of csrc/sweep_tc.cu, rounds > 1 on the mma.sync kernels of csrc/sweep.cu.
+ * Natural block layout (floats), D = 64:
  *      0  u[128]          = msg_k.weight^T attn_lin.weight[0,64:128]   (query part cancels in the softmax)
  *    128  WvT[128][64]    = msg_v.weight^T          8320 bv[64]
  *   8384  WihT[64][192]   = weight_ih_l0^T         20672 WhhT[64][192] = weight_hh_l0^T
@@ -226,14 +228,18 @@ int mgv_vae_func_loss_bwd(const float* g_out, const float* gz, const float* mu, 
  * mgv_struct_unpack_grads applies the chain rule of the composition (Wc = W_ih[:, :64] W_msg, bc = W_ih[:, :64] b_msg) to the gradient
  * blocks and writes, per encoder, d(those parameters) back to back in the same order and natural shapes.
  * level sweep, per listed gate code: [attn_lin.weight, msg_k.weight, msg_v.weight, msg_v.bias, weight_ih_l0, weight_hh_l0,
- *   bias_ih_l0, bias_hh_l0]  ->  pack [MGV_NCODE][MGV_SWEEP_PACK_FLOATS] (blocks of unlisted codes untouched).
+ *   bias_ih_l0, bias_hh_l0]  ->  pack: a buffer of mgv_sweep_pack_bytes() bytes = the natural blocks [MGV_NCODE][MGV_SWEEP_PACK_FLOATS]
+ *   followed by one tensor-core weight image per code (Wc = weight_ih_l0 msg_v.weight as fp16 hi/lo -- bf16 for precision 1 --
+ *   planes in the UMMA layout + composed biases, csrc/sweep_layout.cuh); blocks / images of unlisted codes are untouched.
+ *   This buffer is the `weights` argument of mgv_level_sweep_fwd / _bwd.
  * mgv_sweep_unpack_grads writes per listed code d attn_lin.weight [128] then d msg_k.weight [64][128]; the other gradients are
  * read in place from the gradient block (natural layouts).
  */
 int mgv_struct_pack(const void* const* params, int32_t num_enc, int32_t layernorm, int32_t feat, float* pack, mgv_stream_t stream);
 int mgv_struct_unpack_grads(const void* const* params, int32_t num_enc, int32_t layernorm, int32_t feat,
                             const float* grads, float* out, mgv_stream_t stream);
-int mgv_sweep_pack(const void* const* params, const int32_t* codes, int32_t n, float* pack, mgv_stream_t stream);
+size_t mgv_sweep_pack_bytes(void);
+int mgv_sweep_pack(const void* const* params, const int32_t* codes, int32_t n, float* pack, int32_t precision, mgv_stream_t stream);
 int mgv_sweep_unpack_grads(const void* const* params, const int32_t* codes, int32_t n, const float* grads, float* out,
                            mgv_stream_t stream);
 

@@ -4,7 +4,7 @@
 //   struct encoder  Wc = W_ih[:, :64] W_msg,  bc = W_ih[:, :64] b_msg   (AggConv composed into the GRU input weights,
 //                   digae_layer.py:266-268 + arch/gcn_conv.py:36-42) and the chain rule back to W_msg, b_msg, W_ih;
 //   level sweep     u = msg_k.weight^T attn_lin.weight[0, 64:]  (arch/tfmlp.py:39-42) and back to attn_lin / msg_k.
-#include "mgv_common.cuh"
+#include "sweep_layout.cuh"
 
 namespace {
 
@@ -105,13 +105,56 @@ struct SweepParams {                  // per listed code: attn_lin.weight [1][12
     int n;
 };
 
+// Blocks [0, SWEEP_NAT_BLOCKS) write the natural block; the blocks behind them the tensor-core weight image of the code
+// (sweep_layout.cuh): Wc = W_ih W_v as fp16 hi/lo planes in the UMMA layout + the fp32 tail (u, composed biases).
+constexpr int SWEEP_NAT_BLOCKS = 32;
+constexpr int SWEEP_IMG_ITEMS = G3 * 16 + 384;
+template <bool LOWP>
 __global__ void sweep_pack_kernel(const SweepParams sp, float* __restrict__ pack) {
     const int q = blockIdx.y;
     if (q >= sp.n) return;
     const float* aw = sp.p[q][0]; const float* kw = sp.p[q][1]; const float* vw = sp.p[q][2]; const float* vb = sp.p[q][3];
     const float* wih = sp.p[q][4]; const float* whh = sp.p[q][5]; const float* bih = sp.p[q][6]; const float* bhh = sp.p[q][7];
     float* P = pack + (size_t)sp.code[q] * SW_PACK;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < SW_PACK; i += gridDim.x * blockDim.x) {
+    if (blockIdx.x >= SWEEP_NAT_BLOCKS) {
+        using namespace sweep_layout;
+        uint8_t* img = reinterpret_cast<uint8_t*>(pack) + IMG_OFFSET + (size_t)sp.code[q] * IMG_PAD;
+        const int i = (blockIdx.x - SWEEP_NAT_BLOCKS) * blockDim.x + threadIdx.x;
+        if (i < G3 * 16) {                                   // Wc row g, 8 consecutive input columns: sum_k wih[g][k] vw[k][.]
+            const int g = i >> 4, c = i & 15;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            for (int k = 0; k < D; ++k) {
+                const float w = __ldg(wih + g * D + k);
+                const float4 a = mgv_ldg4(vw + k * D2 + c * 8), b = mgv_ldg4(vw + k * D2 + c * 8 + 4);
+                v[0] = fmaf(w, a.x, v[0]); v[1] = fmaf(w, a.y, v[1]); v[2] = fmaf(w, a.z, v[2]); v[3] = fmaf(w, a.w, v[3]);
+                v[4] = fmaf(w, b.x, v[4]); v[5] = fmaf(w, b.y, v[5]); v[6] = fmaf(w, b.z, v[6]); v[7] = fmaf(w, b.w, v[7]);
+            }
+            uint4 hi, lo;
+            tc::split8p<LOWP>(v, hi, lo);
+            const uint32_t off = (uint32_t)(c >> 3) * KB_W + tc::sw128_off(g, c & 7);
+            *reinterpret_cast<uint4*>(img + I_WC_HI + off) = hi;
+            *reinterpret_cast<uint4*>(img + I_WC_LO + off) = lo;
+        } else if (i < SWEEP_IMG_ITEMS) {
+            const int j = i - G3 * 16;
+            float v = 0.f;
+            if (j < 128) {                                   // u[k] = sum_o aw[64 + o] kw[o][k]
+                for (int o = 0; o < D; ++o) v = fmaf(__ldg(aw + D + o), __ldg(kw + o * D2 + j), v);
+            } else {
+                const int t = (j - 128) >> 6, u = (j - 128) & 63;          // 0 b_r, 1 b_z, 2 b_in, 3 b_hn
+                if (t == 3) v = __ldg(bhh + 2 * D + u);
+                else {
+                    const int g = t * D + u;
+                    v = __ldg(bih + g) + (t < 2 ? __ldg(bhh + g) : 0.f);
+                    for (int k = 0; k < D; ++k) v = fmaf(__ldg(wih + g * D + k), __ldg(vb + k), v);
+                }
+            }
+            reinterpret_cast<float*>(img + I_F32)[j] = v;
+        }
+        return;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < SW_PACK; i += SWEEP_NAT_BLOCKS * blockDim.x) {
         float v = 0.f;
         if (i < 128) {                                               // u[k] = sum_o aw[64 + o] kw[o][k]
             float acc = 0.f;
@@ -185,8 +228,12 @@ extern "C" int mgv_struct_unpack_grads(const void* const* params, int32_t num_en
     return mgv_check_cuda(cudaGetLastError(), "mgv_struct_unpack_grads");
 }
 
-extern "C" int mgv_sweep_pack(const void* const* params, const int32_t* codes, int32_t n, float* pack, mgv_stream_t stream) {
+extern "C" size_t mgv_sweep_pack_bytes(void) { return sweep_layout::PACK_TOTAL_BYTES; }
+
+extern "C" int mgv_sweep_pack(const void* const* params, const int32_t* codes, int32_t n, float* pack, int32_t precision,
+                              mgv_stream_t stream) {
     MGV_REQUIRE(params && codes && pack && n >= 0 && n <= MGV_NCODE, "mgv_sweep_pack: bad argument");
+    MGV_REQUIRE(precision == 0 || precision == 1, "mgv_sweep_pack: precision must be 0 (fp32-accurate) or 1 (bf16)");
     if (n == 0) return MGV_OK;
     SweepParams sp{};
     sp.n = n;
@@ -195,7 +242,9 @@ extern "C" int mgv_sweep_pack(const void* const* params, const int32_t* codes, i
         sp.code[q] = codes[q];
         for (int k = 0; k < 8; ++k) sp.p[q][k] = (const float*)params[q * 8 + k];
     }
-    sweep_pack_kernel<<<dim3(32, n), 256, 0, (cudaStream_t)stream>>>(sp, pack);
+    const dim3 grid(SWEEP_NAT_BLOCKS + (SWEEP_IMG_ITEMS + 255) / 256, n);
+    if (precision == 1) sweep_pack_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(sp, pack);
+    else sweep_pack_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(sp, pack);
     mgv_count_launches(1);
     return mgv_check_cuda(cudaGetLastError(), "mgv_sweep_pack");
 }

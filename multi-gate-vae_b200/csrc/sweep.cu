@@ -13,9 +13,25 @@
 // CTAs are statically specialised per gate code (proportional to the code's node count) so a
 // CTA streams one code's weights (L1/L2 resident) and, in backward, keeps that code's
 // weight-gradient accumulators in shared memory for the whole sweep.
+#include <stdlib.h>
+#include <string.h>
 #include "mgv_mma16.cuh"
 
 long long* mgv_debug_trace();
+// tensor-core kernels of the single-round sweep (sweep_tc.cu)
+int mgv_sweep_tc_grid(int* grid_out);
+int mgv_sweep_tc_fwd(const mgv_schedule* sch, unsigned handled, const int* cta_start, int grid, const float* weights,
+                     const float* hs, float* hf, int32_t* sync, int precision, cudaStream_t st);
+size_t mgv_sweep_tc_bwd_workspace_bytes(int64_t N, int64_t E);
+bool mgv_sweep_tc_bwd_available();
+int mgv_sweep_tc_bwd(const mgv_schedule* sch, unsigned handled, const int* cta_start, int grid, const float* weights,
+                     const float* hs, const float* hf, float* ghs, float* ghf, float* grads, void* ws, size_t ws_bytes,
+                     int32_t* sync, int precision, cudaStream_t st);
+// num_rounds = 1 (the reference default) runs on the tcgen05 kernels; MGV_SWEEP=mma forces the mma.sync kernels (A/B checks)
+static bool sweep_use_tc(int rounds) {
+    const char* e = getenv("MGV_SWEEP");
+    return rounds == 1 && !(e && !strcmp(e, "mma"));
+}
 
 namespace {
 
@@ -971,6 +987,14 @@ extern "C" int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint
     int grid = 0;
     const size_t smem = (size_t)F_SMEM_BYTES;
     MGV_REQUIRE(precision == 0 || precision == 1, "level sweep: precision must be 0 (fp32-accurate) or 1 (bf16)");
+    if (sweep_use_tc(rounds)) {
+        rc = mgv_sweep_tc_grid(&grid);
+        if (rc != MGV_OK) return rc;
+        assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
+        if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;
+        MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
+        return mgv_sweep_tc_fwd(sch, handled_mask, d.cta_start, grid, weights, hs, hf_all, sync, precision, st);
+    }
     const void* fkern = precision == 1 ? (const void*)sweep_fwd_kernel<true> : (const void*)sweep_fwd_kernel<false>;
     rc = coop_grid(fkern, smem, FTHREADS, &grid);
     if (rc != MGV_OK) return rc;
@@ -997,7 +1021,8 @@ extern "C" size_t mgv_sweep_bwd_workspace_bytes(int64_t N, int64_t E) {
     b += mgv_align_up((size_t)N * D2 * 4 + 256, 256);          // dxb
     b += 2 * mgv_align_up((size_t)E * 4 + 256, 256);           // alpha, dscore
     b += mgv_align_up((size_t)grid * GRAD * 4 + 256, 256);     // partial
-    return b + 1024;
+    const size_t tcb = mgv_sweep_tc_bwd_workspace_bytes(N, E);
+    return (b > tcb ? b : tcb) + 1024;
 }
 
 extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint32_t handled_mask,
@@ -1014,6 +1039,18 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     int grid = 0;
     const bool single = rounds == 1;                          // h = 0 everywhere: the 32-node variant without W_hh
     MGV_REQUIRE(precision == 0 || precision == 1, "level sweep: precision must be 0 (fp32-accurate) or 1 (bf16)");
+    if (sweep_use_tc(rounds) && mgv_sweep_tc_bwd_available()) {
+        rc = mgv_sweep_tc_grid(&grid);
+        if (rc != MGV_OK) return rc;
+        assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
+        if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;
+        if (ws_bytes < mgv_sweep_bwd_workspace_bytes(sch->N, sch->E)) {
+            mgv_set_error("mgv_level_sweep_bwd: workspace %zu < %zu bytes", ws_bytes, mgv_sweep_bwd_workspace_bytes(sch->N, sch->E));
+            return MGV_ERR_WORKSPACE;
+        }
+        MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
+        return mgv_sweep_tc_bwd(sch, handled_mask, d.cta_start, grid, weights, hs, hf_all, ghs, ghf, grads, ws, ws_bytes, sync, precision, st);
+    }
     const void* kern = single ? (precision == 1 ? (const void*)sweep_bwd_kernel<32, false, true> : (const void*)sweep_bwd_kernel<32, false, false>)
                               : (precision == 1 ? (const void*)sweep_bwd_kernel<16, true, true> : (const void*)sweep_bwd_kernel<16, true, false>);
     const size_t smem = single ? (size_t)BwdSmem<32, false>::BYTES : (size_t)BwdSmem<16, true>::BYTES;

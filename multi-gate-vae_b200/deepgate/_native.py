@@ -69,7 +69,8 @@ _PROTOTYPES = {
                                              _vp, _vp, _vp, _vp]),
     "mgv_struct_pack": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mgv_struct_unpack_grads": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "mgv_sweep_pack": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    "mgv_sweep_pack_bytes": (_sz, []),
+    "mgv_sweep_pack": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
     "mgv_sweep_unpack_grads": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "mgv_negative_sample": (ctypes.c_int, [_vp, _vp, _i32, _i64, ctypes.c_uint64, _vp, _vp]),
     "mgv_recon_loss_fwd": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),

@@ -91,13 +91,14 @@ def _sweep_tables(params, codes):
     return sel
 
 
-def _sweep_pack(params, codes, device):
-    """[8][66112] weight blocks in the kernel layout (include/mgv_b200.h), one launch."""
-    pack = torch.zeros(nat.NCODE, nat.SWEEP_PACK_FLOATS, dtype=torch.float32, device=device)
+def _sweep_pack(params, codes, device, prec):
+    """Natural weight blocks [8][66112] + the tensor-core weight images (include/mgv_b200.h), one launch."""
+    lib = nat.lib()
+    pack = torch.zeros(lib.mgv_sweep_pack_bytes() // 4, dtype=torch.float32, device=device)
     sel = _sweep_tables(params, codes)
-    with torch.cuda.device(device):
-        nat.check(nat.lib().mgv_sweep_pack(_ptr_table(sel), _code_table(codes), len(codes), nat.ptr(pack),
-                                           nat.stream_of(device)), "mgv_sweep_pack")
+    with nat.on_device(device):
+        nat.check(lib.mgv_sweep_pack(_ptr_table(sel), _code_table(codes), len(codes), nat.ptr(pack), prec,
+                                     nat.stream_of(device)), "mgv_sweep_pack")
     return pack
 
 
@@ -114,7 +115,7 @@ class LevelSweepFunction(torch.autograd.Function):
         for c in codes:
             mask |= 1 << c
         prec = _prec()
-        pack = _sweep_pack(params, codes, dev)
+        pack = _sweep_pack(params, codes, dev, prec)
         hf_all = torch.zeros(rounds, max(N, 1), nat.D, dtype=torch.float32, device=dev)
         sync = torch.zeros(64, dtype=torch.int32, device=dev)
         with nat.on_device(dev):
