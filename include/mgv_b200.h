@@ -89,14 +89,26 @@ int mgv_levelize(const int32_t* in_ptr, const int32_t* out_ptr, const int32_t* o
 /* Node lists per (level, code): order[N] = node ids stably sorted by (level, code) -- ascending
  * id inside a segment, i.e. G.forward_index[layer_mask & type_mask] (dg_ae_model_mig.py:89);
  * seg_ptr[L*MGV_NCODE + 1]; code_count_host[MGV_NCODE] = nodes of each code with level >= 1.
+ * STREAMS: the circuits of a batch never exchange messages, so a batch may be cut into `streams` independent node sets
+ * (stream_of_node int32 [N] in [0, streams), every edge inside one stream -- e.g. a partition of the batch's circuits; NULL
+ * and streams = 1 otherwise).  The lists are then sorted by (stream, level, code): seg_ptr[streams*L*MGV_NCODE + 1], segment
+ * (s, l, c) at index (s*L + l)*MGV_NCODE + c.  The level sweep runs the streams' level chains concurrently, each with its
+ * own barrier; results do not depend on the cut.
  * SYNCHRONISES (returns the per-code counts used to size the persistent grids) -- unless code_count_host is NULL
  * and err_flag is given: then the caller supplies the counts itself (e.g. computed at collate time on the host,
  * where the reference computes forward_level, parser_func_others.py:63) and nothing synchronises.
  */
-size_t mgv_level_lists_workspace_bytes(int64_t N, int32_t L);
-int mgv_build_level_lists(const int32_t* level, const int32_t* code, int32_t N, int32_t L,
-                          int32_t* order, int32_t* seg_ptr, int64_t* code_count_host,
+size_t mgv_level_lists_workspace_bytes(int64_t N, int32_t L);      /* pass streams * L */
+int mgv_build_level_lists(const int32_t* level, const int32_t* code, const int32_t* stream_of_node, int32_t streams,
+                          int32_t N, int32_t L, int32_t* order, int32_t* seg_ptr, int64_t* code_count_host,
                           void* ws, size_t ws_bytes, int32_t* err_flag, mgv_stream_t stream);
+
+/* Row descriptors of the level sweep, in the order of `order` (32 bytes per row, so a tile's static schedule data is ONE
+ * coalesced load instead of the chain order -> in_ptr -> in_src):
+ *   desc[t] = { node = order[t], in_ptr[node], fan-in, out_ptr[node], fan-out, first three predecessors (in_src) or 0 }
+ */
+int mgv_build_sweep_desc(const int32_t* order, const int32_t* in_ptr, const int32_t* in_src, const int32_t* out_ptr,
+                         int32_t N, int32_t* desc, mgv_stream_t stream);
 
 /* Degree order of one CSR direction, for the tensor-core tiles of the struct encoder: order[N] = node ids sorted
  * by DESCENDING degree (degrees >= 255 tie), ascending id inside a degree, so the 128 rows of a tile have
@@ -124,13 +136,13 @@ int mgv_build_degree_order(const int32_t* ptr, const int32_t* idx, int32_t N, in
  *  32960  bih[192]        33152 bhh[192]
  *  33344  Wv[64][128]     41536 Wih[192][64]       53824 Whh[192][64]          (natural copies, backward)
  * hf_all: float [R][N][64], zero-initialised by the caller; slot r = hf after round r.
- * sync: int32 [64] zero-initialised (grid barrier state).
+ * sync: int32 [64] (grid barrier state of up to two streams; zeroed by the call).
  */
 typedef struct mgv_schedule {
     int32_t N, L;
     int64_t E;
     const int32_t* order;      /* [N]   */
-    const int32_t* seg_ptr;    /* [L*MGV_NCODE+1] */
+    const int32_t* seg_ptr;    /* [streams*L*MGV_NCODE+1] */
     const int32_t* in_ptr;     /* [N+1] */
     const int32_t* in_src;     /* [E]   */
     const int32_t* out_ptr;    /* [N+1] */
@@ -143,6 +155,9 @@ typedef struct mgv_schedule {
     const uint32_t* tile_cost_out;
     const int32_t* gdesc_in;         /* [N][4] */
     const int32_t* gdesc_out;
+    int32_t streams;                 /* independent node sets of the level lists (mgv_build_level_lists); 0 or 1 = one */
+    int32_t reserved0;               /* 0 */
+    const int32_t* sweep_desc;       /* [N][8] mgv_build_sweep_desc (needed by the single-round level sweep) */
 } mgv_schedule;
 
 /* precision (all compute entry points): MGV_PRECISION_FP32 = fp32-accurate tensor-core products (fp16 hi/lo planes, three

@@ -2,7 +2,7 @@
 # Builds libmgv_b200.so (C ABI, see include/mgv_b200.h) for sm_100a, in-tree.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="${HERE}/../deepgate/_lib"
+OUT="${MGV_OUT:-${HERE}/../deepgate/_lib}"
 mkdir -p "${OUT}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O2 ${MGV_NVCC_EXTRA:-})

@@ -83,18 +83,39 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (int it = 0; it < (1 << 24); ++it) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
+// Bounded waits: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.  The bound is wall-clock time
+// (%globaltimer, checked every 1024 polls), not a poll count, so kernels slowed down 10-100x by a profiler or
+// compute-sanitizer still run to completion.
+constexpr unsigned long long WAIT_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct WaitGuard {
+    unsigned long long t0 = 0ull;
+    uint32_t polls = 0u;
+    __device__ __forceinline__ void tick() {
+        if ((++polls & 1023u) == 0u) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0ull) t0 = now;
+            else if (now - t0 > WAIT_TIMEOUT_NS) __trap();
+        }
     }
-    __trap();
+};
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    WaitGuard g;
+#pragma unroll 1
+    while (!mbar_try_wait(bar, parity)) g.tick();
 }
 
 // Whole-warp wait that keeps the issue slots of the SM sub-partition free for the warps doing work: lane 0 polls
@@ -102,33 +123,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // waiting roles starves the epilogue warp sharing their scheduler: measured ~8 cycles per instruction.)
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane, unsigned sleep_ns = 64) {
     if (lane == 0) {
-        for (int it = 0; it < (1 << 22); ++it) {
-            uint32_t done;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.b32 %0, 1, 0, p;\n\t}"
-                : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-            if (done) break;
+        WaitGuard g;
+#pragma unroll 1
+        while (!mbar_try_wait(bar, parity)) {
             __nanosleep(sleep_ns);
-            if (it == (1 << 22) - 1) __trap();
+            g.tick();
         }
     }
     __syncwarp();
 }
 // Single-thread variant (the MMA-issue thread).
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned sleep_ns = 64) {
-    for (int it = 0; it < (1 << 22); ++it) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
+    WaitGuard g;
+#pragma unroll 1
+    while (!mbar_try_wait(bar, parity)) {
         __nanosleep(sleep_ns);
+        g.tick();
     }
-    __trap();
 }
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -314,6 +325,19 @@ __device__ __forceinline__ void mma3p(uint32_t d_tmem, uint64_t a_hi, uint64_t a
     else mma3(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, accumulate);
 }
 __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
+// One lane of a fully converged warp (the elect.sync leader): tcgen05.mma / commit are issued under this predicate while the
+// whole warp runs the surrounding control flow, so descriptors stay in uniform registers (a lane == 0 branch makes every
+// operand a per-thread value: ptxas then wraps each UTCHMMA in an R2UR + ELECT loop, ~60 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0u;
+}
 
 // All previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint32_t bar) {

@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(256) levelize_kernel(LevelizeParams p) {
 }
 
 // ------------------------------------------------------------------------------------ level lists
-__global__ void node_keys_kernel(const int32_t* __restrict__ level, const int32_t* __restrict__ code, int n, int L,
+__global__ void node_keys_kernel(const int32_t* __restrict__ level, const int32_t* __restrict__ code,
+                                 const int32_t* __restrict__ stream_of_node, int streams, int n, int L,
                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ hist,
                                  int* __restrict__ bad) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,7 +316,12 @@ __global__ void node_keys_kernel(const int32_t* __restrict__ level, const int32_
     }
     int c = code[v];
     if (c < 0 || c > 6) c = 6;
-    const uint32_t k = (uint32_t)lv * MGV_NCODE + (uint32_t)c;
+    int sn = stream_of_node ? stream_of_node[v] : 0;
+    if (sn < 0 || sn >= streams) {
+        atomicOr(bad, 2);
+        sn = 0;
+    }
+    const uint32_t k = ((uint32_t)sn * (uint32_t)L + (uint32_t)lv) * MGV_NCODE + (uint32_t)c;
     keys[v] = k;
     vals[v] = (uint32_t)v;
     atomicAdd(&hist[k], 1u);
@@ -326,12 +332,25 @@ __global__ void copy_u32_to_i32_kernel(const uint32_t* __restrict__ src, int32_t
     if (i < n) dst[i] = (int32_t)src[i];
 }
 
-__global__ void code_count_kernel(const int32_t* __restrict__ seg_ptr, int L, unsigned long long* __restrict__ out) {
+__global__ void code_count_kernel(const int32_t* __restrict__ seg_ptr, int L, int streams, unsigned long long* __restrict__ out) {
     const int c = threadIdx.x;
     if (c >= MGV_NCODE) return;
     unsigned long long s = 0;
-    for (int l = 1; l < L; ++l) s += (unsigned long long)(seg_ptr[l * MGV_NCODE + c + 1] - seg_ptr[l * MGV_NCODE + c]);
+    for (int l = 0; l < streams * L; ++l)
+        if (l % L) s += (unsigned long long)(seg_ptr[l * MGV_NCODE + c + 1] - seg_ptr[l * MGV_NCODE + c]);
     out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------ sweep row descriptors
+__global__ void sweep_desc_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
+                                  const int32_t* __restrict__ out_ptr, int n, int4* __restrict__ desc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int v = order[t];
+    const int ib = in_ptr[v], ic = in_ptr[v + 1] - ib, ob = out_ptr[v], oc = out_ptr[v + 1] - ob;
+    const int s0 = ic > 0 ? in_src[ib] : 0, s1 = ic > 1 ? in_src[ib + 1] : 0, s2 = ic > 2 ? in_src[ib + 2] : 0;
+    desc[2 * (size_t)t] = make_int4(v, ib, ic, ob);
+    desc[2 * (size_t)t + 1] = make_int4(oc, s0, s1, s2);
 }
 
 // ------------------------------------------------------------------------------------ degree order
@@ -557,11 +576,14 @@ extern "C" size_t mgv_level_lists_workspace_bytes(int64_t N, int32_t L) {
     return b;
 }
 
-extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, int32_t N, int32_t L,
-                                     int32_t* order, int32_t* seg_ptr, int64_t* code_count_host,
+extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, const int32_t* stream_of_node, int32_t streams,
+                                     int32_t N, int32_t L, int32_t* order, int32_t* seg_ptr, int64_t* code_count_host,
                                      void* ws, size_t ws_bytes, int32_t* err_flag, mgv_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     MGV_REQUIRE(N >= 0 && L >= 1 && level && code && order && seg_ptr, "mgv_build_level_lists: bad argument");
+    MGV_REQUIRE(streams >= 1 && (streams == 1 || stream_of_node), "mgv_build_level_lists: streams > 1 needs stream_of_node");
+    const int L1 = L;
+    L = streams * L1;                                     // keys: (stream, level, code)
     MGV_REQUIRE(code_count_host || err_flag, "mgv_build_level_lists: the asynchronous form (no code_count_host) needs err_flag");
     MGV_REQUIRE((int64_t)L * MGV_NCODE < (1ll << 31), "mgv_build_level_lists: too many levels");
     if (ws_bytes < mgv_level_lists_workspace_bytes(N, L)) {
@@ -582,7 +604,7 @@ extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, 
     if (!err_flag) MGV_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
     MGV_CUDA(cudaMemsetAsync(khist, 0, (size_t)(nkeys + 1) * 4, st));
     if (N > 0) {
-        node_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(level, code, N, L, sb.k0, sb.v0, khist, bad);
+        node_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(level, code, stream_of_node, streams, N, L1, sb.k0, sb.v0, khist, bad);
         mgv_count_launches(1);
     }
     int rc = exclusive_scan(khist, (uint32_t*)seg_ptr, nkeys + 1, sb.tmp, st);
@@ -595,7 +617,7 @@ extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, 
         mgv_count_launches(1);
     }
     if (!code_count_host) return mgv_check_cuda(cudaGetLastError(), "mgv_build_level_lists");   // asynchronous form
-    code_count_kernel<<<1, 32, 0, st>>>(seg_ptr, L, counts);
+    code_count_kernel<<<1, 32, 0, st>>>(seg_ptr, L1, streams, counts);
     mgv_count_launches(1);
     MGV_CUDA(cudaGetLastError());
     unsigned long long ch[MGV_NCODE];
@@ -603,7 +625,17 @@ extern "C" int mgv_build_level_lists(const int32_t* level, const int32_t* code, 
     MGV_CUDA(cudaMemcpyAsync(ch, counts, sizeof(ch), cudaMemcpyDeviceToHost, st));
     MGV_CUDA(cudaMemcpyAsync(&bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     MGV_CUDA(cudaStreamSynchronize(st));
-    MGV_REQUIRE(err_flag || bad_h == 0, "mgv_build_level_lists: level outside [0, %d)", L);
+    MGV_REQUIRE(err_flag || bad_h == 0, "mgv_build_level_lists: level outside [0, %d) or stream outside [0, %d)", L1, streams);
     for (int c = 0; c < MGV_NCODE; ++c) code_count_host[c] = (int64_t)ch[c];
     return MGV_OK;
+}
+
+extern "C" int mgv_build_sweep_desc(const int32_t* order, const int32_t* in_ptr, const int32_t* in_src, const int32_t* out_ptr,
+                                    int32_t N, int32_t* desc, mgv_stream_t stream) {
+    MGV_REQUIRE(N >= 0 && order && in_ptr && in_src && out_ptr && desc, "mgv_build_sweep_desc: bad argument");
+    MGV_REQUIRE((reinterpret_cast<uintptr_t>(desc) & 15) == 0, "mgv_build_sweep_desc: desc must be 16-byte aligned");
+    if (N == 0) return MGV_OK;
+    sweep_desc_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(order, in_ptr, in_src, out_ptr, N, reinterpret_cast<int4*>(desc));
+    mgv_count_launches(1);
+    return mgv_check_cuda(cudaGetLastError(), "mgv_build_sweep_desc");
 }

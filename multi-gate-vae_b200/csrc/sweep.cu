@@ -908,21 +908,39 @@ __global__ void __launch_bounds__(BTHREADS, 1) sweep_bwd_kernel(const SweepDev p
     }
 }
 
-// Static CTA -> code assignment, proportional to the per-code node counts (at least one CTA per
-// code that has nodes).
-void assign_ctas(const int64_t* count, unsigned handled, int grid, int* start) {
+// Static CTA -> code assignment, proportional to the estimated work of each code's nodes at level >= 1: a fixed part per node
+// (dense products, pointwise, store) plus a part per predecessor row gathered.  The mean fan-in per code is not known on the
+// host; NOT (code 2 in every gate library of the reference) has one predecessor, the other codes share the remaining in-edges.
+// At least one CTA per code that has nodes.
+void assign_ctas(const int64_t* count, unsigned handled, int grid, int* start, int64_t E = -1) {
     int n[MGV_NCODE];
+    double w[MGV_NCODE];
     double total = 0;
     int active = 0;
+    double others = 0, nots = 0;
     for (int c = 0; c < MGV_NCODE; ++c) {
-        n[c] = 0;
-        if (((handled >> c) & 1u) && count[c] > 0) { total += (double)count[c]; ++active; }
+        if (!(((handled >> c) & 1u) && count[c] > 0)) continue;
+        if (c == 2) nots += (double)count[c]; else others += (double)count[c];
+    }
+    double fan_other = 2.0;
+    if (E >= 0 && others > 0) {
+        fan_other = ((double)E - nots) / others;
+        fan_other = fan_other < 1.0 ? 1.0 : (fan_other > 8.0 ? 8.0 : fan_other);
+    }
+    const char* env = getenv("MGV_SWEEP_FIXED_COST");
+    const double fixed = env ? atof(env) : 24.0;          // measured: a row costs about the same whatever its fan-in
+    for (int c = 0; c < MGV_NCODE; ++c) {
+        n[c] = 0; w[c] = 0;
+        if (((handled >> c) & 1u) && count[c] > 0) {
+            w[c] = (double)count[c] * (fixed + (c == 2 ? 1.0 : fan_other));
+            total += w[c]; ++active;
+        }
     }
     if (active > 0) {
         int used = 0;
         for (int c = 0; c < MGV_NCODE; ++c) {
-            if (!(((handled >> c) & 1u) && count[c] > 0)) continue;
-            int k = (int)((double)grid * (double)count[c] / total);
+            if (w[c] <= 0) continue;
+            int k = (int)((double)grid * w[c] / total);
             if (k < 1) k = 1;
             n[c] = k;
             used += k;
@@ -937,7 +955,7 @@ void assign_ctas(const int64_t* count, unsigned handled, int grid, int* start) {
             int best = -1; double load = -1;
             for (int c = 0; c < MGV_NCODE; ++c) {
                 if (n[c] == 0) continue;
-                const double l = (double)count[c] / n[c];
+                const double l = w[c] / n[c];
                 if (l > load) { load = l; best = c; }
             }
             ++n[best]; ++used;
@@ -957,6 +975,8 @@ int fill_common(SweepDev& d, const mgv_schedule* sch, int rounds, unsigned handl
     d.order = sch->order; d.seg_ptr = sch->seg_ptr; d.in_ptr = sch->in_ptr; d.in_src = sch->in_src;
     d.out_ptr = sch->out_ptr; d.out_pack = sch->out_pack; d.out_slot = sch->out_slot;
     d.weights = weights; d.hs = hs; d.bar = reinterpret_cast<unsigned*>(sync);
+    MGV_REQUIRE(sch->streams <= 1 || sweep_use_tc(rounds),
+                "level sweep: multi-round sweeps (and MGV_SWEEP=mma) need single-stream level lists (mgv_build_level_lists streams = 1)");
     d.ghs = d.ghf = d.dxb = d.alpha = d.dscore = d.partial = d.grads = nullptr;
     d.trace = nullptr;
     return MGV_OK;
@@ -990,7 +1010,7 @@ extern "C" int mgv_level_sweep_fwd(const mgv_schedule* sch, int32_t rounds, uint
     if (sweep_use_tc(rounds)) {
         rc = mgv_sweep_tc_grid(&grid);
         if (rc != MGV_OK) return rc;
-        assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
+        assign_ctas(sch->code_count, handled_mask, grid, d.cta_start, sch->E);
         if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;
         MGV_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(int32_t), st));
         return mgv_sweep_tc_fwd(sch, handled_mask, d.cta_start, grid, weights, hs, hf_all, sync, precision, st);
@@ -1042,7 +1062,7 @@ extern "C" int mgv_level_sweep_bwd(const mgv_schedule* sch, int32_t rounds, uint
     if (sweep_use_tc(rounds) && mgv_sweep_tc_bwd_available()) {
         rc = mgv_sweep_tc_grid(&grid);
         if (rc != MGV_OK) return rc;
-        assign_ctas(sch->code_count, handled_mask, grid, d.cta_start);
+        assign_ctas(sch->code_count, handled_mask, grid, d.cta_start, sch->E);
         if (d.cta_start[MGV_NCODE] == 0) return MGV_OK;
         if (ws_bytes < mgv_sweep_bwd_workspace_bytes(sch->N, sch->E)) {
             mgv_set_error("mgv_level_sweep_bwd: workspace %zu < %zu bytes", ws_bytes, mgv_sweep_bwd_workspace_bytes(sch->N, sch->E));

@@ -10,15 +10,21 @@
 //   GRU(x = W_v xbar + b_v, h = 0):  [r z n]_pre = Wc xbar + bias,  Wc = W_ih W_v (192 x 128, composed once per call),
 //   bias = W_ih b_v + b_ih (+ b_hh for r, z);  r = sig, z = sig, n = tanh(n_pre + r b_hn);  hf_i = (1 - z) n
 //
-// A level moves ~2 KB per gate and has only hundreds to thousands of gates, so a level is LATENCY bound: barrier -> index
-// chain -> row gather -> dense products -> store -> barrier.  The design removes what can be removed from that chain:
-//   * every level is spread over ALL CTAs of its gate code (tile = ceil(segment / CTAs) rows, at most 64), so the gather of
-//     a level runs on every SM at once;
+// A level moves ~2 KB per gate and has only hundreds to thousands of gates, so ONE level is a latency chain: barrier ->
+// row gather -> dense products -> pointwise -> store -> barrier.  The design (a) shortens the chain and (b) runs several
+// chains at once:
+//   * STREAMS: the circuits of a batch are independent, so the schedule cuts the batch into S circuit sets ("streams",
+//     mgv_schedule.streams) with their own (level, code) node lists and their own grid barrier.  A CTA runs S worker groups
+//     (one per stream: 16 / S warps + one tensor-core / barrier warp each) that share the weight image; while one stream
+//     waits on its barrier, its products or a gather, the warp scheduler runs the other -- the level chains overlap;
+//   * every level of a stream is spread over ALL CTAs of its gate code in equal tiles (at most 64 / S rows);
 //   * the products are issued TRANSPOSED -- D^T[gate unit][node] = Wc[gate unit][k] xbar^T[k][node] -- so the tensor-core
 //     time of a tile is proportional to its NODE count (UMMA N = rows rounded to 16) instead of a fixed 128-row M tile;
 //     the accumulator lives in tensor memory with TMEM lane = gate unit, which makes the biases per-thread constants;
-//   * the static part of the index chain (order -> in_ptr -> in_src) is prefetched BEFORE the level barrier is awaited;
-//   * the grid barrier is polled by one thread that then releases the workers through a shared-memory mbarrier.
+//   * gathers run a HALF WARP per node (lane = 4 hs + 4 hf columns), two nodes per warp instruction, with the rows of all
+//     the warp's nodes requested before the first is reduced; the static index chains (order -> in_ptr -> in_src, out_ptr ->
+//     out_pack / out_slot) of the NEXT tile are fetched while the tensor core works on the current one;
+//   * the grid barrier of a stream is polled by its tensor-core warp, which releases the workers through an mbarrier.
 // Operands are fp16 hi/lo planes with three products per K step (mgv_tc.cuh): fp32-accurate.
 #include <stdlib.h>
 #include <string.h>
@@ -34,24 +40,65 @@ constexpr int O_U = 0, O_BV = 8320, O_BIH = 32960, O_BHH = 33152, O_WV = 33344, 
 constexpr int G_U = 0, G_WV = 128, G_BV = 8320, G_WIH = 8384, G_WHH = 20672, G_BIH = 32960, G_BHH = 33152;
 constexpr int NODE_MASK = (1 << MGV_CODE_SHIFT) - 1;
 
-constexpr int WORKERS = 16;                     // worker warps; warp WORKERS issues the MMAs and polls the grid barrier
+constexpr int WORKERS = 16;                     // worker warps of a CTA, split evenly over the streams
 constexpr int NWT = WORKERS * 32;
-constexpr int NTHREADS = NWT + 32;
+constexpr int MAX_STREAMS = 2;
+constexpr int BAR_STRIDE = 32;                  // ints between the grid barrier counters of two streams (own 128-byte line)
+
+// Geometry of a CTA that serves S streams.
+template <int S>
+struct Geo {
+    static constexpr int WPS = WORKERS / S;                // worker warps per stream
+    static constexpr int NSW = WPS * 32;                   // worker threads per stream
+    static constexpr int NTS = 4 * WPS;                    // rows (nodes) of a tile, at most: four per worker warp = UMMA N
+    static constexpr int NTHREADS = NWT + 32 * S;          // + one tensor-core / barrier warp per stream
+    static constexpr uint32_t KBX = NTS * 128u;            // one 64-column K block of a node tile (SW128)
+    // forward, per stream: xbar hi / lo planes (2 K blocks each), z pre-activations [NTS][64] fp32, node ids
+    static constexpr uint32_t F_XB_HI = 0, F_XB_LO = 2 * KBX, F_ZX = 4 * KBX, F_IDS = F_ZX + NTS * D * 4;
+    static constexpr uint32_t F_STRIDE = (F_IDS + NTS * 4 + 1023u) & ~1023u;
+    static constexpr uint32_t F_BAR = IMG_PAD + S * F_STRIDE;                   // mbarriers: w | per stream x_full, acc_full, level
+    static constexpr uint32_t F_TMEM = F_BAR + 128;
+    static constexpr uint32_t F_SMEM = F_TMEM + 64 + 1024;                      // + alignment slack
+    static constexpr uint32_t TF_STRIDE = 2 * NTS, TF_COLS = 128;               // tensor memory per stream: [r | z] lanes, [n | -] lanes
+    // backward, per stream: xbar planes, d-gate planes [3 K blocks r z n][NTS][64], staging GS + ZX / DXS (fp32), ids, misc
+    static constexpr uint32_t B_XB_HI = 0, B_XB_LO = 2 * KBX, B_DG_HI = 4 * KBX, B_DG_LO = 7 * KBX, B_ST = 10 * KBX;
+    static constexpr uint32_t B_IDS = B_ST + NTS * D2 * 4, B_MISC = B_IDS + NTS * 4;
+    static constexpr uint32_t B_STRIDE = (B_MISC + 64 + 1023u) & ~1023u;
+    static constexpr uint32_t B_BAR = IMG_PAD + S * B_STRIDE;                   // w | per stream 7 mbarriers
+    static constexpr uint32_t B_TMEM = B_BAR + 256;
+    static constexpr uint32_t B_SMEM = B_TMEM + 64 + 1024;
+    // tensor memory per stream: [r | z] (re-used for dxbar^T once the gates are consumed), [n | -], d Wc^T (192 columns)
+    static constexpr uint32_t TB_ACC1 = 0, TB_ACC2 = NTS, TB_DX = 0, TB_DW = 2 * NTS, TB_STRIDE = 256, TB_COLS = 512;
+    static_assert(2 * NTS + G3 <= 256 || S == 1, "sweep backward: tensor memory per stream");
+    static_assert(B_SMEM <= 227 * 1024 && F_SMEM <= 227 * 1024, "sweep: shared memory");
+};
 
 struct SweepTC {
-    int N, L;
+    int N, L, S;
     unsigned handled;
     const int* order; const int* seg_ptr; const int* in_ptr; const int* in_src;
     const int* out_ptr; const int* out_pack; const int* out_slot;
+    const int* desc;           // [N][8] per row of `order`: node, in_beg, in_cnt, out_beg, out_cnt, src0, src1, src2 (mgv_build_sweep_desc)
     const uint8_t* image;      // [MGV_NCODE][IMG_PAD] (behind the natural blocks in the pack buffer)
     const float* weights;      // natural blocks (u of every code, for the pulls)
     const float* hs;
     float* hf;                 // [N][64]
     int cta_start[MGV_NCODE + 1];
-    unsigned* bar;             // [0] grid barrier counter
+    unsigned* bar;             // [s * BAR_STRIDE] grid barrier counter of stream s
     // backward
     float* ghs; float* ghf; float* dxb; float* alpha; float* dscore; float* raw;
+    long long* trace;          // MGV_SWEEP_TRACE builds: [CTA][16] accumulated clock64 cycles per phase of worker thread 0
 };
+#ifdef MGV_SWEEP_TRACE
+#define SWT_DECL(n) long long tr_acc[n] = {}, tr_last = clock64()
+#define SWT(slot) do { if (p.trace && tid == 0) { const long long now_ = clock64(); tr_acc[slot] += now_ - tr_last; tr_last = now_; } } while (0)
+#define SWT_FLUSH(n, tiles) do { if (p.trace && tid == 0) { for (int i_ = 0; i_ < (n); ++i_) p.trace[(size_t)blockIdx.x * 16 + i_] = tr_acc[i_]; \
+                                 p.trace[(size_t)blockIdx.x * 16 + (n)] = (tiles); p.trace[(size_t)blockIdx.x * 16 + 15] = code; } } while (0)
+#else
+#define SWT_DECL(n) do { } while (0)
+#define SWT(slot) do { } while (0)
+#define SWT_FLUSH(n, tiles) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ float4 ldcg4(const float* p) {          // L2-coherent load: rows written by other CTAs during the kernel
@@ -85,6 +132,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
     const float y = fminf(fmaxf(x, -14.f), 14.f);
     return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y));
 }
+__device__ __forceinline__ float half_sum(float v) {              // sum over the 16 lanes of a half warp
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float amax4(const float4& a) { return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))); }
 
 __device__ __forceinline__ void find_role(const SweepTC& p, int& code, int& rank, int& nct) {
     code = -1; rank = 0; nct = 1;
@@ -97,16 +151,24 @@ __device__ __forceinline__ void find_role(const SweepTC& p, int& code, int& rank
     }
 }
 
-// Tiles of one (level, code) segment for CTA `rank` of `nct`: the segment is cut into ceil(n / nct) rows per tile (at most
-// NT), tile k belongs to CTA k % nct -- every CTA of the code gets a share of every level.
+// Tiles of one (stream, level, code) segment for CTA `rank` of `nct`: the segment is cut into m * nct EQUAL tiles, m = the
+// smallest count that keeps a tile within `nts` rows -- every CTA of the code gets the same share of every level.  The first
+// tile moves with the level and the stream so that short segments (fewer tiles than CTAs) do not always land on the same CTAs.
 struct TileIter {
-    int sbeg, n, per, ntiles, k;
-    __device__ __forceinline__ void start(const int* __restrict__ seg_ptr, int lvl, int code, int rank, int nct) {
-        sbeg = __ldg(seg_ptr + lvl * MGV_NCODE + code);
-        n = __ldg(seg_ptr + lvl * MGV_NCODE + code + 1) - sbeg;
-        per = n > 0 ? min(NT, (n + nct - 1) / nct) : 1;
-        ntiles = (n + per - 1) / per;
-        k = rank;
+    int sbeg, n, per, ntiles, k, left;
+    __device__ __forceinline__ void start(const SweepTC& p, int s, int lvl, int code, int rank, int nct, int nts) {
+        const int idx = (s * p.L + lvl) * MGV_NCODE + code;
+        sbeg = __ldg(p.seg_ptr + idx);
+        n = __ldg(p.seg_ptr + idx + 1) - sbeg;
+        ntiles = 0; per = 1;
+        if (n > 0) {
+            const int m = (n + nct * nts - 1) / (nct * nts);
+            per = (n + m * nct - 1) / (m * nct);
+            ntiles = (n + per - 1) / per;
+        }
+        const int rot = (lvl * 37 + s * (nct >> 1)) % nct;
+        k = rank - rot; if (k < 0) k += nct;
+        left = 0;
     }
     __device__ __forceinline__ bool next(int nct, int& t0, int& rows) {
         if (k >= ntiles) return false;
@@ -117,40 +179,117 @@ struct TileIter {
     }
 };
 
-// Lane-distributed descriptors of the (at most 4) rows warp `warp` owns in a tile: row i = warp + 16 k is held by the 8
-// lanes of slot k = lane / 8; lane q = lane % 8 of the slot additionally holds the q-th predecessor id.  All of it is static
-// schedule data, so it is loaded before the level barrier is awaited.
-struct RowRegs { int node, beg, cnt, src; };
-__device__ __forceinline__ RowRegs prefetch_rows(const SweepTC& p, int t0, int rows, int warp, int lane) {
+// Lane-distributed static data of the four rows worker warp `ws` owns in a tile: row i = ws + WPS * slot is held by the 8 lanes
+// of slot = lane / 8, lane w = lane % 8 holding word w of the row's schedule descriptor (ONE coalesced load, no index chain):
+//   0 node   1 first in-CSR position   2 fan-in   3 first out-CSR position   4 fan-out   5..7 the first three predecessors
+// Out-edges (backward): lane q holds the q-th successor (out_pack = node | code << 28) and that edge's in-CSR position.
+constexpr int W_NODE = 0, W_BEG = 1, W_CNT = 2, W_OBEG = 3, W_OCNT = 4, W_SRC = 5;
+constexpr int FAST_FANIN = 3, FAST_FANOUT = 8;
+struct RowRegs { int w; };
+struct OutRegs { int cnt, pk, slot; };
+template <int WPS>
+__device__ __forceinline__ RowRegs prefetch_rows(const SweepTC& p, int t0, int rows, int ws, int lane) {
     RowRegs rr;
-    rr.node = -1; rr.beg = 0; rr.cnt = 0; rr.src = 0;
-    const int i = warp + WORKERS * (lane >> 3), q = lane & 7;
-    if (i < rows) {
-        rr.node = __ldg(p.order + t0 + i);
-        rr.beg = __ldg(p.in_ptr + rr.node);
-        rr.cnt = __ldg(p.in_ptr + rr.node + 1) - rr.beg;
-        if (q < rr.cnt) rr.src = __ldg(p.in_src + rr.beg + q);
-    }
+    const int i = ws + WPS * (lane >> 3), w = lane & 7;
+    rr.w = w == W_NODE ? -1 : 0;
+    if (i < rows) rr.w = __ldg(p.desc + (size_t)(t0 + i) * 8 + w);
     return rr;
 }
+__device__ __forceinline__ int row_word(const RowRegs& rr, int slot, int w) { return __shfl_sync(0xffffffffu, rr.w, slot * 8 + w); }
+__device__ __forceinline__ OutRegs prefetch_out(const SweepTC& p, const RowRegs& rr, int lane) {
+    OutRegs o;
+    const int slot = lane >> 3, q = lane & 7;
+    const int beg = row_word(rr, slot, W_OBEG);
+    o.cnt = row_word(rr, slot, W_OCNT);
+    o.pk = -1; o.slot = 0;
+    if (q < o.cnt) { o.pk = __ldg(p.out_pack + beg + q); o.slot = __ldg(p.out_slot + beg + q); }
+    return o;
+}
 
-// Gather + additive attention of ONE node by one warp.  Lane l owns columns 4 (l % 16) .. + 3 of the hs part (l < 16) or the
-// hf part (l >= 16) of the 128-wide row.  `al` receives the first four attention weights (all lanes), used again by the
-// backward's attention phase.  STORE_ALPHA: the weights also go to p.alpha (indexed by in-CSR slot) for the pulls.
+// ---------------------------------------------------------------------------- gather + additive attention, HALF warp per node
+// Lane lp = lane % 16 of a half owns columns 4 lp .. + 3 of the hs part AND of the hf part of the 128-wide row.  Both halves
+// of a warp work on different nodes (slots 2 it + half) in the same instruction.  Rows with more than three predecessors
+// take the whole-warp path below (attend_row_wide); the caller decides per warp.
+struct HalfRow { float4 xs[FAST_FANIN], xf[FAST_FANIN]; int cnt, beg; };
+template <bool HF_CG>
+__device__ __forceinline__ void load_half_row(const SweepTC& p, const float* __restrict__ hf, int slot, const RowRegs& rr, int lp, HalfRow& r) {
+    r.cnt = row_word(rr, slot, W_CNT);
+    r.beg = row_word(rr, slot, W_BEG);
+#pragma unroll
+    for (int q = 0; q < FAST_FANIN; ++q) {
+        const int j = row_word(rr, slot, W_SRC + q);
+        r.xs[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.xf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < r.cnt) {
+            r.xs[q] = mgv_ld4(p.hs + (size_t)j * D + 4 * lp);
+            r.xf[q] = HF_CG ? ldcg4(hf + (size_t)j * D + 4 * lp) : mgv_ld4(hf + (size_t)j * D + 4 * lp);
+        }
+    }
+}
+// softmax over the (at most three) loaded rows; xbar halves out, the attention weights in al[].
+template <bool STORE_ALPHA>
+__device__ __forceinline__ void attend_half(const SweepTC& p, const HalfRow& r, const float4& us, const float4& uf, int lp,
+                                            float4& xbs, float4& xbf, float (&al)[FAST_FANIN]) {
+    float sc[FAST_FANIN];
+#pragma unroll
+    for (int q = 0; q < FAST_FANIN; ++q) sc[q] = half_sum(mgv_dot4(r.xs[q], us) + mgv_dot4(r.xf[q], uf));
+    float mx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < FAST_FANIN; ++q)
+        if (q < r.cnt) mx = fmaxf(mx, sc[q]);
+    float sum = 0.f;
+    xbs = make_float4(0.f, 0.f, 0.f, 0.f);
+    xbf = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < FAST_FANIN; ++q) {
+        al[q] = 0.f;
+        if (q < r.cnt) {
+            al[q] = expf(sc[q] - mx);
+            sum += al[q];
+            mgv_fma4(xbs, al[q], r.xs[q]);
+            mgv_fma4(xbf, al[q], r.xf[q]);
+        }
+    }
+    const float inv = 1.0f / (sum + 1e-16f);
+    xbs = make_float4(xbs.x * inv, xbs.y * inv, xbs.z * inv, xbs.w * inv);
+    xbf = make_float4(xbf.x * inv, xbf.y * inv, xbf.z * inv, xbf.w * inv);
+#pragma unroll
+    for (int q = 0; q < FAST_FANIN; ++q) al[q] *= inv;
+    if (STORE_ALPHA) {
+        const float mine = lp == 0 ? al[0] : (lp == 1 ? al[1] : al[2]);
+        if (lp < r.cnt) p.alpha[r.beg + lp] = mine;
+    }
+}
+// The half warp's 4 + 4 values of row `row` -> fp16 hi/lo planes of a node tile (SW128, K-major; K block 0 = hs part, 1 = hf part).
+template <bool LOWP>
+__device__ __forceinline__ void store_xbar_half(uint32_t xb_hi, uint32_t xb_lo, uint32_t kbx, int row, int lp, const float4& vs, const float4& vf) {
+    const uint32_t off = tc::sw128_off(row, lp >> 1) + (uint32_t)(lp & 1) * 8u;
+    uint32_t h0, l0, h1, l1;
+    split2p<LOWP>(vs.x, vs.y, h0, l0);
+    split2p<LOWP>(vs.z, vs.w, h1, l1);
+    st_shared_v2(xb_hi + off, h0, h1);
+    if (!LOWP) st_shared_v2(xb_lo + off, l0, l1);
+    split2p<LOWP>(vf.x, vf.y, h0, l0);
+    split2p<LOWP>(vf.z, vf.w, h1, l1);
+    st_shared_v2(xb_hi + kbx + off, h0, h1);
+    if (!LOWP) st_shared_v2(xb_lo + kbx + off, l0, l1);
+}
+
+// Whole-warp variant for any fan-in (online softmax past four predecessors; predecessor ids from the in-CSR).  Lane l owns columns 4 (l % 16) .. + 3 of the hs part
+// (l < 16) or the hf part (l >= 16).  `al` receives the first four attention weights.
 template <bool STORE_ALPHA, bool HF_CG>
-__device__ __forceinline__ void attend_row(const SweepTC& p, const float* __restrict__ hf, const float4& u4, int slot, const RowRegs& rr,
-                                           int lane, float4& xbar, float (&al)[4]) {
-    const unsigned full = 0xffffffffu;
-    const int cnt = __shfl_sync(full, rr.cnt, slot * 8), beg = __shfl_sync(full, rr.beg, slot * 8);
+__device__ __forceinline__ void attend_row_wide(const SweepTC& p, const float* __restrict__ hf, const float4& u4, int slot, const RowRegs& rr,
+                                                int lane, float4& xbar, float (&al)[4]) {
+    const int cnt = row_word(rr, slot, W_CNT), beg = row_word(rr, slot, W_BEG);
     const int off = 4 * (lane & 15);
     const float* base = (lane < 16) ? p.hs : hf;
     float4 x[4];
     float sc[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int j = __shfl_sync(full, rr.src, slot * 8 + q);
         x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < cnt) {
+            const int j = __ldg(p.in_src + beg + q);
             const float* row = base + (size_t)j * D + off;
             x[q] = (HF_CG && lane >= 16) ? ldcg4(row) : mgv_ld4(row);
         }
@@ -173,10 +312,10 @@ __device__ __forceinline__ void attend_row(const SweepTC& p, const float* __rest
         }
     }
     if (cnt > 4) {
-        // rare: more than four predecessors -- online softmax over the rest, one at a time (scores parked in p.alpha)
+        // more than four predecessors -- online softmax over the rest, one at a time (scores parked in p.alpha)
         if (STORE_ALPHA && lane < 4) p.alpha[beg + lane] = sc[lane];
         for (int q = 4; q < cnt; ++q) {
-            const int j = (q < 8) ? __shfl_sync(full, rr.src, slot * 8 + q) : __ldg(p.in_src + beg + q);
+            const int j = __ldg(p.in_src + beg + q);
             const float* row = base + (size_t)j * D + off;
             const float4 xq = (HF_CG && lane >= 16) ? ldcg4(row) : mgv_ld4(row);
             const float s = mgv_warp_sum(mgv_dot4(xq, u4));
@@ -205,37 +344,69 @@ __device__ __forceinline__ void attend_row(const SweepTC& p, const float* __rest
         }
     }
 }
-
-// The lane's 4 values of row `row` -> fp16 hi/lo planes of a node tile (SW128, K-major; K block = hs / hf part).
 template <bool LOWP>
-__device__ __forceinline__ void store_xbar(uint32_t xb_hi, uint32_t xb_lo, int row, int lane, const float4& v) {
+__device__ __forceinline__ void store_xbar_wide(uint32_t xb_hi, uint32_t xb_lo, uint32_t kbx, int row, int lane, const float4& v) {
     uint32_t h0, l0, h1, l1;
     split2p<LOWP>(v.x, v.y, h0, l0);
     split2p<LOWP>(v.z, v.w, h1, l1);
-    const uint32_t off = (uint32_t)(lane >> 4) * KB_X + tc::sw128_off(row, (lane & 15) >> 1) + (uint32_t)(lane & 1) * 8u;
+    const uint32_t off = (uint32_t)(lane >> 4) * kbx + tc::sw128_off(row, (lane & 15) >> 1) + (uint32_t)(lane & 1) * 8u;
     st_shared_v2(xb_hi + off, h0, h1);
     if (!LOWP) st_shared_v2(xb_lo + off, l0, l1);
 }
 
-// ======================================================================================= forward
-constexpr uint32_t F_XB_HI = IMG_PAD, F_XB_LO = F_XB_HI + 2 * KB_X;
-constexpr uint32_t F_ZX = F_XB_LO + 2 * KB_X;                    // z pre-activations [NT][64] fp32 (lane exchange)
-constexpr uint32_t F_IDS = F_ZX + NT * D * 4;
-constexpr uint32_t F_BAR = F_IDS + NT * 4;                       // mbarriers: w, x_full, acc_full, level
-constexpr uint32_t F_TMEM = F_BAR + 64;
-constexpr uint32_t F_SMEM = F_TMEM + 64 + 1024;                  // + alignment slack
-constexpr uint32_t TF_ACC1 = 0, TF_ACC2 = NT, TF_COLS = 128;     // tensor memory: [r | z] lanes, [n | -] lanes, NT node columns each
+// Gather + attention of a whole tile by one worker warp (its four rows) -> xbar planes and node ids.  Rows npad > i >= rows are
+// written as exact zeros (the K padding of the backward's weight-gradient product).  al2[it][q]: attention weights of the row
+// of slot 2 it + half (fast path only; the wide path of the backward re-reads p.alpha).  Returns true when the wide path ran
+// (some row of the warp has more than FAST_FANIN predecessors).
+template <bool LOWP, bool STORE_ALPHA, bool HF_CG, int WPS>
+__device__ __forceinline__ bool gather_tile(const SweepTC& p, const float* __restrict__ hf, const float4& us, const float4& uf,
+                                            const RowRegs& rr, int rows, int npad, int ws, int lane, uint32_t xb_hi, uint32_t xb_lo,
+                                            uint32_t kbx, int* IDS, float (&al2)[2][FAST_FANIN]) {
+    const unsigned full = 0xffffffffu;
+    const bool wide = __any_sync(full, (lane & 7) == W_CNT && rr.w > FAST_FANIN);
+    if (!wide) {
+        const int half = lane >> 4, lp = lane & 15;
+        HalfRow r0, r1;
+        load_half_row<HF_CG>(p, hf, half, rr, lp, r0);
+        load_half_row<HF_CG>(p, hf, 2 + half, rr, lp, r1);
+        float4 xbs, xbf;
+        attend_half<STORE_ALPHA>(p, r0, us, uf, lp, xbs, xbf, al2[0]);
+        int i = ws + WPS * half;
+        if (i < npad) store_xbar_half<LOWP>(xb_hi, xb_lo, kbx, i, lp, xbs, xbf);
+        attend_half<STORE_ALPHA>(p, r1, us, uf, lp, xbs, xbf, al2[1]);
+        i = ws + WPS * (2 + half);
+        if (i < npad) store_xbar_half<LOWP>(xb_hi, xb_lo, kbx, i, lp, xbs, xbf);
+    } else {
+        const float4 u4 = lane < 16 ? us : uf;             // lane l of the wide layout owns the columns lane l % 16 of the half layout owns
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int i = ws + WPS * k;
+            if (i < npad) {
+                float4 xbar;
+                float al[4];
+                attend_row_wide<STORE_ALPHA, HF_CG>(p, hf, u4, k, rr, lane, xbar, al);
+                store_xbar_wide<LOWP>(xb_hi, xb_lo, kbx, i, lane, xbar);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int nd = row_word(rr, k, W_NODE);
+        if (lane == 0 && ws + WPS * k < rows) IDS[ws + WPS * k] = nd;
+    }
+    return wide;
+}
 
 // The recompute / forward products of one tile: acc1 = Wc[0:128] xbar^T, acc2 = Wc[128:256] xbar^T (rows 192.. are whatever
 // follows the image: those accumulator lanes are never read).
 template <bool LOWP>
-__device__ __forceinline__ void issue_gate_mmas(uint32_t sbase, uint32_t xb_hi, uint32_t xb_lo, uint32_t acc1, uint32_t acc2, int npad) {
+__device__ __forceinline__ void issue_gate_mmas(uint32_t sbase, uint32_t xb_hi, uint32_t xb_lo, uint32_t kbx, uint32_t acc1, uint32_t acc2, int npad) {
     const uint32_t idesc = tc::make_idesc(128, npad, false, false, LOWP);
 #pragma unroll
     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t wo = (uint32_t)kb * KB_W + 32u * j, xo = (uint32_t)kb * KB_X + 32u * j;
+            const uint32_t wo = (uint32_t)kb * KB_W + 32u * j, xo = (uint32_t)kb * kbx + 32u * j;
             const uint64_t b_hi = tc::desc_k_sw128(xb_hi + xo), b_lo = tc::desc_k_sw128(xb_lo + xo);
             const uint32_t accf = (kb | j) ? 1u : 0u;
             tc::mma3p<LOWP>(acc1, tc::desc_k_sw128(sbase + I_WC_HI + wo), tc::desc_k_sw128(sbase + I_WC_LO + wo), b_hi, b_lo, idesc, accf);
@@ -244,189 +415,11 @@ __device__ __forceinline__ void issue_gate_mmas(uint32_t sbase, uint32_t xb_hi, 
         }
 }
 
-// Grid barrier, split: the workers' thread 0 arrives (release), the MMA warp's thread polls (acquire) and releases the
-// workers through a shared-memory mbarrier.
+// Grid barrier of a stream, split: one worker thread arrives (release), the stream's tensor-core warp polls (acquire) and
+// releases the workers through a shared-memory mbarrier.
 __device__ __forceinline__ void grid_arrive(unsigned* counter) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
 }
-__device__ __forceinline__ void grid_poll(const unsigned* counter, unsigned target) {
-    while (mgv_ld_acquire(counter) < target) __nanosleep(20);
-    __threadfence();
-}
-
-template <bool LOWP>
-__global__ void __launch_bounds__(NTHREADS, 1) sweep_fwd_tc_kernel(const SweepTC p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t bar_w = sbase + F_BAR, bar_x_full = bar_w + 8, bar_acc_full = bar_w + 16, bar_level = bar_w + 24;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + F_TMEM);
-    float* ZX = reinterpret_cast<float*>(sgen + F_ZX);
-    int* IDS = reinterpret_cast<int*>(sgen + F_IDS);
-    int code, rank, nct;
-    find_role(p, code, rank, nct);
-    if (tid == 0) {
-        tc::mbar_init(bar_w, 1);
-        tc::mbar_init(bar_x_full, NWT);
-        tc::mbar_init(bar_acc_full, 1);
-        tc::mbar_init(bar_level, 1);
-        tc::fence_barrier_init();
-        if (code >= 0) {
-            const uint8_t* img = p.image + (size_t)code * IMG_PAD;
-            tc::mbar_expect_tx(bar_w, IMG_BYTES);
-#pragma unroll 1
-            for (uint32_t o = 0; o < I_F32; o += 16384u) tc::bulk_g2s(sbase + o, img + o, 16384u, bar_w);
-            tc::bulk_g2s(sbase + I_F32, img + I_F32, IMG_BYTES - I_F32, bar_w);
-        }
-    }
-    if (warp == WORKERS) tc::tmem_alloc(tmem_slot, TF_COLS);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    const int nsteps = p.L - 1;
-
-    if (warp < WORKERS) {
-        // ===================================================================== workers: gather -> [MMA] -> epilogue
-        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int qd = warp & 3, cg = warp >> 2;
-        const int eu = (qd & 1) * 32 + lane;                   // gate unit of this thread's tensor-memory lane
-        float b_r = 0.f, b_z = 0.f, b_in = 0.f, b_hn = 0.f;
-        if (code >= 0) {
-            tc::mbar_wait_warp(bar_w, 0u, lane);
-            const float* F = reinterpret_cast<const float*>(sgen + I_F32);
-            u4 = *reinterpret_cast<const float4*>(F + 4 * lane);
-            b_r = F[128 + eu]; b_z = F[192 + eu]; b_in = F[256 + eu]; b_hn = F[320 + eu];
-        }
-        (void)b_z;
-        const uint32_t tl = tmem + ((uint32_t)(qd * 32) << 16);
-        uint32_t it = 0;
-        for (int step = 0; step < nsteps; ++step) {
-            const int lvl = step + 1;
-            TileIter ti;
-            int t0 = 0, rows = 0;
-            bool have = false;
-            RowRegs rr;
-            if (code >= 0) {
-                ti.start(p.seg_ptr, lvl, code, rank, nct);
-                have = ti.next(nct, t0, rows);
-                if (have) rr = prefetch_rows(p, t0, rows, warp, lane);
-            }
-            if (step > 0) tc::mbar_wait_warp(bar_level, (uint32_t)((step - 1) & 1), lane, 32);     // level step - 1 is complete everywhere
-            while (have) {
-                const int npad = (rows + 15) & ~15;
-                // ---- gather + attention: rows warp, warp + 16, ..
-#pragma unroll
-                for (int k = 0; k < NT / WORKERS; ++k) {
-                    const int i = warp + WORKERS * k;
-                    if (i < rows) {
-                        float4 xbar;
-                        float al[4];
-                        attend_row<false, true>(p, p.hf, u4, k, rr, lane, xbar, al);
-                        store_xbar<LOWP>(sbase + F_XB_HI, sbase + F_XB_LO, i, lane, xbar);
-                    }
-                }
-                // (lane 0 is q = 0 of slot 0 only: fetch each slot's node id from its first lane)
-#pragma unroll
-                for (int k = 0; k < NT / WORKERS; ++k) {
-                    const int nd = __shfl_sync(0xffffffffu, rr.node, k * 8);
-                    if (lane == 0 && warp + WORKERS * k < rows) IDS[warp + WORKERS * k] = nd;
-                }
-                tc::fence_async_smem();
-                tc::mbar_arrive(bar_x_full);
-                tc::mbar_wait_warp(bar_acc_full, it & 1u, lane, 32);
-                tc::fence_after_sync();
-                // ---- epilogue: TMEM lane = gate unit.  Lanes 64..127 hold z: hand it to the r / n lanes through shared memory
-                const int c0 = cg * 16;
-                if (c0 < npad && qd >= 2) {
-                    float z[16];
-                    tc::tmem_ld16(tl + TF_ACC1 + c0, z);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) ZX[(c0 + c) * D + eu] = z[c];
-                }
-                tc::named_bar_sync(2, NWT);
-                if (c0 < npad && qd < 2) {
-                    float rp[16], np[16];
-                    tc::tmem_ld16(tl + TF_ACC1 + c0, rp);
-                    tc::tmem_ld16(tl + TF_ACC2 + c0, np);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        if (c0 + c < rows) {
-                            const float r = sigmoid_fast(rp[c] + b_r);
-                            const float z = sigmoid_fast(ZX[(c0 + c) * D + eu] + b_z);
-                            const float n = tanh_fast(np[c] + b_in + r * b_hn);
-                            p.hf[(size_t)IDS[c0 + c] * D + eu] = n - z * n;               // (1 - z) n + z h,  h = 0
-                        }
-                    }
-                }
-                tc::fence_before_sync();
-                tc::named_bar_sync(1, NWT);                    // all stores of the tile issued; ZX / IDS / the node tile are free
-                ++it;
-                have = ti.next(nct, t0, rows);
-                if (have) rr = prefetch_rows(p, t0, rows, warp, lane);
-            }
-            if (tid == 0 && step + 1 < nsteps) grid_arrive(p.bar);
-        }
-    } else if (lane == 0) {
-        // ===================================================================== MMA issue + grid barrier polling (one thread)
-        if (code >= 0) tc::mbar_wait_sleep(bar_w, 0u);
-        uint32_t it = 0;
-        for (int step = 0; step < nsteps; ++step) {
-            if (code >= 0) {
-                TileIter ti;
-                ti.start(p.seg_ptr, step + 1, code, rank, nct);
-                int t0, rows;
-                while (ti.next(nct, t0, rows)) {
-                    tc::mbar_wait_sleep(bar_x_full, it & 1u, 32);
-                    tc::fence_after_sync();
-                    issue_gate_mmas<LOWP>(sbase, sbase + F_XB_HI, sbase + F_XB_LO, tmem + TF_ACC1, tmem + TF_ACC2, (rows + 15) & ~15);
-                    tc::mma_commit(bar_acc_full);
-                    ++it;
-                }
-            }
-            if (step + 1 < nsteps) {
-                grid_poll(p.bar, (unsigned)(step + 1) * gridDim.x);
-                tc::mbar_arrive(bar_level);
-            }
-        }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == WORKERS) tc::tmem_dealloc(tmem, TF_COLS);
-}
-
-
-// ======================================================================================= backward
-// Reverse sweep, same tiles and the same transposed products.  Per tile (level l, rows of one gate code):
-//   R  recompute: gather + attention (alpha -> HBM for the pulls) -> xbar planes -> [r | z], [n] pre-activations (tensor memory).
-//      Depends on forward values only, so it runs BEFORE the level barrier is awaited (it hides behind the wait).
-//   P  pull (needs the barrier): d(hs, hf)_i += sum over out-edges (i -> k) of alpha_e dxbar_k + dscore_e u_code(k); the hs half is
-//      accumulated into ghs, the hf half + the incoming d hf is the GRU's output gradient g.
-//   W  pointwise GRU backward (thread = gate unit, TMEM lane): d r, d z, d n -> power-of-two scaled fp16 hi/lo planes DG [node][gate]
-//   MMA  dxbar^T[f][node] = Wc^T[f][g] DG^T[g][node]   (A = the forward's weight image read MN-major, B = DG K-major)
-//        dWc^T[f][g]    += xbar^T[f][node] DG[node][g] (both MN-major from the node tiles; accumulator persistent in tensor memory)
-//   X  dxbar^T -> shared memory [node][f] (transpose)   A  attention backward per node: d alpha_j = dxbar . x_j,
-//      d score_j = alpha_j (d alpha_j - sum alpha d alpha) -> HBM with dxbar for the pulls of the predecessors; d u += sum d score_j x_j
-// Nodes that are only pulled (level 0, codes without an aggregator) are handled after the last level by all CTAs.
-// Weight gradients leave the kernel as raw blocks [d Wc | d u | d b_r d b_z d b_in d b_hn] (vector reductions from all CTAs of a
-// code); sweep_chain_kernel maps them back to the reference's parameters (W_v, b_v, W_ih, b_ih, b_hh).
-constexpr int RAWF = G3 * D2 + D2 + 4 * D;                       // 24960 floats per code
-constexpr int R_WC = 0, R_U = G3 * D2, R_B = G3 * D2 + D2;
-constexpr uint32_t B_XB_HI = IMG_PAD, B_XB_LO = B_XB_HI + 2 * KB_X;
-constexpr uint32_t B_DG_HI = B_XB_LO + 2 * KB_X, B_DG_LO = B_DG_HI + 3 * KB_X;       // d gates [3 K blocks r z n][NT][64]
-constexpr uint32_t B_ST = B_DG_LO + 3 * KB_X;                    // staging: GS [NT][64] + ZX [NT][64], later DXS [NT][128] (fp32)
-constexpr uint32_t B_IDS = B_ST + NT * D2 * 4;
-constexpr uint32_t B_MISC = B_IDS + NT * 4;                      // amax[2], rescale flag
-constexpr uint32_t B_BAR = B_MISC + 64;                          // mbarriers
-constexpr uint32_t B_TMEM = B_BAR + 128;
-constexpr uint32_t B_SMEM = B_TMEM + 64 + 1024;
-static_assert(B_SMEM <= 227 * 1024, "sweep backward: shared memory");
-constexpr uint32_t TB_ACC1 = 0, TB_ACC2 = NT, TB_DX = 2 * NT, TB_DW = 3 * NT, TB_COLS = 512;     // DW: 192 columns
-
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
@@ -436,108 +429,35 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0u;
 }
-// Power of two s with amax * s in [2^8, 2^9) (amax > 0), else 1; kept while amax * cur stays inside [2^2, 2^13].
-__device__ __forceinline__ float pow2_scale_keep(float amax, float cur) {
-    const float v = amax * cur;
-    if (v >= 4.0f && v <= 8192.0f) return cur;
-    if (!(amax > 0.f) || !isfinite(amax)) return cur;
-    const int e = (int)((__float_as_uint(amax) >> 23) & 0xff) - 127;
-    int k = 8 - e;
-    k = k < -100 ? -100 : (k > 100 ? 100 : k);
-    return __uint_as_float((uint32_t)(k + 127) << 23);
+// Whole warp: lane 0 polls the counter and, once the target is reached, releases the workers; the result is warp-uniform.
+__device__ __forceinline__ bool grid_try(const unsigned* counter, unsigned target, uint32_t bar_level, int lane) {
+    unsigned ok = 0u;
+    if (lane == 0) {
+        ok = mgv_ld_acquire(counter) >= target ? 1u : 0u;
+        if (ok) { __threadfence(); tc::mbar_arrive(bar_level); }
+    }
+    return __shfl_sync(0xffffffffu, ok, 0) != 0u;
 }
 
-// sum over out-edges e = (v -> k) of  alpha_e dxbar_k + dscore_e u_code(k)   (128-wide, lane chunk of 4).  Fan-out is heavy
-// tailed and the per-edge chain out_pack -> out_slot -> alpha / dscore -> dxbar row is three dependent loads, so edges are taken a
-// warp at a time: every lane fetches the metadata of one edge, rows are gathered 8 at a time with the ids broadcast by
-// shuffles, and sum_e dscore_e u_code(e) is accumulated per code and applied once at the end.
-__device__ __forceinline__ float4 pull_out_edges(const SweepTC& p, int v, int lane) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int beg = __ldg(p.out_ptr + v), end = __ldg(p.out_ptr + v + 1);
-    float sds[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    unsigned present = 0u;
-    for (int q0 = beg; q0 < end; q0 += 32) {
-        const int q = q0 + lane;
-        int kk = -1, c = 0;
-        float a = 0.f, ds = 0.f;
-        if (q < end) {
-            const int pk = __ldg(p.out_pack + q);
-            c = (pk >> MGV_CODE_SHIFT) & 7;
-            if ((p.handled >> c) & 1u) {
-                kk = pk & NODE_MASK;
-                const int slot = __ldg(p.out_slot + q);
-                a = ldcg1(p.alpha + slot);
-                ds = ldcg1(p.dscore + slot);
-            }
-        }
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) sds[cc] += (kk >= 0 && c == cc + 1) ? ds : 0.f;
-        present |= (kk >= 0) ? (1u << c) : 0u;
-        const int ne = min(32, end - q0);
-        for (int i = 0; i < ne; i += 8) {
-            float4 dx[8];
-            float aa[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int kj = __shfl_sync(0xffffffffu, kk, (i + j) & 31);
-                aa[j] = __shfl_sync(0xffffffffu, a, (i + j) & 31);
-                dx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i + j < ne && kj >= 0) dx[j] = ldcg4(p.dxb + (size_t)kj * D2 + 4 * lane);
-                else aa[j] = 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) mgv_fma4(acc, aa[j], dx[j]);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) present |= __shfl_xor_sync(0xffffffffu, present, o);
-#pragma unroll
-    for (int cc = 0; cc < 6; ++cc) {
-        if ((present >> (cc + 1)) & 1u) {
-            float t = sds[cc];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            mgv_fma4(acc, t, mgv_ldg4(p.weights + (size_t)(cc + 1) * PACK + O_U + 4 * lane));
-        }
-    }
-    return acc;
-}
-
-__device__ __forceinline__ void pull_into_ghs(const SweepTC& p, int node, int lane) {
-    const float4 pl = pull_out_edges(p, node, lane);
-    if (lane < 16) {
-        float* gp = p.ghs + (size_t)node * D + 4 * lane;
-        float4 cur = ldcg4(gp);
-        cur.x += pl.x; cur.y += pl.y; cur.z += pl.z; cur.w += pl.w;
-        mgv_st4(gp, cur);
-    }
-}
-
-template <bool LOWP>
-__global__ void __launch_bounds__(NTHREADS, 1) sweep_bwd_tc_kernel(const SweepTC p, const unsigned pull_only_codes) {
+// ======================================================================================= forward
+template <bool LOWP, int S>
+__global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const SweepTC p) {
+    using G = Geo<S>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t bar_w = sbase + B_BAR, bar_x_full = bar_w + 8, bar_acc_full = bar_w + 16, bar_level = bar_w + 24;
-    const uint32_t bar_dg_full = bar_w + 32, bar_dx_full = bar_w + 40, bar_wg_done = bar_w + 48, bar_rescaled = bar_w + 56;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + B_TMEM);
-    float* GS = reinterpret_cast<float*>(sgen + B_ST);
-    float* ZX = GS + NT * D;
-    float* DXS = GS;
-    int* IDS = reinterpret_cast<int*>(sgen + B_IDS);
-    unsigned* s_misc = reinterpret_cast<unsigned*>(sgen + B_MISC);      // [0], [1] tile amax (float bits), [2] rescale flag
+    const uint32_t bar_w = sbase + G::F_BAR;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + G::F_TMEM);
     int code, rank, nct;
     find_role(p, code, rank, nct);
     if (tid == 0) {
         tc::mbar_init(bar_w, 1);
-        tc::mbar_init(bar_x_full, NWT);
-        tc::mbar_init(bar_acc_full, 1);
-        tc::mbar_init(bar_level, 1);
-        tc::mbar_init(bar_dg_full, NWT);
-        tc::mbar_init(bar_dx_full, 1);
-        tc::mbar_init(bar_wg_done, 1);
-        tc::mbar_init(bar_rescaled, NWT);
+        for (int s = 0; s < S; ++s) {
+            tc::mbar_init(bar_w + 8 + 24 * s, G::NSW);     // x_full
+            tc::mbar_init(bar_w + 16 + 24 * s, 1);         // acc_full
+            tc::mbar_init(bar_w + 24 + 24 * s, 1);         // level
+        }
         tc::fence_barrier_init();
         if (code >= 0) {
             const uint8_t* img = p.image + (size_t)code * IMG_PAD;
@@ -546,355 +466,159 @@ __global__ void __launch_bounds__(NTHREADS, 1) sweep_bwd_tc_kernel(const SweepTC
             for (uint32_t o = 0; o < I_F32; o += 16384u) tc::bulk_g2s(sbase + o, img + o, 16384u, bar_w);
             tc::bulk_g2s(sbase + I_F32, img + I_F32, IMG_BYTES - I_F32, bar_w);
         }
-        s_misc[0] = 0u; s_misc[1] = 0u; s_misc[2] = 0u;
     }
-    if (warp == WORKERS) tc::tmem_alloc(tmem_slot, TB_COLS);
+    if (warp == WORKERS) tc::tmem_alloc(tmem_slot, G::TF_COLS);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const int nsteps = p.L - 1;
+    const int s = warp < WORKERS ? warp / G::WPS : warp - WORKERS;               // stream of this warp
+    const uint32_t bar_x_full = bar_w + 8 + 24 * s, bar_acc_full = bar_x_full + 8, bar_level = bar_x_full + 16;
+    const uint32_t sstream = sbase + IMG_PAD + (uint32_t)s * G::F_STRIDE;
+    const uint32_t xb_hi = sstream + G::F_XB_HI, xb_lo = sstream + G::F_XB_LO;
+    const uint32_t acc1 = tmem + (uint32_t)s * G::TF_STRIDE, acc2 = acc1 + G::NTS;
+    unsigned* gbar = p.bar + s * BAR_STRIDE;
 
     if (warp < WORKERS) {
-        // ===================================================================== workers
-        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int qd = warp & 3, cg = warp >> 2;
-        const int eu = (qd & 1) * 32 + lane;                   // gate unit of this thread's tensor-memory lane (phase W)
-        const int ef = qd * 32 + lane;                         // input feature of this thread's lane (phase X, flush)
+        // ===================================================================== workers of stream s: gather -> [MMA] -> epilogue
+        const int ws = warp % G::WPS, lp = lane & 15;
+        float* ZX = reinterpret_cast<float*>(sgen + IMG_PAD + s * G::F_STRIDE + G::F_ZX);
+        int* IDS = reinterpret_cast<int*>(sgen + IMG_PAD + s * G::F_STRIDE + G::F_IDS);
+        float4 us = make_float4(0.f, 0.f, 0.f, 0.f), uf = us;
+        const int qd = warp & 3, cg = ws >> 2;
+        const int eu = (qd & 1) * 32 + lane;                   // gate unit of this thread's tensor-memory lane
         float b_r = 0.f, b_z = 0.f, b_in = 0.f, b_hn = 0.f;
         if (code >= 0) {
             tc::mbar_wait_warp(bar_w, 0u, lane);
             const float* F = reinterpret_cast<const float*>(sgen + I_F32);
-            u4 = *reinterpret_cast<const float4*>(F + 4 * lane);
+            us = *reinterpret_cast<const float4*>(F + 4 * lp);
+            uf = *reinterpret_cast<const float4*>(F + D + 4 * lp);
             b_r = F[128 + eu]; b_z = F[192 + eu]; b_in = F[256 + eu]; b_hn = F[320 + eu];
         }
-        const uint32_t tl = tmem + ((uint32_t)(qd * 32) << 16);
-        float4 du4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float sb_r = 0.f, sb_z = 0.f, sb_n = 0.f, sb_hn = 0.f;   // bias-gradient partial sums of unit eu (threads with qd < 2)
-        float acc_scale = 1.0f;
+        const uint32_t tl1 = acc1 + ((uint32_t)(qd * 32) << 16), tl2 = acc2 + ((uint32_t)(qd * 32) << 16);
         uint32_t it = 0;
+        SWT_DECL(8);
+        TileIter ti;
+        int t0 = 0, rows = 0;
+        bool have = false;
+        RowRegs rr;
+        rr.w = (lane & 7) == W_NODE ? -1 : 0;
+        if (code >= 0 && nsteps > 0) {
+            ti.start(p, s, 1, code, rank, nct, G::NTS);
+            have = ti.next(nct, t0, rows);
+            if (have) rr = prefetch_rows<G::WPS>(p, t0, rows, ws, lane);
+        }
         for (int step = 0; step < nsteps; ++step) {
-            const int lvl = p.L - 1 - step;
-            TileIter ti;
-            int t0 = 0, rows = 0;
-            bool have = false, waited = (step == 0);
-            if (code >= 0) {
-                ti.start(p.seg_ptr, lvl, code, rank, nct);
-                have = ti.next(nct, t0, rows);
-            }
+            SWT(0);
+            if (step > 0) tc::mbar_wait_warp(bar_level, (uint32_t)((step - 1) & 1), lane, 32);     // level `step` of this stream is complete everywhere
+            SWT(1);
+            // the next tile of this CTA (same level, else the first of the next level): its static data is fetched while the
+            // tensor core works on the current tile
+            int t0n = 0, rowsn = 0;
+            bool haven = false, crossed = false;
+            RowRegs rrn = rr;
             while (have) {
                 const int npad = (rows + 15) & ~15;
-                const RowRegs rr = prefetch_rows(p, t0, rows, warp, lane);
-                // the previous tile's weight-gradient MMAs have read its node tile and d-gate planes
-                if (it > 0) tc::mbar_wait_warp(bar_wg_done, (it - 1) & 1u, lane, 32);
-                // ---- R: recompute gather + attention (alphas kept in registers for phase A, and stored for the pulls)
-                float al[NT / WORKERS][4];
-#pragma unroll
-                for (int k = 0; k < NT / WORKERS; ++k) {
-                    const int i = warp + WORKERS * k;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) al[k][q] = 0.f;
-                    if (i < rows) {
-                        float4 xbar;
-                        attend_row<true, false>(p, p.hf, u4, k, rr, lane, xbar, al[k]);
-                        store_xbar<LOWP>(sbase + B_XB_HI, sbase + B_XB_LO, i, lane, xbar);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NT / WORKERS; ++k) {
-                    const int nd = __shfl_sync(0xffffffffu, rr.node, k * 8);
-                    if (lane == 0 && warp + WORKERS * k < rows) IDS[warp + WORKERS * k] = nd;
-                }
-                // rows rows .. npad - 1 are the K padding of the weight-gradient product: zeros
-                for (int idx = tid; idx < (npad - rows) * 32; idx += NWT) {
-                    const int row = rows + (idx >> 5), j = idx & 31;
-                    const uint32_t off = (uint32_t)((j >> 3) & 1) * KB_X + tc::sw128_off(row, j & 7);
-                    tc::st_shared_v4(sbase + ((j >> 4) ? B_XB_LO : B_XB_HI) + off, make_uint4(0u, 0u, 0u, 0u));
-                }
+                float al2[2][FAST_FANIN];
+                gather_tile<LOWP, false, true, G::WPS>(p, p.hf, us, uf, rr, rows, npad, ws, lane, xb_hi, xb_lo, G::KBX, IDS, al2);
                 tc::fence_async_smem();
                 tc::mbar_arrive(bar_x_full);
-                // ---- the successors' levels are complete everywhere
-                if (!waited) { tc::mbar_wait_warp(bar_level, (uint32_t)((step - 1) & 1), lane, 32); waited = true; }
-                // ---- P: pull
-                float gmax = 0.f;
-#pragma unroll 1
-                for (int k = 0; k < NT / WORKERS; ++k) {
-                    const int i = warp + WORKERS * k;
-                    if (i < rows) {
-                        const int node = __shfl_sync(0xffffffffu, rr.node, k * 8);
-                        const float4 pl = pull_out_edges(p, node, lane);
-                        if (lane < 16) {
-                            float* gp = p.ghs + (size_t)node * D + 4 * lane;
-                            float4 cur = ldcg4(gp);
-                            cur.x += pl.x; cur.y += pl.y; cur.z += pl.z; cur.w += pl.w;
-                            mgv_st4(gp, cur);
-                        } else {
-                            const float4 gin = mgv_ld4(p.ghf + (size_t)node * D + 4 * (lane - 16));
-                            const float4 g4 = make_float4(gin.x + pl.x, gin.y + pl.y, gin.z + pl.z, gin.w + pl.w);
-                            mgv_st4(GS + i * D + 4 * (lane - 16), g4);
-                            gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(g4.x), fabsf(g4.y)), fmaxf(fabsf(g4.z), fabsf(g4.w))));
-                        }
-                    }
+                SWT(2);
+                haven = ti.next(nct, t0n, rowsn);
+                if (!haven && !crossed && step + 1 < nsteps) {
+                    ti.start(p, s, step + 2, code, rank, nct, G::NTS);
+                    crossed = true;
+                    haven = ti.next(nct, t0n, rowsn);
+                    if (haven) rrn = prefetch_rows<G::WPS>(p, t0n, rowsn, ws, lane);
+                    have = false;                              // leave the level after this tile
+                } else if (haven) {
+                    rrn = prefetch_rows<G::WPS>(p, t0n, rowsn, ws, lane);
+                } else {
+                    have = false;
                 }
-                // tile-wide bound of the gate gradients (|d n|, |d z|, |d r| <= max |g| for |b_hn| <= 4): fixes the power-of-two scale
-                // of the d-gate planes BEFORE the pointwise pass, which then writes them straight away
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-                if (lane == 0 && gmax > 0.f) atomicMax(s_misc + (it & 1u), __float_as_uint(gmax));
                 tc::mbar_wait_warp(bar_acc_full, it & 1u, lane, 32);
                 tc::fence_after_sync();
-                // ---- W: pointwise GRU backward.  z lives on TMEM lanes 64..127: through shared memory to the r / n lanes
+                SWT(3);
+                // ---- epilogue: TMEM lane = gate unit.  Lanes 64..127 hold z: those warps hand 1 - z to the r / n lanes through shared
+                // memory.  All columns are computed branch-free first (16 independent dependency chains per thread), then stored.
                 const int c0 = cg * 16;
                 if (c0 < npad && qd >= 2) {
                     float z[16];
-                    tc::tmem_ld16(tl + TB_ACC1 + c0, z);
+                    tc::tmem_ld16(tl1 + c0, z);
                     tc::tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) z[c] = 1.0f - sigmoid_fast(z[c] + b_z);
 #pragma unroll
                     for (int c = 0; c < 16; ++c) ZX[(c0 + c) * D + eu] = z[c];
                 }
-                tc::named_bar_sync(2, NWT);                    // GS (pull), ZX and the tile's gradient bound complete
-                const float scale = pow2_scale_keep(__uint_as_float(s_misc[it & 1u]), acc_scale);
-                const bool rescale = it > 0 && scale != acc_scale;
-                if (tid == 0) { s_misc[(it + 1) & 1u] = 0u; s_misc[2] = rescale ? 1u : 0u; }
+                tc::named_bar_sync(2 + 2 * s, G::NSW);
                 if (c0 < npad && qd < 2) {
                     float rp[16], np[16];
-                    tc::tmem_ld16(tl + TB_ACC1 + c0, rp);
-                    tc::tmem_ld16(tl + TB_ACC2 + c0, np);
+                    tc::tmem_ld16(tl1 + c0, rp);
+                    tc::tmem_ld16(tl2 + c0, np);
                     tc::tmem_ld_wait();
-                    // unit pairs (eu even, eu + 1): the even lane writes the hi plane word, the odd lane the lo plane word
-                    const int ue = eu & ~1;
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        float dg[3] = {0.f, 0.f, 0.f};                                  // d r, d z, d n (pre-activations)
-                        if (c0 + c < rows) {
-                            const float r = sigmoid_fast(rp[c] + b_r);
-                            const float z = sigmoid_fast(ZX[(c0 + c) * D + eu] + b_z);
-                            const float n = tanh_fast(np[c] + b_in + r * b_hn);
-                            const float g = GS[(c0 + c) * D + eu];
-                            const float dni = g * (1.0f - z) * (1.0f - n * n);
-                            dg[2] = dni;
-                            dg[0] = dni * b_hn * r * (1.0f - r);                        // n_pre = gi_n + r gh_n, gh_n = b_hn (h = 0)
-                            dg[1] = -g * n * z * (1.0f - z);                            // h' = (1 - z) n + z h, h = 0
-                            sb_r += dg[0]; sb_z += dg[1]; sb_n += dni; sb_hn += dni * r;
-                        }
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const float mine = dg[t] * scale;
-                            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                            uint32_t hi, lo;
-                            split2p<LOWP>((lane & 1) ? other : mine, (lane & 1) ? mine : other, hi, lo);
-                            const uint32_t off = (uint32_t)t * KB_X + tc::sw128_off(c0 + c, ue >> 3) + (uint32_t)(ue & 7) * 2u;
-                            if (!(lane & 1)) st_shared_b32(sbase + B_DG_HI + off, hi);
-                            else if (!LOWP) st_shared_b32(sbase + B_DG_LO + off, lo);
-                        }
+                        const float r = sigmoid_fast(rp[c] + b_r);
+                        const float n = tanh_fast(np[c] + b_in + r * b_hn);
+                        rp[c] = n * ZX[(c0 + c) * D + eu];                                // (1 - z) n + z h,  h = 0
                     }
-                }
-                tc::fence_async_smem();
-                tc::mbar_arrive(bar_dg_full);
-                // ---- the persistent weight-gradient accumulator changes scale (rare): exact power-of-two rescale in place
-                if (rescale) {
-                    const float f = scale / acc_scale;
-#pragma unroll 1
-                    for (int cc = 0; cc < 3; ++cc) {
-                        float v[16];
-                        tc::tmem_ld16(tl + TB_DW + cg * 48 + 16 * cc, v);
-                        tc::tmem_ld_wait();
-                        uint32_t w[16];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) w[e] = __float_as_uint(v[e] * f);
-                        tc::tmem_st16(tl + TB_DW + cg * 48 + 16 * cc, w);
-                    }
-                    tc::tmem_st_wait();
-                    tc::fence_before_sync();
-                    tc::mbar_arrive(bar_rescaled);
-                }
-                acc_scale = scale;
-                // ---- X: dxbar^T (TMEM lane = input feature) -> [node][feature] in shared memory
-                tc::mbar_wait_warp(bar_dx_full, it & 1u, lane, 32);
-                tc::fence_after_sync();
-                if (c0 < npad) {
-                    float v[16];
-                    tc::tmem_ld16(tl + TB_DX + c0, v);
-                    tc::tmem_ld_wait();
-                    const float inv = 1.0f / scale;
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) DXS[(c0 + c) * D2 + ef] = v[c] * inv;
+                    for (int c = 0; c < 16; ++c)
+                        if (c0 + c < rows) p.hf[(size_t)IDS[c0 + c] * D + eu] = rp[c];
                 }
                 tc::fence_before_sync();
-                tc::named_bar_sync(2, NWT);
-                // ---- A: attention backward, warp per node
-#pragma unroll
-                for (int k = 0; k < NT / WORKERS; ++k) {
-                    const int i = warp + WORKERS * k;
-                    if (i < rows) {
-                        const unsigned full = 0xffffffffu;
-                        const int node = __shfl_sync(full, rr.node, k * 8), cnt = __shfl_sync(full, rr.cnt, k * 8), beg = __shfl_sync(full, rr.beg, k * 8);
-                        const float4 dxb4 = *reinterpret_cast<const float4*>(DXS + i * D2 + 4 * lane);
-                        mgv_st4(p.dxb + (size_t)node * D2 + 4 * lane, dxb4);
-                        const int off = 4 * (lane & 15);
-                        const float* base = (lane < 16) ? p.hs : p.hf;
-                        if (cnt <= 4) {
-                            float4 x[4];
-                            float dal[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int j = __shfl_sync(full, rr.src, k * 8 + q);
-                                x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (q < cnt) x[q] = mgv_ld4(base + (size_t)j * D + off);
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) dal[q] = mgv_warp_sum(mgv_dot4(dxb4, x[q]));
-                            float A = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) A = fmaf(al[k][q], dal[q], A);
-                            float mine = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float ds = al[k][q] * (dal[q] - A);
-                                mgv_fma4(du4, ds, x[q]);
-                                if (lane == q) mine = ds;
-                            }
-                            if (lane < cnt) p.dscore[beg + lane] = mine;
-                        } else {
-                            // rare: more than four predecessors -- two passes over the rows (d alpha parked in p.dscore)
-                            float A = 0.f;
-                            for (int q = 0; q < cnt; ++q) {
-                                const int j = __ldg(p.in_src + beg + q);
-                                const float4 xq = mgv_ld4(base + (size_t)j * D + off);
-                                const float dalq = mgv_warp_sum(mgv_dot4(dxb4, xq));
-                                A = fmaf(p.alpha[beg + q], dalq, A);
-                                if (lane == 0) p.dscore[beg + q] = dalq;
-                            }
-                            __syncwarp();
-                            for (int q = 0; q < cnt; ++q) {
-                                const int j = __ldg(p.in_src + beg + q);
-                                const float4 xq = mgv_ld4(base + (size_t)j * D + off);
-                                const float ds = p.alpha[beg + q] * (p.dscore[beg + q] - A);
-                                mgv_fma4(du4, ds, xq);
-                                __syncwarp();
-                                if (lane == 0) p.dscore[beg + q] = ds;
-                            }
-                        }
-                    }
-                }
-                tc::named_bar_sync(1, NWT);                    // all stores of the tile issued; the staging buffers are free
+                SWT(4);
+                tc::named_bar_sync(1 + 2 * s, G::NSW);         // all stores of the tile issued; ZX / IDS / the node tile are free
+                SWT(5);
                 ++it;
-                have = ti.next(nct, t0, rows);
+                if (have) { t0 = t0n; rows = rowsn; rr = rrn; }
             }
-            if (!waited) tc::mbar_wait_warp(bar_level, (uint32_t)((step - 1) & 1), lane, 32);    // stay in phase with the barrier
-            if (tid == 0) grid_arrive(p.bar);
+            if (!crossed && step + 1 < nsteps && code >= 0) {  // no tile of this CTA at this level
+                ti.start(p, s, step + 2, code, rank, nct, G::NTS);
+                haven = ti.next(nct, t0n, rowsn);
+                if (haven) rrn = prefetch_rows<G::WPS>(p, t0n, rowsn, ws, lane);
+            }
+            if (ws == 0 && lane == 0 && step + 1 < nsteps) grid_arrive(gbar);
+            have = haven && step + 1 < nsteps;
+            t0 = t0n; rows = rowsn; rr = rrn;
+            SWT(6);
         }
-        // ---- every level is done: nodes that are only pulled (level 0; codes without an aggregator at any level)
-        if (nsteps > 0) tc::mbar_wait_warp(bar_level, (uint32_t)((nsteps - 1) & 1), lane, 32);
-        {
-            const int gw = blockIdx.x * WORKERS + warp, nw = gridDim.x * WORKERS;
-            const int end0 = __ldg(p.seg_ptr + MGV_NCODE);
-            for (int tt = gw; tt < end0; tt += nw) pull_into_ghs(p, __ldg(p.order + tt), lane);
-            for (int c = 0; c < MGV_NCODE; ++c) {
-                if (!((pull_only_codes >> c) & 1u)) continue;
-                for (int lvl = 1; lvl < p.L; ++lvl) {
-                    const int sbeg = __ldg(p.seg_ptr + lvl * MGV_NCODE + c), send = __ldg(p.seg_ptr + lvl * MGV_NCODE + c + 1);
-                    for (int tt = sbeg + gw; tt < send; tt += nw) pull_into_ghs(p, __ldg(p.order + tt), lane);
-                }
-            }
-        }
-        // ---- flush: weight gradients (tensor memory), bias and attention-vector gradients (registers) -> raw block of the code
-        if (code >= 0 && it > 0) {
-            float* raw = p.raw + (size_t)code * RAWF;
-            tc::mbar_wait_warp(bar_wg_done, (it - 1) & 1u, lane, 32);
-            tc::fence_after_sync();
-            const float un = 1.0f / acc_scale;
-#pragma unroll 1
-            for (int cc = 0; cc < 3; ++cc) {
-                float v[16];
-                tc::tmem_ld16(tl + TB_DW + cg * 48 + 16 * cc, v);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) red_add1(raw + R_WC + (size_t)(cg * 48 + 16 * cc + e) * D2 + ef, v[e] * un);
-            }
-            if (qd < 2) {
-                red_add1(raw + R_B + eu, sb_r); red_add1(raw + R_B + D + eu, sb_z);
-                red_add1(raw + R_B + 2 * D + eu, sb_n); red_add1(raw + R_B + 3 * D + eu, sb_hn);
-            }
-            red_add1(raw + R_U + 4 * lane, du4.x); red_add1(raw + R_U + 4 * lane + 1, du4.y);
-            red_add1(raw + R_U + 4 * lane + 2, du4.z); red_add1(raw + R_U + 4 * lane + 3, du4.w);
-        }
-    } else if (lane == 0) {
-        // ===================================================================== MMA issue + grid barrier polling (one thread)
-        if (code >= 0) tc::mbar_wait_sleep(bar_w, 0u);
-        uint32_t it = 0, rs_it = 0;
-        bool acc_has = false;
+        SWT_FLUSH(8, it);
+    } else {
+        // ===================================================================== tensor-core issue + grid barrier polling of stream s:
+        // the whole warp runs the control flow (descriptors stay in uniform registers), one elected lane issues
+        if (code >= 0) tc::mbar_wait_warp(bar_w, 0u, lane);
+        uint32_t it = 0;
         for (int step = 0; step < nsteps; ++step) {
-            bool lvl_done = (step == 0);
-            const unsigned target = (unsigned)step * gridDim.x;
-            TileIter ti;
-            int t0 = 0, rows = 0;
-            bool have = false;
             if (code >= 0) {
-                ti.start(p.seg_ptr, p.L - 1 - step, code, rank, nct);
-                have = ti.next(nct, t0, rows);
-            }
-            while (have) {
-                const int npad = (rows + 15) & ~15;
-                // recompute products as soon as the node tile is full -- before or after the level barrier completes
-                bool rc_done = false;
-                while (!rc_done || !lvl_done) {
-                    if (!rc_done && mbar_try(bar_x_full, it & 1u)) {
-                        tc::fence_after_sync();
-                        issue_gate_mmas<LOWP>(sbase, sbase + B_XB_HI, sbase + B_XB_LO, tmem + TB_ACC1, tmem + TB_ACC2, npad);
-                        tc::mma_commit(bar_acc_full);
-                        rc_done = true;
-                    }
-                    if (!lvl_done && mgv_ld_acquire(p.bar) >= target) {
-                        __threadfence();
-                        tc::mbar_arrive(bar_level);
-                        lvl_done = true;
-                    }
-                    if (!rc_done || !lvl_done) __nanosleep(20);
-                }
-                tc::mbar_wait_sleep(bar_dg_full, it & 1u, 32);
-                tc::fence_after_sync();
-                {   // dxbar^T = Wc^T DG^T : A = weight image MN-major (M = 128 input features = the two K blocks), K = 192 gates
-                    const uint32_t idesc = tc::make_idesc(128, npad, true, false, LOWP);
-#pragma unroll
-                    for (int s = 0; s < 12; ++s) {
-                        const uint32_t go = (uint32_t)(s >> 2) * KB_X + 32u * (s & 3);
-                        tc::mma3p<LOWP>(tmem + TB_DX, tc::desc_mn_sw128(sbase + I_WC_HI + 2048u * s, KB_W), tc::desc_mn_sw128(sbase + I_WC_LO + 2048u * s, KB_W),
-                                        tc::desc_k_sw128(sbase + B_DG_HI + go), tc::desc_k_sw128(sbase + B_DG_LO + go), idesc, s ? 1u : 0u);
-                    }
-                    tc::mma_commit(bar_dx_full);
-                }
-                if (*reinterpret_cast<volatile unsigned*>(s_misc + 2)) {
-                    tc::mbar_wait_sleep(bar_rescaled, rs_it & 1u, 32);
+                TileIter ti;
+                ti.start(p, s, step + 1, code, rank, nct, G::NTS);
+                int t0, rows;
+                while (ti.next(nct, t0, rows)) {
+                    tc::mbar_wait_warp(bar_x_full, it & 1u, lane, 20);
                     tc::fence_after_sync();
-                    ++rs_it;
+                    if (tc::elect_one()) {
+                        issue_gate_mmas<LOWP>(sbase, xb_hi, xb_lo, G::KBX, acc1, acc2, (rows + 15) & ~15);
+                        tc::mma_commit(bar_acc_full);
+                    }
+                    __syncwarp();
+                    ++it;
                 }
-                {   // dWc^T += xbar^T DG : both MN-major, K = nodes
-                    const uint32_t idesc = tc::make_idesc(128, G3, true, true, LOWP);
-                    for (int s = 0; s < npad / 16; ++s)
-                        tc::mma3p<LOWP>(tmem + TB_DW, tc::desc_mn_sw128(sbase + B_XB_HI + 2048u * s, KB_X), tc::desc_mn_sw128(sbase + B_XB_LO + 2048u * s, KB_X),
-                                        tc::desc_mn_sw128(sbase + B_DG_HI + 2048u * s, KB_X), tc::desc_mn_sw128(sbase + B_DG_LO + 2048u * s, KB_X), idesc,
-                                        (acc_has || s) ? 1u : 0u);
-                    tc::mma_commit(bar_wg_done);
-                    acc_has = true;
-                }
-                ++it;
-                have = ti.next(nct, t0, rows);
             }
-            if (!lvl_done) {
-                grid_poll(p.bar, target);
-                tc::mbar_arrive(bar_level);
+            if (step + 1 < nsteps) {
+                const unsigned target = (unsigned)(step + 1) * gridDim.x;
+                { tc::WaitGuard wg; while (!grid_try(gbar, target, bar_level, lane)) { __nanosleep(20); wg.tick(); } }
             }
-        }
-        if (nsteps > 0) {
-            grid_poll(p.bar, (unsigned)nsteps * gridDim.x);
-            tc::mbar_arrive(bar_level);
         }
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == WORKERS) tc::tmem_dealloc(tmem, TB_COLS);
+    if (warp == WORKERS) tc::tmem_dealloc(tmem, G::TF_COLS);
 }
+
+#include "sweep_tc_bwd.inc"
 
 // raw blocks -> gradient blocks in the layout of include/mgv_b200.h (chain rule of Wc = W_ih W_v, b = W_ih b_v + b_ih (+ b_hh)):
 //   d W_v = W_ih^T d Wc,  d b_v = W_ih^T d c,  d W_ih = d Wc W_v^T + d c b_v^T,  d b_ih = d c,  d b_hh = [d c_r, d c_z, d b_hn],  d W_hh = 0
@@ -931,20 +655,47 @@ __global__ void sweep_chain_kernel(const float* __restrict__ pack, const float* 
 
 // ======================================================================================= host side (called from sweep.cu)
 using namespace sweep_tc;
+long long* mgv_debug_trace();
+
+namespace {
+int fill(SweepTC& d, const mgv_schedule* sch, unsigned handled, const int* cta_start, const float* weights, const float* hs, float* hf,
+         int32_t* sync) {
+    d.N = sch->N; d.L = sch->L; d.S = sch->streams > 1 ? sch->streams : 1; d.handled = handled;
+    MGV_REQUIRE(d.S <= MAX_STREAMS, "level sweep: a schedule may have at most %d streams", MAX_STREAMS);
+    d.order = sch->order; d.seg_ptr = sch->seg_ptr; d.in_ptr = sch->in_ptr; d.in_src = sch->in_src;
+    d.out_ptr = sch->out_ptr; d.out_pack = sch->out_pack; d.out_slot = sch->out_slot;
+    MGV_REQUIRE(sch->sweep_desc != nullptr, "level sweep: the schedule has no row descriptors (mgv_build_sweep_desc)");
+    d.desc = sch->sweep_desc;
+    d.image = reinterpret_cast<const uint8_t*>(weights) + IMG_OFFSET; d.weights = weights; d.hs = hs; d.hf = hf;
+    for (int c = 0; c <= MGV_NCODE; ++c) d.cta_start[c] = cta_start[c];
+    d.bar = reinterpret_cast<unsigned*>(sync);
+    d.trace = nullptr;
+    return MGV_OK;
+}
+template <int S>
+const void* fwd_kernel(int precision) {
+    return precision == 1 ? (const void*)sweep_fwd_tc_kernel<true, S> : (const void*)sweep_fwd_tc_kernel<false, S>;
+}
+template <int S>
+const void* bwd_kernel(int precision) {
+    return precision == 1 ? (const void*)sweep_bwd_tc_kernel<true, S> : (const void*)sweep_bwd_tc_kernel<false, S>;
+}
+}  // namespace
 
 int mgv_sweep_tc_fwd(const mgv_schedule* sch, unsigned handled, const int* cta_start, int grid, const float* weights,
                      const float* hs, float* hf, int32_t* sync, int precision, cudaStream_t st) {
     SweepTC d{};
-    d.N = sch->N; d.L = sch->L; d.handled = handled;
-    d.order = sch->order; d.seg_ptr = sch->seg_ptr; d.in_ptr = sch->in_ptr; d.in_src = sch->in_src;
-    d.out_ptr = sch->out_ptr; d.out_pack = sch->out_pack; d.out_slot = sch->out_slot;
-    d.image = reinterpret_cast<const uint8_t*>(weights) + IMG_OFFSET; d.weights = weights; d.hs = hs; d.hf = hf;
-    for (int c = 0; c <= MGV_NCODE; ++c) d.cta_start[c] = cta_start[c];
-    d.bar = reinterpret_cast<unsigned*>(sync);
-    const void* kern = precision == 1 ? (const void*)sweep_fwd_tc_kernel<true> : (const void*)sweep_fwd_tc_kernel<false>;
-    MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+    int rc = fill(d, sch, handled, cta_start, weights, hs, hf, sync);
+    if (rc != MGV_OK) return rc;
+#ifdef MGV_SWEEP_TRACE
+    d.trace = getenv("MGV_TRACE_SWEEP_FWD") ? mgv_debug_trace() : nullptr;
+#endif
+    const void* kern = d.S == 2 ? fwd_kernel<2>(precision) : fwd_kernel<1>(precision);
+    const size_t smem = d.S == 2 ? (size_t)Geo<2>::F_SMEM : (size_t)Geo<1>::F_SMEM;
+    const int threads = d.S == 2 ? Geo<2>::NTHREADS : Geo<1>::NTHREADS;
+    MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {&d};
-    MGV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NTHREADS), args, (size_t)F_SMEM, st));
+    MGV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, st));
     mgv_count_launches(1);
     return MGV_OK;
 }
@@ -953,14 +704,13 @@ int mgv_sweep_tc_grid(int* grid_out) {
     int dev = 0, sms = 0, occ = 0;
     MGV_CUDA(cudaGetDevice(&dev));
     MGV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const void* kern = (const void*)sweep_fwd_tc_kernel<false>;
-    MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-    MGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, (size_t)F_SMEM));
-    MGV_REQUIRE(occ >= 1, "level sweep: the tensor-core forward kernel does not fit on an SM");
+    const void* kern = bwd_kernel<2>(0);
+    MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<2>::B_SMEM));
+    MGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Geo<2>::NTHREADS, (size_t)Geo<2>::B_SMEM));
+    MGV_REQUIRE(occ >= 1, "level sweep: the tensor-core kernels do not fit on an SM");
     *grid_out = sms;                     // one CTA per SM (tensor memory and the weight image are per CTA)
     return MGV_OK;
 }
-
 
 bool mgv_sweep_tc_bwd_available() { return true; }
 
@@ -976,12 +726,8 @@ int mgv_sweep_tc_bwd(const mgv_schedule* sch, unsigned handled, const int* cta_s
                      const float* hs, const float* hf, float* ghs, float* ghf, float* grads, void* ws, size_t ws_bytes,
                      int32_t* sync, int precision, cudaStream_t st) {
     SweepTC d{};
-    d.N = sch->N; d.L = sch->L; d.handled = handled;
-    d.order = sch->order; d.seg_ptr = sch->seg_ptr; d.in_ptr = sch->in_ptr; d.in_src = sch->in_src;
-    d.out_ptr = sch->out_ptr; d.out_pack = sch->out_pack; d.out_slot = sch->out_slot;
-    d.image = reinterpret_cast<const uint8_t*>(weights) + IMG_OFFSET; d.weights = weights; d.hs = hs; d.hf = const_cast<float*>(hf);
-    for (int c = 0; c <= MGV_NCODE; ++c) d.cta_start[c] = cta_start[c];
-    d.bar = reinterpret_cast<unsigned*>(sync);
+    int rc = fill(d, sch, handled, cta_start, weights, hs, const_cast<float*>(hf), sync);
+    if (rc != MGV_OK) return rc;
     MgvArena a(ws, ws_bytes);
     d.dxb = a.take<float>((size_t)sch->N * D2);
     d.alpha = a.take<float>((size_t)sch->E + 1);
@@ -989,14 +735,19 @@ int mgv_sweep_tc_bwd(const mgv_schedule* sch, unsigned handled, const int* cta_s
     d.raw = a.take<float>((size_t)MGV_NCODE * RAWF);
     MGV_REQUIRE(a.ok(), "mgv_sweep_tc_bwd: workspace too small");
     d.ghs = ghs; d.ghf = ghf;
+#ifdef MGV_SWEEP_TRACE
+    d.trace = getenv("MGV_TRACE_SWEEP_FWD") ? nullptr : mgv_debug_trace();
+#endif
     unsigned pull_only = 0u;                                  // codes without an aggregator that do occur at a level >= 1
     for (int c = 0; c < MGV_NCODE; ++c)
         if (!((handled >> c) & 1u) && sch->code_count[c] > 0) pull_only |= 1u << c;
     MGV_CUDA(cudaMemsetAsync(d.raw, 0, (size_t)MGV_NCODE * RAWF * sizeof(float), st));
-    const void* kern = precision == 1 ? (const void*)sweep_bwd_tc_kernel<true> : (const void*)sweep_bwd_tc_kernel<false>;
-    MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM));
+    const void* kern = d.S == 2 ? bwd_kernel<2>(precision) : bwd_kernel<1>(precision);
+    const size_t smem = d.S == 2 ? (size_t)Geo<2>::B_SMEM : (size_t)Geo<1>::B_SMEM;
+    const int threads = d.S == 2 ? Geo<2>::NTHREADS : Geo<1>::NTHREADS;
+    MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {&d, &pull_only};
-    MGV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(NTHREADS), args, (size_t)B_SMEM, st));
+    MGV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, st));
     sweep_chain_kernel<<<dim3((GRAD + 255) / 256, MGV_NCODE), 256, 0, st>>>(weights, d.raw, grads, handled);
     mgv_count_launches(2);
     return mgv_check_cuda(cudaGetLastError(), "mgv_sweep_tc_bwd");

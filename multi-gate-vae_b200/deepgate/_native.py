@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libmgv_b200.so")
+# MGV_B200_LIB: development knob -- load another build of the same library (e.g. the phase-trace build of scripts/)
+LIB_PATH = os.environ.get("MGV_B200_LIB") or os.path.join(_HERE, "_lib", "libmgv_b200.so")
 
 D = 64
 NCODE = 8
@@ -36,7 +37,8 @@ class mgv_schedule(ctypes.Structure):
                 ("out_ptr", _vp), ("out_pack", _vp), ("out_slot", _vp),
                 ("code_count", _i64 * NCODE),
                 ("deg_order_in", _vp), ("deg_order_out", _vp), ("tile_cost_in", _vp), ("tile_cost_out", _vp),
-                ("gdesc_in", _vp), ("gdesc_out", _vp)]
+                ("gdesc_in", _vp), ("gdesc_out", _vp), ("streams", _i32), ("reserved0", _i32),
+                ("sweep_desc", _vp)]
 
 
 _SP = ctypes.POINTER(mgv_schedule)
@@ -50,7 +52,8 @@ _PROTOTYPES = {
     "mgv_levelize_workspace_bytes": (_sz, [_i64]),
     "mgv_levelize": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, ctypes.POINTER(_i32), _vp, _sz, _vp]),
     "mgv_level_lists_workspace_bytes": (_sz, [_i64, _i32]),
-    "mgv_build_level_lists": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _vp, _vp]),
+    "mgv_build_level_lists": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, ctypes.POINTER(_i64), _vp, _sz, _vp, _vp]),
+    "mgv_build_sweep_desc": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mgv_degree_order_workspace_bytes": (_sz, [_i64]),
     "mgv_build_degree_order": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mgv_level_sweep_fwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _i32, _vp]),

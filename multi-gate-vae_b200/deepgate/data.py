@@ -87,7 +87,29 @@ def collate(circuits):
     out.ptr = torch.tensor(starts, dtype=torch.long)
     out.num_graphs = len(circuits)
     attach_schedule_meta(out)
+    attach_streams(out, counts)
     return out
+
+
+SWEEP_STREAMS = 2          # independent circuit sets the level sweep runs concurrently (csrc/sweep_tc.cu)
+
+
+def attach_streams(batch, counts, streams=SWEEP_STREAMS):
+    """Cut the circuits of a batch into ``streams`` sets of near-equal size (largest first onto the lighter set) and record the
+    set of every node in ``batch.sweep_stream`` (int32 [N]).  Circuits never exchange messages, so the level sweep may run the
+    sets' level chains concurrently, each with its own barrier (mgv_b200.h, mgv_build_level_lists); the results do not depend
+    on the cut.  Batches of one circuit keep a single stream."""
+    if len(counts) < 2 or streams < 2:
+        return batch
+    load = [0] * streams
+    table = [0] * len(counts)
+    for i in sorted(range(len(counts)), key=lambda i: -counts[i]):
+        k = min(range(streams), key=lambda k: load[k])
+        table[i] = k
+        load[k] += counts[i]
+    batch.sweep_stream = torch.repeat_interleave(torch.tensor(table, dtype=torch.int32), torch.tensor(counts))
+    batch.sweep_streams = streams
+    return batch
 
 
 def attach_schedule_meta(batch):

@@ -57,7 +57,8 @@ class LevelModel(nn.Module):
 
     # ------------------------------------------------------------------ hot path
     def forward(self, G):
-        sched = schedule_for_batch(G)
+        # circuit-set streams are a feature of the single-round tensor-core sweep (csrc/sweep_tc.cu)
+        sched = schedule_for_batch(G, streams=None if self.num_rounds == 1 else 1)
         encoder = getattr(self, self.ENCODER_ATTR)
         # the reference feeds one_hot(G.x[:, 1], 6) although G.x is already one-hot, i.e. the
         # feature is one_hot(1{gate code == 1}, 6)  (dg_ae_model_mig.py:71)

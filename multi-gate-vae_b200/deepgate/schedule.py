@@ -9,9 +9,11 @@ Holds int32 device arrays:
   in_ptr/in_src      predecessors by node id, ascending original edge id
   out_ptr/out_pack/out_slot  successors (out_pack = dst | code(dst) << 28)
   level              ASAP level per node
-  order/seg_ptr      node ids sorted by (level, code), segment boundaries [L*8+1]
+  order/seg_ptr      node ids sorted by (stream, level, code), segment boundaries [streams*L*8+1]
+                     (streams = independent circuit sets of the batch, data.attach_streams; 1 unless asked for)
 """
 import ctypes
+import os
 
 import torch
 
@@ -89,8 +91,10 @@ class GraphCSR(object):
                                                      nat.ptr(ws), nb, nat.stream_of(dev)), "mgv_build_degree_order")
         self.level = None
         self.L = 1
+        self.streams = 1
         self.order = None
         self.seg_ptr = None
+        self.sweep_desc = None
         self.code_count = [0] * nat.NCODE
         self._struct = None
 
@@ -109,10 +113,11 @@ class GraphCSR(object):
                                        info, nat.ptr(ws), nb, nat.stream_of(self.device)), "mgv_levelize")
         return level[:self.N], max(int(info[0]), 1)
 
-    def set_levels(self, level=None, num_levels=None, code_count=None):
+    def set_levels(self, level=None, num_levels=None, code_count=None, stream_of_node=None, streams=1):
         """Attach levels (given, e.g. ``G.forward_level``, or computed) and build the
-        (level, code)-segmented node lists.  With ``num_levels`` and ``code_count`` supplied (host metadata of the
-        batch, data.attach_schedule_meta) nothing here synchronises with the device."""
+        (stream, level, code)-segmented node lists.  With ``num_levels`` and ``code_count`` supplied (host metadata of the
+        batch, data.attach_schedule_meta) nothing here synchronises with the device.  ``stream_of_node`` (int32 [N] in
+        [0, streams)) cuts the batch into independent node sets (whole circuits), see data.attach_streams."""
         if self.code is None:
             raise RuntimeError("mgv_b200: a level schedule needs gate codes")
         if level is None:
@@ -127,19 +132,32 @@ class GraphCSR(object):
                 # one device->host sync, as the reference's max(G.forward_level).item() (dg_ae_model_mig.py:67)
                 L = int(lvl.max().item()) + 1 if self.N > 0 else 1
         self.level, self.L = lvl, L
+        streams = int(streams) if stream_of_node is not None else 1
+        if streams > 1:
+            stream_of_node = nat.require_cuda(stream_of_node.reshape(-1).to(torch.int32).contiguous(), "sweep_stream", torch.int32)
+            if stream_of_node.numel() != self.N:
+                raise RuntimeError("mgv_b200: sweep_stream must have one entry per node")
+        else:
+            stream_of_node, streams = None, 1
+        self.streams = streams
         i32 = dict(dtype=torch.int32, device=self.device)
         self.order = torch.empty(max(self.N, 1), **i32)
-        self.seg_ptr = torch.empty(L * nat.NCODE + 1, **i32)
+        self.seg_ptr = torch.empty(streams * L * nat.NCODE + 1, **i32)
         use_async = code_count is not None and level is not None and num_levels is not None
         counts = (ctypes.c_int64 * nat.NCODE)()
         lib = nat.lib()
         with torch.cuda.device(self.device):
-            nb = lib.mgv_level_lists_workspace_bytes(self.N, L)
+            nb = lib.mgv_level_lists_workspace_bytes(self.N, streams * L)
             ws = nat.workspace(nb, self.device)
-            nat.check(lib.mgv_build_level_lists(nat.ptr(lvl), nat.ptr(self.code), self.N, L, nat.ptr(self.order),
+            nat.check(lib.mgv_build_level_lists(nat.ptr(lvl), nat.ptr(self.code), nat.ptr(stream_of_node), streams,
+                                                self.N, L, nat.ptr(self.order),
                                                 nat.ptr(self.seg_ptr), None if use_async else counts, nat.ptr(ws), nb,
                                                 nat.ptr(error_word(self.device)) if use_async else None,
                                                 nat.stream_of(self.device)), "mgv_build_level_lists")
+            # row descriptors of the level sweep (one coalesced load per tile row instead of the index chain)
+            self.sweep_desc = torch.empty(max(self.N, 1), 8, **i32)
+            nat.check(lib.mgv_build_sweep_desc(nat.ptr(self.order), nat.ptr(self.in_ptr), nat.ptr(self.in_src), nat.ptr(self.out_ptr),
+                                               self.N, nat.ptr(self.sweep_desc), nat.stream_of(self.device)), "mgv_build_sweep_desc")
         self.code_count = [int(c) for c in (code_count if use_async else counts)]
         self._struct = None
         return self
@@ -157,6 +175,8 @@ class GraphCSR(object):
             s.deg_order_in, s.deg_order_out = nat.ptr(self.deg_order_in), nat.ptr(self.deg_order_out)
             s.tile_cost_in, s.tile_cost_out = nat.ptr(self.tile_cost_in), nat.ptr(self.tile_cost_out)
             s.gdesc_in, s.gdesc_out = nat.ptr(self.gdesc_in), nat.ptr(self.gdesc_out)
+            s.streams, s.reserved0 = self.streams, 0
+            s.sweep_desc = nat.ptr(self.sweep_desc)
             self._struct = s
         return ctypes.byref(self._struct)
 
@@ -183,13 +203,21 @@ def csr_for(edge_index, num_nodes):
     return csr
 
 
-def schedule_for_batch(G):
+def schedule_for_batch(G, streams=None):
     """Level schedule of a batch ``G`` (cached on the object).  Uses ``G.forward_level`` when the
-    batch carries it (the reference computes it at dataset build, parser_func_others.py:63)."""
+    batch carries it (the reference computes it at dataset build, parser_func_others.py:63) and the batch's circuit
+    sets ``G.sweep_stream`` (data.attach_streams) unless ``streams=1`` asks for plain (level, code) lists."""
     sch = getattr(G, "_mgv_schedule", None)
     ei = G.edge_index
     n = int(G.gate.shape[0])
-    if sch is not None and sch.N == n and sch.edge_index.data_ptr() == ei.data_ptr() and sch.E == ei.size(1):
+    sos = getattr(G, "sweep_stream", None)
+    want = int(getattr(G, "sweep_streams", 1)) if (sos is not None and sos.numel() == n and sos.is_cuda) else 1
+    if streams is not None:
+        want = min(want, int(streams))
+    if os.environ.get("MGV_SWEEP_STREAMS"):                   # development knob: force the number of streams (1 or 2)
+        want = min(want, int(os.environ["MGV_SWEEP_STREAMS"]))
+    if (sch is not None and sch.N == n and sch.edge_index.data_ptr() == ei.data_ptr() and sch.E == ei.size(1)
+            and sch.streams == want):
         return sch
     if not ei.is_cuda:
         raise RuntimeError("mgv_b200: the batch must be on a CUDA device (no CPU path); call batch.to('cuda')")
@@ -199,7 +227,8 @@ def schedule_for_batch(G):
     L, counts = getattr(G, "num_levels", None), getattr(G, "level_code_count", None)
     has_meta = level is not None and L is not None and counts is not None and len(counts) == nat.NCODE
     sch = GraphCSR(ei.contiguous(), n, code=code, validate=not has_meta)
-    sch.set_levels(level, L if has_meta else None, counts if has_meta else None)
+    sch.set_levels(level, L if has_meta else None, counts if has_meta else None,
+                   stream_of_node=sos if want > 1 else None, streams=want)
     try:
         G._mgv_schedule = sch
     except Exception:

@@ -275,11 +275,23 @@ def test_async_schedule_equals_sync_schedule_and_flags_bad_input():
     host = deepgate.circuits_to_batch(synth.make_circuits("mig4", 5, 16, 400, cfg=32, window=30))
     assert host.num_levels == int(host.forward_level.max()) + 1
     G = host.copy_to("cuda", non_blocking=False)
-    a = schedule_for_batch(G)                                       # asynchronous form (metadata present)
+    a = schedule_for_batch(G, streams=1)                            # asynchronous form (metadata present)
     b = GraphCSR(G.edge_index.contiguous(), G.x.size(0), code=G.gate.reshape(-1)).set_levels(G.forward_level)
-    assert a.L == b.L and a.code_count == b.code_count
-    for k in ("in_ptr", "in_src", "out_ptr", "out_pack", "out_slot", "order", "seg_ptr", "deg_order_in", "deg_order_out"):
+    assert a.L == b.L and a.code_count == b.code_count and a.streams == b.streams == 1
+    for k in ("in_ptr", "in_src", "out_ptr", "out_pack", "out_slot", "order", "seg_ptr", "deg_order_in", "deg_order_out", "sweep_desc"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
+    # the same batch cut into its two circuit sets (data.attach_streams): lists sorted by (stream, level, code)
+    c = schedule_for_batch(G)
+    d = GraphCSR(G.edge_index.contiguous(), G.x.size(0), code=G.gate.reshape(-1)).set_levels(
+        G.forward_level, stream_of_node=G.sweep_stream, streams=2)
+    assert c.streams == d.streams == 2 and c.code_count == d.code_count == a.code_count
+    assert torch.equal(c.order, d.order) and torch.equal(c.seg_ptr, d.seg_ptr)
+    key = (G.sweep_stream.long() * a.L + G.forward_level.long()) * 8 + G.gate.reshape(-1).long().clamp(0, 6)
+    assert torch.equal(c.order.long(), torch.sort(key, stable=True).indices)
+    assert torch.equal(c.seg_ptr.long(), torch.cat([key.new_zeros(1), torch.bincount(key, minlength=2 * a.L * 8).cumsum(0)]))
+    o = c.order.long()
+    assert torch.equal(c.sweep_desc[:, 0].long(), o)
+    assert torch.equal(c.sweep_desc[:, 2], (c.in_ptr[1:] - c.in_ptr[:-1])[o]) and torch.equal(c.sweep_desc[:, 4], (c.out_ptr[1:] - c.out_ptr[:-1])[o])
     check_deferred_errors()
     bad = G.edge_index.clone()
     bad[0, 0] = G.x.size(0) + 5
@@ -289,6 +301,40 @@ def test_async_schedule_equals_sync_schedule_and_flags_bad_input():
     check_deferred_errors()                                         # flag was cleared
     with pytest.raises(RuntimeError):
         GraphCSR(bad, G.x.size(0), code=G.gate.reshape(-1), validate=True)
+
+
+def test_sweep_result_does_not_depend_on_the_stream_cut():
+    """One stream (the reference's plain level order) and two circuit-set streams give the same embeddings bit for bit
+    (the arithmetic of a node does not depend on which stream runs it) and the same gradients up to summation order."""
+    import deepgate
+    from deepgate import synth, ops
+    from deepgate.schedule import schedule_for_batch
+    from oracle import dg_oracle as O
+    host = deepgate.circuits_to_batch(synth.make_circuits("xmg", 7, 16, 700, cfg=41, window=40))
+    G = host.copy_to("cuda", non_blocking=False)
+    enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, s_rounds=1, t_rounds=1, layernorm=True)
+    model = deepgate.dg_ae_model_xmg.Model(struct_encoder=enc, num_rounds=1, dim_hidden=64)
+    model.load_state_dict(O.synth_state_dict("xmg", 3), strict=False)
+    model = model.cuda()
+    codes = [c for c, _ in model.GATE_MODULES]
+    mods = [(getattr(model, "aggr_%s_func" % s), getattr(model, "update_%s_func" % s)) for _, s in model.GATE_MODULES]
+    torch.manual_seed(5)
+    hs0 = torch.randn(G.x.size(0), 64, device="cuda")
+    gout = torch.randn(G.x.size(0), 64, device="cuda")
+    res = []
+    for streams in (1, 2):
+        sch = schedule_for_batch(G, streams=streams)
+        assert sch.streams == streams
+        hs = hs0.clone().requires_grad_(True)
+        model.zero_grad(set_to_none=True)
+        hf = ops.level_sweep(hs, sch, 1, codes, mods)
+        (hf * gout).sum().backward()
+        res.append((hf.detach().clone(), hs.grad.clone(), {k: v.grad.clone() for k, v in model.named_parameters() if v.grad is not None}))
+    assert float((res[0][0] - res[1][0]).abs().max()) <= 1e-6 * float(res[0][0].abs().max())
+    print("stream cut: hf bit-identical", torch.equal(res[0][0], res[1][0]))
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-5 * float(res[0][1].abs().max())
+    for k, g in res[0][2].items():
+        assert float((g - res[1][2][k]).abs().max()) <= 2e-5 * max(float(g.abs().max()), 1e-6), k
 
 
 # --------------------------------------------------------------------------- bf16 configuration (stated tolerance)
