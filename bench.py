@@ -34,6 +34,8 @@ WORKLOADS = {
     "cfg2": dict(kind="aig", mix="aig", batch=64, n_pi=(16, 64), n_gates=(500, 1500), window=None, rounds=1, cfg=2),
     "cfg3-xmg": dict(kind="xmg", mix="xmg", batch=64, n_pi=(16, 64), n_gates=(500, 1500), window=None, rounds=2, cfg=3),
     "cfg3-xag": dict(kind="xag", mix="xag", batch=64, n_pi=(16, 64), n_gates=(500, 1500), window=None, rounds=2, cfg=3),
+    "cfg4": dict(kind="xmg", mix="xmg", batch=64, n_pi=(16, 64), n_gates=(500, 1500), window=None, rounds=1, cfg=4,
+                 variational=True, precision="bf16"),
     "cfg5-k1": dict(kind="mig", mix="mig", batch=1, n_pi=16, n_gates=100000, window=880, rounds=1, cfg=5),
     "cfg5-k8": dict(kind="mig", mix="mig", batch=8, n_pi=16, n_gates=100000, window=880, rounds=1, cfg=5),
     "cfg5-k64": dict(kind="mig", mix="mig", batch=64, n_pi=16, n_gates=100000, window=880, rounds=1, cfg=5),
@@ -176,6 +178,10 @@ def pick_sample(w, budget_s=20.0):
 
 
 def run_reference(args, w):
+    """The reference's CPU path (oracle port with the reference's literal per-node ``subgraph`` loop) on the host cores, on the
+    SAME batch the B200 arm times.  Every timed step runs the full batch when the whole run then fits the time budget
+    (calibrated from a quarter-batch warm-up step, cost ~ nodes^2); otherwise the first step is the full batch and the rest a
+    bounded sample, and ``sample`` says so."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -183,23 +189,32 @@ def run_reference(args, w):
     torch.set_num_threads(cores)
     hb = make_host_batch(w, 0, 0)
     P = cpu_params(w["kind"])
-    ns = pick_sample(w, min(8.0, 120.0 / max(args.steps, 1)))
-    for _ in range(args.warmup):
-        cpu_step(w["kind"], P, hb, w["rounds"], max(1, ns // 4))
+    full = w["batch"]
+    quarter = max(1, full // 4)
+    est_full = None
+    for _ in range(max(args.warmup, 1)):
+        dt, _g = cpu_step(w["kind"], P, hb, w["rounds"], quarter)
+        est_full = dt * (hb.ptr[full].item() / max(hb.ptr[quarter].item(), 1)) ** 2
+    budget = float(os.environ.get("MGV_REF_BUDGET_S", 240.0))
+    n_full = max(1, min(args.steps, int(budget / max(est_full, 1e-3))))
+    ns_rest = full if n_full == args.steps else pick_sample(w, max(1.0, (budget - n_full * est_full) / max(args.steps - n_full, 1)))
     tot_t, tot_g = 0.0, 0
-    for _ in range(args.steps):
-        dt, gates = cpu_step(w["kind"], P, hb, w["rounds"], ns)
+    for i in range(args.steps):
+        dt, gates = cpu_step(w["kind"], P, hb, w["rounds"], full if i < n_full else ns_rest)
         tot_t += dt
         tot_g += gates
     val = tot_g / tot_t
-    sample = "%d of %d circuits per step (%d gates), oracle port, per-node subgraph loop as in the reference" % (
-        ns, w["batch"], tot_g // max(args.steps, 1))
+    sample = "%d of %d timed steps on the full batch of %d circuits%s; oracle port, per-node subgraph loop as in the reference" % (
+        n_full, args.steps, full, "" if n_full == args.steps else ", the rest on %d circuits" % ns_rest)
+    st = batch_stats(hb, w["kind"])
     print(json.dumps({
         "impl": "reference", "metric": "gates_per_s_fwd_bwd", "value": val, "unit": "gates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "model": "DG_AE-" + w["kind"], "circuits_per_gpu": w["batch"],
-                   "note": "CPU host cores; step = bounded sample of the workload"},
+                   "nodes_per_gpu": float(st["N"]), "edges_per_gpu": float(st["E"]), "levels": float(st["L"]),
+                   "sweep_rounds": w["rounds"], "s_rounds": 4, "t_rounds": 4, "layernorm": True, "dim_hidden": 64,
+                   "step": "forward + recon/prob/func losses + backward (no optimizer step) on the host cores"},
         "cpu_baseline": {"value": val, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -227,31 +242,30 @@ def _restore_stdout():
         _SAVED_STDOUT = None
 
 
-def run_ours(args, w):
-    _stdout_to_stderr()
+def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cpu_baseline=False):
+    """Times `steps` train steps of workload `w` (after the setup pass and `warmup` steps) device-resident and end to end.
+    Returns the record of this workload (the caller prints it, or nests it under "workloads")."""
     import deepgate
     from deepgate import _native, ops
     from oracle import dg_oracle as O   # only for cpu_baseline (rank 0, N == 1) and the seeded weights helper
-    rank = int(os.environ.get("RANK", 0))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
+    variational = bool(w.get("variational", False))
+    precision = w.get("precision", "fp32")
     enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, enable_reverse=True, s_rounds=4,
                                                      t_rounds=4, layernorm=True)
     mod = getattr(deepgate, "dg_ae_model_" + w["kind"])
-    model = mod.Model(struct_encoder=enc, num_rounds=w["rounds"], dim_hidden=64)
-    model.load_state_dict(O.synth_state_dict(w["kind"], 2), strict=False)      # same random-init weights on every rank
+    model = mod.Model(struct_encoder=enc, num_rounds=w["rounds"], dim_hidden=64, **({"variational": True} if variational else {}))
+    sd = O.synth_state_dict(w["kind"], 2, variational=True) if variational else O.synth_state_dict(w["kind"], 2)
+    model.load_state_dict(sd, strict=False)                # same random-init weights on every rank
     tmp = tempfile.mkdtemp(prefix="mgv_bench_")
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):          # the Trainer prints its device like the reference's: stdout carries ONE JSON line
         trainer = deepgate.Trainer(None, model, training_id="bench", save_dir=tmp, lr=1e-4,
                                    rc_prob_func_weight=list(LOSS_W), device=str(dev), batch_size=w["batch"],
                                    distributed=False)
+    if variational:
+        trainer.kl_weight = 1.0                            # cfg4: the KL term is part of the objective
+    ops.set_precision(precision)
     model.train()
-    nb = args.batches
     host = [make_host_batch(w, rank, i).pin_memory() for i in range(nb)]
     stats = [batch_stats(b, w["kind"]) for b in host]
     resident = [b.copy_to(dev, non_blocking=False) for b in host]
@@ -309,37 +323,42 @@ def run_ours(args, w):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item())
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(clocks_index) if clocks_index is not None else None
+    if sampler:
+        sampler.start()
     # setup (not a warm-up step): one pass over every DISTINCT batch so that the caching allocator owns blocks for
     # each batch's sizes -- a first-seen batch inside the timed region costs cudaMalloc calls of several hundred MB
     # (measured: 7.8 instead of 4.6 ms / step with --warmup 3 and 4 distinct batches)
     for i in range(nb):
         step_resident(i)
         step_e2e(i)
-    for i in range(args.warmup):
+    for i in range(warmup):
         step_resident(i)
         step_e2e(i)
     launches0 = _native.lib().mgv_kernel_launches()
     ops.PROFILE = {}
-    sampler.mark_begin()
-    ms = timed(step_resident, args.steps)
-    sampler.mark_end()
+    if sampler:
+        sampler.mark_begin()
+    ms = timed(step_resident, steps)
+    if sampler:
+        sampler.mark_end()
     torch.cuda.synchronize(dev)
     prof = ops.profile_summary()
     ops.PROFILE = None
     launches = _native.lib().mgv_kernel_launches() - launches0
-    clocks = sampler.stop()                   # clocks are sampled over the device-resident timed region only: nvidia-smi polling
-    #                                           takes driver locks that the per-step synchronising end-to-end loop is sensitive to
+    # clocks are sampled over the device-resident timed region only: nvidia-smi polling takes driver locks that the per-step
+    # synchronising end-to-end loop is sensitive to
+    clocks = sampler.stop() if sampler else None
     step_e2e(0)                               # untimed: back from the resident loop to the host-fed path
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
     if e2e_trace:
-        for t in e2e_trace[-args.steps:]:
+        for t in e2e_trace[-steps:]:
             print("e2e step: h2d issue %.2f  train_step host %.2f  loss.item() wait %.2f ms" % t, file=sys.stderr)
     from deepgate.schedule import check_deferred_errors
     check_deferred_errors()                   # asynchronous input validation of every schedule built above
+    ops.set_precision("fp32")
 
-    g_local = sum(gates_per_step[i % nb] for i in range(args.steps))
+    g_local = sum(gates_per_step[i % nb] for i in range(steps))
     g_all = torch.tensor([float(g_local)], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(g_all)
@@ -353,9 +372,12 @@ def run_ours(args, w):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_source = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"
+    tc_sweep = w["rounds"] == 1               # single-round sweeps run on the tcgen05 kernels (csrc/sweep_tc.cu)
+    k_fwd, k_bwd = ("sweep_fwd_tc_kernel", "sweep_bwd_tc_kernel") if tc_sweep else ("sweep_fwd_kernel", "sweep_bwd_kernel")
     per_launch = {
-        "level_sweep_fwd": ("sweep_fwd_kernel", 1, "sweep_fwd_bytes"),
-        "level_sweep_bwd": ("sweep_bwd_kernel", 1, "sweep_bwd_bytes"),
+        "level_sweep_fwd": (k_fwd, 1, "sweep_fwd_bytes"),
+        "level_sweep_bwd": (k_bwd, 1, "sweep_bwd_bytes"),
         "struct_encoder_fwd": ("struct_fwd_tc_kernel", 8, "struct_fwd_bytes"),   # 2 * s_rounds step launches per call
         # backward step = struct_bwd_pw_kernel (recompute + pointwise + data gradient) followed by struct_bwd_wgrad_kernel
         # (weight gradient); the two are timed together (one library call) and share the step's algorithmic bytes
@@ -368,34 +390,46 @@ def run_ours(args, w):
             calls, tot = prof[name]
             avg_launch_ms = tot / calls / nl
             ach = mean_stats[key] * (w["rounds"] if "sweep" in name else 1) / (avg_launch_ms * 1e-3) / 1e9
-            kernels[kern] = {"ms_per_step": tot / args.steps, "avg_launch_ms": avg_launch_ms, "launches_per_step": nl,
+            kernels[kern] = {"ms_per_step": tot / steps, "avg_launch_ms": avg_launch_ms, "launches_per_step": nl,
                              "achieved_gbs": ach, "frac": ach / peak}
+    traffic_table = {}
+    try:
+        traffic_table = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(wname, {})
+    except Exception:
+        pass
+
+    def traffic_of(*kerns):
+        """DRAM bytes per launch from the committed ncu --set full captures of this workload (else None)."""
+        tot = 0
+        for k in kerns:
+            ent = traffic_table.get(k)
+            if not ent:
+                return None
+            tot += ent["dram_read_bytes"] + ent["dram_write_bytes"]
+        return tot
+
     top = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     roofline = None
     if top:
-        # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this workload (else null)
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            ent = tj.get(args.workload, {}).get(top)
-            if ent:
-                traffic = ent["dram_read_bytes"] + ent["dram_write_bytes"]
-        except Exception:
-            pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": traffic,
+                    "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": traffic_of(*top.split("+")),
                     "algorithmic_bytes_per_launch": mean_stats[per_launch[[k for k, v in per_launch.items() if v[0] == top][0]][2]],
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                    "share_of_step": kernels[top]["ms_per_step"] / (ms / args.steps)}
-    sweep_ms = sum(kernels[k]["ms_per_step"] for k in ("sweep_fwd_kernel", "sweep_bwd_kernel") if k in kernels)
+                    "peak_source": peak_source, "share_of_step": kernels[top]["ms_per_step"] / (ms / steps)}
+    sweep_ms = sum(kernels[k]["ms_per_step"] for k in (k_fwd, k_bwd) if k in kernels)
     sweep = None
     if sweep_ms > 0:
         sweep_bytes = (mean_stats["sweep_fwd_bytes"] + mean_stats["sweep_bwd_bytes"]) * w["rounds"]
+        ach = sweep_bytes / (sweep_ms * 1e-3) / 1e9
         sweep = {"gates_per_s": mean_stats["gates"] * w["rounds"] / (sweep_ms * 1e-3), "ms_fwd_bwd": sweep_ms,
-                 "achieved_gbs": sweep_bytes / (sweep_ms * 1e-3) / 1e9, "frac": sweep_bytes / (sweep_ms * 1e-3) / 1e9 / peak}
+                 "achieved_gbs": ach, "frac": ach / peak,
+                 # the level-propagation kernels (forward + backward launch of a step) against the HBM roofline
+                 "roofline": {"kernel": k_fwd + "+" + k_bwd, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                              "frac": ach / peak, "traffic": traffic_of(k_fwd, k_bwd),
+                              "algorithmic_bytes_per_launch": sweep_bytes, "peak_source": peak_source,
+                              "share_of_step": sweep_ms / (ms / steps)}}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         P = cpu_params(w["kind"])
@@ -405,26 +439,62 @@ def run_ours(args, w):
         cpu = {"value": gates / dt, "unit": "gates/s", "cores": cores, "kind": "port",
                "sample": "1 train step on %d of %d circuits (%d gates, %.1f s), oracle port with the reference's "
                          "per-node subgraph loop" % (ns, w["batch"], gates, dt)}
+    h2d = sum(b.nbytes() for b in host) / len(host)
+    losses = "recon/prob/func" + ("/KL" if variational else "")
+    rec = {
+        "metric": "gates_per_s_fwd_bwd", "value": value, "unit": "gates/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": wname, "model": ("DG_VAE-" if variational else "DG_AE-") + w["kind"], "circuits_per_gpu": w["batch"],
+                   "nodes_per_gpu": mean_stats["N"], "edges_per_gpu": mean_stats["E"], "levels": mean_stats["L"],
+                   "gates_per_step_per_gpu": mean_stats["gates"] * w["rounds"], "sweep_rounds": w["rounds"],
+                   "s_rounds": 4, "t_rounds": 4, "layernorm": True, "dim_hidden": 64, "parallelism": "dp%d" % world,
+                   "step": "schedule build + forward + %s losses + backward + allreduce + Adam" % losses,
+                   "ranks": "every rank draws its own circuits, with the same circuit sizes on all ranks (size-bucketed sampler)",
+                   "setup": "one untimed pass over each distinct batch before the warm-up steps (allocator pools)",
+                   "l2": "%d distinct batches rotated; per-batch working set (struct states %d MB) exceeds the 126 MB L2"
+                         % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},
+        "e2e": {"value": e2e, "unit": "gates/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "level_sweep": sweep, "cpu_baseline": cpu}
+    # free this workload's device memory before the next one is measured
+    del trainer, model, resident, host
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return rec
+
+
+# Workloads measured after the headline one and nested under "workloads" in the same JSON line (short runs: the named sizes
+# of BASELINE.json's configs 3, 4 and 5 next to the headline config 2).
+SUB_WORKLOADS = (("cfg5-k64", 3, 3, 1), ("cfg3-xmg", 5, 3, 2), ("cfg4", 5, 3, 2))      # name, steps, warm-up, distinct batches
+
+
+def run_ours(args, w):
+    _stdout_to_stderr()
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    rec = measure(w, args.workload, args.steps, args.warmup, args.batches, dev, rank, world, clocks_index=local,
+                  cpu_baseline=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+    subs = {}
+    if not args.no_sub_workloads and args.workload == "cfg2":
+        for name, st, wu, nb in SUB_WORKLOADS:
+            try:
+                r = measure(WORKLOADS[name], name, st, wu, nb, dev, rank, world)
+                subs[name] = {k: r[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "dtype", "config", "e2e",
+                                                 "gpu_launches", "roofline", "kernels", "level_sweep")}
+            except Exception as e:                          # a sub-workload must never cost the headline line
+                subs[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    rec["workloads"] = subs
     if rank == 0:
-        h2d = sum(b.nbytes() for b in host) / len(host)
         _restore_stdout()
-        print(json.dumps({
-            "metric": "gates_per_s_fwd_bwd", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "model": "DG_AE-" + w["kind"], "circuits_per_gpu": w["batch"],
-                       "nodes_per_gpu": mean_stats["N"], "edges_per_gpu": mean_stats["E"], "levels": mean_stats["L"],
-                       "gates_per_step_per_gpu": mean_stats["gates"] * w["rounds"], "sweep_rounds": w["rounds"],
-                       "s_rounds": 4, "t_rounds": 4, "layernorm": True, "dim_hidden": 64, "parallelism": "dp%d" % world,
-                       "step": "schedule build + forward + recon/prob/func losses + backward + allreduce + Adam",
-                       "ranks": "every rank draws its own circuits, with the same circuit sizes on all ranks (size-bucketed sampler)",
-                       "setup": "one untimed pass over each distinct batch before the warm-up steps (allocator pools)",
-                       "l2": "%d distinct batches rotated; per-batch working set (struct states %d MB) exceeds the 126 MB L2"
-                             % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},
-            "e2e": {"value": e2e, "unit": "gates/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
-            "level_sweep": sweep, "cpu_baseline": cpu}))
+        print(json.dumps(rec))
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -438,6 +508,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batches", type=int, default=4, help="distinct synthetic batches rotated through the steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-workloads", action="store_true", help="skip the short cfg3 / cfg4 / cfg5 runs nested under 'workloads'")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

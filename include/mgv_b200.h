@@ -118,6 +118,10 @@ int mgv_build_sweep_desc(const int32_t* order, const int32_t* in_ptr, const int3
  * gdesc[N][4] (16-byte aligned): {node, first CSR slot, degree, first neighbour id} per row of the order.
  */
 size_t mgv_degree_order_workspace_bytes(int64_t N);
+/* The same gdesc / tile_cost for a degree order that already exists (e.g. built on the host when the batch was collated,
+ * where the reference computes forward_level, parser_func_others.py:43-78): no sort, workspace as above. */
+int mgv_build_degree_tiles(const int32_t* ptr, const int32_t* idx, const int32_t* order, int32_t N, int32_t* gdesc,
+                           uint32_t* tile_cost, void* ws, size_t ws_bytes, mgv_stream_t stream);
 int mgv_build_degree_order(const int32_t* ptr, const int32_t* idx, int32_t N, int32_t* order, int32_t* gdesc,
                            uint32_t* tile_cost, void* ws, size_t ws_bytes, mgv_stream_t stream);
 

@@ -448,6 +448,30 @@ extern "C" int mgv_build_degree_order(const int32_t* ptr, const int32_t* idx, in
     return mgv_check_cuda(cudaGetLastError(), "mgv_build_degree_order");
 }
 
+// Tile descriptors and tile costs of a degree order that already exists (built on the host at collate time, data.py): the part of
+// mgv_build_degree_order behind the sort.
+extern "C" int mgv_build_degree_tiles(const int32_t* ptr, const int32_t* idx, const int32_t* order, int32_t N, int32_t* gdesc,
+                                      uint32_t* tile_cost, void* ws, size_t ws_bytes, mgv_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MGV_REQUIRE(N >= 0 && ptr && idx && order && gdesc && tile_cost, "mgv_build_degree_tiles: bad argument");
+    if (ws_bytes < mgv_degree_order_workspace_bytes(N)) {
+        mgv_set_error("mgv_build_degree_tiles: workspace too small");
+        return MGV_ERR_WORKSPACE;
+    }
+    const int ntiles = (N + MGV_TILE_ROWS - 1) / MGV_TILE_ROWS;
+    MgvArena a(ws, ws_bytes);
+    uint32_t* tmp = a.take<uint32_t>(scan_tmp_count((size_t)ntiles + 2));
+    if (N > 0) {
+        gather_desc_kernel<<<(N + 255) / 256, 256, 0, st>>>(ptr, idx, order, N, reinterpret_cast<int4*>(gdesc));
+        mgv_count_launches(1);
+    }
+    tile_cost_kernel<<<(ntiles + 1 + 7) / 8, 256, 0, st>>>(ptr, order, N, ntiles, tile_cost);
+    mgv_count_launches(1);
+    int rc = exclusive_scan(tile_cost, tile_cost, ntiles + 1, tmp, st);
+    if (rc != MGV_OK) return rc;
+    return mgv_check_cuda(cudaGetLastError(), "mgv_build_degree_tiles");
+}
+
 extern "C" size_t mgv_csr_workspace_bytes(int64_t N, int64_t E) {
     size_t b = 0;
     b += 4 * mgv_align_up((size_t)E * 4 + 256, 256);                 // k0 v0 k1 v1

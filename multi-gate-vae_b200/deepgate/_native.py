@@ -56,6 +56,7 @@ _PROTOTYPES = {
     "mgv_build_sweep_desc": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mgv_degree_order_workspace_bytes": (_sz, [_i64]),
     "mgv_build_degree_order": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mgv_build_degree_tiles": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mgv_level_sweep_fwd": (ctypes.c_int, [_SP, _i32, _u32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mgv_sweep_bwd_grid": (ctypes.c_int, []),
     "mgv_sweep_bwd_workspace_bytes": (_sz, [_i64, _i64]),

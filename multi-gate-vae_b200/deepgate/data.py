@@ -10,6 +10,8 @@ PyTorch-Geometric is not a dependency of this package.
 import torch
 
 _CAT_LAST = ("edge_index", "tt_pair_index", "rc_pair_index")
+_CIRCUIT_CSR = ("csr_in_src", "csr_in_deg", "csr_out_dst", "csr_out_slot", "csr_out_deg")     # per-circuit, merged by attach_host_schedule
+CODE_SHIFT = 28           # out_pack = successor | code(successor) << 28   (include/mgv_b200.h)
 
 
 class OrderedData(object):
@@ -76,6 +78,8 @@ def collate(circuits):
     for n in counts:
         starts.append(starts[-1] + n)
     for key in first.keys():
+        if key in _CIRCUIT_CSR:
+            continue
         vals = [c[key] for c in circuits]
         if not torch.is_tensor(vals[0]):
             out[key] = vals[0]
@@ -88,6 +92,7 @@ def collate(circuits):
     out.num_graphs = len(circuits)
     attach_schedule_meta(out)
     attach_streams(out, counts)
+    attach_host_schedule(out, circuits, starts)
     return out
 
 
@@ -126,6 +131,58 @@ def attach_schedule_meta(batch):
     code = torch.where((gate.reshape(-1) < 0) | (gate.reshape(-1) > 6), torch.full_like(code, 6), code)
     batch.num_levels = int(lvl.max()) + 1
     batch.level_code_count = torch.bincount(code[lvl >= 1], minlength=8)[:8].tolist()
+    return batch
+
+
+def _stable_order(key, bound):
+    """Stable argsort of small non-negative integer keys (radix sort in numpy for keys that fit 16 bits)."""
+    import numpy as np
+    k = key.astype(np.uint8 if bound <= 256 else (np.uint16 if bound <= 65536 else np.int64))
+    return np.argsort(k, kind="stable").astype(np.int32)
+
+
+def attach_host_schedule(batch, circuits, starts):
+    """The batch's integer schedule, built on the HOST when the batch is collated (in the data-loader worker, where the
+    reference builds ``forward_level``): in / out-edge CSR = the circuits' own CSRs (parser_func_others.attach_circuit_csr)
+    concatenated with node / edge offsets, the (stream, level, code) node lists and the two degree orders.  The arrays travel
+    with the batch (``sched_*``, int32) and ``schedule.schedule_for_batch`` wraps them -- the train step then launches no sort.
+    Every array is bit-identical to what csrc/schedule.cu builds on the device (tests/test_gpu_parity.py)."""
+    import numpy as np
+    lvl = getattr(batch, "forward_level", None)
+    gate = getattr(batch, "gate", None)
+    if lvl is None or gate is None or not all(getattr(c, "csr_in_src", None) is not None for c in circuits):
+        return batch
+    n = int(batch.x.size(0))
+    if lvl.numel() != n or gate.shape[0] != n:
+        return batch
+    code_raw = gate.reshape(-1).numpy().astype(np.int64)
+    code = np.where((code_raw < 0) | (code_raw > 6), 6, code_raw)
+    estarts = [0]
+    for c in circuits:
+        estarts.append(estarts[-1] + int(c.csr_in_src.numel()))
+    in_deg = np.concatenate([c.csr_in_deg.numpy() for c in circuits]).astype(np.int64)
+    out_deg = np.concatenate([c.csr_out_deg.numpy() for c in circuits]).astype(np.int64)
+    in_ptr = np.zeros(n + 1, dtype=np.int64); np.cumsum(in_deg, out=in_ptr[1:])
+    out_ptr = np.zeros(n + 1, dtype=np.int64); np.cumsum(out_deg, out=out_ptr[1:])
+    in_src = np.concatenate([c.csr_in_src.numpy().astype(np.int64) + s0 for c, s0 in zip(circuits, starts)]) if estarts[-1] else np.zeros(0, np.int64)
+    out_dst = np.concatenate([c.csr_out_dst.numpy().astype(np.int64) + s0 for c, s0 in zip(circuits, starts)]) if estarts[-1] else np.zeros(0, np.int64)
+    out_slot = np.concatenate([c.csr_out_slot.numpy().astype(np.int64) + e0 for c, e0 in zip(circuits, estarts)]) if estarts[-1] else np.zeros(0, np.int64)
+    out_pack = out_dst | (code[out_dst] << CODE_SHIFT)
+    L = int(batch.num_levels)
+    sos = getattr(batch, "sweep_stream", None)
+    streams = int(getattr(batch, "sweep_streams", 1)) if sos is not None else 1
+    lv = lvl.reshape(-1).numpy().astype(np.int64)
+    key = ((sos.numpy().astype(np.int64) if streams > 1 else 0) * L + lv) * 8 + code
+    nkeys = streams * L * 8
+    order = _stable_order(key, nkeys)
+    seg_ptr = np.zeros(nkeys + 1, dtype=np.int64); np.cumsum(np.bincount(key, minlength=nkeys), out=seg_ptr[1:])
+    i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.int32)))
+    batch.sched_in_ptr, batch.sched_in_src = i32(in_ptr), i32(in_src if in_src.size else np.zeros(1))
+    batch.sched_out_ptr, batch.sched_out_pack, batch.sched_out_slot = i32(out_ptr), i32(out_pack if out_pack.size else np.zeros(1)), i32(out_slot if out_slot.size else np.zeros(1))
+    batch.sched_order, batch.sched_seg_ptr = i32(order if n else np.zeros(1)), i32(seg_ptr)
+    batch.sched_deg_order_in = i32(_stable_order(255 - np.minimum(in_deg, 255), 256) if n else np.zeros(1))
+    batch.sched_deg_order_out = i32(_stable_order(255 - np.minimum(out_deg, 255), 256) if n else np.zeros(1))
+    batch.sched_streams = streams
     return batch
 
 

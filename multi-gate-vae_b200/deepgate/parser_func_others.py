@@ -34,6 +34,29 @@ def parse_pyg_mlpgate(x, edge_index, y, tt_sim, tt_pair_index, num_gate_types=6,
                     forward_level=fl, forward_index=idx, backward_level=bl, backward_index=idx.clone())
     g.gate = torch.as_tensor(x[:, 1:2].astype(np.float32))
     g.prob = torch.as_tensor(np.asarray(y, dtype=np.float32)).reshape(n, 1)
+    attach_circuit_csr(g)
+    return g
+
+
+def attach_circuit_csr(g):
+    """In / out-edge CSR of ONE circuit in local node and edge ids, computed here -- where the reference computes
+    ``forward_level`` (parser_func_others.py:63) -- so that a batch's CSR is a concatenation with offsets at collate time
+    (data.attach_host_schedule) instead of sorts on the device in every step.  Within a node, edges keep their original
+    order (the order ``subgraph`` concatenates them in, utils/dag_utils.py:91-105)."""
+    n = int(g.x.size(0))
+    ei = g.edge_index.numpy()
+    src, dst = ei[0], ei[1]
+    if src.size and (min(src.min(), dst.min()) < 0 or max(src.max(), dst.max()) >= n):
+        raise IndexError("edge_index refers to a node outside [0, %d)" % n)
+    by_dst = np.argsort(dst, kind="stable")
+    by_src = np.argsort(src, kind="stable")
+    pos_in = np.empty(src.size, dtype=np.int64)
+    pos_in[by_dst] = np.arange(src.size)
+    g.csr_in_src = torch.from_numpy(src[by_dst].astype(np.int32))
+    g.csr_in_deg = torch.from_numpy(np.bincount(dst, minlength=n).astype(np.int32))
+    g.csr_out_dst = torch.from_numpy(dst[by_src].astype(np.int32))
+    g.csr_out_slot = torch.from_numpy(pos_in[by_src].astype(np.int32))
+    g.csr_out_deg = torch.from_numpy(np.bincount(src, minlength=n).astype(np.int32))
     return g
 
 

@@ -46,6 +46,47 @@ class GraphCSR(object):
     """In/out-edge CSR of ``edge_index`` ([2, E] int64, row 0 = source).  ``validate=True`` checks node ids
     synchronously; ``False`` defers the check to ``check_deferred_errors()`` and never syncs."""
 
+    @classmethod
+    def from_host_schedule(cls, G):
+        """Wrap the integer schedule the batch carries (data.attach_host_schedule: CSR, level lists and degree orders built
+        on the host at collate time) -- no sort runs on the device; only the tile descriptors / costs and the sweep's row
+        descriptors are derived here (7 small launches)."""
+        self = cls.__new__(cls)
+        ei = G.edge_index
+        dev = ei.device
+        self.device, self.edge_index = dev, ei
+        self.N, self.E = int(G.gate.shape[0]), int(ei.size(1))
+        self.code = nat.require_cuda(G.gate.reshape(-1).to(torch.int32).contiguous(), "code", torch.int32)
+        for k in ("in_ptr", "in_src", "out_ptr", "out_pack", "out_slot", "order", "seg_ptr", "deg_order_in", "deg_order_out"):
+            setattr(self, k, nat.require_cuda(getattr(G, "sched_" + k), "sched_" + k, torch.int32))
+        self.level = G.forward_level
+        self.L = max(int(G.num_levels), 1)
+        self.streams = int(G.sched_streams)
+        self.code_count = [int(c) for c in G.level_code_count]
+        if self.in_ptr.numel() != self.N + 1 or self.order.numel() != max(self.N, 1) or \
+                self.seg_ptr.numel() != self.streams * self.L * nat.NCODE + 1:
+            raise RuntimeError("mgv_b200: the batch's host-built schedule does not match its nodes / levels")
+        i32 = dict(dtype=torch.int32, device=dev)
+        ntiles = (self.N + nat.TILE_ROWS - 1) // nat.TILE_ROWS
+        self.tile_cost_in = torch.empty(ntiles + 1, **i32)
+        self.tile_cost_out = torch.empty(ntiles + 1, **i32)
+        self.gdesc_in = torch.empty(max(self.N, 1), 4, **i32)
+        self.gdesc_out = torch.empty(max(self.N, 1), 4, **i32)
+        self.sweep_desc = torch.empty(max(self.N, 1), 8, **i32)
+        lib = nat.lib()
+        with nat.on_device(dev):
+            nb = lib.mgv_degree_order_workspace_bytes(self.N)
+            ws = nat.workspace(nb, dev)
+            st = nat.stream_of(dev)
+            for p_, i_, o_, g_, c_ in ((self.in_ptr, self.in_src, self.deg_order_in, self.gdesc_in, self.tile_cost_in),
+                                       (self.out_ptr, self.out_pack, self.deg_order_out, self.gdesc_out, self.tile_cost_out)):
+                nat.check(lib.mgv_build_degree_tiles(nat.ptr(p_), nat.ptr(i_), nat.ptr(o_), self.N, nat.ptr(g_), nat.ptr(c_),
+                                                     nat.ptr(ws), nb, st), "mgv_build_degree_tiles")
+            nat.check(lib.mgv_build_sweep_desc(nat.ptr(self.order), nat.ptr(self.in_ptr), nat.ptr(self.in_src), nat.ptr(self.out_ptr),
+                                               self.N, nat.ptr(self.sweep_desc), st), "mgv_build_sweep_desc")
+        self._struct = None
+        return self
+
     def __init__(self, edge_index, num_nodes, code=None, validate=True):
         nat.require_cuda(edge_index, "edge_index", torch.int64)
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
@@ -221,6 +262,16 @@ def schedule_for_batch(G, streams=None):
         return sch
     if not ei.is_cuda:
         raise RuntimeError("mgv_b200: the batch must be on a CUDA device (no CPU path); call batch.to('cuda')")
+    host_sched = getattr(G, "sched_order", None)
+    if (host_sched is not None and host_sched.is_cuda and int(getattr(G, "sched_streams", 1)) == want
+            and getattr(G, "num_levels", None) is not None and not os.environ.get("MGV_DEVICE_SCHEDULE")):
+        sch = GraphCSR.from_host_schedule(G)
+        try:
+            G._mgv_schedule = sch
+        except Exception:
+            pass
+        _last["key"], _last["csr"] = _key(ei, n), sch
+        return sch
     code = G.gate.reshape(-1)
     level = getattr(G, "forward_level", None)
     level = level if (level is not None and level.numel() == n) else None

@@ -280,12 +280,19 @@ def test_async_schedule_equals_sync_schedule_and_flags_bad_input():
     assert a.L == b.L and a.code_count == b.code_count and a.streams == b.streams == 1
     for k in ("in_ptr", "in_src", "out_ptr", "out_pack", "out_slot", "order", "seg_ptr", "deg_order_in", "deg_order_out", "sweep_desc"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
-    # the same batch cut into its two circuit sets (data.attach_streams): lists sorted by (stream, level, code)
+    # the same batch cut into its two circuit sets (data.attach_streams): lists sorted by (stream, level, code).  c wraps the
+    # schedule the HOST built at collate time (per-circuit CSRs merged by offset, data.attach_host_schedule); d is built on the
+    # device from edge_index: every array must be bit-identical
     c = schedule_for_batch(G)
+    assert getattr(G, "sched_order", None) is not None and c.in_ptr.data_ptr() == G.sched_in_ptr.data_ptr()
     d = GraphCSR(G.edge_index.contiguous(), G.x.size(0), code=G.gate.reshape(-1)).set_levels(
         G.forward_level, stream_of_node=G.sweep_stream, streams=2)
-    assert c.streams == d.streams == 2 and c.code_count == d.code_count == a.code_count
-    assert torch.equal(c.order, d.order) and torch.equal(c.seg_ptr, d.seg_ptr)
+    assert c.streams == d.streams == 2 and c.code_count == d.code_count == a.code_count and c.L == d.L
+    for k in ("in_ptr", "out_ptr", "order", "seg_ptr", "deg_order_in", "deg_order_out", "sweep_desc", "gdesc_in", "gdesc_out",
+              "tile_cost_in", "tile_cost_out"):
+        assert torch.equal(getattr(c, k), getattr(d, k)), k
+    for k in ("in_src", "out_pack", "out_slot"):
+        assert torch.equal(getattr(c, k)[:c.E], getattr(d, k)[:c.E]), k
     key = (G.sweep_stream.long() * a.L + G.forward_level.long()) * 8 + G.gate.reshape(-1).long().clamp(0, 6)
     assert torch.equal(c.order.long(), torch.sort(key, stable=True).indices)
     assert torch.equal(c.seg_ptr.long(), torch.cat([key.new_zeros(1), torch.bincount(key, minlength=2 * a.L * 8).cumsum(0)]))

@@ -1,0 +1,55 @@
+"""Host-built integer schedule (data.attach_host_schedule: per-circuit CSRs from the parser merged by offset at collate time)
+against a direct construction from the collated ``edge_index`` -- the definition csrc/schedule.cu implements on the device
+(stable by original edge id inside a node, as utils/dag_utils.py:91-105 ``subgraph`` concatenates a node's edges)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "multi-gate-vae_b200"), ROOT]
+
+
+def test_merged_circuit_csr_equals_global_sort():
+    import deepgate
+    from deepgate import synth
+    b = deepgate.circuits_to_batch(synth.make_circuits("xmg", 9, (4, 12), (30, 300), cfg=71, window=25))
+    n, E = b.x.size(0), b.edge_index.size(1)
+    src, dst = b.edge_index[0], b.edge_index[1]
+    by_dst = torch.sort(dst, stable=True).indices
+    by_src = torch.sort(src, stable=True).indices
+    assert torch.equal(b.sched_in_src.long(), src[by_dst])
+    assert torch.equal(b.sched_in_ptr.long(), torch.cat([dst.new_zeros(1), torch.bincount(dst, minlength=n).cumsum(0)]))
+    assert torch.equal(b.sched_out_ptr.long(), torch.cat([dst.new_zeros(1), torch.bincount(src, minlength=n).cumsum(0)]))
+    code = b.gate.reshape(-1).long()
+    out_dst = dst[by_src]
+    assert torch.equal(b.sched_out_pack.long(), out_dst | (code[out_dst] << 28))
+    pos_in = torch.empty(E, dtype=torch.long)
+    pos_in[by_dst] = torch.arange(E)
+    assert torch.equal(b.sched_out_slot.long(), pos_in[by_src])
+    # every out-edge's slot points at the matching in-edge entry
+    assert torch.equal(b.sched_in_src.long()[b.sched_out_slot.long()], src[by_src])
+    L = b.num_levels
+    key = (b.sweep_stream.long() * L + b.forward_level.long()) * 8 + code
+    assert b.sched_streams == 2 and torch.equal(b.sched_order.long(), torch.sort(key, stable=True).indices)
+    assert torch.equal(b.sched_seg_ptr.long(), torch.cat([key.new_zeros(1), torch.bincount(key, minlength=2 * L * 8).cumsum(0)]))
+    indeg = torch.bincount(dst, minlength=n)
+    assert torch.equal(b.sched_deg_order_in.long(), torch.sort(255 - indeg.clamp(max=255), stable=True).indices)
+    outdeg = torch.bincount(src, minlength=n)
+    assert torch.equal(b.sched_deg_order_out.long(), torch.sort(255 - outdeg.clamp(max=255), stable=True).indices)
+
+
+def test_streams_cut_whole_circuits_evenly():
+    import deepgate
+    from deepgate import synth
+    b = deepgate.circuits_to_batch(synth.make_circuits("aig", 7, 8, (50, 400), cfg=72))
+    s = b.sweep_stream.long()
+    # a circuit lies in ONE stream; every edge stays inside a stream; the two sets are balanced (largest-first greedy)
+    for g in range(b.num_graphs):
+        assert len(set(s[b.ptr[g]:b.ptr[g + 1]].tolist())) == 1
+    assert torch.equal(s[b.edge_index[0]], s[b.edge_index[1]])
+    sizes = torch.bincount(s, minlength=2).tolist()
+    biggest = int((b.ptr[1:] - b.ptr[:-1]).max())
+    assert abs(sizes[0] - sizes[1]) <= biggest
+    one = deepgate.circuits_to_batch(synth.make_circuits("aig", 1, 8, 50, cfg=73))
+    assert getattr(one, "sweep_stream", None) is None and one.sched_streams == 1
