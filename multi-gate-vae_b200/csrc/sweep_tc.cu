@@ -28,6 +28,8 @@
 // Operands are fp16 hi/lo planes with three products per K step (mgv_tc.cuh): fp32-accurate.
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <type_traits>
 #include "sweep_layout.cuh"
 
 namespace sweep_tc {
@@ -86,18 +88,22 @@ struct SweepTC {
     int cta_start[MGV_NCODE + 1];
     unsigned* bar;             // [s * BAR_STRIDE] grid barrier counter of stream s
     // backward
-    float* ghs; float* ghf; float* dxb; float* alpha; float* dscore; float* raw;
+    float* ghs; float* ghf; float* dxb; float* alpha; float* anode; float* sds; float* raw;   // anode [N]: A = dxbar . xbar; sds [N][8]
     long long* trace;          // MGV_SWEEP_TRACE builds: [CTA][16] accumulated clock64 cycles per phase of worker thread 0
 };
 #ifdef MGV_SWEEP_TRACE
 #define SWT_DECL(n) long long tr_acc[n] = {}, tr_last = clock64()
 #define SWT(slot) do { if (p.trace && tid == 0) { const long long now_ = clock64(); tr_acc[slot] += now_ - tr_last; tr_last = now_; } } while (0)
-#define SWT_FLUSH(n, tiles) do { if (p.trace && tid == 0) { for (int i_ = 0; i_ < (n); ++i_) p.trace[(size_t)blockIdx.x * 16 + i_] = tr_acc[i_]; \
-                                 p.trace[(size_t)blockIdx.x * 16 + (n)] = (tiles); p.trace[(size_t)blockIdx.x * 16 + 15] = code; } } while (0)
+#define SWT_FLUSH(n, tiles) do { if (p.trace && tid == 0) { for (int i_ = 0; i_ < (n); ++i_) p.trace[(size_t)blockIdx.x * 32 + i_] = tr_acc[i_]; \
+                                 p.trace[(size_t)blockIdx.x * 32 + (n)] = (tiles); p.trace[(size_t)blockIdx.x * 32 + 15] = code; } } while (0)
+#define SWT_SUB(slot) do { if (p.trace && threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd((unsigned long long*)p.trace + (size_t)blockIdx.x * 32 + (slot), (unsigned long long)(now_ - sub_last)); sub_last = now_; } } while (0)
+#define SWT_SUB_BEGIN long long sub_last = clock64()
 #else
 #define SWT_DECL(n) do { } while (0)
 #define SWT(slot) do { } while (0)
 #define SWT_FLUSH(n, tiles) do { } while (0)
+#define SWT_SUB(slot) do { } while (0)
+#define SWT_SUB_BEGIN do { } while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------ small helpers
@@ -132,6 +138,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
     const float y = fminf(fmaxf(x, -14.f), 14.f);
     return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * y));
 }
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[CW]) {
+    if constexpr (CW == 16) tc::tmem_ld16(taddr, v);
+    else tc::tmem_ld8(taddr, v);
+}
+// Columns of a tile each column group of a stream takes in the pointwise phases: 16, or 8 when a 16-column tile is shared by
+// two column groups (the phases are instruction-latency bound per thread: half the columns, half the time).
+template <int NCG>
+__device__ __forceinline__ int cols_per_group(int npad) { return (NCG == 2 && npad == 16) ? 8 : 16; }
 __device__ __forceinline__ float half_sum(float v) {              // sum over the 16 lanes of a half warp
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -366,16 +381,19 @@ __device__ __forceinline__ bool gather_tile(const SweepTC& p, const float* __res
     const bool wide = __any_sync(full, (lane & 7) == W_CNT && rr.w > FAST_FANIN);
     if (!wide) {
         const int half = lane >> 4, lp = lane & 15;
+        const bool second = npad > 2 * WPS;                // rows 2 WPS .. exist (slots 2, 3): warp-uniform
         HalfRow r0, r1;
         load_half_row<HF_CG>(p, hf, half, rr, lp, r0);
-        load_half_row<HF_CG>(p, hf, 2 + half, rr, lp, r1);
+        if (second) load_half_row<HF_CG>(p, hf, 2 + half, rr, lp, r1);
         float4 xbs, xbf;
         attend_half<STORE_ALPHA>(p, r0, us, uf, lp, xbs, xbf, al2[0]);
         int i = ws + WPS * half;
         if (i < npad) store_xbar_half<LOWP>(xb_hi, xb_lo, kbx, i, lp, xbs, xbf);
-        attend_half<STORE_ALPHA>(p, r1, us, uf, lp, xbs, xbf, al2[1]);
-        i = ws + WPS * (2 + half);
-        if (i < npad) store_xbar_half<LOWP>(xb_hi, xb_lo, kbx, i, lp, xbs, xbf);
+        if (second) {
+            attend_half<STORE_ALPHA>(p, r1, us, uf, lp, xbs, xbf, al2[1]);
+            i = ws + WPS * (2 + half);
+            if (i < npad) store_xbar_half<LOWP>(xb_hi, xb_lo, kbx, i, lp, xbs, xbf);
+        }
     } else {
         const float4 u4 = lane < 16 ? us : uf;             // lane l of the wide layout owns the columns lane l % 16 of the half layout owns
 #pragma unroll 1
@@ -541,33 +559,38 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
                 tc::fence_after_sync();
                 SWT(3);
                 // ---- epilogue: TMEM lane = gate unit.  Lanes 64..127 hold z: those warps hand 1 - z to the r / n lanes through shared
-                // memory.  All columns are computed branch-free first (16 independent dependency chains per thread), then stored.
-                const int c0 = cg * 16;
-                if (c0 < npad && qd >= 2) {
-                    float z[16];
-                    tc::tmem_ld16(tl1 + c0, z);
-                    tc::tmem_ld_wait();
+                // memory.  All columns are computed branch-free first (independent dependency chains per thread), then stored.
+                auto epilogue = [&](auto cw_tag) {
+                    constexpr int CW = decltype(cw_tag)::value;
+                    const int c0 = cg * CW;
+                    if (c0 < npad && qd >= 2) {
+                        float z[CW];
+                        tmem_ld_cols<CW>(tl1 + c0, z);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) z[c] = 1.0f - sigmoid_fast(z[c] + b_z);
+                        for (int c = 0; c < CW; ++c) z[c] = 1.0f - sigmoid_fast(z[c] + b_z);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) ZX[(c0 + c) * D + eu] = z[c];
-                }
-                tc::named_bar_sync(2 + 2 * s, G::NSW);
-                if (c0 < npad && qd < 2) {
-                    float rp[16], np[16];
-                    tc::tmem_ld16(tl1 + c0, rp);
-                    tc::tmem_ld16(tl2 + c0, np);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const float r = sigmoid_fast(rp[c] + b_r);
-                        const float n = tanh_fast(np[c] + b_in + r * b_hn);
-                        rp[c] = n * ZX[(c0 + c) * D + eu];                                // (1 - z) n + z h,  h = 0
+                        for (int c = 0; c < CW; ++c) ZX[(c0 + c) * D + eu] = z[c];
                     }
+                    tc::named_bar_sync(2 + 2 * s, G::NSW);
+                    if (c0 < npad && qd < 2) {
+                        float rp[CW], np[CW];
+                        tmem_ld_cols<CW>(tl1 + c0, rp);
+                        tmem_ld_cols<CW>(tl2 + c0, np);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        if (c0 + c < rows) p.hf[(size_t)IDS[c0 + c] * D + eu] = rp[c];
-                }
+                        for (int c = 0; c < CW; ++c) {
+                            const float r = sigmoid_fast(rp[c] + b_r);
+                            const float n = tanh_fast(np[c] + b_in + r * b_hn);
+                            rp[c] = n * ZX[(c0 + c) * D + eu];                            // (1 - z) n + z h,  h = 0
+                        }
+#pragma unroll
+                        for (int c = 0; c < CW; ++c)
+                            if (c0 + c < rows) p.hf[(size_t)IDS[c0 + c] * D + eu] = rp[c];
+                    }
+                };
+                if (cols_per_group<G::WPS / 4>(npad) == 8) epilogue(std::integral_constant<int, 8>{});
+                else epilogue(std::integral_constant<int, 16>{});
                 tc::fence_before_sync();
                 SWT(4);
                 tc::named_bar_sync(1 + 2 * s, G::NSW);         // all stores of the tile issued; ZX / IDS / the node tile are free
@@ -619,6 +642,41 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
 }
 
 #include "sweep_tc_bwd.inc"
+
+// d u_code = sum over ALL nodes v of sds[v][code - 1] x_v, x_v = [hs_v || hf_v]  (sds: the per-code sums of dscore over v's out-edges,
+// written by the backward's pulls) -> added to the raw blocks.  One streaming pass over the embeddings, warp per node, lane = 4 columns.
+__global__ void __launch_bounds__(256) sweep_du_kernel(const float* __restrict__ sds, const float* __restrict__ hs, const float* __restrict__ hf,
+                                                       int n, float* __restrict__ raw, unsigned handled) {
+    __shared__ float red[8][6][D2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 acc[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* base = lane < 16 ? hs : hf;
+    const int off = 4 * (lane & 15);
+    for (int v = blockIdx.x * 8 + warp; v < n; v += gridDim.x * 8) {
+        const float4 s0 = mgv_ldg4(sds + (size_t)v * 8), s1 = mgv_ldg4(sds + (size_t)v * 8 + 4);
+        const float sv[6] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y};
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) any |= sv[c] != 0.f;
+        if (!any) continue;
+        const float4 x = mgv_ldg4(base + (size_t)v * D + off);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) mgv_fma4(acc[c], sv[c], x);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) *reinterpret_cast<float4*>(&red[warp][c][4 * lane]) = acc[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 6 * D2; i += 256) {
+        const int c = i / D2;
+        if (!((handled >> (c + 1)) & 1u)) continue;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][c][i % D2];
+        if (t != 0.f) red_add1(raw + (size_t)(c + 1) * RAWF + R_U + (i % D2), t);
+    }
+}
 
 // raw blocks -> gradient blocks in the layout of include/mgv_b200.h (chain rule of Wc = W_ih W_v, b = W_ih b_v + b_ih (+ b_hh)):
 //   d W_v = W_ih^T d Wc,  d b_v = W_ih^T d c,  d W_ih = d Wc W_v^T + d c b_v^T,  d b_ih = d c,  d b_hh = [d c_r, d c_z, d b_hn],  d W_hh = 0
@@ -717,7 +775,9 @@ bool mgv_sweep_tc_bwd_available() { return true; }
 size_t mgv_sweep_tc_bwd_workspace_bytes(int64_t N, int64_t E) {
     size_t b = 0;
     b += mgv_align_up((size_t)N * D2 * 4 + 256, 256);          // dxb
-    b += 2 * mgv_align_up((size_t)E * 4 + 256, 256);           // alpha, dscore
+    b += mgv_align_up((size_t)E * 4 + 256, 256);               // alpha
+    b += mgv_align_up((size_t)N * 4 + 256, 256);               // A per node
+    b += mgv_align_up((size_t)N * 8 * 4 + 256, 256);           // sds per node and code
     b += mgv_align_up((size_t)MGV_NCODE * RAWF * 4 + 256, 256);
     return b + 1024;
 }
@@ -731,7 +791,8 @@ int mgv_sweep_tc_bwd(const mgv_schedule* sch, unsigned handled, const int* cta_s
     MgvArena a(ws, ws_bytes);
     d.dxb = a.take<float>((size_t)sch->N * D2);
     d.alpha = a.take<float>((size_t)sch->E + 1);
-    d.dscore = a.take<float>((size_t)sch->E + 1);
+    d.anode = a.take<float>((size_t)sch->N + 1);
+    d.sds = a.take<float>((size_t)sch->N * 8 + 8);
     d.raw = a.take<float>((size_t)MGV_NCODE * RAWF);
     MGV_REQUIRE(a.ok(), "mgv_sweep_tc_bwd: workspace too small");
     d.ghs = ghs; d.ghf = ghf;
@@ -742,13 +803,21 @@ int mgv_sweep_tc_bwd(const mgv_schedule* sch, unsigned handled, const int* cta_s
     for (int c = 0; c < MGV_NCODE; ++c)
         if (!((handled >> c) & 1u) && sch->code_count[c] > 0) pull_only |= 1u << c;
     MGV_CUDA(cudaMemsetAsync(d.raw, 0, (size_t)MGV_NCODE * RAWF * sizeof(float), st));
+    MGV_CUDA(cudaMemsetAsync(d.sds, 0, (size_t)sch->N * 8 * sizeof(float), st));      // every node is pulled exactly once and writes its row; belt and braces
     const void* kern = d.S == 2 ? bwd_kernel<2>(precision) : bwd_kernel<1>(precision);
     const size_t smem = d.S == 2 ? (size_t)Geo<2>::B_SMEM : (size_t)Geo<1>::B_SMEM;
     const int threads = d.S == 2 ? Geo<2>::NTHREADS : Geo<1>::NTHREADS;
     MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {&d, &pull_only};
     MGV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, st));
+    {
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int blocks = (int)std::min<int64_t>((int64_t)sms * 4, ((int64_t)sch->N + 7) / 8);
+        if (blocks > 0) sweep_du_kernel<<<blocks, 256, 0, st>>>(d.sds, hs, hf, sch->N, d.raw, handled);
+    }
     sweep_chain_kernel<<<dim3((GRAD + 255) / 256, MGV_NCODE), 256, 0, st>>>(weights, d.raw, grads, handled);
-    mgv_count_launches(2);
+    mgv_count_launches(3);
     return mgv_check_cuda(cudaGetLastError(), "mgv_sweep_tc_bwd");
 }

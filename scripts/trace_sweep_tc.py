@@ -35,13 +35,13 @@ torch.cuda.synchronize()
 for k, (n, ms) in ops.profile_summary().items():
     print("%s: %.3f ms per call, %.2f us per level" % (k, ms / n, 1e3 * ms / n / max(sch.L - 1, 1)))
 ops.PROFILE = None
-tr = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+tr = torch.zeros(148 * 32, dtype=torch.int64, device=dev)
 lib.mgv_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
 hf = ops.level_sweep(hs, sch, w["rounds"], codes, mods)
 hf.sum().backward()
 torch.cuda.synchronize()
 lib.mgv_debug_set_trace(ctypes.c_void_p(0))
-t = tr.view(148, 16).cpu().double()
+t = tr.view(148, 32).cpu().double()
 if which == "fwd":
     names = ["prefetch (+tile iter)", "wait level barrier", "gather+attention", "wait MMA", "epilogue", "end-of-tile sync", "grid arrive"]
     ntile_col = 8
@@ -61,4 +61,7 @@ for c in sorted(set(codes_of.tolist())):
     busy = tot[sel] - t[sel, wait_col]
     print("code %d: %3d CTAs  busy cycles per level mean %7.0f max %7.0f   tiles mean %.1f max %d" % (
         c, int(sel.sum()), busy.mean() / max(sch.L - 1, 1), busy.max() / max(sch.L - 1, 1), t[sel, ntile_col].mean(), int(t[sel, ntile_col].max())))
+if which == "bwd":
+    for i, n in ((16, "P: scalar loads issued"), (17, "P: row loads issued"), (18, "P: wait + reduce"), (19, "P: u / d u"), (20, "P: stores")):
+        print("%-32s mean %10.0f cycles  %5.1f%%   per level %7.0f" % (n, t[:, i].mean(), 100 * t[:, i].mean() / tot.mean(), t[:, i].mean() / max(sch.L - 1, 1)))
 print("code counts", sch.code_count, "streams", sch.streams)
