@@ -280,6 +280,30 @@ int mgv_recon_loss_fwd(const float* st, int32_t N, const int64_t* pos, int64_t E
 int mgv_recon_loss_bwd(const float* st, int32_t N, const int64_t* pos, int64_t Ep, const int64_t* neg, int64_t En,
                        const float* sig, const float* g_loss, float* gst, mgv_stream_t stream);
 
+/* ------------------------------------------------------------------ fused readout head (probability MLP + clamp + L1 loss)
+ * Replaces Model.pred_prob's MLP(64, 32, 1, num_layer = 3, p_drop, batchnorm, relu) (dg_ae_model_mig.py:44, arch/mlp.py:14-56), the
+ * clamp to [0, 1] (dg_ae_model_mig.py:150-152) and nn.L1Loss of trainer.py:154-156: forward ONE launch, backward ONE launch.
+ *   params: HOST array of 14 DEVICE pointers, fp32: fc.0.weight [32][64], fc.0.bias, bn1.weight, bn1.bias, bn1.running_mean,
+ *           bn1.running_var, fc.4.weight [32][32], fc.4.bias, bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var,
+ *           fc.8.weight [1][32], fc.8.bias.  training != 0: batch statistics (biased variance), running statistics updated in
+ *           place with `momentum` (unbiased variance), dropout with keep probability 1 - p_drop from a counter-based hash of
+ *           (seed, node, layer, channel); training == 0: running statistics, no dropout.
+ *   x float [N][64]; target float [N] or NULL; pred float [N] out = clamp(mlp(x), 0, 1); loss float [1] out = mean |pred - target|
+ *   saved float [N][64] out (pre-normalisation activations), stats float [128] out (mean / 1 / std of both BatchNorms): for the backward
+ *   mask uint32 [N][2] out or NULL: keep bits of the two dropout layers (bit c = channel c kept), for tests
+ *   sync int32 [1] (grid barrier, zeroed by the call); ws >= mgv_readout_workspace_bytes(N)
+ * Backward: g_pred float [N] or NULL (d L / d pred), g_loss device float or NULL (d L / d loss); gx float [N][64] out;
+ *   grads float [3297] out: d fc.0.weight 2048 | d fc.0.bias 32 | d bn1.weight 32 | d bn1.bias 32 | d fc.4.weight 1024 | d fc.4.bias 32 |
+ *   d bn2.weight 32 | d bn2.bias 32 | d fc.8.weight 32 | d fc.8.bias 1.  Same seed / p_drop / training as the forward.
+ */
+size_t mgv_readout_workspace_bytes(int64_t N);
+int mgv_readout_fwd(const float* x, int64_t N, const void* const* params, int32_t training, float p_drop, uint64_t seed,
+                    float momentum, float eps, const float* target, float* pred, float* loss, float* saved, float* stats,
+                    uint32_t* mask, void* ws, size_t ws_bytes, int32_t* sync, mgv_stream_t stream);
+int mgv_readout_bwd(const float* x, int64_t N, const void* const* params, int32_t training, float p_drop, uint64_t seed,
+                    const float* target, const float* saved, const float* stats, const float* g_pred, const float* g_loss,
+                    float* gx, float* grads, void* ws, size_t ws_bytes, int32_t* sync, mgv_stream_t stream);
+
 /* ------------------------------------------------------------------ tensor-core self test (diagnostic)
  * One 128-row tcgen05 tile product through the operand layouts / descriptors / fp16 hi-lo split the kernels
  * use (csrc/mgv_tc.cuh).  D is fp32 row-major.

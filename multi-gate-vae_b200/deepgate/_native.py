@@ -79,6 +79,11 @@ _PROTOTYPES = {
     "mgv_negative_sample": (ctypes.c_int, [_vp, _vp, _i32, _i64, ctypes.c_uint64, _vp, _vp]),
     "mgv_recon_loss_fwd": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "mgv_recon_loss_bwd": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "mgv_readout_workspace_bytes": (_sz, [_i64]),
+    "mgv_readout_fwd": (ctypes.c_int, [_vp, _i64, _vp, _i32, ctypes.c_float, ctypes.c_uint64, ctypes.c_float, ctypes.c_float,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "mgv_readout_bwd": (ctypes.c_int, [_vp, _i64, _vp, _i32, ctypes.c_float, ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _vp, _vp, _sz, _vp, _vp]),
     "mgv_linear_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mgv_linear_wgrad": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mgv_tc_selftest": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _i32, _vp]),

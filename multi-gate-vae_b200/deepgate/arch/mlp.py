@@ -1,7 +1,9 @@
-"""Readout MLP (reference arch/mlp.py:14-56): Linear / BatchNorm1d / ReLU / Dropout stack.
-torch.nn modules (adjacent to the hot path, SURVEY.md section 8 a11 / f#3) except that the Linear layers take their
-weight gradient from csrc/linear.cu (ops.Linear: the node-dimension reduction is one SM's work for a library GEMM); the
-layer indices inside ``fc`` fix the checkpoint keys (readout_prob.fc.{0,1,4,5,8}.*)."""
+"""Readout MLP (reference arch/mlp.py:14-56): Linear / BatchNorm1d / ReLU / Dropout stack; the layer indices inside ``fc`` fix
+the checkpoint keys (readout_prob.fc.{0,1,4,5,8}.*).  The modules are torch.nn (callable stand-alone on any device, like the
+reference's); in the model's readout configuration (64 -> 32 -> 32 -> 1, batchnorm, relu, dropout) ``Model.pred_prob`` and the
+Trainer's probability loss run through the fused head of csrc/readout.cu instead (``fused_head_ok`` / ops.readout_head)."""
+import os
+
 import torch.nn as nn
 
 from ..ops import Linear
@@ -31,6 +33,17 @@ class MLP(nn.Module):
         if tanh:
             layers.append(nn.Tanh())
         self.fc = nn.Sequential(*layers)
+
+    def fused_head_ok(self, x):
+        """True when csrc/readout.cu implements exactly this stack for ``x`` (CUDA fp32 [N, 64])."""
+        fc = self.fc
+        return (x.is_cuda and x.dim() == 2 and x.size(1) == 64 and len(fc) == 9
+                and isinstance(fc[0], nn.Linear) and fc[0].out_features == 32 and isinstance(fc[1], nn.BatchNorm1d)
+                and isinstance(fc[2], nn.ReLU) and isinstance(fc[3], nn.Dropout) and isinstance(fc[4], nn.Linear)
+                and fc[4].out_features == 32 and isinstance(fc[5], nn.BatchNorm1d) and isinstance(fc[6], nn.ReLU)
+                and isinstance(fc[7], nn.Dropout) and isinstance(fc[8], nn.Linear) and fc[8].out_features == 1
+                and fc[1].track_running_stats and fc[1].affine and fc[5].track_running_stats and fc[5].affine
+                and fc[3].p == fc[7].p and not os.environ.get("MGV_READOUT_TORCH"))
 
     def forward(self, x):
         return self.fc(x)

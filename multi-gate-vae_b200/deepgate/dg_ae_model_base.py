@@ -97,7 +97,17 @@ class LevelModel(nn.Module):
 
     # ------------------------------------------------------------------ heads (torch.nn, adjacent to the path)
     def pred_prob(self, hf):
+        if self.readout_prob.fused_head_ok(hf):
+            return ops.readout_head(hf, None, self.readout_prob)[0]
         return torch.clamp(self.readout_prob(hf), min=0.0, max=1.0)
+
+    def pred_prob_loss(self, hf, target):
+        """(pred_prob(hf), nn.L1Loss()(pred_prob(hf), target)) -- trainer.py:154-156 -- in one fused launch."""
+        if self.readout_prob.fused_head_ok(hf) and target is not None and target.is_cuda:
+            pred, loss = ops.readout_head(hf, target, self.readout_prob)
+            return pred, loss
+        pred = self.pred_prob(hf)
+        return pred, torch.nn.functional.l1_loss(pred, target)
 
     def recon_loss(self, hs, pos_edge_index, neg_edge_index=None):
         """dg_ae_model_mig.py:169-191.  The decoder + BCE terms run in one fused kernel (ops.recon_loss); missing

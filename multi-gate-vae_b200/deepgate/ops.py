@@ -473,3 +473,90 @@ def vae_func_loss(mu=None, logstd=None, eps=None, hf=None, tt_pair_index=None, t
     if mu is None:
         return None, None, None, func
     return z[0], z[1], kl, (func if tt_pair_index is not None else None)
+
+
+# =========================================================================== fused readout head (probability MLP + clamp + L1 loss)
+_READOUT_CALLS = [0]
+
+
+class ReadoutFunction(torch.autograd.Function):
+    """pred = clamp(MLP(x), 0, 1) and, with a target, loss = mean |pred - target| -- one launch forward, one backward
+    (csrc/readout.cu; reference arch/mlp.py:14-56, dg_ae_model_mig.py:150-152, trainer.py:154-156).
+    ``bufs`` = (bn1.running_mean, bn1.running_var, bn2.running_mean, bn2.running_var), updated in place in training mode;
+    ``params`` = (fc0.w, fc0.b, bn1.w, bn1.b, fc4.w, fc4.b, bn2.w, bn2.b, fc8.w, fc8.b)."""
+
+    @staticmethod
+    def forward(ctx, x, target, training, p_drop, seed, momentum, eps, want_mask, bufs, *params):
+        nat.require_cuda(x, "hf")
+        dev = x.device
+        x_c = _f32(x, "hf")
+        N = x_c.shape[0]
+        t_c = None if target is None else _f32(target.reshape(-1), "prob")
+        if t_c is not None and t_c.numel() != N:
+            raise RuntimeError("mgv_b200: the readout target must have one entry per node")
+        ps = [_f32(p, "readout parameter") for p in params]
+        table = [ps[0], ps[1], ps[2], ps[3], bufs[0], bufs[1], ps[4], ps[5], ps[6], ps[7], bufs[2], bufs[3], ps[8], ps[9]]
+        f32 = dict(dtype=torch.float32, device=dev)
+        pred = torch.empty(N, 1, **f32)
+        loss = torch.empty((), **f32)
+        saved = torch.empty(max(N, 1), 64, **f32)
+        stats = torch.empty(128, **f32)
+        mask = torch.empty(max(N, 1), 2, dtype=torch.int32, device=dev) if want_mask else None
+        sync = torch.empty(1, dtype=torch.int32, device=dev)
+        lib = nat.lib()
+        with nat.on_device(dev), _timed("readout_fwd", dev):
+            nb = lib.mgv_readout_workspace_bytes(N)
+            ws = nat.workspace(nb, dev)
+            nat.check(lib.mgv_readout_fwd(nat.ptr(x_c), N, _ptr_table(table), int(bool(training)), float(p_drop), int(seed),
+                                          float(momentum), float(eps), nat.ptr(t_c), nat.ptr(pred), nat.ptr(loss), nat.ptr(saved),
+                                          nat.ptr(stats), nat.ptr(mask), nat.ptr(ws), nb, nat.ptr(sync), nat.stream_of(dev)),
+                      "mgv_readout_fwd")
+        ctx.save_for_backward(x_c, t_c, saved, stats, *table)
+        ctx.cfg = (int(bool(training)), float(p_drop), int(seed))
+        ctx.mark_non_differentiable(*[t for t in (mask,) if t is not None])
+        if t_c is None:
+            loss = loss.zero_()
+        return (pred, loss, mask) if want_mask else (pred, loss)
+
+    @staticmethod
+    def backward(ctx, g_pred, g_loss, *unused):
+        x_c, t_c, saved, stats = ctx.saved_tensors[:4]
+        table = list(ctx.saved_tensors[4:])
+        training, p_drop, seed = ctx.cfg
+        dev = x_c.device
+        N = x_c.shape[0]
+        gp = None if g_pred is None else _f32(g_pred.reshape(-1), "g_pred")
+        gl = None if (g_loss is None or t_c is None) else _f32(g_loss.reshape(1), "g_loss")
+        gx = torch.empty(max(N, 1), 64, dtype=torch.float32, device=dev)
+        grads = torch.empty(3297, dtype=torch.float32, device=dev)
+        sync = torch.empty(1, dtype=torch.int32, device=dev)
+        lib = nat.lib()
+        with nat.on_device(dev), _timed("readout_bwd", dev):
+            nb = lib.mgv_readout_workspace_bytes(N)
+            ws = nat.workspace(nb, dev)
+            nat.check(lib.mgv_readout_bwd(nat.ptr(x_c), N, _ptr_table(table), training, p_drop, seed, nat.ptr(t_c), nat.ptr(saved),
+                                          nat.ptr(stats), nat.ptr(gp), nat.ptr(gl), nat.ptr(gx), nat.ptr(grads), nat.ptr(ws), nb,
+                                          nat.ptr(sync), nat.stream_of(dev)), "mgv_readout_bwd")
+        g = grads
+        out = (g[0:2048].view(32, 64), g[2048:2080], g[2080:2112], g[2112:2144], g[2144:3168].view(32, 32), g[3168:3200],
+               g[3200:3232], g[3232:3264], g[3264:3296].view(1, 32), g[3296:3297])
+        return (gx[:N], None, None, None, None, None, None, None, None) + out          # disjoint views of one fresh buffer
+
+
+def readout_head(x, target, mlp, want_mask=False):
+    """``mlp``: arch.mlp.MLP in its readout configuration (Linear-BatchNorm-ReLU-Dropout x 2 + Linear, 64 -> 32 -> 32 -> 1)."""
+    fc = mlp.fc
+    bn1, bn2 = fc[1], fc[5]
+    training = mlp.training
+    seed = 0
+    if training:
+        _READOUT_CALLS[0] += 1
+        seed = (torch.initial_seed() * 0x9E3779B1 + _READOUT_CALLS[0]) & 0x7FFFFFFFFFFFFFFF
+        with torch.no_grad():
+            bn1.num_batches_tracked += 1
+            bn2.num_batches_tracked += 1
+    momentum = bn1.momentum if bn1.momentum is not None else 0.1
+    return ReadoutFunction.apply(x, target, training, fc[3].p if training else 0.0, seed, momentum, bn1.eps, want_mask,
+                                 (bn1.running_mean, bn1.running_var, bn2.running_mean, bn2.running_var),
+                                 fc[0].weight, fc[0].bias, bn1.weight, bn1.bias, fc[4].weight, fc[4].bias, bn2.weight, bn2.bias,
+                                 fc[8].weight, fc[8].bias)

@@ -184,8 +184,11 @@ class Trainer(object):
             batch = split_edges(batch)
         hs, hf = self.model(batch)
         loss, pred_bin, gt_bin = self.model.recon_loss(hs, batch.train_pos_edge_index, neg_edge_index)
-        prob = self.model.pred_prob(hf)
-        prob_loss = self.reg_loss(prob, batch["prob"])
+        if hasattr(self.model, "pred_prob_loss"):                  # fused MLP + clamp + L1 (csrc/readout.cu)
+            prob, prob_loss = self.model.pred_prob_loss(hf, batch["prob"])
+        else:
+            prob = self.model.pred_prob(hf)
+            prob_loss = self.reg_loss(prob, batch["prob"])
         # func loss: 1 - cos -> z-norm -> L1 against z-norm(tt_sim)   (trainer.py:157-163), fused kernel
         _, _, _, func_loss = ops.vae_func_loss(hf=hf, tt_pair_index=batch["tt_pair_index"], tt_sim=batch["tt_sim"])
         status = {"recon_loss": loss, "pred_bin": pred_bin, "gt_bin": gt_bin, "prob_loss": prob_loss,

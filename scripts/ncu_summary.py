@@ -20,7 +20,7 @@ with open(out, "w") as f:
         f.write("\n")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     srows = list(csv.reader(io.StringIO(src)))
-    if len(srows) > 3:
+    if len(srows) > 3 and "# Samples" in srows[1]:
         h = srows[1]
         iS, isrc, iex = h.index("# Samples"), h.index("Source"), h.index("Instructions Executed")
         data = [r for r in srows[2:] if len(r) > iS and r[iS].isdigit()]
