@@ -44,12 +44,14 @@ HANDLED = {"aig": (1, 2), "mig": (1, 2, 3, 4), "xmg": (1, 2, 3, 4, 5), "xag": (2
 LOSS_W = (1.0, 4.0, 4.0)      # stage-3 weights of the reference schedule (train.py:91)
 
 
-def make_host_batch(w, rank, idx):
+def make_host_batch(w, rank, idx, own_sizes=False):
     import deepgate
     from deepgate import synth
-    # ranks draw different circuits of the SAME sizes (size-bucketed sampler): weak scaling without size skew between ranks
+    # ranks draw different circuits of the SAME sizes (size-bucketed sampler): weak scaling without size skew between ranks.
+    # own_sizes: every rank also draws its own circuit SIZES (the reference's plain DistributedSampler, trainer.py:179-192).
     circuits = synth.make_circuits(w["mix"], w["batch"], w["n_pi"], w["n_gates"],
-                                   cfg=w["cfg"] + 100 * rank + 10 * idx, window=w["window"], size_cfg=w["cfg"] + 10 * idx)
+                                   cfg=w["cfg"] + 100 * rank + 10 * idx, window=w["window"],
+                                   size_cfg=w["cfg"] + 10 * idx + (1000 * rank if own_sizes else 0))
     return deepgate.circuits_to_batch(circuits)
 
 
@@ -242,7 +244,7 @@ def _restore_stdout():
         _SAVED_STDOUT = None
 
 
-def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cpu_baseline=False):
+def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cpu_baseline=False, own_sizes=False):
     """Times `steps` train steps of workload `w` (after the setup pass and `warmup` steps) device-resident and end to end.
     Returns the record of this workload (the caller prints it, or nests it under "workloads")."""
     import deepgate
@@ -266,7 +268,7 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
         trainer.kl_weight = 1.0                            # cfg4: the KL term is part of the objective
     ops.set_precision(precision)
     model.train()
-    host = [make_host_batch(w, rank, i).pin_memory() for i in range(nb)]
+    host = [make_host_batch(w, rank, i, own_sizes).pin_memory() for i in range(nb)]
     stats = [batch_stats(b, w["kind"]) for b in host]
     resident = [b.copy_to(dev, non_blocking=False) for b in host]
     gates_per_step = [s["gates"] * w["rounds"] for s in stats]
@@ -457,7 +459,8 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
                    "gates_per_step_per_gpu": mean_stats["gates"] * w["rounds"], "sweep_rounds": w["rounds"],
                    "s_rounds": 4, "t_rounds": 4, "layernorm": True, "dim_hidden": 64, "parallelism": "dp%d" % world,
                    "step": "schedule build + forward + %s losses + backward + allreduce + Adam" % losses,
-                   "ranks": "every rank draws its own circuits, with the same circuit sizes on all ranks (size-bucketed sampler)",
+                   "ranks": ("every rank draws its own circuits AND its own circuit sizes (plain DistributedSampler)" if own_sizes else
+                             "every rank draws its own circuits, with the same circuit sizes on all ranks (size-bucketed sampler)"),
                    "setup": "one untimed pass over each distinct batch before the warm-up steps (allocator pools)",
                    "l2": "%d distinct batches rotated; per-batch working set (struct states %d MB) exceeds the 126 MB L2"
                          % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},
@@ -499,6 +502,13 @@ def run_ours(args, w):
             except Exception as e:                          # a sub-workload must never cost the headline line
                 subs[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     rec["workloads"] = subs
+    if world > 1 and not args.no_sub_workloads:
+        # the same workload without the size-bucketed sampler: per-rank batches differ in nodes / levels, the step waits for the slowest rank
+        try:
+            r = measure(w, args.workload, min(args.steps, 10), 3, args.batches, dev, rank, world, own_sizes=True)
+            rec["unbucketed_sizes"] = {k: r[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step", "e2e", "config")}
+        except Exception as e:
+            rec["unbucketed_sizes"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0:
         _restore_stdout()
         print(json.dumps(rec))

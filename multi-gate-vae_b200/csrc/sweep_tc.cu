@@ -374,7 +374,7 @@ __device__ __forceinline__ void store_xbar_wide(uint32_t xb_hi, uint32_t xb_lo, 
 // of slot 2 it + half (fast path only; the wide path of the backward re-reads p.alpha).  Returns true when the wide path ran
 // (some row of the warp has more than FAST_FANIN predecessors).
 template <bool LOWP, bool STORE_ALPHA, bool HF_CG, int WPS>
-__device__ __forceinline__ bool gather_tile(const SweepTC& p, const float* __restrict__ hf, const float4& us, const float4& uf,
+__device__ __forceinline__ bool gather_tile(const SweepTC& p, const float* __restrict__ hf, const float* F32,
                                             const RowRegs& rr, int rows, int npad, int ws, int lane, uint32_t xb_hi, uint32_t xb_lo,
                                             uint32_t kbx, int* IDS, float (&al2)[2][FAST_FANIN]) {
     const unsigned full = 0xffffffffu;
@@ -385,6 +385,8 @@ __device__ __forceinline__ bool gather_tile(const SweepTC& p, const float* __res
         HalfRow r0, r1;
         load_half_row<HF_CG>(p, hf, half, rr, lp, r0);
         if (second) load_half_row<HF_CG>(p, hf, 2 + half, rr, lp, r1);
+        // the attention vector comes from the weight image in shared memory each time (registers are the scarce resource here)
+        const float4 us = *reinterpret_cast<const float4*>(F32 + 4 * lp), uf = *reinterpret_cast<const float4*>(F32 + D + 4 * lp);
         float4 xbs, xbf;
         attend_half<STORE_ALPHA>(p, r0, us, uf, lp, xbs, xbf, al2[0]);
         int i = ws + WPS * half;
@@ -395,7 +397,7 @@ __device__ __forceinline__ bool gather_tile(const SweepTC& p, const float* __res
             if (i < npad) store_xbar_half<LOWP>(xb_hi, xb_lo, kbx, i, lp, xbs, xbf);
         }
     } else {
-        const float4 u4 = lane < 16 ? us : uf;             // lane l of the wide layout owns the columns lane l % 16 of the half layout owns
+        const float4 u4 = *reinterpret_cast<const float4*>(F32 + 4 * lane);      // lane l of the wide layout owns columns 4 l .. + 3 of the 128
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const int i = ws + WPS * k;
@@ -500,18 +502,15 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
 
     if (warp < WORKERS) {
         // ===================================================================== workers of stream s: gather -> [MMA] -> epilogue
-        const int ws = warp % G::WPS, lp = lane & 15;
+        const int ws = warp % G::WPS;
         float* ZX = reinterpret_cast<float*>(sgen + IMG_PAD + s * G::F_STRIDE + G::F_ZX);
         int* IDS = reinterpret_cast<int*>(sgen + IMG_PAD + s * G::F_STRIDE + G::F_IDS);
-        float4 us = make_float4(0.f, 0.f, 0.f, 0.f), uf = us;
         const int qd = warp & 3, cg = ws >> 2;
         const int eu = (qd & 1) * 32 + lane;                   // gate unit of this thread's tensor-memory lane
+        const float* F = reinterpret_cast<const float*>(sgen + I_F32);        // fp32 tail of the weight image: u | b_r | b_z | b_in | b_hn
         float b_r = 0.f, b_z = 0.f, b_in = 0.f, b_hn = 0.f;
         if (code >= 0) {
             tc::mbar_wait_warp(bar_w, 0u, lane);
-            const float* F = reinterpret_cast<const float*>(sgen + I_F32);
-            us = *reinterpret_cast<const float4*>(F + 4 * lp);
-            uf = *reinterpret_cast<const float4*>(F + D + 4 * lp);
             b_r = F[128 + eu]; b_z = F[192 + eu]; b_in = F[256 + eu]; b_hn = F[320 + eu];
         }
         const uint32_t tl1 = acc1 + ((uint32_t)(qd * 32) << 16), tl2 = acc2 + ((uint32_t)(qd * 32) << 16);
@@ -539,7 +538,7 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
             while (have) {
                 const int npad = (rows + 15) & ~15;
                 float al2[2][FAST_FANIN];
-                gather_tile<LOWP, false, true, G::WPS>(p, p.hf, us, uf, rr, rows, npad, ws, lane, xb_hi, xb_lo, G::KBX, IDS, al2);
+                gather_tile<LOWP, false, true, G::WPS>(p, p.hf, F, rr, rows, npad, ws, lane, xb_hi, xb_lo, G::KBX, IDS, al2);
                 tc::fence_async_smem();
                 tc::mbar_arrive(bar_x_full);
                 SWT(2);
@@ -692,6 +691,7 @@ __global__ void sweep_chain_kernel(const float* __restrict__ pack, const float* 
     if (i < G_WV) v = R[R_U + i];
     else if (i < G_BV) {                                   // d W_v[k][f] = sum_g W_ih[g][k] d Wc[g][f]
         const int k = (i - G_WV) / D2, f = (i - G_WV) % D2;
+#pragma unroll 16
         for (int g = 0; g < G3; ++g) v = fmaf(__ldg(W + O_WIH + g * D + k), __ldg(R + R_WC + g * D2 + f), v);
     } else if (i < G_WIH) {                                // d b_v[k] = sum_g W_ih[g][k] d c[g]
         const int k = i - G_BV;
@@ -699,6 +699,7 @@ __global__ void sweep_chain_kernel(const float* __restrict__ pack, const float* 
     } else if (i < G_WHH) {                                // d W_ih[g][k] = sum_f d Wc[g][f] W_v[k][f] + d c[g] b_v[k]
         const int g = (i - G_WIH) / D, k = (i - G_WIH) % D;
         v = __ldg(R + R_B + g) * __ldg(W + O_BV + k);
+#pragma unroll 16
         for (int f = 0; f < D2; ++f) v = fmaf(__ldg(R + R_WC + g * D2 + f), __ldg(W + O_WV + k * D2 + f), v);
     } else if (i < G_BIH) v = 0.f;                         // d W_hh: h = 0 in a single-round sweep
     else if (i < G_BHH) v = R[R_B + (i - G_BIH)];
