@@ -126,7 +126,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, in
         WaitGuard g;
 #pragma unroll 1
         while (!mbar_try_wait(bar, parity)) {
-            __nanosleep(sleep_ns);
+            if (sleep_ns) __nanosleep(sleep_ns);           // 0: try_wait itself suspends the thread for a hardware-defined time
             g.tick();
         }
     }

@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
         }
         for (int step = 0; step < nsteps; ++step) {
             SWT(0);
-            if (step > 0) tc::mbar_wait_warp(bar_level, (uint32_t)((step - 1) & 1), lane, 32);     // level `step` of this stream is complete everywhere
+            if (step > 0) tc::mbar_wait_warp(bar_level, (uint32_t)((step - 1) & 1), lane, 0);     // level `step` of this stream is complete everywhere
             SWT(1);
             // the next tile of this CTA (same level, else the first of the next level): its static data is fetched while the
             // tensor core works on the current tile
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
                 } else {
                     have = false;
                 }
-                tc::mbar_wait_warp(bar_acc_full, it & 1u, lane, 32);
+                tc::mbar_wait_warp(bar_acc_full, it & 1u, lane, 0);
                 tc::fence_after_sync();
                 SWT(3);
                 // ---- epilogue: TMEM lane = gate unit.  Lanes 64..127 hold z: those warps hand 1 - z to the r / n lanes through shared
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
                 ti.start(p, s, step + 1, code, rank, nct, G::NTS);
                 int t0, rows;
                 while (ti.next(nct, t0, rows)) {
-                    tc::mbar_wait_warp(bar_x_full, it & 1u, lane, 20);
+                    tc::mbar_wait_warp(bar_x_full, it & 1u, lane, 0);
                     tc::fence_after_sync();
                     if (tc::elect_one()) {
                         issue_gate_mmas<LOWP>(sbase, xb_hi, xb_lo, G::KBX, acc1, acc2, (rows + 15) & ~15);
