@@ -86,6 +86,7 @@ struct SweepTC {
     const float* hs;
     float* hf;                 // [N][64]
     int cta_start[MGV_NCODE + 1];
+    int cl_size, cl_code[MGV_NCODE];   // cluster mode: CTAs per cluster (= gate codes with nodes) and the code of each cluster rank
     unsigned* bar;             // [s * BAR_STRIDE] grid barrier counter of stream s
     // backward
     float* ghs; float* ghf; float* dxb; float* alpha; float* anode; float* sds; float* raw;   // anode [N]: A = dxbar . xbar; sds [N][8]
@@ -459,9 +460,21 @@ __device__ __forceinline__ bool grid_try(const unsigned* counter, unsigned targe
     return __shfl_sync(0xffffffffu, ok, 0) != 0u;
 }
 
+// Cluster barrier, split (all threads of all CTAs of the cluster execute both): release / acquire at cluster scope cover the
+// global-memory rows the CTAs of a cluster hand to each other between levels.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // ======================================================================================= forward
-template <bool LOWP, int S>
+// CL = false: grid mode -- S (1 or 2) circuit-set streams, every level of a stream spread over all CTAs of its gate code, one grid
+//             barrier per stream and level (cooperative launch).  For batches of few large circuits.
+// CL = true : cluster mode -- the batch is cut into many circuit sets (mgv_schedule.streams > 2); a thread-block CLUSTER of one
+//             CTA per gate code walks whole streams on its own, levels separated by the hardware cluster barrier: no grid-wide
+//             synchronisation at all, clusters never wait for each other.  For batches of many small circuits (the reference's
+//             training batches), where a level is a fraction of a tile per CTA and the grid barrier is 40 % of a level.
+template <bool LOWP, int S, bool CL>
 __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const SweepTC p) {
+    static_assert(!CL || S == 1, "cluster mode runs one stream at a time per CTA");
     using G = Geo<S>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -470,7 +483,13 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
     const uint32_t bar_w = sbase + G::F_BAR;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + G::F_TMEM);
     int code, rank, nct;
-    find_role(p, code, rank, nct);
+    int s_first = 0, s_step = 1, s_end = 1;                 // schedule streams this CTA walks (grid mode: its warps' own one)
+    if constexpr (CL) {
+        code = p.cl_code[blockIdx.x % p.cl_size]; rank = 0; nct = 1;
+        s_first = blockIdx.x / p.cl_size; s_step = gridDim.x / p.cl_size; s_end = p.S;
+    } else {
+        find_role(p, code, rank, nct);
+    }
     if (tid == 0) {
         tc::mbar_init(bar_w, 1);
         for (int s = 0; s < S; ++s) {
@@ -493,7 +512,8 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const int nsteps = p.L - 1;
-    const int s = warp < WORKERS ? warp / G::WPS : warp - WORKERS;               // stream of this warp
+    const int s = CL ? 0 : (warp < WORKERS ? warp / G::WPS : warp - WORKERS);    // stream slot (resources) of this warp
+    if constexpr (!CL) { s_first = s; s_end = s + 1; }
     const uint32_t bar_x_full = bar_w + 8 + 24 * s, bar_acc_full = bar_x_full + 8, bar_level = bar_x_full + 16;
     const uint32_t sstream = sbase + IMG_PAD + (uint32_t)s * G::F_STRIDE;
     const uint32_t xb_hi = sstream + G::F_XB_HI, xb_lo = sstream + G::F_XB_LO;
@@ -501,7 +521,7 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
     unsigned* gbar = p.bar + s * BAR_STRIDE;
 
     if (warp < WORKERS) {
-        // ===================================================================== workers of stream s: gather -> [MMA] -> epilogue
+        // ===================================================================== workers of stream slot s: gather -> [MMA] -> epilogue
         const int ws = warp % G::WPS;
         float* ZX = reinterpret_cast<float*>(sgen + IMG_PAD + s * G::F_STRIDE + G::F_ZX);
         int* IDS = reinterpret_cast<int*>(sgen + IMG_PAD + s * G::F_STRIDE + G::F_IDS);
@@ -516,19 +536,23 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
         const uint32_t tl1 = acc1 + ((uint32_t)(qd * 32) << 16), tl2 = acc2 + ((uint32_t)(qd * 32) << 16);
         uint32_t it = 0;
         SWT_DECL(8);
+        for (int sx = s_first; sx < s_end; sx += s_step) {     // schedule stream (grid mode: one; cluster mode: every s_step-th)
         TileIter ti;
         int t0 = 0, rows = 0;
         bool have = false;
         RowRegs rr;
         rr.w = (lane & 7) == W_NODE ? -1 : 0;
         if (code >= 0 && nsteps > 0) {
-            ti.start(p, s, 1, code, rank, nct, G::NTS);
+            ti.start(p, sx, 1, code, rank, nct, G::NTS);
             have = ti.next(nct, t0, rows);
             if (have) rr = prefetch_rows<G::WPS>(p, t0, rows, ws, lane);
         }
         for (int step = 0; step < nsteps; ++step) {
             SWT(0);
-            if (step > 0) tc::mbar_wait_warp(bar_level, (uint32_t)((step - 1) & 1), lane, 0);     // level `step` of this stream is complete everywhere
+            if (step > 0) {                                    // level `step` of this stream is complete everywhere
+                if constexpr (CL) cluster_wait();
+                else tc::mbar_wait_warp(bar_level, (uint32_t)((step - 1) & 1), lane, 0);
+            }
             SWT(1);
             // the next tile of this CTA (same level, else the first of the next level): its static data is fetched while the
             // tensor core works on the current tile
@@ -544,7 +568,7 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
                 SWT(2);
                 haven = ti.next(nct, t0n, rowsn);
                 if (!haven && !crossed && step + 1 < nsteps) {
-                    ti.start(p, s, step + 2, code, rank, nct, G::NTS);
+                    ti.start(p, sx, step + 2, code, rank, nct, G::NTS);
                     crossed = true;
                     haven = ti.next(nct, t0n, rowsn);
                     if (haven) rrn = prefetch_rows<G::WPS>(p, t0n, rowsn, ws, lane);
@@ -598,14 +622,18 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
                 if (have) { t0 = t0n; rows = rowsn; rr = rrn; }
             }
             if (!crossed && step + 1 < nsteps && code >= 0) {  // no tile of this CTA at this level
-                ti.start(p, s, step + 2, code, rank, nct, G::NTS);
+                ti.start(p, sx, step + 2, code, rank, nct, G::NTS);
                 haven = ti.next(nct, t0n, rowsn);
                 if (haven) rrn = prefetch_rows<G::WPS>(p, t0n, rowsn, ws, lane);
             }
-            if (ws == 0 && lane == 0 && step + 1 < nsteps) grid_arrive(gbar);
+            if (step + 1 < nsteps) {
+                if constexpr (CL) { __syncwarp(); cluster_arrive(); }
+                else if (ws == 0 && lane == 0) grid_arrive(gbar);
+            }
             have = haven && step + 1 < nsteps;
             t0 = t0n; rows = rowsn; rr = rrn;
             SWT(6);
+        }
         }
         SWT_FLUSH(8, it);
     } else {
@@ -613,10 +641,11 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
         // the whole warp runs the control flow (descriptors stay in uniform registers), one elected lane issues
         if (code >= 0) tc::mbar_wait_warp(bar_w, 0u, lane);
         uint32_t it = 0;
+        for (int sx = s_first; sx < s_end; sx += s_step)
         for (int step = 0; step < nsteps; ++step) {
             if (code >= 0) {
                 TileIter ti;
-                ti.start(p, s, step + 1, code, rank, nct, G::NTS);
+                ti.start(p, sx, step + 1, code, rank, nct, G::NTS);
                 int t0, rows;
                 while (ti.next(nct, t0, rows)) {
                     tc::mbar_wait_warp(bar_x_full, it & 1u, lane, 0);
@@ -630,8 +659,15 @@ __global__ void __launch_bounds__(Geo<S>::NTHREADS, 1) sweep_fwd_tc_kernel(const
                 }
             }
             if (step + 1 < nsteps) {
-                const unsigned target = (unsigned)(step + 1) * gridDim.x;
-                { tc::WaitGuard wg; while (!grid_try(gbar, target, bar_level, lane)) { __nanosleep(20); wg.tick(); } }
+                if constexpr (CL) {
+                    __syncwarp();
+                    cluster_arrive();
+                    cluster_wait();
+                } else {
+                    const unsigned target = (unsigned)(step + 1) * gridDim.x;
+                    tc::WaitGuard wg;
+                    while (!grid_try(gbar, target, bar_level, lane)) { __nanosleep(20); wg.tick(); }
+                }
             }
         }
     }
@@ -720,7 +756,6 @@ namespace {
 int fill(SweepTC& d, const mgv_schedule* sch, unsigned handled, const int* cta_start, const float* weights, const float* hs, float* hf,
          int32_t* sync) {
     d.N = sch->N; d.L = sch->L; d.S = sch->streams > 1 ? sch->streams : 1; d.handled = handled;
-    MGV_REQUIRE(d.S <= MAX_STREAMS, "level sweep: a schedule may have at most %d streams", MAX_STREAMS);
     d.order = sch->order; d.seg_ptr = sch->seg_ptr; d.in_ptr = sch->in_ptr; d.in_src = sch->in_src;
     d.out_ptr = sch->out_ptr; d.out_pack = sch->out_pack; d.out_slot = sch->out_slot;
     MGV_REQUIRE(sch->sweep_desc != nullptr, "level sweep: the schedule has no row descriptors (mgv_build_sweep_desc)");
@@ -731,13 +766,36 @@ int fill(SweepTC& d, const mgv_schedule* sch, unsigned handled, const int* cta_s
     d.trace = nullptr;
     return MGV_OK;
 }
-template <int S>
+template <int S, bool CL>
 const void* fwd_kernel(int precision) {
-    return precision == 1 ? (const void*)sweep_fwd_tc_kernel<true, S> : (const void*)sweep_fwd_tc_kernel<false, S>;
+    return precision == 1 ? (const void*)sweep_fwd_tc_kernel<true, S, CL> : (const void*)sweep_fwd_tc_kernel<false, S, CL>;
 }
-template <int S>
+// Cluster mode: one CTA per gate code that has nodes; as many clusters as fit (at most one per stream).
+int cluster_setup(SweepTC& d, const mgv_schedule* sch, unsigned handled) {
+    d.cl_size = 0;
+    for (int c = 0; c < MGV_NCODE; ++c)
+        if (((handled >> c) & 1u) && sch->code_count[c] > 0) d.cl_code[d.cl_size++] = c;
+    return d.cl_size;
+}
+int cluster_launch(const void* kern, int threads, size_t smem, int cl_size, int streams, void** args, cudaStream_t st) {
+    MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(cl_size);
+    int fit = 0;
+    MGV_CUDA(cudaOccupancyMaxActiveClusters(&fit, kern, &cfg));
+    MGV_REQUIRE(fit >= 1, "level sweep: a cluster of %d CTAs does not fit on the device", cl_size);
+    const int clusters = streams < fit ? streams : fit;
+    cfg.gridDim = dim3(clusters * cl_size);
+    MGV_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+    return MGV_OK;
+}
+template <int S, bool CL>
 const void* bwd_kernel(int precision) {
-    return precision == 1 ? (const void*)sweep_bwd_tc_kernel<true, S> : (const void*)sweep_bwd_tc_kernel<false, S>;
+    return precision == 1 ? (const void*)sweep_bwd_tc_kernel<true, S, CL> : (const void*)sweep_bwd_tc_kernel<false, S, CL>;
 }
 }  // namespace
 
@@ -749,11 +807,18 @@ int mgv_sweep_tc_fwd(const mgv_schedule* sch, unsigned handled, const int* cta_s
 #ifdef MGV_SWEEP_TRACE
     d.trace = getenv("MGV_TRACE_SWEEP_FWD") ? mgv_debug_trace() : nullptr;
 #endif
-    const void* kern = d.S == 2 ? fwd_kernel<2>(precision) : fwd_kernel<1>(precision);
+    void* args[] = {&d};
+    if (d.S > MAX_STREAMS) {                              // many circuit sets: clusters walk them independently
+        if (cluster_setup(d, sch, handled) == 0) return MGV_OK;
+        rc = cluster_launch(fwd_kernel<1, true>(precision), Geo<1>::NTHREADS, (size_t)Geo<1>::F_SMEM, d.cl_size, d.S, args, st);
+        if (rc != MGV_OK) return rc;
+        mgv_count_launches(1);
+        return MGV_OK;
+    }
+    const void* kern = d.S == 2 ? fwd_kernel<2, false>(precision) : fwd_kernel<1, false>(precision);
     const size_t smem = d.S == 2 ? (size_t)Geo<2>::F_SMEM : (size_t)Geo<1>::F_SMEM;
     const int threads = d.S == 2 ? Geo<2>::NTHREADS : Geo<1>::NTHREADS;
     MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void* args[] = {&d};
     MGV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, st));
     mgv_count_launches(1);
     return MGV_OK;
@@ -763,7 +828,7 @@ int mgv_sweep_tc_grid(int* grid_out) {
     int dev = 0, sms = 0, occ = 0;
     MGV_CUDA(cudaGetDevice(&dev));
     MGV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const void* kern = bwd_kernel<2>(0);
+    const void* kern = bwd_kernel<2, false>(0);
     MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<2>::B_SMEM));
     MGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Geo<2>::NTHREADS, (size_t)Geo<2>::B_SMEM));
     MGV_REQUIRE(occ >= 1, "level sweep: the tensor-core kernels do not fit on an SM");
@@ -805,12 +870,18 @@ int mgv_sweep_tc_bwd(const mgv_schedule* sch, unsigned handled, const int* cta_s
         if (!((handled >> c) & 1u) && sch->code_count[c] > 0) pull_only |= 1u << c;
     MGV_CUDA(cudaMemsetAsync(d.raw, 0, (size_t)MGV_NCODE * RAWF * sizeof(float), st));
     MGV_CUDA(cudaMemsetAsync(d.sds, 0, (size_t)sch->N * 8 * sizeof(float), st));      // every node is pulled exactly once and writes its row; belt and braces
-    const void* kern = d.S == 2 ? bwd_kernel<2>(precision) : bwd_kernel<1>(precision);
-    const size_t smem = d.S == 2 ? (size_t)Geo<2>::B_SMEM : (size_t)Geo<1>::B_SMEM;
-    const int threads = d.S == 2 ? Geo<2>::NTHREADS : Geo<1>::NTHREADS;
-    MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {&d, &pull_only};
-    MGV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, st));
+    if (d.S > MAX_STREAMS) {                              // many circuit sets: clusters walk them independently
+        MGV_REQUIRE(cluster_setup(d, sch, handled) > 0, "level sweep backward: no gate code to propagate");
+        rc = cluster_launch(bwd_kernel<1, true>(precision), Geo<1>::NTHREADS, (size_t)Geo<1>::B_SMEM, d.cl_size, d.S, args, st);
+        if (rc != MGV_OK) return rc;
+    } else {
+        const void* kern = d.S == 2 ? bwd_kernel<2, false>(precision) : bwd_kernel<1, false>(precision);
+        const size_t smem = d.S == 2 ? (size_t)Geo<2>::B_SMEM : (size_t)Geo<1>::B_SMEM;
+        const int threads = d.S == 2 ? Geo<2>::NTHREADS : Geo<1>::NTHREADS;
+        MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MGV_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, smem, st));
+    }
     {
         int sms = 148, dev = 0;
         cudaGetDevice(&dev);

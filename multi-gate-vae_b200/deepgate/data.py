@@ -96,14 +96,40 @@ def collate(circuits):
     return out
 
 
-SWEEP_STREAMS = 2          # independent circuit sets the level sweep runs concurrently (csrc/sweep_tc.cu)
+SM_COUNT = 148             # B200
+# Batches of at least this many circuits would run the level sweep in cluster mode.  Measured on B200 (cfg2: 64 AIG circuits of
+# 500-1500 gates, 19 levels): cluster mode 0.155 / 0.543 ms forward / backward against 0.144 / 0.463 ms with two streams in grid
+# mode -- without the grid barrier a level still costs one tile chain per circuit (~4 / 12 us), and a circuit's level is no
+# longer spread over several CTAs.  So the default keeps two streams; ``MGV_SWEEP_STREAMS=<n>`` selects cluster mode.
+CLUSTER_MIN_CIRCUITS = None
 
 
-def attach_streams(batch, counts, streams=SWEEP_STREAMS):
+def choose_streams(batch, counts):
+    """How many independent circuit sets ("streams") the level sweep gets (csrc/sweep_tc.cu):
+      * many circuits (the reference's training batches): one set per thread-block cluster -- a cluster of one CTA per gate
+        code walks its sets alone, levels separated by the hardware cluster barrier, no grid-wide synchronisation;
+      * few circuits: two sets whose level chains overlap inside every CTA, grid barrier per set and level;
+      * one circuit: a single stream.
+    ``MGV_SWEEP_STREAMS`` overrides (development knob; 1, 2 or a cluster-mode count > 2)."""
+    import os
+    n = len(counts)
+    env = os.environ.get("MGV_SWEEP_STREAMS")
+    if env:
+        return max(1, min(int(env), n))
+    if n < 2:
+        return 1
+    if CLUSTER_MIN_CIRCUITS is None or n < CLUSTER_MIN_CIRCUITS:
+        return 2
+    codes = sum(1 for c in getattr(batch, "level_code_count", [1, 1]) if c > 0) or 1
+    return max(3, min(n, SM_COUNT // codes))
+
+
+def attach_streams(batch, counts, streams=None):
     """Cut the circuits of a batch into ``streams`` sets of near-equal size (largest first onto the lighter set) and record the
     set of every node in ``batch.sweep_stream`` (int32 [N]).  Circuits never exchange messages, so the level sweep may run the
-    sets' level chains concurrently, each with its own barrier (mgv_b200.h, mgv_build_level_lists); the results do not depend
-    on the cut.  Batches of one circuit keep a single stream."""
+    sets' level chains independently (mgv_b200.h, mgv_build_level_lists); the results do not depend on the cut.  Batches of one
+    circuit keep a single stream."""
+    streams = choose_streams(batch, counts) if streams is None else streams
     if len(counts) < 2 or streams < 2:
         return batch
     load = [0] * streams

@@ -253,10 +253,8 @@ def schedule_for_batch(G, streams=None):
     n = int(G.gate.shape[0])
     sos = getattr(G, "sweep_stream", None)
     want = int(getattr(G, "sweep_streams", 1)) if (sos is not None and sos.numel() == n and sos.is_cuda) else 1
-    if streams is not None:
-        want = min(want, int(streams))
-    if os.environ.get("MGV_SWEEP_STREAMS"):                   # development knob: force the number of streams (1 or 2)
-        want = min(want, int(os.environ["MGV_SWEEP_STREAMS"]))
+    if want > 1 and streams is not None and int(streams) < want:
+        want = 1                                               # the cut cannot be coarsened here: plain (level, code) lists
     if (sch is not None and sch.N == n and sch.edge_index.data_ptr() == ei.data_ptr() and sch.E == ei.size(1)
             and sch.streams == want):
         return sch

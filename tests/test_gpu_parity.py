@@ -310,14 +310,19 @@ def test_async_schedule_equals_sync_schedule_and_flags_bad_input():
         GraphCSR(bad, G.x.size(0), code=G.gate.reshape(-1), validate=True)
 
 
-def test_sweep_result_does_not_depend_on_the_stream_cut():
-    """One stream (the reference's plain level order) and two circuit-set streams give the same embeddings bit for bit
-    (the arithmetic of a node does not depend on which stream runs it) and the same gradients up to summation order."""
+@pytest.mark.parametrize("cut", [2, 7, 3])
+def test_sweep_result_does_not_depend_on_the_stream_cut(cut, monkeypatch):
+    """One stream (the reference's plain level order), two circuit-set streams (grid mode) and one set per cluster (cluster mode:
+    7 sets = one circuit each, 3 sets = clusters walking several circuits per level) give the same embeddings (the arithmetic of a
+    node does not depend on which stream runs it) and the same gradients up to summation order."""
     import deepgate
     from deepgate import synth, ops
     from deepgate.schedule import schedule_for_batch
     from oracle import dg_oracle as O
+    monkeypatch.setenv("MGV_SWEEP_STREAMS", str(cut))
     host = deepgate.circuits_to_batch(synth.make_circuits("xmg", 7, 16, 700, cfg=41, window=40))
+    monkeypatch.delenv("MGV_SWEEP_STREAMS")
+    assert host.sched_streams == cut
     G = host.copy_to("cuda", non_blocking=False)
     enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, s_rounds=1, t_rounds=1, layernorm=True)
     model = deepgate.dg_ae_model_xmg.Model(struct_encoder=enc, num_rounds=1, dim_hidden=64)
@@ -329,7 +334,7 @@ def test_sweep_result_does_not_depend_on_the_stream_cut():
     hs0 = torch.randn(G.x.size(0), 64, device="cuda")
     gout = torch.randn(G.x.size(0), 64, device="cuda")
     res = []
-    for streams in (1, 2):
+    for streams in (1, cut):
         sch = schedule_for_batch(G, streams=streams)
         assert sch.streams == streams
         hs = hs0.clone().requires_grad_(True)

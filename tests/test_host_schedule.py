@@ -10,9 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "multi-gate-vae_b200"), ROOT]
 
 
-def test_merged_circuit_csr_equals_global_sort():
+def test_merged_circuit_csr_equals_global_sort(monkeypatch):
     import deepgate
     from deepgate import synth
+    monkeypatch.setenv("MGV_SWEEP_STREAMS", "9")       # cluster-mode cut: one circuit set per circuit
     b = deepgate.circuits_to_batch(synth.make_circuits("xmg", 9, (4, 12), (30, 300), cfg=71, window=25))
     n, E = b.x.size(0), b.edge_index.size(1)
     src, dst = b.edge_index[0], b.edge_index[1]
@@ -29,10 +30,11 @@ def test_merged_circuit_csr_equals_global_sort():
     assert torch.equal(b.sched_out_slot.long(), pos_in[by_src])
     # every out-edge's slot points at the matching in-edge entry
     assert torch.equal(b.sched_in_src.long()[b.sched_out_slot.long()], src[by_src])
-    L = b.num_levels
+    L, S = b.num_levels, b.sched_streams
+    assert S == 9
     key = (b.sweep_stream.long() * L + b.forward_level.long()) * 8 + code
-    assert b.sched_streams == 2 and torch.equal(b.sched_order.long(), torch.sort(key, stable=True).indices)
-    assert torch.equal(b.sched_seg_ptr.long(), torch.cat([key.new_zeros(1), torch.bincount(key, minlength=2 * L * 8).cumsum(0)]))
+    assert torch.equal(b.sched_order.long(), torch.sort(key, stable=True).indices)
+    assert torch.equal(b.sched_seg_ptr.long(), torch.cat([key.new_zeros(1), torch.bincount(key, minlength=S * L * 8).cumsum(0)]))
     indeg = torch.bincount(dst, minlength=n)
     assert torch.equal(b.sched_deg_order_in.long(), torch.sort(255 - indeg.clamp(max=255), stable=True).indices)
     outdeg = torch.bincount(src, minlength=n)
@@ -53,3 +55,13 @@ def test_streams_cut_whole_circuits_evenly():
     assert abs(sizes[0] - sizes[1]) <= biggest
     one = deepgate.circuits_to_batch(synth.make_circuits("aig", 1, 8, 50, cfg=73))
     assert getattr(one, "sweep_stream", None) is None and one.sched_streams == 1
+    # a cluster-mode cut (more than two sets) of many circuits stays balanced
+    import os
+    os.environ["MGV_SWEEP_STREAMS"] = "37"
+    try:
+        many = deepgate.circuits_to_batch(synth.make_circuits("aig", 100, 8, (20, 60), cfg=74))
+    finally:
+        del os.environ["MGV_SWEEP_STREAMS"]
+    assert many.sched_streams == 37 and int(many.sweep_stream.max()) == 36
+    sizes = torch.bincount(many.sweep_stream.long())
+    assert int(sizes.max()) - int(sizes.min()) <= int((many.ptr[1:] - many.ptr[:-1]).max())
