@@ -182,8 +182,8 @@ def pick_sample(w, budget_s=20.0):
 def run_reference(args, w):
     """The reference's CPU path (oracle port with the reference's literal per-node ``subgraph`` loop) on the host cores, on the
     SAME batch the B200 arm times.  Every timed step runs the full batch when the whole run then fits the time budget
-    (calibrated from a quarter-batch warm-up step, cost ~ nodes^2); otherwise the first step is the full batch and the rest a
-    bounded sample, and ``sample`` says so."""
+    (calibrated by one untimed full-batch step); otherwise the first steps are the full batch and the rest a bounded sample,
+    and ``sample`` says so."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -193,10 +193,9 @@ def run_reference(args, w):
     P = cpu_params(w["kind"])
     full = w["batch"]
     quarter = max(1, full // 4)
-    est_full = None
-    for _ in range(max(args.warmup, 1)):
-        dt, _g = cpu_step(w["kind"], P, hb, w["rounds"], quarter)
-        est_full = dt * (hb.ptr[full].item() / max(hb.ptr[quarter].item(), 1)) ** 2
+    for _ in range(max(args.warmup - 1, 0)):              # warm-up: quarter batches, then ONE full batch that calibrates the budget
+        cpu_step(w["kind"], P, hb, w["rounds"], quarter)
+    est_full, _g = cpu_step(w["kind"], P, hb, w["rounds"], full)
     budget = float(os.environ.get("MGV_REF_BUDGET_S", 240.0))
     n_full = max(1, min(args.steps, int(budget / max(est_full, 1e-3))))
     ns_rest = full if n_full == args.steps else pick_sample(w, max(1.0, (budget - n_full * est_full) / max(args.steps - n_full, 1)))
@@ -409,6 +408,9 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
 
     def traffic_of(*kerns):
         """DRAM bytes per launch from the committed ncu --set full captures of this workload (else None)."""
+        joined = traffic_table.get("+".join(kerns))
+        if joined:
+            return joined["dram_read_bytes"] + joined["dram_write_bytes"]
         tot = 0
         for k in kerns:
             ent = traffic_table.get(k)

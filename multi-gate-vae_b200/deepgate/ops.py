@@ -117,7 +117,7 @@ class LevelSweepFunction(torch.autograd.Function):
         prec = _prec()
         pack = _sweep_pack(params, codes, dev, prec)
         hf_all = torch.zeros(rounds, max(N, 1), nat.D, dtype=torch.float32, device=dev)
-        sync = torch.zeros(64, dtype=torch.int32, device=dev)
+        sync = torch.empty(64, dtype=torch.int32, device=dev)          # zeroed by the call
         with nat.on_device(dev):
             with _timed("level_sweep_fwd", dev):
               nat.check(lib.mgv_level_sweep_fwd(sched.c_struct(), rounds, mask, nat.ptr(pack), nat.ptr(hs_c),
@@ -137,10 +137,12 @@ class LevelSweepFunction(torch.autograd.Function):
         dev = hs_c.device
         N, D = sched.N, nat.D
         ghs = torch.zeros(max(N, 1), D, dtype=torch.float32, device=dev)
-        ghf = torch.zeros(max(N, 1), D, dtype=torch.float32, device=dev)
-        ghf[:N] = g_hf
+        if N > 0:
+            ghf = g_hf.to(torch.float32).contiguous().clone()             # in/out for the library: a private copy
+        else:
+            ghf = torch.zeros(1, D, dtype=torch.float32, device=dev)
         grads = torch.empty(nat.NCODE, nat.SWEEP_GRAD_FLOATS, dtype=torch.float32, device=dev)
-        sync = torch.zeros(64, dtype=torch.int32, device=dev)
+        sync = torch.empty(64, dtype=torch.int32, device=dev)          # zeroed by the call
         with nat.on_device(dev):
             nb = lib.mgv_sweep_bwd_workspace_bytes(N, sched.E)
             ws = nat.workspace(nb, dev)
