@@ -325,6 +325,16 @@ size_t mgv_linear_wgrad_workspace_bytes(int64_t N, int32_t I, int32_t O);
 int mgv_linear_wgrad(const float* x, const float* gy, int64_t N, int32_t I, int32_t O, float* dW, float* db,
                      void* ws, size_t ws_bytes, mgv_stream_t stream);
 
+/* Forward and data gradient of the same layers on the tensor cores (csrc/linear_tc.cu; fp16 hi/lo planes, fp32-accurate):
+ *     out[N][P] = in[N][Q] . M[P][Q]^T (+ bias[P]),  P, Q in {64, 128}
+ *   transposed = 0: M = W, W given as [P][Q]  (y = x W^T + b: P = out features, Q = in features)
+ *   transposed = 1: M = W^T, W given as [Q][P]  (gx = gy W: P = in features, Q = out features; bias NULL)
+ * Replaces torch.addmm / AddmmBackward's data GEMM (cuBLAS fp32 SIMT, 37 us at N = 65 818) for hs_linear, hs_decompose and the
+ * four Linear layers of DirectedGVAE.sample (digvae_model.py:105-142).
+ */
+int mgv_linear_tc(const float* in, int64_t N, const float* W, const float* bias, int32_t P, int32_t Q, int32_t transposed,
+                  float* out, mgv_stream_t stream);
+
 int mgv_tc_selftest(int32_t mode, const float* A, const float* B, float* D, int32_t K, int32_t N, mgv_stream_t stream);
 
 #define MGV_OK 0

@@ -86,6 +86,7 @@ _PROTOTYPES = {
                                        _vp, _vp, _vp, _sz, _vp, _vp]),
     "mgv_linear_wgrad_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mgv_linear_wgrad": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "mgv_linear_tc": (ctypes.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "mgv_tc_selftest": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i32, _i32, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -8,6 +8,7 @@ Every function fails loudly when its inputs are not on a CUDA device or the libr
 missing; nothing here falls back to PyTorch ops for the arithmetic.
 """
 import ctypes
+import os
 
 import torch
 
@@ -153,14 +154,18 @@ class LevelSweepFunction(torch.autograd.Function):
                       "mgv_level_sweep_bwd")
         sel = _sweep_tables(params, codes)
         extra = torch.empty(max(len(codes), 1), 128 + D * 2 * D, dtype=torch.float32, device=dev)
-        zero = torch.zeros(D * 2 * D, dtype=torch.float32, device=dev)     # query / key-bias / attn-bias cancel in the softmax
+        # query / key-bias / attn-bias cancel in the softmax: exact zeros, one DISJOINT slice per parameter (gradients must not alias)
+        ZQ = 1 + D * 2 * D + 2 * D
+        zero = torch.zeros(max(len(codes), 1), ZQ, dtype=torch.float32, device=dev)
         with nat.on_device(dev):
             nat.check(lib.mgv_sweep_unpack_grads(_ptr_table(sel), _code_table(list(codes)), len(codes), nat.ptr(grads),
                                                  nat.ptr(extra), nat.stream_of(dev)), "mgv_sweep_unpack_grads")
         out = []
         for i, c in enumerate(codes):
             g = grads[c]
-            out += [extra[i, :128].view(1, 2 * D), zero[:1], zero.view(D, 2 * D), zero[:D], extra[i, 128:].view(D, 2 * D), zero[:D],
+            z = zero[i]
+            out += [extra[i, :128].view(1, 2 * D), z[:1], z[1:1 + D * 2 * D].view(D, 2 * D), z[1 + D * 2 * D:1 + D * 2 * D + D],
+                    extra[i, 128:].view(D, 2 * D), z[1 + D * 2 * D + D:],
                     g[128:8320].view(D, 2 * D), g[8320:8384],
                     g[8384:20672].view(3 * D, D), g[20672:32960].view(3 * D, D), g[32960:33152], g[33152:33344]]
         return (ghs[:N], None, None, None) + tuple(out)
@@ -178,9 +183,26 @@ def level_sweep(hs, sched, rounds, codes, modules):
 
 
 # =========================================================================== small Linear layers (one row per node)
+def _linear_tc(inp, weight, bias, P, Q, transposed):
+    """out[N][P] = inp[N][Q] . M[P][Q]^T (+ bias) on the tensor cores (csrc/linear_tc.cu)."""
+    dev = inp.device
+    N = inp.shape[0]
+    out = torch.empty(N, P, dtype=torch.float32, device=dev)
+    lib = nat.lib()
+    with nat.on_device(dev), _timed("linear_tc", dev):
+        nat.check(lib.mgv_linear_tc(nat.ptr(inp), N, nat.ptr(weight), nat.ptr(bias), P, Q, int(transposed), nat.ptr(out),
+                                    nat.stream_of(dev)), "mgv_linear_tc")
+    return out
+
+
+def _tc_shape(weight):
+    return weight.shape[0] in (64, 128) and weight.shape[1] in (64, 128) and not os.environ.get("MGV_LINEAR_TORCH")
+
+
 class LinearFunction(torch.autograd.Function):
-    """y = x W^T + b.  Forward and d x are library GEMMs (N x O x I, parallel over the nodes); d W / d b sum over the
-    NODES into at most 128 x 128 outputs -- one tile on one SM for a library GEMM -- and run in csrc/linear.cu."""
+    """y = x W^T + b.  Forward and d x: tcgen05 tiles over the nodes (csrc/linear_tc.cu) for 64 / 128-wide layers, library
+    GEMMs otherwise; d W / d b sum over the NODES into at most 128 x 128 outputs -- one tile on one SM for a library GEMM --
+    and run in csrc/linear.cu."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -188,6 +210,9 @@ class LinearFunction(torch.autograd.Function):
         x_c = _f32(x, "x")
         ctx.save_for_backward(x_c, weight)
         ctx.has_bias = bias is not None
+        if _tc_shape(weight) and x_c.shape[0] > 0:
+            O, I = weight.shape
+            return _linear_tc(x_c, _f32(weight, "weight"), None if bias is None else _f32(bias, "bias"), O, I, False)
         return torch.addmm(bias, x_c, weight.t()) if bias is not None else x_c @ weight.t()
 
     @staticmethod
@@ -197,7 +222,12 @@ class LinearFunction(torch.autograd.Function):
         gy_c = _f32(gy, "gy")
         O, I = weight.shape
         N = x_c.shape[0]
-        gx = gy_c @ weight if ctx.needs_input_grad[0] else None
+        if not ctx.needs_input_grad[0]:
+            gx = None
+        elif _tc_shape(weight) and N > 0:
+            gx = _linear_tc(gy_c, _f32(weight, "weight"), None, I, O, True)
+        else:
+            gx = gy_c @ weight
         dW = torch.empty_like(weight, dtype=torch.float32)
         db = torch.empty(O, dtype=torch.float32, device=dev) if ctx.has_bias else None
         lib = nat.lib()

@@ -1,4 +1,5 @@
-"""csrc/linear.cu (weight / bias gradient of the per-node nn.Linear layers) against torch.autograd in float64."""
+"""csrc/linear.cu (weight / bias gradient of the per-node nn.Linear layers) and csrc/linear_tc.cu (their forward and data
+gradient on the tensor cores, 64 / 128-wide layers) against torch.autograd in float64."""
 import pytest
 import torch
 
@@ -6,7 +7,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("N,I,O,bias", [(1000, 128, 64, True), (4097, 64, 128, True), (777, 64, 32, True), (5000, 32, 32, True),
-                                        (3001, 32, 1, True), (33, 70, 17, False), (1, 6, 3, True)])
+                                        (3001, 32, 1, True), (33, 70, 17, False), (1, 6, 3, True),
+                                        # tensor-core shapes: one row, a ragged last tile, more tiles than SMs, no bias
+                                        (1, 64, 64, True), (129, 128, 128, True), (65818, 128, 64, True), (40000, 64, 128, False),
+                                        (300, 64, 64, False)])
 def test_linear_matches_autograd(N, I, O, bias):
     from deepgate import ops
     g = torch.Generator().manual_seed(N + I + O)
@@ -26,6 +30,21 @@ def test_linear_matches_autograd(N, I, O, bias):
     assert float((lin.weight.grad.double() - wd.grad).abs().max()) <= tol * max(1.0, float(wd.grad.abs().max()))
     if bias:
         assert float((lin.bias.grad.double() - bd.grad).abs().max()) <= tol * max(1.0, float(bd.grad.abs().max()))
+
+
+def test_tensor_core_path_is_taken_and_matches_the_library_path(monkeypatch):
+    from deepgate import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5000, 128, generator=g).cuda()
+    lin = ops.Linear(128, 64).cuda()
+    ops.PROFILE = {}
+    y = lin(x)
+    torch.cuda.synchronize()
+    assert "linear_tc" in ops.PROFILE
+    ops.PROFILE = None
+    monkeypatch.setenv("MGV_LINEAR_TORCH", "1")
+    y_lib = lin(x)
+    assert float((y - y_lib).abs().max()) <= 2e-6 * float(y_lib.abs().max())
 
 
 def test_linear_state_dict_keys_are_nn_linear():
