@@ -400,6 +400,8 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
             ach = mean_stats[key] * (w["rounds"] if "sweep" in name else 1) / (avg_launch_ms * 1e-3) / 1e9
             kernels[kern] = {"ms_per_step": tot / steps, "avg_launch_ms": avg_launch_ms, "launches_per_step": nl,
                              "achieved_gbs": ach, "frac": ach / peak}
+    # every other library call that is bracketed by events (one or two launches each): ms per step
+    other = {name: tot / steps for name, (calls, tot) in prof.items() if name not in per_launch and calls > 0}
     traffic_table = {}
     try:
         traffic_table = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(wname, {})
@@ -468,7 +470,7 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
                          % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},
         "e2e": {"value": e2e, "unit": "gates/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "other_calls_ms_per_step": other,
         "level_sweep": sweep, "cpu_baseline": cpu}
     # free this workload's device memory before the next one is measured
     del trainer, model, resident, host

@@ -44,6 +44,7 @@ struct RdBwd {
     float* gx;                             // [N][64] out
     float* grads;                          // flat out (zeroed by the host): see mgv_b200.h
     float* dz1;                            // [N][32] scratch
+    float* partial;                        // [blocks][3297] per-block parameter-gradient partial sums
     double* acc;                           // [4][32]: S2a, S2b, S1a, S1b
     unsigned* bar;
 };
@@ -51,11 +52,12 @@ constexpr int G_W1 = 0, G_B1 = 2048, G_G1 = 2080, G_BE1 = 2112, G_W2 = 2144, G_B
 
 __device__ __forceinline__ float keep_scale(unsigned long long seed, long long n, int layer, int c, float p, float sc) {
     if (p <= 0.f) return 1.0f;
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(n * 64 + layer * 32 + c + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+    // counter-based: murmur3's 32-bit finaliser over the element index, keyed by both halves of the seed
+    uint32_t h = (uint32_t)(n * 64 + layer * 32 + c) ^ (uint32_t)seed;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    h += (uint32_t)(seed >> 32) + (uint32_t)(n >> 26);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
     return u >= p ? sc : 0.f;
 }
 __device__ __forceinline__ float warp_sum(float v) {
@@ -85,7 +87,7 @@ __device__ __forceinline__ float dot32(float h, const float (&w)[DH], float b) {
     return a0 + a1;
 }
 
-__global__ void __launch_bounds__(RD_THREADS) readout_fwd_kernel(const RdFwd p) {
+__global__ void __launch_bounds__(RD_THREADS, 2) readout_fwd_kernel(const RdFwd p) {
     __shared__ __align__(16) float xs[RD_WARPS][NB][DI];
     __shared__ double red[RD_WARPS][2][DH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,16 +145,24 @@ __global__ void __launch_bounds__(RD_THREADS) readout_fwd_kernel(const RdFwd p) 
     for (int j = 0; j < DH; ++j) w2[j] = __ldg(P.W2 + lane * DH + j);
     const float g1 = __ldg(P.g1 + lane) * is1, o1 = __ldg(P.be1 + lane) - mean1 * g1, b2 = __ldg(P.b2 + lane);
     s = 0.0; q = 0.0;
-    for (long long n = gw * NB; n < p.N; n = ((n + 1) % NB) ? n + 1 : n + 1 + (nw - 1) * NB) {
-        const float y1 = p.saved[n * 64 + lane];
-        const float k1 = train ? keep_scale(p.seed, n, 0, lane, p.p_drop, sc) : 1.0f;
-        const float h1 = fmaxf(fmaf(y1, g1, o1), 0.f) * k1;
-        const float y2 = dot32(h1, w2, b2);
-        p.saved[n * 64 + DH + lane] = y2;
-        s += (double)y2; q += (double)y2 * (double)y2;
-        if (p.mask) {
-            const unsigned bits = __ballot_sync(0xffffffffu, k1 != 0.f);
-            if (lane == 0) p.mask[n * 2] = bits;
+    for (long long n0 = gw * NB; n0 < p.N; n0 += nw * NB) {        // four nodes per trip: their loads and hashes overlap
+        float y1[NB], k1[NB], y2[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) y1[i] = (n0 + i < p.N) ? p.saved[(n0 + i) * 64 + lane] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) k1[i] = train ? keep_scale(p.seed, n0 + i, 0, lane, p.p_drop, sc) : 1.0f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) y2[i] = dot32(fmaxf(fmaf(y1[i], g1, o1), 0.f) * k1[i], w2, b2);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (n0 + i < p.N) {
+                p.saved[(n0 + i) * 64 + DH + lane] = y2[i];
+                s += (double)y2[i]; q += (double)y2[i] * (double)y2[i];
+            }
+            if (p.mask) {
+                const unsigned bits = __ballot_sync(0xffffffffu, k1[i] != 0.f);
+                if (lane == 0 && n0 + i < p.N) p.mask[(n0 + i) * 2] = bits;
+            }
         }
     }
     float mean2, is2;
@@ -182,19 +192,30 @@ __global__ void __launch_bounds__(RD_THREADS) readout_fwd_kernel(const RdFwd p) 
     // ------------------------------------------------------------------ pass 3: h2 -> y3 -> clamp -> |pred - target|
     const float g2 = __ldg(P.g2 + lane) * is2, o2 = __ldg(P.be2 + lane) - mean2 * g2, w3 = __ldg(P.W3 + lane), b3 = __ldg(P.b3);
     double lsum = 0.0;
-    for (long long n = gw * NB; n < p.N; n = ((n + 1) % NB) ? n + 1 : n + 1 + (nw - 1) * NB) {
-        const float y2 = p.saved[n * 64 + DH + lane];
-        const float k2 = train ? keep_scale(p.seed, n, 1, lane, p.p_drop, sc) : 1.0f;
-        const float h2 = fmaxf(fmaf(y2, g2, o2), 0.f) * k2;
-        const float y3 = warp_sum(h2 * w3) + b3;
-        const float pr = fminf(fmaxf(y3, 0.f), 1.f);
-        if (p.mask) {
-            const unsigned bits = __ballot_sync(0xffffffffu, k2 != 0.f);
-            if (lane == 0) p.mask[n * 2 + 1] = bits;
-        }
-        if (lane == 0) {
-            p.pred[n] = pr;
-            if (p.target) lsum += (double)fabsf(pr - __ldg(p.target + n));
+    for (long long n0 = gw * NB; n0 < p.N; n0 += nw * NB) {
+        float y2[NB], k2[NB], y3[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) y2[i] = (n0 + i < p.N) ? p.saved[(n0 + i) * 64 + DH + lane] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) k2[i] = train ? keep_scale(p.seed, n0 + i, 1, lane, p.p_drop, sc) : 1.0f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) y3[i] = fmaxf(fmaf(y2[i], g2, o2), 0.f) * k2[i] * w3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < NB; ++i) y3[i] += __shfl_xor_sync(0xffffffffu, y3[i], o);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const long long n = n0 + i;
+            const float pr = fminf(fmaxf(y3[i] + b3, 0.f), 1.f);
+            if (p.mask) {
+                const unsigned bits = __ballot_sync(0xffffffffu, k2[i] != 0.f);
+                if (lane == 0 && n < p.N) p.mask[n * 2 + 1] = bits;
+            }
+            if (lane == 0 && n < p.N) {
+                p.pred[n] = pr;
+                if (p.target) lsum += (double)fabsf(pr - __ldg(p.target + n));
+            }
         }
     }
     if (p.target) {
@@ -211,21 +232,39 @@ __global__ void __launch_bounds__(RD_THREADS) readout_fwd_kernel(const RdFwd p) 
     }
 }
 
-// Adds a warp's per-lane accumulators to the block's shared array, then the block's array to global memory.
-__device__ __forceinline__ void block_accumulate(float* sh, int idx, float v) { atomicAdd(sh + idx, v); }
+// Sum of every warp's per-lane accumulators v[NV] over the RD_WARPS warps of the block, as a tree through `scratch`
+// ([RD_WARPS / 2][NV][32] floats): three rounds of (upper half writes, lower half adds) instead of RD_WARPS serial turns or
+// shared-memory float atomics (CAS loops).  Afterwards warp 0 holds the block sums.  Deterministic.
+template <int NV>
+__device__ __forceinline__ void block_tree_add(float (&v)[NV], float* scratch, int warp, int lane) {
+#pragma unroll 1
+    for (int half = RD_WARPS / 2; half >= 1; half >>= 1) {
+        if (warp >= half && warp < 2 * half) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) scratch[((warp - half) * NV + i) * 32 + lane] = v[i];
+        }
+        __syncthreads();
+        if (warp < half) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[i] += scratch[(warp * NV + i) * 32 + lane];
+        }
+        __syncthreads();
+    }
+}
+constexpr int RD_SCRATCH_BYTES = (RD_WARPS / 2) * 65 * 32 * 4;          // pass C: d W1 row (64) + d b1 per lane
 
-__global__ void __launch_bounds__(RD_THREADS) readout_bwd_kernel(const RdBwd p) {
+__global__ void __launch_bounds__(RD_THREADS, 2) readout_bwd_kernel(const RdBwd p) {
     __shared__ __align__(16) float xs[RD_WARPS][NB][DI];
     __shared__ __align__(16) float W1s[DH][DI];
-    __shared__ float gsh[3297];
     __shared__ double red[RD_WARPS][2][DH];
+    extern __shared__ __align__(16) float scratch[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * RD_WARPS + warp, nw = (long long)gridDim.x * RD_WARPS;
     const RdParams& P = p.P;
     const bool train = p.training != 0;
     const float sc = (train && p.p_drop > 0.f) ? 1.0f / (1.0f - p.p_drop) : 1.0f;
     const float pd = train ? p.p_drop : 0.f;
-    for (int i = threadIdx.x; i < 3297; i += RD_THREADS) gsh[i] = 0.f;
+    float* part = p.partial + (size_t)blockIdx.x * 3297;        // this block's parameter-gradient partial sums
     for (int i = threadIdx.x; i < DH * DI; i += RD_THREADS) W1s[i / DI][i % DI] = __ldg(P.W1 + i);
     __syncthreads();
     const float mean1 = p.stats[lane], is1 = p.stats[DH + lane], mean2 = p.stats[2 * DH + lane], is2 = p.stats[3 * DH + lane];
@@ -234,37 +273,66 @@ __global__ void __launch_bounds__(RD_THREADS) readout_bwd_kernel(const RdBwd p) 
     const float gl = p.g_loss ? __ldg(p.g_loss) / (float)(p.N > 0 ? p.N : 1) : 0.f;
     const double invN = 1.0 / (double)(p.N > 0 ? p.N : 1);
 
-    // d z2 of node n (the gradient at the second BatchNorm's output, after ReLU / dropout), with xhat2 and h2
-    auto dz2_of = [&](long long n, float& xh2, float& h2, float& dp) -> float {
-        const float y2 = p.saved[n * 64 + DH + lane];
-        xh2 = (y2 - mean2) * is2;
-        const float a2 = fmaf(xh2, g2, be2);
-        const float k2 = keep_scale(p.seed, n, 1, lane, pd, sc);
-        h2 = fmaxf(a2, 0.f) * k2;
-        const float y3 = warp_sum(h2 * w3) + b3;
-        const float pr = fminf(fmaxf(y3, 0.f), 1.f);
-        float d = p.g_pred ? __ldg(p.g_pred + n) : 0.f;
-        if (p.target) {
-            const float diff = pr - __ldg(p.target + n);
-            d += gl * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
+    // d z2 of the NB nodes n0 .. (the gradient at the second BatchNorm's output, after ReLU / dropout), with xhat2, h2 and d pred;
+    // the nodes' loads, hashes and reductions are interleaved (independent dependency chains)
+    auto dz2_group = [&](long long n0, float (&xh2)[NB], float (&h2)[NB], float (&dp)[NB], float (&dz2)[NB]) {
+        float y2[NB], k2[NB], d[NB], tg[NB], a2[NB], y3[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const long long n = n0 + i;
+            const bool ok = n < p.N;
+            y2[i] = ok ? p.saved[n * 64 + DH + lane] : 0.f;
+            d[i] = (ok && p.g_pred) ? __ldg(p.g_pred + n) : 0.f;
+            tg[i] = (ok && p.target) ? __ldg(p.target + n) : 0.f;
         }
-        dp = (y3 >= 0.f && y3 <= 1.f) ? d : 0.f;
-        return a2 > 0.f ? dp * w3 * k2 : 0.f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) k2[i] = keep_scale(p.seed, n0 + i, 1, lane, pd, sc);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            xh2[i] = (y2[i] - mean2) * is2;
+            a2[i] = fmaf(xh2[i], g2, be2);
+            h2[i] = fmaxf(a2[i], 0.f) * k2[i];
+            y3[i] = h2[i] * w3;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < NB; ++i) y3[i] += __shfl_xor_sync(0xffffffffu, y3[i], o);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const float y = y3[i] + b3;
+            const float pr = fminf(fmaxf(y, 0.f), 1.f);
+            float dd = d[i];
+            if (p.target) {
+                const float diff = pr - tg[i];
+                dd += gl * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
+            }
+            dp[i] = (n0 + i < p.N && y >= 0.f && y <= 1.f) ? dd : 0.f;
+            dz2[i] = a2[i] > 0.f ? dp[i] * w3 * k2[i] : 0.f;
+        }
     };
     // ------------------------------------------------------------------ pass A: d W3, d b3, sums of the second BatchNorm
     {
         double sa = 0.0, sb = 0.0;
         float dw3 = 0.f, db3 = 0.f;
-        for (long long n = gw * NB; n < p.N; n = ((n + 1) % NB) ? n + 1 : n + 1 + (nw - 1) * NB) {
-            float xh2, h2, dp;
-            const float dz2 = dz2_of(n, xh2, h2, dp);
-            dw3 = fmaf(dp, h2, dw3); db3 += dp;
-            sa += (double)dz2; sb += (double)dz2 * (double)xh2;
+        for (long long n0 = gw * NB; n0 < p.N; n0 += nw * NB) {
+            float xh2[NB], h2[NB], dp[NB], dz2[NB];
+            dz2_group(n0, xh2, h2, dp, dz2);
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                dw3 = fmaf(dp[i], h2[i], dw3); db3 += dp[i];
+                sa += (double)dz2[i]; sb += (double)dz2[i] * (double)xh2[i];
+            }
         }
-        block_accumulate(gsh, G_W3 + lane, dw3);
-        if (lane == 0) block_accumulate(gsh, G_B3, db3);
-        block_accumulate(gsh, G_BE2 + lane, (float)sa);
-        block_accumulate(gsh, G_G2 + lane, (float)sb);
+        {
+            float v[4] = {dw3, db3, (float)sa, (float)sb};
+            block_tree_add<4>(v, scratch, warp, lane);
+            if (warp == 0) {
+                part[G_W3 + lane] = v[0];
+                if (lane == 0) part[G_B3] = v[1];              // d pred is warp-uniform: every lane holds the same sum
+                part[G_BE2 + lane] = v[2]; part[G_G2 + lane] = v[3];
+            }
+        }
         red[warp][0][lane] = sa; red[warp][1][lane] = sb;
         __syncthreads();
         if (warp == 0) {
@@ -282,33 +350,53 @@ __global__ void __launch_bounds__(RD_THREADS) readout_bwd_kernel(const RdBwd p) 
         for (int c = 0; c < DH; ++c) { w2t[c] = __ldg(P.W2 + c * DH + lane); dw2[c] = 0.f; }
         float db2 = 0.f;
         double sa = 0.0, sb = 0.0;
-        for (long long n = gw * NB; n < p.N; n = ((n + 1) % NB) ? n + 1 : n + 1 + (nw - 1) * NB) {
-            float xh2, h2, dp;
-            const float dz2 = dz2_of(n, xh2, h2, dp);
-            const float dy2 = g2 * is2 * (dz2 - s2a - xh2 * s2b);
-            db2 += dy2;
-            const float y1 = p.saved[n * 64 + lane];
-            const float xh1 = (y1 - mean1) * is1;
-            const float a1 = fmaf(xh1, g1, be1);
-            const float k1 = keep_scale(p.seed, n, 0, lane, pd, sc);
-            const float h1 = fmaxf(a1, 0.f) * k1;
-            float dh1 = 0.f;
+        for (long long n0 = gw * NB; n0 < p.N; n0 += nw * NB) {
+            float xh2[NB], h2[NB], dp[NB], dz2[NB];
+            float y1[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) y1[i] = (n0 + i < p.N) ? p.saved[(n0 + i) * 64 + lane] : 0.f;
+            dz2_group(n0, xh2, h2, dp, dz2);
+            float dy2[NB], xh1[NB], a1[NB], k1[NB], h1[NB], dh1[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                dy2[i] = (n0 + i < p.N) ? g2 * is2 * (dz2[i] - s2a - xh2[i] * s2b) : 0.f;
+                db2 += dy2[i];
+                xh1[i] = (y1[i] - mean1) * is1;
+                a1[i] = fmaf(xh1[i], g1, be1);
+                k1[i] = keep_scale(p.seed, n0 + i, 0, lane, pd, sc);
+                h1[i] = fmaxf(a1[i], 0.f) * k1[i];
+                dh1[i] = 0.f;
+            }
 #pragma unroll
             for (int c = 0; c < DH; ++c) {
-                const float dyc = __shfl_sync(0xffffffffu, dy2, c);
-                dh1 = fmaf(dyc, w2t[c], dh1);                  // d h1[lane] = sum_c d y2[c] W2[c][lane]
-                dw2[c] = fmaf(dyc, h1, dw2[c]);                // d W2[c][lane] += d y2[c] h1[lane]
-            }
-            const float dz1 = a1 > 0.f ? dh1 * k1 : 0.f;
-            p.dz1[n * DH + lane] = dz1;
-            sa += (double)dz1; sb += (double)dz1 * (double)xh1;
-        }
 #pragma unroll
-        for (int c = 0; c < DH; ++c) block_accumulate(gsh, G_W2 + c * DH + lane, dw2[c]);
-        block_accumulate(gsh, G_B2 + lane, db2);
-        block_accumulate(gsh, G_BE1 + lane, (float)sa);
-        block_accumulate(gsh, G_G1 + lane, (float)sb);
-        __syncthreads();
+                for (int i = 0; i < NB; ++i) {
+                    const float dyc = __shfl_sync(0xffffffffu, dy2[i], c);
+                    dh1[i] = fmaf(dyc, w2t[c], dh1[i]);            // d h1[lane] = sum_c d y2[c] W2[c][lane]
+                    dw2[c] = fmaf(dyc, h1[i], dw2[c]);             // d W2[c][lane] += d y2[c] h1[lane]
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                if (n0 + i < p.N) {
+                    const float dz1 = a1[i] > 0.f ? dh1[i] * k1[i] : 0.f;
+                    p.dz1[(n0 + i) * DH + lane] = dz1;
+                    sa += (double)dz1; sb += (double)dz1 * (double)xh1[i];
+                }
+            }
+        }
+        {
+            float v[DH + 3];
+#pragma unroll
+            for (int c = 0; c < DH; ++c) v[c] = dw2[c];
+            v[DH] = db2; v[DH + 1] = (float)sa; v[DH + 2] = (float)sb;
+            block_tree_add<DH + 3>(v, scratch, warp, lane);
+            if (warp == 0) {
+#pragma unroll
+                for (int c = 0; c < DH; ++c) part[G_W2 + c * DH + lane] = v[c];
+                part[G_B2 + lane] = v[DH]; part[G_BE1 + lane] = v[DH + 1]; part[G_G1 + lane] = v[DH + 2];
+            }
+        }
         red[warp][0][lane] = sa; red[warp][1][lane] = sb;
         __syncthreads();
         if (warp == 0) {
@@ -354,14 +442,25 @@ __global__ void __launch_bounds__(RD_THREADS) readout_bwd_kernel(const RdBwd p) 
             }
             __syncwarp();
         }
+        {
+            float v[DI + 1];
 #pragma unroll
-        for (int k = 0; k < DI; ++k) block_accumulate(gsh, G_W1 + lane * DI + k, dw1[k]);
-        block_accumulate(gsh, G_B1 + lane, db1);
+            for (int k = 0; k < DI; ++k) v[k] = dw1[k];
+            v[DI] = db1;
+            block_tree_add<DI + 1>(v, scratch, warp, lane);
+            if (warp == 0) {
+#pragma unroll
+                for (int k = 0; k < DI; ++k) part[G_W1 + lane * DI + k] = v[k];
+                part[G_B1 + lane] = v[DI];
+            }
+        }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3297; i += RD_THREADS) {
-        const float v = gsh[i];
-        if (v != 0.f) atomicAdd(p.grads + i, v);
+    // per-block partial sums are in global memory (no atomics): every gradient element is summed over the blocks
+    mgv_grid_sync(p.bar, gridDim.x);
+    for (int i = blockIdx.x * RD_THREADS + threadIdx.x; i < 3297; i += gridDim.x * RD_THREADS) {
+        float t = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(p.partial + (size_t)b * 3297 + i);
+        p.grads[i] = t;
     }
 }
 
@@ -376,11 +475,12 @@ int fill_params(RdParams& P, const void* const* params) {
     return MGV_OK;
 }
 
-int coop_blocks(const void* kern, long long N, int* out) {
+int coop_blocks(const void* kern, long long N, int* out, size_t dyn_smem = 0) {
     int dev = 0, sms = 0, occ = 0;
     MGV_CUDA(cudaGetDevice(&dev));
     MGV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    MGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RD_THREADS, 0));
+    if (dyn_smem) MGV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    MGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RD_THREADS, dyn_smem));
     MGV_REQUIRE(occ >= 1, "readout: kernel does not fit on an SM");
     long long want = (N + RD_WARPS * NB - 1) / (RD_WARPS * NB);
     const long long cap = (long long)sms * (occ > 2 ? 2 : occ);
@@ -390,8 +490,10 @@ int coop_blocks(const void* kern, long long N, int* out) {
 
 }  // namespace
 
+constexpr int RD_MAX_BLOCKS = 1024;        // upper bound of the cooperative grid (2 blocks per SM)
 extern "C" size_t mgv_readout_workspace_bytes(int64_t N) {
-    return mgv_align_up((size_t)(N > 0 ? N : 1) * DH * 4 + 256, 256) + mgv_align_up(192 * sizeof(double), 256) + 1024;
+    return mgv_align_up((size_t)(N > 0 ? N : 1) * DH * 4 + 256, 256) + mgv_align_up(192 * sizeof(double), 256) +
+           mgv_align_up((size_t)RD_MAX_BLOCKS * 3297 * 4 + 256, 256) + 1024;
 }
 
 extern "C" int mgv_readout_fwd(const float* x, int64_t N, const void* const* params, int32_t training, float p_drop, uint64_t seed,
@@ -439,18 +541,22 @@ extern "C" int mgv_readout_bwd(const float* x, int64_t N, const void* const* par
     MgvArena a(ws, ws_bytes);
     p.dz1 = a.take<float>((size_t)(N > 0 ? N : 1) * DH);
     p.acc = a.take<double>(192);
+    p.partial = a.take<float>((size_t)RD_MAX_BLOCKS * 3297);
     p.x = x; p.N = N; p.training = training; p.p_drop = p_drop; p.seed = seed;
     p.target = g_loss ? target : nullptr; p.saved = saved; p.stats = stats; p.g_pred = g_pred; p.g_loss = g_loss;
     p.gx = gx; p.grads = grads; p.bar = reinterpret_cast<unsigned*>(sync);
     MGV_CUDA(cudaMemsetAsync(p.acc, 0, 192 * sizeof(double), st));
     MGV_CUDA(cudaMemsetAsync(sync, 0, sizeof(int32_t), st));
-    MGV_CUDA(cudaMemsetAsync(grads, 0, 3297 * sizeof(float), st));
-    if (N == 0) return MGV_OK;
+    if (N == 0) {
+        MGV_CUDA(cudaMemsetAsync(grads, 0, 3297 * sizeof(float), st));
+        return MGV_OK;
+    }
     int blocks = 0;
-    rc = coop_blocks((const void*)readout_bwd_kernel, N, &blocks);
+    rc = coop_blocks((const void*)readout_bwd_kernel, N, &blocks, (size_t)RD_SCRATCH_BYTES);
     if (rc != MGV_OK) return rc;
+    MGV_REQUIRE(blocks <= RD_MAX_BLOCKS, "mgv_readout_bwd: grid of %d blocks exceeds the partial buffer", blocks);
     void* args[] = {&p};
-    MGV_CUDA(cudaLaunchCooperativeKernel((const void*)readout_bwd_kernel, dim3(blocks), dim3(RD_THREADS), args, 0, st));
+    MGV_CUDA(cudaLaunchCooperativeKernel((const void*)readout_bwd_kernel, dim3(blocks), dim3(RD_THREADS), args, (size_t)RD_SCRATCH_BYTES, st));
     mgv_count_launches(1);
     return MGV_OK;
 }
