@@ -51,13 +51,48 @@ class OrderedData(object):
         return self
 
     def copy_to(self, device, non_blocking=True):
-        """A new batch object on ``device`` (the source, e.g. pinned host memory, is left untouched)."""
+        """A new batch object on ``device`` (the source, e.g. pinned host memory, is left untouched).  A packed batch
+        (``pack()``) travels as ONE copy and its tensors are views of the device buffer."""
         out = OrderedData()
+        packed = getattr(self, "_packed", None)
+        if packed is not None and torch.device(device).type == "cuda":
+            buf, table = packed
+            dbuf = buf.to(device, non_blocking=non_blocking)
+            out._dbuf = dbuf                            # the one device allocation behind every field
+            for k, off, nbytes, dtype, shape in table:
+                setattr(out, k, dbuf[off:off + nbytes].view(dtype).view(shape))
+            for k, v in vars(self).items():
+                if not k.startswith("_") and not torch.is_tensor(v):
+                    setattr(out, k, v)
+            return out
         for k, v in vars(self).items():
             if k.startswith("_"):
                 continue
             setattr(out, k, v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v)
         return out
+
+    def pack(self, pin=True):
+        """Lay all tensors of the (host) batch out in one contiguous, optionally pinned, byte buffer (256-byte aligned pieces) so
+        that ``copy_to`` is a single host -> device copy instead of one per field (30 small copies cost 0.27 ms of host time per
+        step); the fields become views of the buffer."""
+        fields = [(k, v) for k, v in vars(self).items() if torch.is_tensor(v) and not k.startswith("_")]
+        if any(v.is_cuda for _, v in fields):
+            return self
+        table, total = [], 0
+        for k, v in fields:
+            total = (total + 255) // 256 * 256
+            nbytes = v.numel() * v.element_size()
+            table.append((k, total, nbytes, v.dtype, tuple(v.shape)))
+            total += nbytes
+        buf = torch.empty(max(total, 1), dtype=torch.uint8)
+        if pin and torch.cuda.is_available():
+            buf = buf.pin_memory()
+        for (k, v), (_, off, nbytes, dtype, shape) in zip(fields, table):
+            view = buf[off:off + nbytes].view(dtype).view(shape)
+            view.copy_(v)
+            setattr(self, k, view)
+        self._packed = (buf, table)
+        return self
 
     def nbytes(self):
         return sum(v.numel() * v.element_size() for v in vars(self).values() if torch.is_tensor(v))
@@ -218,3 +253,49 @@ class DataLoader(torch.utils.data.DataLoader):
     def __init__(self, dataset, batch_size=1, shuffle=False, **kw):
         kw.pop("collate_fn", None)
         super().__init__(dataset, batch_size, shuffle, collate_fn=collate, **kw)
+
+
+class CudaPrefetcher(object):
+    """Iterates host batches (an iterable of ``OrderedData``, e.g. a ``DataLoader``) and yields them on ``device``, with the
+    host -> device copy of batch i + 1 issued on a side stream while the caller works on batch i.  The reference moves every
+    batch with a blocking ``batch.to(device)`` inside the step (trainer.py:201); here the copy (pinned memory, asynchronous)
+    hides behind the previous step.  The yielded tensors are safe to use on the current stream (event wait +
+    ``record_stream``)."""
+
+    def __init__(self, batches, device, pin=True):
+        self.batches, self.device, self.pin = batches, torch.device(device), pin
+        self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+
+    def _upload(self, host):
+        if self.stream is None:
+            return host.to(self.device), None
+        if getattr(host, "_packed", None) is None and self.pin:
+            host = host.pack()                         # one pinned buffer, one copy
+        with torch.cuda.stream(self.stream):
+            dev = host.copy_to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            nxt = self._upload(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._upload(next(it))          # batch i + 1 travels while the caller computes on batch i
+            except StopIteration:
+                nxt = None
+            if ev is not None:
+                main = torch.cuda.current_stream(self.device)
+                main.wait_event(ev)
+                dbuf = getattr(cur, "_dbuf", None)
+                for v in ([dbuf] if dbuf is not None else [v for v in vars(cur).values() if torch.is_tensor(v)]):
+                    v.record_stream(main)
+            yield cur
+
+    def __len__(self):
+        return len(self.batches)

@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .data import DataLoader
+from .data import CudaPrefetcher, DataLoader
 from .utils.utils import AverageMeter
 
 
@@ -256,8 +256,8 @@ class Trainer(object):
         for epoch in range(num_epoch):
             for phase in ("train", "val"):
                 self.model.train(phase == "train")
-                for batch in loaders[phase]:
-                    batch = batch.to(self.device)
+                # host -> device copy of batch i + 1 behind the step on batch i (the reference: blocking batch.to(device), trainer.py:201)
+                for batch in CudaPrefetcher(loaders[phase], self.device):
                     t0 = time.time()
                     if phase == "train":
                         status = self.train_step(batch)

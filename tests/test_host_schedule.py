@@ -65,3 +65,14 @@ def test_streams_cut_whole_circuits_evenly():
     assert many.sched_streams == 37 and int(many.sweep_stream.max()) == 36
     sizes = torch.bincount(many.sweep_stream.long())
     assert int(sizes.max()) - int(sizes.min()) <= int((many.ptr[1:] - many.ptr[:-1]).max())
+
+
+def test_prefetcher_yields_every_batch_in_order():
+    import deepgate
+    from deepgate import synth
+    batches = [deepgate.circuits_to_batch(synth.make_circuits("aig", 2, 4, 20 + 5 * i, cfg=80 + i)) for i in range(3)]
+    got = list(deepgate.CudaPrefetcher(batches, "cpu"))
+    assert len(got) == 3 and len(deepgate.CudaPrefetcher(batches, "cpu")) == 3
+    for a, b in zip(got, batches):
+        assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.sched_in_src, b.sched_in_src)
+    assert list(deepgate.CudaPrefetcher([], "cpu")) == []
