@@ -348,11 +348,17 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
     for i in range(warmup):
         step_resident(i)
         step_e2e(i)
+    # untimed: three rotations in the mode that is timed next -- the caching allocator re-settles when the step mix changes and a
+    # cudaMalloc inside a timed step stalls it for 5-90 ms (max over ranks: one rank is enough)
+    for i in range(max(3 * nb, 12)):
+        step_resident(i)
     launches0 = _native.lib().mgv_kernel_launches()
     ops.PROFILE = {}
     if sampler:
         sampler.mark_begin()
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     ms = timed(step_resident, steps)
+    mallocs_resident = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
     if sampler:
         sampler.mark_end()
     torch.cuda.synchronize(dev)
@@ -369,8 +375,9 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
         step_e2e(i)
     alloc0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     ms_e2e = timed(step_e2e, steps)
+    mallocs_e2e = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - alloc0
     if os.environ.get("MGV_BENCH_VERBOSE"):
-        print("cudaMalloc calls inside the end-to-end timed region: %d" % (torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - alloc0), file=sys.stderr)
+        print("cudaMalloc calls inside the timed regions: resident %d, end-to-end %d" % (mallocs_resident, mallocs_e2e), file=sys.stderr)
     if e2e_trace:
         for t in e2e_trace[-steps:]:
             print("e2e step: h2d issue %.2f  train_step host %.2f  loss.item() wait %.2f ms" % t, file=sys.stderr)
@@ -484,7 +491,8 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
                          % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},
         "e2e": {"value": e2e, "unit": "gates/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "other_calls_ms_per_step": other,
+        "gpu_launches": int(launches), "cuda_mallocs_in_timed_regions": {"resident": int(mallocs_resident), "e2e": int(mallocs_e2e)},
+        "clocks": clocks, "roofline": roofline, "kernels": kernels, "other_calls_ms_per_step": other,
         "level_sweep": sweep, "cpu_baseline": cpu}
     # free this workload's device memory before the next one is measured
     del feed, trainer, model, resident, host
