@@ -516,7 +516,9 @@ def run_ours(args, w):
     dev = torch.device("cuda", local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
-    rec = measure(w, args.workload, args.steps, args.warmup, args.batches, dev, rank, world, clocks_index=local,
+    # clocks are sampled by rank 0 only (its GPU): one nvidia-smi poller per rank makes 8 processes hammer the driver's locks and
+    # the host cores during the timed region of an 8-rank run
+    rec = measure(w, args.workload, args.steps, args.warmup, args.batches, dev, rank, world, clocks_index=local if rank == 0 else None,
                   cpu_baseline=(rank == 0 and world == 1 and not args.no_cpu_baseline))
     subs = {}
     if not args.no_sub_workloads and args.workload == "cfg2":
