@@ -76,3 +76,24 @@ def test_prefetcher_yields_every_batch_in_order():
     for a, b in zip(got, batches):
         assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.sched_in_src, b.sched_in_src)
     assert list(deepgate.CudaPrefetcher([], "cpu")) == []
+
+
+def test_packed_batch_is_one_buffer_with_the_same_fields():
+    """``OrderedData.pack()``: every tensor becomes a view of ONE byte buffer (256-byte aligned pieces), values unchanged; a copy of
+    the packed batch has the same fields and the plain-Python schedule metadata."""
+    import deepgate
+    from deepgate import synth
+    b = deepgate.circuits_to_batch(synth.make_circuits("mig", 3, 8, 40, cfg=90))
+    before = {k: getattr(b, k).clone() for k in b.keys() if torch.is_tensor(getattr(b, k))}
+    meta = (b.num_levels, list(b.level_code_count), b.sched_streams, b.num_graphs)
+    b.pack(pin=False)
+    buf, table = b._packed
+    base = buf.data_ptr()
+    for k, off, nbytes, dtype, shape in table:
+        v = getattr(b, k)
+        assert v.data_ptr() == base + off and off % 256 == 0 and v.dtype == dtype and tuple(v.shape) == shape
+        assert torch.equal(v, before[k]), k
+    assert set(k for k, *_ in table) == set(before)
+    c = b.copy_to("cpu")
+    assert all(torch.equal(getattr(c, k), before[k]) for k in before)
+    assert (c.num_levels, list(c.level_code_count), c.sched_streams, c.num_graphs) == meta
