@@ -273,6 +273,11 @@ int mgv_sweep_unpack_grads(const void* const* params, const int32_t* codes, int3
  */
 int mgv_negative_sample(const int32_t* out_ptr, const int32_t* out_pack, int32_t N, int64_t count, uint64_t seed,
                         int64_t* neg, mgv_stream_t stream);
+/* The per-batch edge "split" of the training loop with val_ratio = test_ratio = 0 (preprocessing.py:8-83 as called at
+ * trainer.py:133: every edge is a training edge, in random order; the reference's N x N mask is unused there and is not
+ * built).  out int64 [2][E] = edge_index[:, pi], pi a pseudo-random permutation keyed by `seed` (4-round Feistel network with
+ * cycle walking: one launch, O(E), no sort).  out must not alias edge_index. */
+int mgv_permute_edges(const int64_t* edge_index, int64_t E, uint64_t seed, int64_t* out, mgv_stream_t stream);
 int mgv_recon_loss_fwd(const float* st, int32_t N, const int64_t* pos, int64_t Ep, const int64_t* neg, int64_t En,
                        float* out, float* sig, int32_t* pred, void* ws, size_t ws_bytes, int32_t* err_flag,
                        mgv_stream_t stream);

@@ -34,6 +34,7 @@ __global__ void struct_pack_kernel(const StructParams sp, float* __restrict__ pa
             const int o = i / NLDC, c = i % NLDC;
             if (c < D) {                                              // Wc[o][c] = sum_k wih[o][k] w[k][c]
                 float acc = 0.f;
+#pragma unroll 32
                 for (int k = 0; k < D; ++k) acc = fmaf(__ldg(wih + o * ldw + k), __ldg(w + k * D + c), acc);
                 v = acc;
             } else if (c < D + sp.feat) v = __ldg(wih + o * ldw + c);
@@ -43,6 +44,7 @@ __global__ void struct_pack_kernel(const StructParams sp, float* __restrict__ pa
         } else if (i < O_BIH) {
             const int o = i - O_BC;
             float acc = 0.f;
+#pragma unroll 32
             for (int k = 0; k < D; ++k) acc = fmaf(__ldg(wih + o * ldw + k), __ldg(b + k), acc);
             v = acc;
         } else if (i < O_BHH) v = __ldg(bih + i - O_BIH);
@@ -62,36 +64,58 @@ __global__ void struct_unpack_kernel(const StructParams sp, const float* __restr
     const int ldw = D + sp.feat;
     const int per_dir = D * D + D + G3 * ldw + G3 * D + 2 * G3;
     float* O = out + (size_t)enc * per_enc + (size_t)dir * per_dir;
-    // msg.weight transposed in shared memory: the d weight_ih dot products below run over c with lanes over k, which would
-    // read w[k][c] at a 256-byte lane stride (32 sectors per load: measured 3.9 M sectors, 61 us for this kernel)
-    __shared__ float wT[D][D + 1];
-    for (int i = threadIdx.x; i < D * D; i += blockDim.x) wT[i % D][i / D] = __ldg(w + i);
+    // One output per thread (the host sizes the grid: 256-thread blocks over per_dir).  The parameters are cold in L2 by the end
+    // of the backward and the dot products walk them at a row stride, so everything a block reads of them is staged in shared
+    // memory by ONE wave of independent loads first (the version that read weight_ih inside the 192-step loops was a chain of
+    // DRAM misses: 62 us per call).  Blocks 0 .. 15 own d msg.weight rows k0 .. k0 + 3 and, from the same staged columns, d msg.bias.
+    __shared__ float wT[D][D + 1];          // msg.weight transposed: the d weight_ih products run over c with lanes over k
+    __shared__ float s_a[G3][4];            // weight_ih[:, k0 .. k0 + 3]
+    __shared__ float s_b[D];
+    const int i0 = blockIdx.x * blockDim.x, i = i0 + threadIdx.x;
+    const bool dw_block = i0 < D * D;                                          // block-uniform (D * D is a multiple of 256)
+    const bool dih_block = i0 + (int)blockDim.x > D * D + D && i0 < D * D + D + G3 * ldw;
+    const int k0 = i0 / D;
+    if (dw_block)
+        for (int t = threadIdx.x; t < G3 * 4; t += blockDim.x) s_a[t >> 2][t & 3] = __ldg(wih + (t >> 2) * ldw + k0 + (t & 3));
+    if (dih_block) {
+        for (int t = threadIdx.x; t < D * D; t += blockDim.x) wT[t % D][t / D] = __ldg(w + t);
+        if (threadIdx.x < D) s_b[threadIdx.x] = __ldg(b + threadIdx.x);
+    }
     __syncthreads();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_dir; i += gridDim.x * blockDim.x) {
+    if (dw_block && threadIdx.x < 128) {                                       // d b[k0 + q] = sum_o wih[o][k0 + q] gbc[o], warp q
+        const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < G3 / 32; ++t) acc = fmaf(s_a[lane + 32 * t][q], __ldg(G + O_BC + lane + 32 * t), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) O[D * D + k0 + q] = acc;
+    }
+    if (i < per_dir) {
         float v;
         int j = i;
+        bool store = true;
         if (j < D * D) {                                             // d w[k][c] = sum_o wih[o][k] gWc[o][c]
             const int k = j / D, c = j % D;
             float acc = 0.f;
-#pragma unroll 8
-            for (int o = 0; o < G3; ++o) acc = fmaf(__ldg(wih + o * ldw + k), __ldg(G + O_WCX + o * NLDC + c), acc);
+#pragma unroll 16
+            for (int o = 0; o < G3; ++o) acc = fmaf(s_a[o][k - k0], __ldg(G + O_WCX + o * NLDC + c), acc);
             v = acc;
-        } else if ((j -= D * D) < D) {                               // d b[k] = sum_o wih[o][k] gbc[o]
-            float acc = 0.f;
-            for (int o = 0; o < G3; ++o) acc = fmaf(__ldg(wih + o * ldw + j), __ldg(G + O_BC + o), acc);
-            v = acc;
+        } else if ((j -= D * D) < D) {                               // d b: written by the blocks above
+            v = 0.f;
+            store = false;
         } else if ((j -= D) < G3 * ldw) {                            // d wih[o][k<64] = sum_c gWc[o][c] w[k][c] + gbc[o] b[k]
             const int o = j / ldw, k = j % ldw;
             if (k < D) {
-                float acc = __ldg(G + O_BC + o) * __ldg(b + k);
-#pragma unroll 8
+                float acc = __ldg(G + O_BC + o) * s_b[k];
+#pragma unroll 16
                 for (int c = 0; c < D; ++c) acc = fmaf(__ldg(G + O_WCX + o * NLDC + c), wT[c][k], acc);
                 v = acc;
             } else v = __ldg(G + O_WCX + o * NLDC + k);
         } else if ((j -= G3 * ldw) < G3 * D) v = __ldg(G + O_WHH + (j / D) * NLDM + j % D);
         else if ((j -= G3 * D) < G3) v = __ldg(G + O_BIH + j);
         else v = __ldg(G + O_BHH + j - G3);
-        O[i] = v;
+        if (store) O[i] = v;
     }
     if (sp.layernorm && dir == 0 && blockIdx.x == 0 && threadIdx.x < 2 * D) {
         const float* G1 = G + SPACK;
@@ -223,7 +247,7 @@ extern "C" int mgv_struct_unpack_grads(const void* const* params, int32_t num_en
     const int ldw = D + feat;
     const int per_dir = D * D + D + G3 * ldw + G3 * D + 2 * G3;
     const int per_enc = 2 * per_dir + (layernorm ? 2 * D : 0);
-    struct_unpack_kernel<<<dim3(128, num_enc * 2), 256, 0, (cudaStream_t)stream>>>(sp, grads, out, per_enc);
+    struct_unpack_kernel<<<dim3((per_dir + 255) / 256, num_enc * 2), 256, 0, (cudaStream_t)stream>>>(sp, grads, out, per_enc);
     mgv_count_launches(1);
     return mgv_check_cuda(cudaGetLastError(), "mgv_struct_unpack_grads");
 }

@@ -39,6 +39,31 @@ __global__ void neg_sample_kernel(const int* __restrict__ out_ptr, const int* __
     neg[count + e] = v;
 }
 
+// Keyed pseudo-random bijection of [0, 2^(2 hb)): four Feistel rounds with the splitmix finaliser as round function.
+__device__ __forceinline__ uint64_t feistel4(uint64_t x, int hb, uint64_t seed) {
+    const uint64_t mask = (1ull << hb) - 1ull;
+    uint64_t l = x >> hb, r = x & mask;
+#pragma unroll
+    for (int round = 0; round < 4; ++round) {
+        const uint64_t t = l ^ (mix64(r ^ seed ^ ((uint64_t)round << 56)) & mask);
+        l = r;
+        r = t;
+    }
+    return (l << hb) | r;
+}
+
+// out[:, i] = ei[:, pi(i)], pi = the Feistel bijection of the smallest even-width power-of-two domain >= E, cycle-walked back
+// into [0, E) (a walk that starts inside [0, E) returns to it: pi restricted this way is a bijection of [0, E); the domain is
+// < 4 E, so a walk takes < 4 steps on average).
+__global__ void permute_edges_kernel(const int64_t* __restrict__ ei, int64_t E, int hb, uint64_t seed, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E) return;
+    uint64_t x = (uint64_t)i;
+    do x = feistel4(x, hb, seed); while (x >= (uint64_t)E);
+    out[i] = ei[x];
+    out[E + i] = ei[E + x];
+}
+
 struct ReconDev {
     const float* st;
     const int64_t* pos; int64_t ep;
@@ -140,6 +165,16 @@ extern "C" int mgv_negative_sample(const int32_t* out_ptr, const int32_t* out_pa
     neg_sample_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_ptr, out_pack, N, count, seed, neg);
     mgv_count_launches(1);
     return mgv_check_cuda(cudaGetLastError(), "mgv_negative_sample");
+}
+
+extern "C" int mgv_permute_edges(const int64_t* edge_index, int64_t E, uint64_t seed, int64_t* out, mgv_stream_t stream) {
+    MGV_REQUIRE(E >= 0 && (E == 0 || (edge_index && out && edge_index != out)), "mgv_permute_edges: bad argument (in place is not supported)");
+    if (E == 0) return MGV_OK;
+    int hb = 1;
+    while ((1ull << (2 * hb)) < (uint64_t)E) ++hb;
+    permute_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, (cudaStream_t)stream>>>(edge_index, E, hb, seed, out);
+    mgv_count_launches(1);
+    return mgv_check_cuda(cudaGetLastError(), "mgv_permute_edges");
 }
 
 extern "C" int mgv_recon_loss_fwd(const float* st, int32_t N, const int64_t* pos, int64_t Ep, const int64_t* neg, int64_t En,

@@ -134,16 +134,11 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
     if (tid < 2 * D) s_ln[tid] = __ldg(reinterpret_cast<const float*>(image + IMG_W) + tid);
     if (tid < 4) s_amax[tid] = 0u;
     if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
-    int tile_beg, tile_end;
-    {
-        // equal tile counts per CTA: with the operand tile bulk-copied, a tile's time is set by the epilogue (constant per
-        // 128 nodes), not by its neighbour count as in the forward's cost model
-        const long long nt = p.tile_end - p.tile_beg;
-        tile_beg = p.tile_beg + (int)(nt * blockIdx.x / gridDim.x);
-        tile_end = p.tile_beg + (int)(nt * (blockIdx.x + 1) / gridDim.x);
-        tile_beg = max(tile_beg, p.tile_beg);
-        tile_end = min(tile_end, p.tile_end);
-    }
+    // Equal tile counts per CTA (with the operand tile bulk-copied a tile's time is set by the epilogue: constant per 128
+    // nodes), dealt ROUND-ROBIN: rows are in degree order, so the few tiles whose gather of hub rows outlasts the epilogue
+    // (fan-out direction) sit next to each other -- a contiguous range put all of them on CTA 0 (measured: 141 us per launch
+    // in the fan-out direction against 100 us in the fan-in direction).
+    const int tile_beg = p.tile_beg + (int)blockIdx.x, tile_end = p.tile_end, tile_step = (int)gridDim.x;
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -168,15 +163,15 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             dn[ps] = (tile_beg < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
         }
         int it = 0;
-        for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+        for (int tile = tile_beg; tile < tile_end; tile += tile_step, ++it) {
             if (lane == 0) PTRACE_MAX(13);
             int4 dc[4];
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) dc[ps] = dn[ps];
 #pragma unroll
             for (int ps = 0; ps < 4; ++ps) {
-                const int r = (tile + 1) * TM + gw * 16 + ps * 4 + rg;
-                dn[ps] = (tile + 1 < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
+                const int r = (tile + tile_step) * TM + gw * 16 + ps * 4 + rg;
+                dn[ps] = (tile + tile_step < tile_end && r < p.N) ? __ldg(gdesc + r) : make_int4(-1, 0, 0, 0);
             }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {           // the lane's 4 rows, two at a time
@@ -284,12 +279,12 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             load_tile(tile_beg);
             issue_recompute(0u);
             int it = 0;
-            for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+            for (int tile = tile_beg; tile < tile_end; tile += tile_step, ++it) {
                 const uint32_t ph = (uint32_t)(it & 1);
                 // the tile buffer is free once the recompute MMAs have read it and the epilogue has copied its h rows
                 tc::mbar_wait_sleep(bar_acc_full, ph, 32);
                 tc::mbar_wait_sleep(bar_h_read, ph, 32);
-                if (tile + 1 < tile_end) load_tile(tile + 1);
+                if (tile + tile_step < tile_end) load_tile(tile + tile_step);
                 tc::mbar_wait_sleep(bar_dg_full, ph, 32);
                 tc::fence_after_sync();
                 PTRACE(7);
@@ -318,7 +313,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 }
                 // the next tile's recompute runs behind the data-gradient MMAs (in issue order) while the epilogue stores
                 // this tile's outputs: it only writes T_ACC, which the epilogue is done with
-                if (tile + 1 < tile_end) {
+                if (tile + tile_step < tile_end) {
                     tc::mbar_wait_sleep(bar_dg_stored, ph, 32);      // the epilogue re-reads the planes for their HBM copy
                     issue_recompute(ph ^ 1u);
                 }
@@ -351,7 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         float run_scale = 1.0f;
         const uint64_t pol_stream = tc::l2_policy_evict_first();      // hand-off buffers: written once, read once by the next kernel
         int it = 0;
-        for (int tile = tile_beg; tile < tile_end; ++tile, ++it) {
+        for (int tile = tile_beg; tile < tile_end; tile += tile_step, ++it) {
             const uint32_t ph = (uint32_t)(it & 1);
             const bool valid = tile * TM + row < p.N;
             const int node = valid ? p.order[tile * TM + row] : 0;

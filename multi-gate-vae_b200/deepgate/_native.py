@@ -77,6 +77,7 @@ _PROTOTYPES = {
     "mgv_sweep_pack": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
     "mgv_sweep_unpack_grads": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "mgv_negative_sample": (ctypes.c_int, [_vp, _vp, _i32, _i64, ctypes.c_uint64, _vp, _vp]),
+    "mgv_permute_edges": (ctypes.c_int, [_vp, _i64, ctypes.c_uint64, _vp, _vp]),
     "mgv_recon_loss_fwd": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "mgv_recon_loss_bwd": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mgv_readout_workspace_bytes": (_sz, [_i64]),

@@ -97,7 +97,7 @@ def _sweep_pack(params, codes, device, prec):
     lib = nat.lib()
     pack = torch.zeros(lib.mgv_sweep_pack_bytes() // 4, dtype=torch.float32, device=device)
     sel = _sweep_tables(params, codes)
-    with nat.on_device(device):
+    with nat.on_device(device), _timed("sweep_pack", device):
         nat.check(lib.mgv_sweep_pack(_ptr_table(sel), _code_table(codes), len(codes), nat.ptr(pack), prec,
                                      nat.stream_of(device)), "mgv_sweep_pack")
     return pack
@@ -157,7 +157,7 @@ class LevelSweepFunction(torch.autograd.Function):
         # query / key-bias / attn-bias cancel in the softmax: exact zeros, one DISJOINT slice per parameter (gradients must not alias)
         ZQ = 1 + D * 2 * D + 2 * D
         zero = torch.zeros(max(len(codes), 1), ZQ, dtype=torch.float32, device=dev)
-        with nat.on_device(dev):
+        with nat.on_device(dev), _timed("sweep_unpack_grads", dev):
             nat.check(lib.mgv_sweep_unpack_grads(_ptr_table(sel), _code_table(list(codes)), len(codes), nat.ptr(grads),
                                                  nat.ptr(extra), nat.stream_of(dev)), "mgv_sweep_unpack_grads")
         out = []
@@ -274,7 +274,7 @@ def _struct_pack(enc_params, layernorm, device):
             feat = f
         flat += [_f32(t, "struct encoder parameter") for t in ps]
     pack = torch.empty(len(enc_params), 2, nat.STRUCT_PACK_FLOATS, dtype=torch.float32, device=device)
-    with torch.cuda.device(device):
+    with torch.cuda.device(device), _timed("struct_pack", device):
         nat.check(nat.lib().mgv_struct_pack(_ptr_table(flat), len(enc_params), int(bool(layernorm)), feat, nat.ptr(pack),
                                             nat.stream_of(device)), "mgv_struct_pack")
     return pack
@@ -339,7 +339,7 @@ class StructEncoderFunction(torch.autograd.Function):
         per_enc = 2 * per_dir + (2 * D if ctx.layernorm else 0)
         flat = [_f32(t, "struct encoder parameter") for t in params]
         buf = torch.empty(num_enc, per_enc, dtype=torch.float32, device=dev)
-        with nat.on_device(dev):
+        with nat.on_device(dev), _timed("struct_unpack_grads", dev):
             nat.check(lib.mgv_struct_unpack_grads(_ptr_table(flat), num_enc, int(bool(ctx.layernorm)), feat, nat.ptr(grads),
                                                   nat.ptr(buf), nat.stream_of(dev)), "mgv_struct_unpack_grads")
         out = []
@@ -390,6 +390,22 @@ def negative_sample(csr, count):
         nat.check(lib.mgv_negative_sample(nat.ptr(csr.out_ptr), nat.ptr(csr.out_pack), csr.N, int(count), seed,
                                           nat.ptr(neg), nat.stream_of(dev)), "mgv_negative_sample")
     return neg
+
+
+def permute_edges(edge_index):
+    """``edge_index[:, perm]`` for a pseudo-random permutation of the edges, one launch (csrc/recon.cu, ``mgv_permute_edges``):
+    the per-batch edge split of the training loop (preprocessing.py:8-83 with val_ratio = test_ratio = 0).  Seeded from torch's
+    global seed and a call counter."""
+    ei = nat.require_cuda(edge_index.contiguous(), "edge_index", torch.int64)
+    if ei.dim() != 2 or ei.shape[0] != 2:
+        raise RuntimeError("mgv_b200: edge_index must be [2, E]")
+    out = torch.empty_like(ei)
+    _NEG_COUNTER[0] += 1
+    seed = (torch.initial_seed() * 0xD1B54A32D192ED03 + _NEG_COUNTER[0]) & 0xFFFFFFFFFFFFFFFF
+    with nat.on_device(ei.device):
+        nat.check(nat.lib().mgv_permute_edges(nat.ptr(ei), int(ei.shape[1]), seed, nat.ptr(out), nat.stream_of(ei.device)),
+                  "mgv_permute_edges")
+    return out
 
 
 class ReconLossFunction(torch.autograd.Function):

@@ -27,9 +27,11 @@ from .utils.utils import AverageMeter
 def split_edges(batch):
     """``general_train_test_split_edges`` with val_ratio = test_ratio = 0 (preprocessing.py:8-83):
     every edge is a training edge, in random order."""
-    # argsort of uniform keys: a uniformly random permutation without torch.randperm's host-side work on CUDA
-    perm = torch.argsort(torch.rand(batch.edge_index.size(1), device=batch.edge_index.device))
-    batch.train_pos_edge_index = batch.edge_index[:, perm]
+    ei = batch.edge_index
+    if ei.is_cuda:
+        batch.train_pos_edge_index = ops.permute_edges(ei)       # one launch, no sort (csrc/recon.cu)
+    else:                                                        # host-side callers (data preparation, CPU tests of the loop)
+        batch.train_pos_edge_index = ei[:, torch.randperm(ei.size(1))]
     return batch
 
 

@@ -497,3 +497,22 @@ def test_struct_forward_at_the_tile_search_boundaries(n_nodes):
     err_s = (s.cpu() - so).abs().max(dim=1).values
     assert float(err_s.max()) < TOL * float(so.abs().max()), int(err_s.argmax())
     assert rel(t, to) < TOL
+
+
+@pytest.mark.parametrize("E", [0, 1, 2, 3, 17, 256, 257, 4097, 98256])
+def test_edge_split_is_a_random_permutation_of_the_edges(E):
+    """``split_edges`` (preprocessing.py:8-83 with zero val / test ratios): ``train_pos_edge_index`` holds every edge exactly once,
+    source and target moved together, in an order that changes from call to call (``mgv_permute_edges``, Feistel + cycle walking)."""
+    from deepgate import ops
+    g = torch.Generator().manual_seed(E)
+    ei = torch.randint(0, 1 << 20, (2, E), generator=g, dtype=torch.int64).cuda()
+    a, b = ops.permute_edges(ei), ops.permute_edges(ei)
+    assert a.shape == ei.shape and a.dtype == torch.int64
+    key = lambda t: torch.sort(t[0] * (1 << 21) + t[1]).values
+    assert torch.equal(key(a), key(ei)) and torch.equal(key(b), key(ei))
+    if E >= 256:
+        assert (a[0] != ei[0]).float().mean() > 0.9 and (a[0] != b[0]).float().mean() > 0.9
+        # the order is not a shift or another low-complexity map: neighbours in the output come from far apart
+        pos = {int(k): i for i, k in enumerate((ei[0] * (1 << 21) + ei[1]).tolist())}
+        src = torch.tensor([pos[int(k)] for k in (a[0] * (1 << 21) + a[1]).tolist()][:4096])
+        assert (src[1:] - src[:-1]).abs().float().mean() > E / 8
