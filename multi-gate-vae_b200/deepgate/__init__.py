@@ -11,7 +11,7 @@ from .dg_ae_model_xmg import Model
 from .dg_ae_model_xag import Model
 
 from .trainer import Trainer
-from .data import OrderedData, DataLoader, CudaPrefetcher, collate
+from .data import OrderedData, DataLoader, CudaPrefetcher, DeferredScalars, collate
 from . import parser, parser_func, parser_func_others
 from .parser import NpzParser, CircuitDataset, read_npz_file
 from .parser_func_others import parse_pyg_mlpgate, circuits_to_batch

@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .data import CudaPrefetcher, DataLoader
+from .data import CudaPrefetcher, DataLoader, DeferredScalars
 from .utils.utils import AverageMeter
 
 
@@ -251,28 +251,48 @@ class Trainer(object):
                                   num_workers=self.num_workers, sampler=sampler)
             return DataLoader(ds, batch_size=self.batch_size, shuffle=True, drop_last=True, num_workers=self.num_workers)
 
-        from .schedule import check_deferred_errors
+        from .schedule import check_deferred_errors, error_word
         loaders = {"train": loader(train_dataset), "val": loader(val_dataset)}
         meters = {k: AverageMeter() for k in ("time", "recon", "prob", "func", "acc")}
+        on_cuda = str(self.device).startswith("cuda")
+
+        def account(vals):
+            # two steps late (DeferredScalars, lag 2): the losses, the accuracy and the deferred input-validation word of a step are read
+            # while the next step is already queued -- the reference's .item() / .cpu() per batch (trainer.py:219-226) drains the
+            # device once per step.  A batch that failed validation never reached the parameters (_guarded_step).
+            recon, prob, func, acc = vals[:4]
+            if len(vals) > 4 and vals[4]:
+                check_deferred_errors()
+            meters["recon"].update(recon)
+            meters["prob"].update(prob)
+            meters["func"].update(func)
+            meters["acc"].update(acc)
+
         print("[INFO] Start training, lr = {:.4f}".format(self.optimizer.param_groups[0]["lr"]))
         for epoch in range(num_epoch):
             for phase in ("train", "val"):
                 self.model.train(phase == "train")
+                reader = DeferredScalars(self.device, lag=2)
+                t0 = time.time()
                 # host -> device copy of batch i + 1 behind the step on batch i (the reference: blocking batch.to(device), trainer.py:201)
                 for batch in CudaPrefetcher(loaders[phase], self.device):
-                    t0 = time.time()
                     if phase == "train":
                         status = self.train_step(batch)
                     else:
                         with torch.no_grad():
                             status = self.run_batch(batch)
-                    pred, gt = status["pred_bin"].cpu().numpy(), status["gt_bin"].cpu().numpy()
-                    check_deferred_errors()          # the stream is idle after the read-back above: one 4-byte read
-                    meters["time"].update(time.time() - t0)
-                    meters["recon"].update(status["recon_loss"].item())
-                    meters["prob"].update(status["prob_loss"].item())
-                    meters["func"].update(status["func_loss"].item())
-                    meters["acc"].update(float(np.mean(pred == gt)))
+                    acc = (status["pred_bin"] == status["gt_bin"]).to(torch.float32).mean()
+                    vals = [status["recon_loss"], status["prob_loss"], status["func_loss"], acc]
+                    if on_cuda:
+                        vals.append(error_word(self.device)[0])
+                    done = reader.push(*vals)
+                    if done is not None:
+                        account(done)
+                    meters["time"].update(time.time() - t0)      # wall time per batch, everything included
+                    t0 = time.time()
+                for done in reader.drain():
+                    account(done)
+                check_deferred_errors()
                 if phase == "train" and self.model_epoch % 10 == 0 and self.rank == 0:
                     self.save(os.path.join(self.log_dir, "model_{:}.pth".format(self.model_epoch)))
                     self.save(os.path.join(self.log_dir, "model_last.pth"))
