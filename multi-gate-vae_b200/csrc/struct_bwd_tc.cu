@@ -99,6 +99,9 @@ __device__ __forceinline__ float pow2_scale_keep(float amax, float cur) {
 }
 
 // ======================================================================================= recompute + pointwise + data gradient
+// LOWP = bf16 mode: one plane of bf16 operands everywhere (the forward saved only the hi planes of its tiles), single products,
+// no tile scale (bf16 has the fp32 exponent range), half the hand-off bytes.
+template <bool LOWP>
 __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -248,31 +251,41 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
         if (lane == 0 && tile_beg < tile_end) {
             auto load_tile = [&](int t) {       // the forward's saved operand tile -> the (idle) tile buffer
                 const uint8_t* src = p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)t * A_TILE_BYTES;
-                tc::mbar_expect_tx(bar_t_full, A_TILE_BYTES);
+                if (LOWP) {                     // hi planes only: agg 16 KB, h 16 KB, x 4 KB
+                    tc::mbar_expect_tx(bar_t_full, 36864u);
 #pragma unroll 1
-                for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_g2s(sbase + A_AGG_HI + o, src + o, 8192u, bar_t_full);
+                    for (uint32_t o = 0; o < 16384u; o += 8192u) {
+                        tc::bulk_g2s(sbase + A_AGG_HI + o, src + o, 8192u, bar_t_full);
+                        tc::bulk_g2s(sbase + A_H_HI + o, src + (A_H_HI - A_AGG_HI) + o, 8192u, bar_t_full);
+                    }
+                    tc::bulk_g2s(sbase + A_X_HI, src + (A_X_HI - A_AGG_HI), 4096u, bar_t_full);
+                } else {
+                    tc::mbar_expect_tx(bar_t_full, A_TILE_BYTES);
+#pragma unroll 1
+                    for (uint32_t o = 0; o < A_TILE_BYTES; o += 8192u) tc::bulk_g2s(sbase + A_AGG_HI + o, src + o, 8192u, bar_t_full);
+                }
             };
             auto issue_recompute = [&](uint32_t tph) {     // the 39 recompute MMAs of a tile (bit-identical products to the forward)
                 tc::mbar_wait_sleep(bar_t_full, tph, 32);
                 tc::fence_after_sync();
                 const uint32_t d = tmem + T_ACC;
-                tc::mma3(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
-                         tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false), 0u);
+                tc::mma3p<LOWP>(d, tc::desc_k_plain16(sbase + A_X_HI), tc::desc_k_plain16(sbase + A_X_LO),
+                         tc::desc_k_plain16(sbase + WX_HI), tc::desc_k_plain16(sbase + WX_LO), tc::make_idesc(128, 256, false, false, LOWP), 0u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    tc::mma3(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                    tc::mma3p<LOWP>(d, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
                              tc::desc_k_sw128(sbase + WHH_HI + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 32 * j),
-                             tc::make_idesc(128, 128, false, false), 1u);
+                             tc::make_idesc(128, 128, false, false, LOWP), 1u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    tc::mma3(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
+                    tc::mma3p<LOWP>(d + 192u, tc::desc_k_sw128(sbase + A_H_HI + 32 * j), tc::desc_k_sw128(sbase + A_H_LO + 32 * j),
                              tc::desc_k_sw128(sbase + WHH_HI + 16384 + 32 * j), tc::desc_k_sw128(sbase + WHH_LO + 16384 + 32 * j),
-                             tc::make_idesc(128, 64, false, false), 1u);
+                             tc::make_idesc(128, 64, false, false, LOWP), 1u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    tc::mma3(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
+                    tc::mma3p<LOWP>(d, tc::desc_k_sw128(sbase + A_AGG_HI + 32 * j), tc::desc_k_sw128(sbase + A_AGG_LO + 32 * j),
                              tc::desc_k_sw128(sbase + WC_HI + 32 * j), tc::desc_k_sw128(sbase + WC_LO + 32 * j),
-                             tc::make_idesc(128, 192, false, false), 1u);
+                             tc::make_idesc(128, 192, false, false, LOWP), 1u);
                 tc::mma_commit(bar_acc_full);
             };
             tc::mbar_wait_sleep(bar_w, 0u);
@@ -290,23 +303,23 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                 PTRACE(7);
                 if (!p.first) {
                     const uint32_t o = tmem + T_OUT;
-                    const uint32_t i128 = tc::make_idesc(128, 128, false, true), i64 = tc::make_idesc(128, 64, false, true);
+                    const uint32_t i128 = tc::make_idesc(128, 128, false, true, LOWP), i64 = tc::make_idesc(128, 64, false, true, LOWP);
 #pragma unroll
                     for (int s = 0; s < 8; ++s) {        // d r, d z: [d agg | d part] += d g . [Wc | Whh] rows 16 s ..
                         const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, WHH_HI - WC_HI),
+                        tc::mma3p_ts<LOWP>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, WHH_HI - WC_HI),
                                             tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, WHH_LO - WC_LO), i128, 1u);
                     }
 #pragma unroll
                     for (int s = 8; s < 12; ++s) {       // d gi_n: d agg += . Wc rows 128 ..
                         const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, 0),
+                        tc::mma3p_ts<LOWP>(o, a, a + 8u, tc::desc_mn_sw128(sbase + WC_HI + 2048u * s, 0),
                                             tc::desc_mn_sw128(sbase + WC_LO + 2048u * s, 0), i64, 1u);
                     }
 #pragma unroll
                     for (int s = 12; s < 16; ++s) {      // d gh_n: d part += . Whh rows 128 ..
                         const uint32_t a = tmem + T_ACC + 16u * s;
-                        tc::mma3p_ts<false>(o + 64u, a, a + 8u, tc::desc_mn_sw128(sbase + WHH_HI + 2048u * (s - 4), 0),
+                        tc::mma3p_ts<LOWP>(o + 64u, a, a + 8u, tc::desc_mn_sw128(sbase + WHH_HI + 2048u * (s - 4), 0),
                                             tc::desc_mn_sw128(sbase + WHH_LO + 2048u * (s - 4), 0), i64, 1u);
                     }
                     tc::mma_commit(bar_out_full);
@@ -356,14 +369,21 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 const uint32_t off = tc::sw128_off(row, 4 * wg + c8);
-                const uint4 hi = *reinterpret_cast<const uint4*>(sgen + A_H_HI + off), lo = *reinterpret_cast<const uint4*>(sgen + A_H_LO + off);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
-                const __half2* l2 = reinterpret_cast<const __half2*>(&lo);
+                const uint4 hi = *reinterpret_cast<const uint4*>(sgen + A_H_HI + off);
                 float h[8];
+                if (LOWP) {                     // the bf16 operand the forward multiplied (bf16 mode: h to 2^-9)
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(&hi);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 a = __half22float2(h2[e]), bq = __half22float2(l2[e]);
-                    h[2 * e] = a.x + bq.x; h[2 * e + 1] = a.y + bq.y;
+                    for (int e = 0; e < 4; ++e) { h[2 * e] = __uint_as_float(w[e] << 16); h[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+                } else {
+                    const uint4 lo = *reinterpret_cast<const uint4*>(sgen + A_H_LO + off);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
+                    const __half2* l2 = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 a = __half22float2(h2[e]), bq = __half22float2(l2[e]);
+                        h[2 * e] = a.x + bq.x; h[2 * e + 1] = a.y + bq.y;
+                    }
                 }
                 tc::tmem_st8f(t_out + u0 + 8 * c8, h);
             }
@@ -488,7 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
             for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
             if (lane == 0) atomicMax(s_amax + (it % 3), __float_as_uint(amax));
             tc::named_bar_sync(1, EPI_T);
-            const float scale = pow2_scale_keep(__uint_as_float(s_amax[it % 3]), run_scale);
+            const float scale = LOWP ? 1.0f : pow2_scale_keep(__uint_as_float(s_amax[it % 3]), run_scale);
             run_scale = scale;
             if (tid == 0) {
                 s_amax[(it + 2) % 3] = 0u;
@@ -506,10 +526,17 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     float v[16];
                     tc::tmem_ld16(t_acc + 16 * s, v);
                     tc::tmem_ld_wait();
-                    uint32_t pk[16];
+                    if (LOWP) {
+                        uint32_t pk[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) tc::split2(v[2 * e] * scale, v[2 * e + 1] * scale, pk[e], pk[8 + e]);
-                    tc::tmem_st16(t_acc + 16 * s, pk);
+                        for (int e = 0; e < 8; ++e) pk[e] = tc::pack_bf16x2(v[2 * e], v[2 * e + 1]);
+                        tc::tmem_st8(t_acc + 16 * s, pk);
+                    } else {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) tc::split2(v[2 * e] * scale, v[2 * e + 1] * scale, pk[e], pk[8 + e]);
+                        tc::tmem_st16(t_acc + 16 * s, pk);
+                    }
                 }
                 // accumulator init of the data-gradient MMAs: d agg = 0, d part = scale * g z
                 if (!p.first) {
@@ -549,10 +576,12 @@ __global__ void __launch_bounds__(THREADS, 1) struct_bwd_pw_kernel(const BwdTC p
                     tc::stg_v4_hint(hb + 1024, make_uint4(pk[4], pk[5], pk[6], pk[7]), pol_stream);
                     tc::stg_v4_hint(hb + 2048, make_uint4(qk[0], qk[1], qk[2], qk[3]), pol_stream);
                     tc::stg_v4_hint(hb + 3072, make_uint4(qk[4], qk[5], qk[6], qk[7]), pol_stream);
-                    tc::stg_v4_hint(hb + 65536, make_uint4(pk[8], pk[9], pk[10], pk[11]), pol_stream);
-                    tc::stg_v4_hint(hb + 65536 + 1024, make_uint4(pk[12], pk[13], pk[14], pk[15]), pol_stream);
-                    tc::stg_v4_hint(hb + 65536 + 2048, make_uint4(qk[8], qk[9], qk[10], qk[11]), pol_stream);
-                    tc::stg_v4_hint(hb + 65536 + 3072, make_uint4(qk[12], qk[13], qk[14], qk[15]), pol_stream);
+                    if (!LOWP) {
+                        tc::stg_v4_hint(hb + 65536, make_uint4(pk[8], pk[9], pk[10], pk[11]), pol_stream);
+                        tc::stg_v4_hint(hb + 65536 + 1024, make_uint4(pk[12], pk[13], pk[14], pk[15]), pol_stream);
+                        tc::stg_v4_hint(hb + 65536 + 2048, make_uint4(qk[8], qk[9], qk[10], qk[11]), pol_stream);
+                        tc::stg_v4_hint(hb + 65536 + 3072, make_uint4(qk[12], qk[13], qk[14], qk[15]), pol_stream);
+                    }
                 }
             }
             tc::fence_before_sync();
@@ -642,6 +671,7 @@ struct WgTC {
 };
 #define WTRACE(slot) do { if (p.trace && i < 16) p.trace[(((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + i) * 16 + (slot)] = clock64(); } while (0)
 
+template <bool LOWP>
 __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const WgTC p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -677,25 +707,27 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
                 WTRACE(0);
                 tc::mbar_wait_sleep(bar_empty + 8 * s, (uint32_t)(((i >> 1) & 1) ^ 1));
                 WTRACE(1);
-                tc::mbar_expect_tx(bar_full + 8 * s, ST_BYTES);
+                tc::mbar_expect_tx(bar_full + 8 * s, LOWP ? 51200u : ST_BYTES);
                 const uint8_t* dg = p.dgbuf + ((size_t)enc * p.chunk_cap + tile) * DG_TILE_BYTES + (size_t)h * 32768;
                 const uint8_t* at = p.tiles + (size_t)enc * p.tiles_enc_stride + (size_t)(p.tile_base + tile) * A_TILE_BYTES;
                 const uint32_t st = sbase + (uint32_t)s * ST_BYTES, bar = bar_full + 8 * s;
                 tc::bulk_g2s_hint(st + ST_DG_HI, dg, 16384u, bar, pol);
                 tc::bulk_g2s_hint(st + ST_DG_HI + 16384u, dg + 16384, 16384u, bar, pol);
-                tc::bulk_g2s_hint(st + ST_DG_LO, dg + 65536, 16384u, bar, pol);
-                tc::bulk_g2s_hint(st + ST_DG_LO + 16384u, dg + 65536 + 16384, 16384u, bar, pol);
                 tc::bulk_g2s_hint(st + ST_AGG_HI, at + 0 + h * 8192, 8192u, bar, pol);
-                tc::bulk_g2s_hint(st + ST_AGG_LO, at + 16384 + h * 8192, 8192u, bar, pol);
                 tc::bulk_g2s_hint(st + ST_H_HI, at + 32768 + h * 8192, 8192u, bar, pol);
-                tc::bulk_g2s_hint(st + ST_H_LO, at + 49152 + h * 8192, 8192u, bar, pol);
                 tc::bulk_g2s_hint(st + ST_X_HI, at + 65536 + h * 2048, 2048u, bar, pol);
-                tc::bulk_g2s_hint(st + ST_X_LO, at + 69632 + h * 2048, 2048u, bar, pol);
+                if (!LOWP) {
+                    tc::bulk_g2s_hint(st + ST_DG_LO, dg + 65536, 16384u, bar, pol);
+                    tc::bulk_g2s_hint(st + ST_DG_LO + 16384u, dg + 65536 + 16384, 16384u, bar, pol);
+                    tc::bulk_g2s_hint(st + ST_AGG_LO, at + 16384 + h * 8192, 8192u, bar, pol);
+                    tc::bulk_g2s_hint(st + ST_H_LO, at + 49152 + h * 8192, 8192u, bar, pol);
+                    tc::bulk_g2s_hint(st + ST_X_LO, at + 69632 + h * 2048, 2048u, bar, pol);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t i128 = tc::make_idesc(128, 128, true, true), i16 = tc::make_idesc(128, 16, true, true);
+            const uint32_t i128 = tc::make_idesc(128, 128, true, true, LOWP), i16 = tc::make_idesc(128, 16, true, true, LOWP);
             for (int i = 0; i < nhalf; ++i) {
                 const int s = i & 1;
                 WTRACE(4);
@@ -713,8 +745,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
                         // d gates^T: 16 chunks of 8 gates 1 KB apart (SBO), 8-node K groups 128 B apart (LBO), no swizzle
                         const uint64_t a_hi = tc::make_desc(st + ST_DG_HI + 16384u * g + 256u * j, 128, 1024, tc::LAYOUT_NONE);
                         const uint64_t a_lo = tc::make_desc(st + ST_DG_LO + 16384u * g + 256u * j, 128, 1024, tc::LAYOUT_NONE);
-                        tc::mma3(tmem + 160u * g, a_hi, a_lo, b_hi, b_lo, i128, acc);
-                        tc::mma3(tmem + 160u * g + 128u, a_hi, a_lo, x_hi, x_lo, i16, acc);
+                        tc::mma3p<LOWP>(tmem + 160u * g, a_hi, a_lo, b_hi, b_lo, i128, acc);
+                        tc::mma3p<LOWP>(tmem + 160u * g + 128u, a_hi, a_lo, x_hi, x_lo, i16, acc);
                     }
                 }
                 tc::mma_commit(bar_empty + 8 * s);
@@ -730,7 +762,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) struct_bwd_wgrad_kernel(const Wg
             tc::mbar_wait_warp(bar_full + 8 * s, (uint32_t)((i >> 1) & 1), lane, 32);
             if (tid == 64) WTRACE(2);
             const float m = smin / p.scales[(size_t)enc * p.chunk_cap + tile];
-            if (m != 1.0f) {
+            if (!LOWP && m != 1.0f) {
                 const __half2 m2 = __float2half2_rn(m);
                 uint4* st = reinterpret_cast<uint4*>(sgen + (size_t)s * ST_BYTES);
 #pragma unroll 4
@@ -832,7 +864,7 @@ int chunk_tiles() {
 }
 
 bool use_legacy(int precision) {
-    if (precision != 0) return true;
+    (void)precision;                    // both precisions run the tcgen05 kernels (bf16: single-plane instantiations)
     const char* e = getenv("MGV_STRUCT_BWD");
     return e && !strcmp(e, "mma");
 }
@@ -908,11 +940,15 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
     float* scales = a.take<float>((size_t)num_enc * cap);
     unsigned* smin = a.take<unsigned>((size_t)chunks * 2);
     MGV_REQUIRE(a.ok(), "mgv_struct_encoder_bwd: workspace layout overflow");
-    rc = mgv_struct_build_image(weights, num_enc, image, 0, st);
+    MGV_REQUIRE(precision == 0 || precision == 1, "struct encoder: precision must be 0 (fp32-accurate) or 1 (bf16)");
+    rc = mgv_struct_build_image(weights, num_enc, image, precision, st);
     if (rc != MGV_OK) return rc;
     MGV_CUDA(cudaMemsetAsync(partial, 0, (size_t)num_enc * gxp * 2 * SGRAD * sizeof(float), st));
-    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
-    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM));
+    const bool lowp = precision == 1;
+    const void* pw_fn = lowp ? (const void*)struct_bwd_pw_kernel<true> : (const void*)struct_bwd_pw_kernel<false>;
+    const void* wg_fn = lowp ? (const void*)struct_bwd_wgrad_kernel<true> : (const void*)struct_bwd_wgrad_kernel<false>;
+    MGV_CUDA(cudaFuncSetAttribute(pw_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
+    MGV_CUDA(cudaFuncSetAttribute(wg_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM));
 
     for (int k = steps; k >= 1; --k) {
         const int dir = (k & 1) ? 0 : 1;
@@ -940,13 +976,15 @@ extern "C" int mgv_struct_encoder_bwd(const mgv_schedule* sch, int32_t num_enc, 
             p.dgbuf = dgbuf; p.scales = scales; p.smin = smin + 2 * ch;
             p.partial = partial; p.gxp = gxp; p.chunk_cap = cap;
             p.trace = (k == 2 && ch == 0 && !getenv("MGV_TRACE_WGRAD")) ? mgv_debug_trace() : nullptr;
-            struct_bwd_pw_kernel<<<dim3(gx, num_enc), THREADS, P_SMEM, st>>>(p);
+            if (lowp) struct_bwd_pw_kernel<true><<<dim3(gx, num_enc), THREADS, P_SMEM, st>>>(p);
+            else struct_bwd_pw_kernel<false><<<dim3(gx, num_enc), THREADS, P_SMEM, st>>>(p);
             WgTC w{};
             w.ntiles = te - tb; w.chunk_cap = cap; w.dir = dir; w.gxp = gxp;
             w.tiles = p.tiles; w.tiles_enc_stride = p.tiles_enc_stride; w.tile_base = tb;
             w.dgbuf = dgbuf; w.scales = scales; w.smin = smin + 2 * ch; w.partial = partial;
             w.trace = (k == 2 && ch == 0 && getenv("MGV_TRACE_WGRAD")) ? mgv_debug_trace() : nullptr;
-            struct_bwd_wgrad_kernel<<<dim3(gx, num_enc), W_THREADS, W_SMEM, st>>>(w);
+            if (lowp) struct_bwd_wgrad_kernel<true><<<dim3(gx, num_enc), W_THREADS, W_SMEM, st>>>(w);
+            else struct_bwd_wgrad_kernel<false><<<dim3(gx, num_enc), W_THREADS, W_SMEM, st>>>(w);
             mgv_count_launches(2);
         }
     }

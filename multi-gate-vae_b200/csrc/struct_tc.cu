@@ -72,7 +72,7 @@ __device__ __forceinline__ void split_store_sw128(uint32_t hi_base, uint32_t lo_
     if (!LOWP) tc::st_shared_v4(lo_base + off, lo);
     if (gt) {       // read once, much later, by the backward: do not let it displace the state rows in L2
         tc::stg_v4_hint(gt + g_hi + off, hi, pol);
-        tc::stg_v4_hint(gt + g_lo + off, lo, pol);
+        if (!LOWP) tc::stg_v4_hint(gt + g_lo + off, lo, pol);
     }
 }
 
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__((EW + 128 / (4 * RPL) + 1) * 32, 1) struct_fwd
                     if (!LOWP) tc::st_shared_v4(sbase + A_X_LO + off, lo);
                     if (gt) {
                         tc::stg_v4_hint(gt + (A_X_HI - A_AGG_HI) + off, hi, pol_stream);
-                        tc::stg_v4_hint(gt + (A_X_LO - A_AGG_HI) + off, lo, pol_stream);
+                        if (!LOWP) tc::stg_v4_hint(gt + (A_X_LO - A_AGG_HI) + off, lo, pol_stream);
                     }
                 }
             }
@@ -512,8 +512,8 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         p.prev = states + (size_t)(k - 1) * slot;
         p.next = states + (size_t)k * slot;
         p.enc_stride = enc_stride;
-        // tile buffer [enc][step][tile][A_TILE_BYTES] (fp16 hi/lo planes: not written in bf16 mode, whose backward re-gathers)
-        p.tiles = (tiles && precision == 0) ? (uint8_t*)tiles + (size_t)(k - 1) * ntiles * A_TILE_BYTES : nullptr;
+        // tile buffer [enc][step][tile][A_TILE_BYTES] (fp16 hi/lo planes; bf16 mode writes its single bf16 plane into the hi slots)
+        p.tiles = tiles ? (uint8_t*)tiles + (size_t)(k - 1) * ntiles * A_TILE_BYTES : nullptr;
         p.tiles_enc_stride = (size_t)steps * ntiles * A_TILE_BYTES;
         p.trace = (k == trace_step) ? g_trace : nullptr;
         if (precision == 1) struct_fwd_tc_kernel<true, 4, 4><<<dim3(gx, num_enc), 13 * 32, F_SMEM, st>>>(p);

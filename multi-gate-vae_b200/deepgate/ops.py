@@ -294,8 +294,8 @@ class StructEncoderFunction(torch.autograd.Function):
         pack = _struct_pack(enc_params, layernorm, dev)
         states = torch.empty(num_enc, 2 * rounds + 1, max(N, 1), nat.D, dtype=torch.float32, device=dev)
         # training: the forward also saves every step's tensor-core operand tile; the backward recomputes from those
-        # instead of gathering the neighbour sums a second time (fp32-accurate mode; the bf16 backward re-gathers)
-        need_tiles = prec == 0 and N > 0 and any(ctx.needs_input_grad[5:])
+        # instead of gathering the neighbour sums a second time (bf16 mode: the single bf16 plane of each tile)
+        need_tiles = N > 0 and any(ctx.needs_input_grad[5:])
         tiles = (torch.empty(lib.mgv_struct_tiles_bytes(N, num_enc, rounds), dtype=torch.uint8, device=dev)
                  if need_tiles else None)
         with nat.on_device(dev):

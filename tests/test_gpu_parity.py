@@ -439,6 +439,49 @@ def test_struct_backward_paths_agree_on_a_large_heavy_tailed_graph(monkeypatch):
             assert rel(g1[k], g0[k]) < 1e-4, (env, k, rel(g1[k], g0[k]))
 
 
+def test_struct_backward_bf16_tensor_core_path_matches_the_bf16_mma_path(monkeypatch):
+    """bf16 mode: the tcgen05 backward (single bf16 plane: the forward's saved hi planes, bf16 gate-gradient planes, no tile
+    scale) against the mma.sync bf16 backward (MGV_STRUCT_BWD=mma, which gathers again and reads h in fp32) and against the
+    fp32-accurate gradients.  Both bf16 paths round the same operands to bf16 and accumulate in fp32; they differ by the order of
+    the sums and by h being read from the bf16 plane (2^-9): 2e-2 of the gradient's max-norm.  Against fp32: 5e-2 (BF16 gradient
+    tolerance of the configuration)."""
+    import deepgate
+    from deepgate import ops, synth
+    G = deepgate.circuits_to_batch(synth.make_circuits("mig", 4, 12, 3000, cfg=31), "cuda")
+    sd = O.synth_state_dict("mig", 43, layernorm=True)
+    code = G.gate.reshape(-1).long()
+    feat = torch.nn.functional.one_hot((code == 1).long(), 6).float()
+    gsrc = torch.Generator().manual_seed(6)
+    ws = torch.randn(G.x.size(0), 64, generator=gsrc).cuda()
+    wt = torch.randn(G.x.size(0), 64, generator=gsrc).cuda()
+
+    def run(env, precision):
+        for k in ("MGV_STRUCT_BWD", "MGV_STRUCT_CHUNK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ops.set_precision(precision)
+        try:
+            enc = deepgate.digae_layer.DirectMultiGCNEncoder(dim_hidden=64, dim_feature=6, s_rounds=2, t_rounds=2, layernorm=True).cuda()
+            enc.load_state_dict({k[len("mig_struct_encoder."):]: v for k, v in sd.items() if k.startswith("mig_struct_encoder.")})
+            s, t = enc(feat, feat, G.edge_index)
+            ((s * ws).sum() + (t * wt).sum()).backward()
+            torch.cuda.synchronize()
+        finally:
+            ops.set_precision("fp32")
+        return s.detach(), t.detach(), {k: p.grad.clone() for k, p in enc.named_parameters()}
+
+    s32, t32, g32 = run({}, "fp32")
+    s0, t0, g0 = run({"MGV_STRUCT_BWD": "mma"}, "bf16")
+    for env in ({}, {"MGV_STRUCT_CHUNK": "16"}):
+        s1, t1, g1 = run(env, "bf16")
+        assert torch.equal(s0, s1) and torch.equal(t0, t1)            # same forward kernel (the tile saving does not change it)
+        assert rel(s1, s32) > 1e-5, "bf16 mode did not engage"
+        for k in g0:
+            assert rel(g1[k], g0[k]) < 2e-2, (env, k, rel(g1[k], g0[k]))
+            assert rel(g1[k], g32[k]) < 5e-2, (env, k, rel(g1[k], g32[k]))
+
+
 @pytest.mark.parametrize("n_nodes", [1, 2, 127, 128, 129, 256, 385])
 def test_struct_backward_paths_agree_at_tile_boundaries(n_nodes, monkeypatch):
     """Node counts around the 128-row tile size (and degenerate graphs): tcgen05 backward vs mma.sync backward."""
