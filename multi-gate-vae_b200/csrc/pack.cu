@@ -149,6 +149,7 @@ __global__ void sweep_pack_kernel(const SweepParams sp, float* __restrict__ pack
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = 0.f;
+#pragma unroll 8
             for (int k = 0; k < D; ++k) {
                 const float w = __ldg(wih + g * D + k);
                 const float4 a = mgv_ldg4(vw + k * D2 + c * 8), b = mgv_ldg4(vw + k * D2 + c * 8 + 4);
@@ -164,6 +165,7 @@ __global__ void sweep_pack_kernel(const SweepParams sp, float* __restrict__ pack
             const int j = i - G3 * 16;
             float v = 0.f;
             if (j < 128) {                                   // u[k] = sum_o aw[64 + o] kw[o][k]
+#pragma unroll 32
                 for (int o = 0; o < D; ++o) v = fmaf(__ldg(aw + D + o), __ldg(kw + o * D2 + j), v);
             } else {
                 const int t = (j - 128) >> 6, u = (j - 128) & 63;          // 0 b_r, 1 b_z, 2 b_in, 3 b_hn
@@ -171,6 +173,7 @@ __global__ void sweep_pack_kernel(const SweepParams sp, float* __restrict__ pack
                 else {
                     const int g = t * D + u;
                     v = __ldg(bih + g) + (t < 2 ? __ldg(bhh + g) : 0.f);
+#pragma unroll 32
                     for (int k = 0; k < D; ++k) v = fmaf(__ldg(wih + g * D + k), __ldg(vb + k), v);
                 }
             }

@@ -479,12 +479,13 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
     const size_t slot = (size_t)N * D;
     const size_t enc_stride = (size_t)(steps + 1) * slot;
     // launch shape: 16 gather warps x 2 rows per lane + 8 epilogue warps (25 warps, 72 registers), or the 13-warp shape
-    // (8 gather warps x 4 rows, 4 epilogue warps, 128 registers) with MGV_STRUCT_FWD=v1 (A/B) and in bf16 mode
+    // (8 gather warps x 4 rows, 4 epilogue warps, 128 registers) with MGV_STRUCT_FWD=v1 (A/B)
     const char* fwd_env = getenv("MGV_STRUCT_FWD");
-    const bool wide = precision == 0 && !(fwd_env && !strcmp(fwd_env, "v1"));
+    const bool wide = !(fwd_env && !strcmp(fwd_env, "v1"));
     MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<false, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
     MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<false, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
     MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+    MGV_CUDA(cudaFuncSetAttribute((const void*)struct_fwd_tc_kernel<true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
     int dev = 0, sms = 0;
     MGV_CUDA(cudaGetDevice(&dev));
     MGV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -516,7 +517,8 @@ extern "C" int mgv_struct_encoder_fwd(const mgv_schedule* sch, int32_t num_enc, 
         p.tiles = tiles ? (uint8_t*)tiles + (size_t)(k - 1) * ntiles * A_TILE_BYTES : nullptr;
         p.tiles_enc_stride = (size_t)steps * ntiles * A_TILE_BYTES;
         p.trace = (k == trace_step) ? g_trace : nullptr;
-        if (precision == 1) struct_fwd_tc_kernel<true, 4, 4><<<dim3(gx, num_enc), 13 * 32, F_SMEM, st>>>(p);
+        if (precision == 1 && wide) struct_fwd_tc_kernel<true, 2, 8><<<dim3(gx, num_enc), 25 * 32, F_SMEM, st>>>(p);
+        else if (precision == 1) struct_fwd_tc_kernel<true, 4, 4><<<dim3(gx, num_enc), 13 * 32, F_SMEM, st>>>(p);
         else if (wide) struct_fwd_tc_kernel<false, 2, 8><<<dim3(gx, num_enc), 25 * 32, F_SMEM, st>>>(p);
         else struct_fwd_tc_kernel<false, 4, 4><<<dim3(gx, num_enc), 13 * 32, F_SMEM, st>>>(p);
         mgv_count_launches(1);

@@ -727,15 +727,16 @@ __global__ void sweep_chain_kernel(const float* __restrict__ pack, const float* 
     if (i < G_WV) v = R[R_U + i];
     else if (i < G_BV) {                                   // d W_v[k][f] = sum_g W_ih[g][k] d Wc[g][f]
         const int k = (i - G_WV) / D2, f = (i - G_WV) % D2;
-#pragma unroll 16
+#pragma unroll 32
         for (int g = 0; g < G3; ++g) v = fmaf(__ldg(W + O_WIH + g * D + k), __ldg(R + R_WC + g * D2 + f), v);
     } else if (i < G_WIH) {                                // d b_v[k] = sum_g W_ih[g][k] d c[g]
         const int k = i - G_BV;
-        for (int g = 0; g < G3; ++g) v = fmaf(__ldg(W + O_WIH + g * D + k), __ldg(R + R_B + g), v);
+#pragma unroll 32
+        for (int g = 0; g < G3; ++g) v = fmaf(__ldg(W + O_WIH + g * D + k), __ldg(R + R_B + g), v);     // 64 threads: keep the loads in flight
     } else if (i < G_WHH) {                                // d W_ih[g][k] = sum_f d Wc[g][f] W_v[k][f] + d c[g] b_v[k]
         const int g = (i - G_WIH) / D, k = (i - G_WIH) % D;
         v = __ldg(R + R_B + g) * __ldg(W + O_BV + k);
-#pragma unroll 16
+#pragma unroll 32
         for (int f = 0; f < D2; ++f) v = fmaf(__ldg(R + R_WC + g * D2 + f), __ldg(W + O_WV + k * D2 + f), v);
     } else if (i < G_BIH) v = 0.f;                         // d W_hh: h = 0 in a single-round sweep
     else if (i < G_BHH) v = R[R_B + (i - G_BIH)];

@@ -35,6 +35,21 @@ def split_edges(batch):
     return batch
 
 
+class _WeightedSum(torch.autograd.Function):
+    """sum_i w_i x_i of 0-dim losses: stack + dot forward, one scale backward (the expression w0 * a + w1 * b + w2 * c is five
+    tiny launches forward and eight backward)."""
+
+    @staticmethod
+    def forward(ctx, wvec, *xs):
+        ctx.save_for_backward(wvec)
+        return torch.dot(torch.stack([x.reshape(()) for x in xs]), wvec)
+
+    @staticmethod
+    def backward(ctx, g):
+        (wvec,) = ctx.saved_tensors
+        return (None,) + tuple((g * wvec).unbind(0))
+
+
 class FlatGradAllReduce(object):
     """Mean of the gradients over ranks through one flat fp32 buffer (0.96-1.56 MB for these models)."""
 
@@ -208,9 +223,19 @@ class Trainer(object):
 
     def total_loss(self, status):
         w = self.rc_prob_func_weight
-        total = w[0] * status["recon_loss"] + w[1] * status["prob_loss"] + w[2] * status["func_loss"]
+        terms = [status["recon_loss"], status["prob_loss"], status["func_loss"]]
+        weights = [float(w[0]), float(w[1]), float(w[2])]
         if self.kl_weight and "kl_loss" in status:
-            total = total + self.kl_weight * status["kl_loss"]
+            terms.append(status["kl_loss"])
+            weights.append(float(self.kl_weight))
+        if all(t.is_cuda and t.dtype == torch.float32 for t in terms):
+            key = (tuple(weights), terms[0].device)
+            if getattr(self, "_wvec_key", None) != key:
+                self._wvec_key, self._wvec = key, torch.tensor(weights, dtype=torch.float32, device=terms[0].device)
+            return _WeightedSum.apply(self._wvec, *terms)
+        total = weights[0] * terms[0]
+        for wi, t in zip(weights[1:], terms[1:]):
+            total = total + wi * t
         return total
 
     def train_step(self, batch, neg_edge_index=None):
