@@ -512,7 +512,7 @@ def measure(w, wname, steps, warmup, nb, dev, rank, world, clocks_index=None, cp
                              "every rank draws its own circuits, with the same circuit sizes on all ranks (size-bucketed sampler)"),
                    "setup": "one untimed pass over each distinct batch before the warm-up steps (allocator pools)",
                    "e2e_feed": "deepgate.CudaPrefetcher over pinned host batches: one host->device copy per step, issued on a side stream "
-                               "while the previous step computes (as Trainer.train does); loss.item() every step",
+                               "while the previous step computes (as Trainer.train does); every step's loss read back (e2e.result_read)",
                    "l2": "%d distinct batches rotated; per-batch working set (struct states %d MB) exceeds the 126 MB L2"
                          % (nb, int(2 * 9 * mean_stats["N"] * 256 / 1e6))},
         "e2e": {"value": e2e, "unit": "gates/s", "ms_per_step": ms_e2e / steps,
