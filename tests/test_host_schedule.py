@@ -4,6 +4,7 @@ against a direct construction from the collated ``edge_index`` -- the definition
 import os
 import sys
 
+import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -97,3 +98,46 @@ def test_packed_batch_is_one_buffer_with_the_same_fields():
     c = b.copy_to("cpu")
     assert all(torch.equal(getattr(c, k), before[k]) for k in before)
     assert (c.num_levels, list(c.level_code_count), c.sched_streams, c.num_graphs) == meta
+
+
+def test_deferred_scalars_return_every_value_once_in_order():
+    """``DeferredScalars``: values come back ``lag`` pushes late, in order, each exactly once; ``drain`` returns the rest."""
+    from deepgate import DeferredScalars
+    for lag in (0, 1, 2, 3):
+        r = DeferredScalars("cpu", lag=lag)
+        got = []
+        for i in range(7):
+            out = r.push(torch.tensor(float(i)), torch.tensor(10 * i, dtype=torch.int32))
+            assert (out is None) == (lag > 0 and i < lag)
+            if out is not None:
+                got.append(out)
+        got += r.drain()
+        assert got == [[float(i), float(10 * i)] for i in range(7)], (lag, got)
+        assert r.drain() == []
+    with pytest.raises(ValueError):
+        DeferredScalars("cpu", width=1).push(torch.tensor(1.0), torch.tensor(2.0))
+
+
+def test_weighted_loss_sum_matches_the_expression_and_its_gradients():
+    """``Trainer.total_loss``'s one-function weighted sum: value and gradients of w0 a + w1 b + w2 c (+ wk kl)."""
+    from deepgate.trainer import _WeightedSum
+    w = [1.0, 4.0, 4.0, 0.25]
+    xs = [torch.tensor(v, requires_grad=True) for v in (0.7, 0.11, 2.5, 13.0)]
+    ys = [x.detach().clone().requires_grad_(True) for x in xs]
+    a = _WeightedSum.apply(torch.tensor(w), *xs)
+    b = sum(wi * y for wi, y in zip(w, ys))
+    assert abs(float(a) - float(b)) < 1e-6
+    (3.0 * a).backward()
+    (3.0 * b).backward()
+    assert all(abs(float(x.grad) - float(y.grad)) < 1e-6 for x, y in zip(xs, ys))
+
+
+def test_edge_split_on_a_host_batch_keeps_every_edge():
+    """``split_edges`` on a CPU batch (data preparation): a permutation of the columns of ``edge_index``."""
+    import deepgate
+    from deepgate import synth
+    from deepgate.trainer import split_edges
+    b = deepgate.circuits_to_batch(synth.make_circuits("aig", 2, 6, 50, cfg=3))
+    split_edges(b)
+    key = lambda t: torch.sort(t[0] * (1 << 20) + t[1]).values
+    assert b.train_pos_edge_index.shape == b.edge_index.shape and torch.equal(key(b.train_pos_edge_index), key(b.edge_index))
